@@ -1,0 +1,108 @@
+/*
+ * velo_oracle.h -- C interface of the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a dependency-free CPU restatement of the
+ * reference's ingest hot path (victl/VeloSLAM: HDLParser.cxx, TransformManager.cxx,
+ * TimeLine.h, type_defs.h).  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may load it.  The product
+ * (libveloslam_b200.so) never links, loads or calls anything in oracle/.
+ *
+ * Parity pin: the reference ships no golden vectors or known-answer tests for this
+ * path, so the restatement is pinned two ways:
+ *   1. hand-derived known-answer tests (tests/test_oracle_kat.py);
+ *   2. oracle/_ref -- the reference's own HDLParser.cxx / TransformManager.cxx /
+ *      TimeLine.h / type_defs.* compiled verbatim against shim headers
+ *      (oracle/ref_shim/, see oracle/build_ref.py) and compared output-for-output
+ *      (tests/test_oracle_vs_ref.py).  Where oracle/_ref is not built the header
+ *      of that test says so and parity is "unpinned" beyond (1).
+ *
+ * Time: boost::posix_time::ptime (microsecond resolution) is restated as
+ * int64 microseconds since the Unix epoch.
+ */
+#ifndef VELO_ORACLE_H
+#define VELO_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vo_parser vo_parser;
+
+typedef struct vo_frame_info {
+  int64_t timestamp_us;     /* HDLFrame::timestamp; INT64_MIN when never initialised */
+  int32_t skips;            /* HDLFrame::skips; -1 when never initialised            */
+  int32_t n_lasers;         /* points.size()                                         */
+  int32_t n_points;         /* sum over lasers                                       */
+  int32_t n_packets;        /* packets.size() (first packet of a frame is doubled)   */
+  int32_t is_hdl64_order;   /* 1 when splitFrame applied HDL64BeamLUT                */
+  int32_t pad;
+  double  carpose_TRV[9];   /* carpose T[3], R[3], V[3]                              */
+  double  carpose_seconds_pos; /* -1 == invalid pose (type_defs.cxx:56)              */
+} vo_frame_info;
+
+vo_parser* vo_create(void);
+void       vo_destroy(vo_parser*);
+
+/* Calibration as the five raw db.xml values per laser (HDLParser.cxx:822-839) plus the
+ * number of enabled_ items equal to 1 (HDLParser.cxx:785-799). */
+void vo_set_calibration(vo_parser*, const double* rot_deg, const double* vert_deg,
+                        const double* dist_cm, const double* voff_cm, const double* hoff_cm,
+                        int n_rows, int n_enabled);
+void vo_set_laser_selection(vo_parser*, const int32_t sel[64]);
+void vo_set_points_skip(vo_parser*, int32_t points_skip);
+void vo_set_crop(vo_parser*, int32_t crop_returns, int32_t crop_inside, const double region[6]);
+
+/* TransformManager */
+void    vo_clear_poses(vo_parser*);
+void    vo_add_pose(vo_parser*, int64_t t_us, const double T[3], const double R[3], const double V[3]);
+int32_t vo_num_poses(vo_parser*);
+/* interpolateTransform: returns its bool; out_TRV = T,R,V; *seconds_pos = -1 or 0 */
+int32_t vo_interpolate(vo_parser*, int64_t t_us, double out_TRV[9], double* seconds_pos);
+/* PoseTransform::getMatrix of a TRV triple: out = 3x4 row-major [L | t] */
+void    vo_pose_matrix(const double TRV[9], double out[12]);
+
+/* Parser state */
+void vo_unload(vo_parser*);                       /* HDLParser::unloadData            */
+void vo_set_firing_skip(vo_parser*, int32_t s);   /* getFrame sets firingSkip = skip  */
+void vo_get_state(vo_parser*, int32_t out[4]);    /* lastAzimuth, firingSkip, frameMetaInited, isHDL64Data */
+
+/* Streaming decode */
+void vo_process_packet(vo_parser*, const uint8_t* data, uint32_t len, int64_t t_us);
+void vo_process_packets(vo_parser*, const uint8_t* data, int64_t n, int64_t stride,
+                        const int64_t* t_us);
+void vo_split_frame(vo_parser*);                  /* splitFrame(), used by getFrame's tail */
+
+/* Completed frames (HDLParser::getAllFrames order) */
+int32_t vo_num_frames(vo_parser*);
+void    vo_clear_frames(vo_parser*);
+int32_t vo_frame_get_info(vo_parser*, int32_t f, vo_frame_info* out);
+int32_t vo_frame_laser_counts(vo_parser*, int32_t f, int32_t* counts);
+/* laser-major concatenation in the frame's final laser order */
+int32_t vo_frame_points(vo_parser*, int32_t f, float* xyzi, uint16_t* azimuth, float* distance);
+/* number of points currently sitting in the open (not yet split) frame */
+int64_t vo_open_frame_points(vo_parser*);
+
+/* Emission trace: one record per pushed point, in emission (stream) order */
+void    vo_trace_enable(vo_parser*, int32_t on);
+int64_t vo_trace_size(vo_parser*);
+void    vo_trace_fetch(vo_parser*, int32_t* packet, uint8_t* block, uint8_t* dsr, uint8_t* laser,
+                       int32_t* frame, float* x, float* y, float* z, uint8_t* intensity,
+                       uint16_t* azimuth, uint16_t* raw_distance, uint32_t* tadj_us);
+
+/* Offline index (HDLParser::readFrameInformation) over an in-memory packet array.
+ * Returns the number of frames; fills up to cap entries. */
+int32_t vo_read_frame_information(const uint8_t* data, int64_t n, int64_t stride,
+                                  const int64_t* t_us, int32_t* start_packet,
+                                  int32_t* skips, int64_t* timestamp_us, int32_t cap);
+/* HDLParser::getFrame over an in-memory packet array: decode from (start_packet, skip)
+ * until the first split (or force a split at the end).  The frame is appended to the
+ * parser's frame list.  Returns 1 on success. */
+int32_t vo_get_frame(vo_parser*, const uint8_t* data, int64_t n, int64_t stride,
+                     const int64_t* t_us, int64_t start_packet, int32_t skip);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
