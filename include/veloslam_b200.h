@@ -1,0 +1,209 @@
+/*
+ * veloslam_b200.h -- C ABI of the B200-native Velodyne ingest hot path.
+ *
+ * Drop-in boundary for victl/VeloSLAM's packet decode -> calibrated points -> rotation
+ * segmentation -> per-packet motion compensation.  The reference has no FFI layer: its
+ * boundary is the public C++ API of HDLParser (HDLParser.h:84-147) and TransformManager
+ * (TransformManager.h:80-123).  Each entry point below names the reference interface it
+ * replaces; the C++ facade in veloslam_b200/cpp/ keeps the reference's class and method
+ * names on top of this ABI.
+ *
+ * Plain C: pointers and sizes only, no exceptions, no C++/torch types.  Every function
+ * returns a vs_status (0 == ok); vs_last_error() gives the message of the last failure on
+ * a context.  There is no CPU fallback: without a CUDA device vs_create() fails.
+ *
+ * Threading (same contract as the reference's parserMutex, HDLSource.cxx:214): calls on
+ * one context must be externally serialised; different contexts are independent.
+ *
+ * Time is int64 microseconds since the Unix epoch (boost::posix_time::ptime restated).
+ */
+#ifndef VELOSLAM_B200_H
+#define VELOSLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VS_API __attribute__((visibility("default")))
+#else
+#define VS_API
+#endif
+
+#define VS_PACKET_BYTES 1206      /* HDLParser.cxx:982 */
+#define VS_BLOCKS_PER_PACKET 12   /* type_defs.h:19 HDL_FIRING_PER_PKT */
+#define VS_RETURNS_PER_BLOCK 32   /* type_defs.h:17 HDL_LASER_PER_FIRING */
+#define VS_MAX_LASERS 64          /* type_defs.h:18 HDL_MAX_NUM_LASERS */
+#define VS_PCAP_RECORD_BYTES 1264 /* vtkPacketFileReader.h:57-66: 16 + 42 + 1206 */
+#define VS_PCAP_PAYLOAD_OFFSET 82 /* 24-byte global header + 16 + 42 */
+#define VS_TIME_NONE INT64_MIN    /* ptime not_a_date_time */
+
+typedef enum vs_status {
+  VS_OK = 0,
+  VS_ERR_INVALID_ARG = 1,
+  VS_ERR_NOT_CALIBRATED = 2, /* decode before vs_set_calibration (HDLParser.cxx:512-516) */
+  VS_ERR_CUDA = 3,
+  VS_ERR_CAPACITY = 4,       /* batch/pose/frame capacity exceeded */
+  VS_ERR_NO_DEVICE = 5,
+  VS_ERR_HALO = 6,           /* halo too short to resolve the carried state */
+  VS_ERR_STATE = 7           /* bad ticket / slot busy */
+} vs_status;
+
+typedef enum vs_mode {
+  /* HDLParser::processHDLPacket as called per packet by the online consumer
+   * (HDLSource.cxx:209-225), bug-compatible (SURVEY.md F4 a-d). */
+  VS_MODE_STREAMING = 0,
+  /* HDLParser::readFrameInformation + getFrame (HDLParser.cxx:1065-1160, 505-544): every
+   * block decoded, frame origin = pose at the packet that holds the frame's first block. */
+  VS_MODE_OFFLINE = 1
+} vs_mode;
+
+/* Flags for vs_submit*(). */
+#define VS_FLAG_DEVICE_INPUT 1u   /* packets / times are device pointers (already in HBM) */
+#define VS_FLAG_PCAP_TIMES 2u     /* take packet times from the pcap record headers
+                                     (ts_sec + 8 h, ts_usec: type_defs.cxx:69-72); pkts must
+                                     then point at the first record's payload, stride 1264 */
+
+/* One <px> item of the calibration db.xml in its raw units (HDLParser.cxx:818-832). */
+typedef struct vs_laser_corr {
+  double rot_correction_deg;          /* rotCorrection_          */
+  double vert_correction_deg;         /* vertCorrection_         */
+  double dist_correction_cm;          /* distCorrection_         */
+  double vert_offset_correction_cm;   /* vertOffsetCorrection_   */
+  double horiz_offset_correction_cm;  /* horizOffsetCorrection_  */
+} vs_laser_corr;
+
+/* HDLParser::setLaserSelection / setPointsSkip / setCropReturns / setCropInside /
+ * setCropRegion (HDLParser.cxx:367-455). */
+typedef struct vs_filters {
+  uint64_t laser_mask;     /* bit i == laserSelections[i] */
+  int32_t  points_skip;
+  int32_t  crop_returns;
+  int32_t  crop_inside;
+  int32_t  reserved;
+  double   crop_region[6]; /* xl, xu, yl, yu, zl, zu */
+} vs_filters;
+
+/* The parser state that survives a packet (HDLParser.cxx:196-216), passed by value between
+ * batches; vs_carry_init() gives the state after HDLParser::unloadData(). */
+typedef struct vs_carry {
+  int32_t last_azimuth;        /* lastAzimuth, -1 == none yet             */
+  int32_t firing_skip;         /* firingSkip                              */
+  int32_t frame_meta_inited;   /* frameMetaInited of the open frame       */
+  int32_t is_hdl64;            /* sticky isHDL64Data                      */
+  double  origin_T[3];         /* currentFrame->carpose->T (frame origin) */
+  int64_t frame_timestamp_us;  /* open frame: HDLFrame::timestamp         */
+  int32_t frame_skips;         /* open frame: HDLFrame::skips             */
+  int32_t frame_carpose_valid; /* open frame: carpose->seconds_pos != -1  */
+  double  frame_carpose[9];    /* open frame: carpose T, R, V             */
+  int64_t frames_closed;       /* running totals since vs_carry_init      */
+  int64_t points_emitted;
+  int64_t packets_seen;
+} vs_carry;
+
+/* One frame (HDLFrame.h:13-47) as an index into the batch's point columns.  Points of
+ * frame f are the contiguous range [first_point, first_point + n_points) in emission
+ * order (packet, block, laser-in-block) -- the order in which the reference pushes them;
+ * laser_counts gives the size of each HDLFrame::points[laser] list. */
+typedef struct vs_frame {
+  int64_t  first_point;
+  int64_t  n_points;
+  int64_t  timestamp_us;     /* VS_TIME_NONE when the reference never initialises it */
+  int32_t  start_packet;     /* packet (index in the submitted array) and block where   */
+  int32_t  start_block;      /* the frame begins; start_packet -1: an earlier batch      */
+  int32_t  meta_packet;      /* packet that set timestamp/carpose/skips; -1 carry, -2 none */
+  int32_t  skips;            /* HDLFrame::skips; -1 when never initialised              */
+  int32_t  closed;           /* 1: closed by a wrap inside this batch                   */
+  int32_t  hdl64_order;      /* 1: reference re-orders lasers by HDL64BeamLUT at close  */
+  int32_t  carpose_valid;    /* carpose->seconds_pos != -1                              */
+  int32_t  reserved;
+  double   carpose[9];       /* T, R (deg), V                                           */
+  uint32_t laser_counts[VS_MAX_LASERS]; /* by laser id as pushed (before HDL64BeamLUT)  */
+} vs_frame;
+
+/* Result of one batch.  Column pointers are DEVICE pointers owned by the context and stay
+ * valid until the slot's next submit.  frames is a host array owned by the context. */
+typedef struct vs_result {
+  int64_t n_packets;          /* packets decoded (halo excluded)                   */
+  int64_t n_points;           /* emitted points                                    */
+  int32_t n_frames;           /* closed frames + 1 (the last entry is the open one) */
+  int32_t n_closed;
+  const float*    x;          /* metres, after the per-packet rigid transform      */
+  const float*    y;
+  const float*    z;
+  const uint8_t*  intensity;
+  const uint8_t*  laser;      /* HDLFrame::points row the reference pushes into    */
+  const uint16_t* azimuth;    /* PointMeta::azimuth (adjusted, mod 36000)          */
+  const uint16_t* distance;   /* raw 2 mm units                                    */
+  const uint32_t* t_us;       /* (packet time - t_base) + rounded firing offset    */
+  const vs_frame* frames;
+  vs_carry carry_out;
+  int64_t t_base_us;
+  int64_t first_upper_block;  /* first decoded 0xddff block (packet*12+block), -1 none */
+  float   gpu_ms;             /* device time of the batch's kernels (CUDA events)  */
+  int32_t n_kernel_launches;
+} vs_result;
+
+typedef struct vs_ctx vs_ctx;
+
+/* Library / build info: "veloslam_b200 <version> sm_100a". */
+VS_API const char* vs_version(void);
+
+/* Replaces `new HDLParser` + `new TransformManager` (HDLParser.cxx:284-288).
+ * max_batch_packets bounds one submit (halo included); n_slots in {1,2} result slots. */
+VS_API int vs_create(int device, int64_t max_batch_packets, int64_t max_poses, int n_slots, vs_ctx** out);
+VS_API void vs_destroy(vs_ctx* ctx);
+VS_API const char* vs_last_error(vs_ctx* ctx);
+
+/* HDLParser::setCorrectionsFile -> loadCorrectionsFile (HDLParser.cxx:458-475, 771-858):
+ * n_rows calibration rows (id_ == index) and the count of enabled_ items equal to 1. */
+VS_API int vs_set_calibration(vs_ctx* ctx, const vs_laser_corr* corr, int n_rows, int n_lasers_enabled);
+VS_API int vs_set_filters(vs_ctx* ctx, const vs_filters* f);
+
+/* TransformManager::addTransform / clearTransforms as an immutable snapshot per batch
+ * (TransformManager.cxx:61-79): n poses sorted by strictly increasing time, trv = n x 9
+ * doubles (T[3], R[3] degrees, V[3]).  n == 0 clears. */
+VS_API int vs_set_poses(vs_ctx* ctx, const int64_t* t_us, const double* trv, int64_t n);
+/* TransformManager::interpolateTransform (TransformManager.cxx:149-177) on the host copy of
+ * the snapshot.  Returns VS_OK; *found = its bool, *valid = (seconds_pos != -1). */
+VS_API int vs_interpolate(vs_ctx* ctx, int64_t t_us, double out_trv[9], int32_t* found, int32_t* valid);
+
+VS_API void vs_carry_init(vs_carry* c);
+
+/* HDLParser::processHDLPacket for a batch of n packets (HDLParser.cxx:489, 980-1055).
+ * pkts: n records of VS_PACKET_BYTES payload at `stride` bytes (1206 dense, 1264 = pcap
+ * records); pkt_time_us: n packet times (ignored with VS_FLAG_PCAP_TIMES).  The first
+ * n_halo packets only rebuild parser state (multi-GPU shards) and emit nothing; with
+ * n_halo > 0 the carry-in is ignored and the state is resolved from the halo.
+ * t_base_us: origin of the t_us column (VS_TIME_NONE: time of the first decoded packet,
+ * host input only).  Host buffers are copied asynchronously; they must stay valid until
+ * vs_wait returns. */
+VS_API int vs_submit(vs_ctx* ctx, const uint8_t* pkts, int64_t stride, const int64_t* pkt_time_us,
+              int64_t n, int64_t n_halo, int mode, uint32_t flags, int64_t t_base_us,
+              const vs_carry* carry_in, uint64_t* ticket);
+/* Replaces HDLParser::getAllFrames (HDLParser.cxx:495-498): blocks until the batch is done. */
+VS_API int vs_wait(vs_ctx* ctx, uint64_t ticket, vs_result* out);
+/* Copy point columns [first, first+count) of a finished batch to host arrays (any may be
+ * NULL).  Synchronous. */
+VS_API int vs_fetch_points(vs_ctx* ctx, uint64_t ticket, int64_t first, int64_t count, float* x,
+                    float* y, float* z, uint8_t* intensity, uint8_t* laser, uint16_t* azimuth,
+                    uint16_t* distance, uint32_t* t_us);
+
+/* HDLParser::readFrameInformation (HDLParser.cxx:1065-1160) over a packet array: fills up
+ * to cap entries (start packet, start block == skips, timestamp) and returns the count in
+ * *n_frames.  Equivalent to a VS_MODE_OFFLINE submit that skips the decode. */
+VS_API int vs_read_frame_information(vs_ctx* ctx, const uint8_t* pkts, int64_t stride,
+                              const int64_t* pkt_time_us, int64_t n, uint32_t flags,
+                              int32_t* start_packet, int32_t* skips, int64_t* timestamp_us,
+                              int32_t cap, int32_t* n_frames);
+
+/* The CUDA stream the context launches on (cudaStream_t), for callers that time or order
+ * work against it. */
+VS_API void* vs_stream(vs_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,46 @@
+"""In-tree build of the CUDA C-ABI library (sm_100a only).
+
+`nvcc` cross-compiles without a GPU; the resulting `veloslam_b200/libveloslam_b200.so` is
+git-ignored but travels to the GPU box with the repo snapshot.
+"""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libveloslam_b200.so")
+SOURCES = [os.path.join(CSRC, "vs_capi.cu")]
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("vs_kernels.cuh", "vs_device.cuh")] + \
+    [os.path.join(os.path.dirname(HERE), "include", "veloslam_b200.h")]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    # host side restates reference arithmetic: no FMA contraction there either
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
+    "-shared", "-cudart", "static",
+]
+
+
+def find_nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=...)")
+
+
+def build_library(force=False, verbose=False):
+    """Compile libveloslam_b200.so if missing or older than its sources."""
+    if (not force and os.path.exists(LIB)
+            and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in DEPS)):
+        return LIB
+    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", LIB] + SOURCES
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force=True, verbose=True))

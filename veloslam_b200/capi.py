@@ -1,0 +1,301 @@
+"""ctypes binding of the C ABI declared in include/veloslam_b200.h.
+
+This is harness code for tests and bench.py: the product is the shared library.  It fails
+loudly when the CUDA library is missing -- there is no CPU fallback and this module never
+touches oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import LIB
+
+INT64_MIN = -(2 ** 63)
+VS_TIME_NONE = INT64_MIN
+MODE_STREAMING, MODE_OFFLINE = 0, 1
+FLAG_DEVICE_INPUT, FLAG_PCAP_TIMES = 1, 2
+STATUS = {0: "VS_OK", 1: "VS_ERR_INVALID_ARG", 2: "VS_ERR_NOT_CALIBRATED", 3: "VS_ERR_CUDA",
+          4: "VS_ERR_CAPACITY", 5: "VS_ERR_NO_DEVICE", 6: "VS_ERR_HALO", 7: "VS_ERR_STATE"}
+
+EXPORTS = ["vs_version", "vs_create", "vs_destroy", "vs_last_error", "vs_set_calibration",
+           "vs_set_filters", "vs_set_poses", "vs_interpolate", "vs_carry_init", "vs_submit",
+           "vs_wait", "vs_fetch_points", "vs_read_frame_information", "vs_stream"]
+
+
+class LaserCorr(C.Structure):
+    _fields_ = [("rot_correction_deg", C.c_double), ("vert_correction_deg", C.c_double),
+                ("dist_correction_cm", C.c_double), ("vert_offset_correction_cm", C.c_double),
+                ("horiz_offset_correction_cm", C.c_double)]
+
+
+class Filters(C.Structure):
+    _fields_ = [("laser_mask", C.c_uint64), ("points_skip", C.c_int32),
+                ("crop_returns", C.c_int32), ("crop_inside", C.c_int32), ("reserved", C.c_int32),
+                ("crop_region", C.c_double * 6)]
+
+
+class Carry(C.Structure):
+    _fields_ = [("last_azimuth", C.c_int32), ("firing_skip", C.c_int32),
+                ("frame_meta_inited", C.c_int32), ("is_hdl64", C.c_int32),
+                ("origin_T", C.c_double * 3), ("frame_timestamp_us", C.c_int64),
+                ("frame_skips", C.c_int32), ("frame_carpose_valid", C.c_int32),
+                ("frame_carpose", C.c_double * 9), ("frames_closed", C.c_int64),
+                ("points_emitted", C.c_int64), ("packets_seen", C.c_int64)]
+
+
+class Frame(C.Structure):
+    _fields_ = [("first_point", C.c_int64), ("n_points", C.c_int64), ("timestamp_us", C.c_int64),
+                ("start_packet", C.c_int32), ("start_block", C.c_int32),
+                ("meta_packet", C.c_int32), ("skips", C.c_int32), ("closed", C.c_int32),
+                ("hdl64_order", C.c_int32), ("carpose_valid", C.c_int32), ("reserved", C.c_int32),
+                ("carpose", C.c_double * 9), ("laser_counts", C.c_uint32 * 64)]
+
+
+class Result(C.Structure):
+    _fields_ = [("n_packets", C.c_int64), ("n_points", C.c_int64), ("n_frames", C.c_int32),
+                ("n_closed", C.c_int32), ("x", C.c_void_p), ("y", C.c_void_p), ("z", C.c_void_p),
+                ("intensity", C.c_void_p), ("laser", C.c_void_p), ("azimuth", C.c_void_p),
+                ("distance", C.c_void_p), ("t_us", C.c_void_p), ("frames", C.POINTER(Frame)),
+                ("carry_out", Carry), ("t_base_us", C.c_int64), ("first_upper_block", C.c_int64),
+                ("gpu_ms", C.c_float), ("n_kernel_launches", C.c_int32)]
+
+
+class VeloError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{STATUS.get(code, code)}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libveloslam_b200.so; raises if the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB):
+        raise RuntimeError(f"{LIB} is missing: build it with __graft_entry__.build() "
+                           "(python -m veloslam_b200.build); there is no CPU fallback")
+    L = C.CDLL(LIB)
+    vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+    L.vs_version.restype = C.c_char_p
+    L.vs_version.argtypes = []
+    L.vs_create.restype = C.c_int
+    L.vs_create.argtypes = [C.c_int, i64, i64, C.c_int, C.POINTER(vp)]
+    L.vs_destroy.restype = None
+    L.vs_destroy.argtypes = [vp]
+    L.vs_last_error.restype = C.c_char_p
+    L.vs_last_error.argtypes = [vp]
+    L.vs_set_calibration.restype = C.c_int
+    L.vs_set_calibration.argtypes = [vp, C.POINTER(LaserCorr), C.c_int, C.c_int]
+    L.vs_set_filters.restype = C.c_int
+    L.vs_set_filters.argtypes = [vp, C.POINTER(Filters)]
+    L.vs_set_poses.restype = C.c_int
+    L.vs_set_poses.argtypes = [vp, vp, vp, i64]
+    L.vs_interpolate.restype = C.c_int
+    L.vs_interpolate.argtypes = [vp, i64, C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(i32)]
+    L.vs_carry_init.restype = None
+    L.vs_carry_init.argtypes = [C.POINTER(Carry)]
+    L.vs_submit.restype = C.c_int
+    L.vs_submit.argtypes = [vp, vp, i64, vp, i64, i64, C.c_int, C.c_uint32, i64,
+                            C.POINTER(Carry), C.POINTER(u64)]
+    L.vs_wait.restype = C.c_int
+    L.vs_wait.argtypes = [vp, u64, C.POINTER(Result)]
+    L.vs_fetch_points.restype = C.c_int
+    L.vs_fetch_points.argtypes = [vp, u64, i64, i64] + [vp] * 8
+    L.vs_read_frame_information.restype = C.c_int
+    L.vs_read_frame_information.argtypes = [vp, vp, i64, vp, i64, C.c_uint32, vp, vp, vp, i32,
+                                            C.POINTER(i32)]
+    L.vs_stream.restype = vp
+    L.vs_stream.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def carry_init():
+    c = Carry()
+    load_library().vs_carry_init(C.byref(c))
+    return c
+
+
+def _ptr(a):
+    """Address of a numpy array, a torch tensor (host or device) or a raw int."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+class FrameView:
+    """Python copy of one vs_frame."""
+
+    def __init__(self, f):
+        self.first_point = int(f.first_point)
+        self.n_points = int(f.n_points)
+        self.timestamp_us = int(f.timestamp_us)
+        self.start_packet = int(f.start_packet)
+        self.start_block = int(f.start_block)
+        self.meta_packet = int(f.meta_packet)
+        self.skips = int(f.skips)
+        self.closed = bool(f.closed)
+        self.hdl64_order = bool(f.hdl64_order)
+        self.carpose_valid = bool(f.carpose_valid)
+        self.carpose = np.array(list(f.carpose), dtype=np.float64)
+        self.laser_counts = np.array(list(f.laser_counts), dtype=np.int64)
+
+
+class BatchResult:
+    def __init__(self, ctx, ticket, r):
+        self._ctx = ctx
+        self.ticket = ticket
+        self.n_packets = int(r.n_packets)
+        self.n_points = int(r.n_points)
+        self.n_frames = int(r.n_frames)
+        self.n_closed = int(r.n_closed)
+        self.frames = [FrameView(r.frames[i]) for i in range(r.n_frames)]
+        self.carry_out = Carry.from_buffer_copy(r.carry_out)
+        self.t_base_us = int(r.t_base_us)
+        self.first_upper_block = int(r.first_upper_block)
+        self.gpu_ms = float(r.gpu_ms)
+        self.n_kernel_launches = int(r.n_kernel_launches)
+        self.device_ptrs = {k: getattr(r, k) for k in
+                            ("x", "y", "z", "intensity", "laser", "azimuth", "distance", "t_us")}
+
+    def fetch(self, first=0, count=None, columns=None):
+        """Copy point columns to host numpy arrays."""
+        return self._ctx.fetch_points(self.ticket, first,
+                                      self.n_points - first if count is None else count, columns)
+
+
+COLUMNS = (("x", np.float32), ("y", np.float32), ("z", np.float32), ("intensity", np.uint8),
+           ("laser", np.uint8), ("azimuth", np.uint16), ("distance", np.uint16),
+           ("t_us", np.uint32))
+
+
+class Context:
+    """One parser + pose snapshot on one GPU (vs_ctx)."""
+
+    def __init__(self, device=0, max_batch_packets=1 << 16, max_poses=1 << 16, n_slots=1):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.vs_create(device, max_batch_packets, max_poses, n_slots, C.byref(h))
+        if rc != 0:
+            raise VeloError(rc, self._L.vs_last_error(None).decode() or "vs_create failed")
+        self._h = h
+        self.device = device
+        self.max_batch_packets = max_batch_packets
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.vs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise VeloError(rc, self._L.vs_last_error(self._h).decode())
+
+    # -- configuration --------------------------------------------------------------
+    def set_calibration(self, calib):
+        n = calib.n_rows
+        arr = (LaserCorr * max(n, 1))()
+        for i in range(n):
+            arr[i] = LaserCorr(calib.rot_deg[i], calib.vert_deg[i], calib.dist_cm[i],
+                               calib.voff_cm[i], calib.hoff_cm[i])
+        self._check(self._L.vs_set_calibration(self._h, arr, n, calib.n_enabled))
+
+    def set_filters(self, laser_selection=None, points_skip=0, crop_returns=0, crop_inside=0,
+                    crop_region=(0, 0, 0, 0, 0, 0)):
+        mask = (1 << 64) - 1
+        if laser_selection is not None:
+            mask = 0
+            for i, v in enumerate(laser_selection):
+                if v:
+                    mask |= 1 << i
+        f = Filters(mask, points_skip, int(bool(crop_returns)), int(bool(crop_inside)), 0,
+                    (C.c_double * 6)(*[float(v) for v in crop_region]))
+        self._check(self._L.vs_set_filters(self._h, C.byref(f)))
+
+    def set_poses(self, t_us, trv):
+        t = np.ascontiguousarray(t_us, dtype=np.int64)
+        v = np.ascontiguousarray(trv, dtype=np.float64).reshape(-1, 9) if len(t) else \
+            np.zeros((0, 9))
+        assert v.shape[0] == t.shape[0]
+        self._check(self._L.vs_set_poses(self._h, _ptr(t) if len(t) else None,
+                                         _ptr(v) if len(t) else None, len(t)))
+
+    def interpolate(self, t_us):
+        out = (C.c_double * 9)()
+        found, valid = C.c_int32(), C.c_int32()
+        self._check(self._L.vs_interpolate(self._h, int(t_us), out, C.byref(found),
+                                           C.byref(valid)))
+        return bool(found.value), np.array(list(out)), bool(valid.value)
+
+    # -- batches ----------------------------------------------------------------------
+    def submit(self, pkts, pkt_time_us, n=None, stride=None, n_halo=0, mode=MODE_STREAMING,
+               flags=0, t_base_us=VS_TIME_NONE, carry=None):
+        """pkts: (n, stride) uint8 numpy array / torch tensor, or a raw address with n & stride."""
+        if n is None:
+            n = int(pkts.shape[0])
+        if stride is None:
+            stride = int(pkts.shape[1]) if pkts.ndim == 2 else 1206
+        tk = C.c_uint64()
+        cptr = C.byref(carry) if carry is not None else None
+        self._check(self._L.vs_submit(self._h, _ptr(pkts), stride, _ptr(pkt_time_us), n, n_halo,
+                                      mode, flags, t_base_us, cptr, C.byref(tk)))
+        self._keepalive = (pkts, pkt_time_us)
+        return tk.value
+
+    def wait(self, ticket):
+        r = Result()
+        self._check(self._L.vs_wait(self._h, ticket, C.byref(r)))
+        return BatchResult(self, ticket, r)
+
+    def decode(self, pkts, pkt_time_us, **kw):
+        return self.wait(self.submit(pkts, pkt_time_us, **kw))
+
+    def fetch_points(self, ticket, first, count, columns=None):
+        names = [c for c, _ in COLUMNS] if columns is None else list(columns)
+        out = {}
+        ptrs = []
+        for name, dt in COLUMNS:
+            if name in names:
+                out[name] = np.empty(max(count, 0), dtype=dt)
+                ptrs.append(out[name].ctypes.data if count > 0 else None)
+            else:
+                ptrs.append(None)
+        self._check(self._L.vs_fetch_points(self._h, ticket, first, count, *ptrs))
+        return out
+
+    def fetch_into(self, ticket, first, count, host_ptrs):
+        """vs_fetch_points into caller-owned (e.g. pinned) buffers: host_ptrs = 8 addresses."""
+        self._check(self._L.vs_fetch_points(self._h, ticket, first, count, *host_ptrs))
+
+    def read_frame_information(self, pkts, pkt_time_us, flags=0):
+        n, stride = int(pkts.shape[0]), int(pkts.shape[1])
+        cap = 12 * n + 1
+        sp = np.zeros(cap, np.int32)
+        sk = np.zeros(cap, np.int32)
+        ts = np.zeros(cap, np.int64)
+        nf = C.c_int32()
+        self._check(self._L.vs_read_frame_information(
+            self._h, _ptr(pkts), stride, _ptr(pkt_time_us), n, flags, _ptr(sp), _ptr(sk),
+            _ptr(ts), cap, C.byref(nf)))
+        return sp[:nf.value].copy(), sk[:nf.value].copy(), ts[:nf.value].copy()
+
+    def stream(self):
+        return self._L.vs_stream(self._h)

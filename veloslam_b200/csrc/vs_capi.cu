@@ -1,0 +1,1008 @@
+// vs_capi.cu -- C-ABI implementation (include/veloslam_b200.h) over the sm_100a kernels.
+//
+// One context = one parser + one pose snapshot on one GPU.  Each result slot owns a CUDA
+// stream, its device buffers and pinned host mirrors of the small tables, so that with two
+// slots the H2D copy of batch k+1 overlaps the kernels and D2H of batch k.
+// No CPU fallback: without a device vs_create fails.
+#include "../../include/veloslam_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "vs_kernels.cuh"
+
+using namespace vsd;
+
+namespace {
+
+constexpr int kEagerFrames = 64;  // frame-table rows copied back with the header
+
+struct HostFrameRow {  // pinned mirror of the per-frame device tables
+  std::vector<long long> first;
+  std::vector<int> start;
+};
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+  // device
+  uint8_t* d_in = nullptr;  // staged packets (host input path only, allocated lazily)
+  size_t d_in_bytes = 0;
+  long long* d_time = nullptr;
+  const long long* d_time_used = nullptr;  // times of the batch in flight (may be caller-owned)
+  PktSeg* d_seg = nullptr;
+  double* d_pose_mat = nullptr;
+  float *d_x = nullptr, *d_y = nullptr, *d_z = nullptr;
+  uint8_t *d_inten = nullptr, *d_laser = nullptr;
+  uint16_t *d_az = nullptr, *d_dist = nullptr;
+  uint32_t* d_t = nullptr;
+  uint8_t* d_zero = nullptr;  // one allocation zeroed per batch: look-back words, counters,
+  size_t zero_bytes = 0;      //   per-frame laser counts
+  unsigned long long *d_st_map = nullptr, *d_st_wrap = nullptr, *d_st_cnt = nullptr;
+  int* d_counters = nullptr;
+  unsigned* d_frame_counts = nullptr;
+  uint8_t* d_ff = nullptr;  // one allocation set to 0xff per batch: first_point / start_block
+  long long* d_frame_first = nullptr;
+  int* d_frame_start = nullptr;
+  int* d_frame_meta_pkt = nullptr;
+  long long* d_frame_meta_time = nullptr;
+  int* d_frame_skips = nullptr;
+  BatchHeader* d_hdr = nullptr;
+  // pinned host
+  BatchHeader* h_hdr = nullptr;
+  BatchHeader* h_hdr_init = nullptr;
+  long long* h_frame_first = nullptr;
+  int* h_frame_start = nullptr;
+  int* h_frame_meta_pkt = nullptr;
+  long long* h_frame_meta_time = nullptr;
+  int* h_frame_skips = nullptr;
+  unsigned* h_frame_counts = nullptr;
+  size_t h_frames_cap = 0;
+  // bookkeeping of the batch in flight
+  bool busy = false;
+  bool done = false;
+  uint64_t ticket = 0;
+  int64_t n = 0, halo = 0;
+  int mode = 0;
+  uint32_t flags = 0;
+  int64_t t_base = 0;
+  vs_carry carry_in;
+  int n_launches = 0;
+  bool index_only = false;
+  std::vector<vs_frame> frames;
+  vs_result result;
+};
+
+}  // namespace
+
+struct vs_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int64_t max_packets = 0;
+  int64_t max_poses = 0;
+  int64_t frame_cap = 0;
+  int n_slots = 1;
+  Slot slots[2];
+  uint64_t next_ticket = 1;
+  bool calibrated = false;
+  DevConfig h_cfg;
+  DevConfig* d_cfg = nullptr;
+  double *d_lut_sin = nullptr, *d_lut_cos = nullptr;
+  long long* d_pose_t = nullptr;
+  double* d_pose_trv = nullptr;
+  std::vector<int64_t> pose_t;
+  std::vector<double> pose_trv;
+  int dec_blocks_per_sm = 2;
+  std::string err;
+};
+
+namespace {
+
+thread_local std::string g_create_err;
+
+int fail(vs_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define VS_CUDA(call)                                                                       \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(ctx, VS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+  } while (0)
+
+inline double to_radians_h(double x) { return (x * M_PI) / 180.0; }  // HDLParser.cxx:59
+
+// TransformManager::interpolateTransform (TransformManager.cxx:149-177) over the sorted host
+// snapshot; bracket = clamp(lower_bound, 1, N-1) (TimeLine.h:384-468 net semantics).
+void host_interpolate(const vs_ctx* c, int64_t t, double out[9], bool* found, bool* valid) {
+  const int64_t n = (int64_t)c->pose_t.size();
+  for (int i = 0; i < 9; ++i) out[i] = 0.0;
+  *found = false;
+  *valid = false;
+  if (n == 0) return;
+  *found = true;
+  if (n == 1) {
+    const double* f = c->pose_trv.data();
+    const double sec = (float)(t - c->pose_t[0]) / 1e6f;  // long / float, TransformManager.cxx:161
+    for (int i = 0; i < 3; ++i) {
+      out[6 + i] = f[6 + i];
+      out[3 + i] = f[3 + i];
+      out[i] = f[i] + f[6 + i] * sec;
+    }
+    return;
+  }
+  int64_t i = std::lower_bound(c->pose_t.begin(), c->pose_t.end(), t) - c->pose_t.begin();
+  i = std::min(std::max<int64_t>(i, 1), n - 1);
+  const double* f = c->pose_trv.data() + (i - 1) * 9;
+  const double* b = c->pose_trv.data() + i * 9;
+  const double ratio = double(t - c->pose_t[i - 1]) / (c->pose_t[i] - c->pose_t[i - 1]);
+  for (int k = 0; k < 9; ++k) out[k] = f[k] + ((b[k] - f[k]) * ratio);
+  *valid = true;
+}
+
+void free_slot(Slot& s) {
+  cudaFree(s.d_in);
+  cudaFree(s.d_time);
+  cudaFree(s.d_seg);
+  cudaFree(s.d_pose_mat);
+  cudaFree(s.d_x);
+  cudaFree(s.d_y);
+  cudaFree(s.d_z);
+  cudaFree(s.d_inten);
+  cudaFree(s.d_laser);
+  cudaFree(s.d_az);
+  cudaFree(s.d_dist);
+  cudaFree(s.d_t);
+  cudaFree(s.d_zero);
+  cudaFree(s.d_ff);
+  cudaFree(s.d_frame_meta_pkt);
+  cudaFree(s.d_frame_meta_time);
+  cudaFree(s.d_frame_skips);
+  cudaFree(s.d_hdr);
+  cudaFreeHost(s.h_hdr);
+  cudaFreeHost(s.h_hdr_init);
+  cudaFreeHost(s.h_frame_first);
+  cudaFreeHost(s.h_frame_start);
+  cudaFreeHost(s.h_frame_meta_pkt);
+  cudaFreeHost(s.h_frame_meta_time);
+  cudaFreeHost(s.h_frame_skips);
+  cudaFreeHost(s.h_frame_counts);
+  if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+  if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+  if (s.ev_done) cudaEventDestroy(s.ev_done);
+  if (s.stream) cudaStreamDestroy(s.stream);
+  s = Slot();
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int alloc_slot(vs_ctx* ctx, Slot& s) {
+  const int64_t np = ctx->max_packets;
+  const int64_t pts = np * 384;
+  const int64_t fc = ctx->frame_cap;
+  VS_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  VS_CUDA(cudaEventCreate(&s.ev_k0));
+  VS_CUDA(cudaEventCreate(&s.ev_k1));
+  VS_CUDA(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+  VS_CUDA(cudaMalloc(&s.d_time, np * sizeof(long long)));
+  VS_CUDA(cudaMalloc(&s.d_seg, np * sizeof(PktSeg)));
+  VS_CUDA(cudaMalloc(&s.d_pose_mat, np * 12 * sizeof(double)));
+  VS_CUDA(cudaMalloc(&s.d_x, pts * sizeof(float)));
+  VS_CUDA(cudaMalloc(&s.d_y, pts * sizeof(float)));
+  VS_CUDA(cudaMalloc(&s.d_z, pts * sizeof(float)));
+  VS_CUDA(cudaMalloc(&s.d_inten, pts));
+  VS_CUDA(cudaMalloc(&s.d_laser, pts));
+  VS_CUDA(cudaMalloc(&s.d_az, pts * sizeof(uint16_t)));
+  VS_CUDA(cudaMalloc(&s.d_dist, pts * sizeof(uint16_t)));
+  VS_CUDA(cudaMalloc(&s.d_t, pts * sizeof(uint32_t)));
+  // zeroed-per-batch block: [st_map | st_wrap | st_cnt | counters | frame_counts]
+  const size_t seg_tiles = (size_t)((np + kSegThreads - 1) / kSegThreads);
+  const size_t dec_tiles = (size_t)((np + kTilePkts - 1) / kTilePkts);
+  size_t off = 0;
+  const size_t o_map = off;
+  off += align_up(seg_tiles * 8, 256);
+  const size_t o_wrap = off;
+  off += align_up(seg_tiles * 8, 256);
+  const size_t o_cnt = off;
+  off += align_up(dec_tiles * 8, 256);
+  const size_t o_ctr = off;
+  off += 256;
+  const size_t o_fc = off;
+  off += (size_t)fc * kMaxLasers * sizeof(unsigned);
+  s.zero_bytes = off;
+  VS_CUDA(cudaMalloc(&s.d_zero, off));
+  s.d_st_map = reinterpret_cast<unsigned long long*>(s.d_zero + o_map);
+  s.d_st_wrap = reinterpret_cast<unsigned long long*>(s.d_zero + o_wrap);
+  s.d_st_cnt = reinterpret_cast<unsigned long long*>(s.d_zero + o_cnt);
+  s.d_counters = reinterpret_cast<int*>(s.d_zero + o_ctr);
+  s.d_frame_counts = reinterpret_cast<unsigned*>(s.d_zero + o_fc);
+  VS_CUDA(cudaMalloc(&s.d_ff, (size_t)fc * 12));
+  s.d_frame_first = reinterpret_cast<long long*>(s.d_ff);
+  s.d_frame_start = reinterpret_cast<int*>(s.d_ff + (size_t)fc * 8);
+  VS_CUDA(cudaMalloc(&s.d_frame_meta_pkt, fc * sizeof(int)));
+  VS_CUDA(cudaMalloc(&s.d_frame_meta_time, fc * sizeof(long long)));
+  VS_CUDA(cudaMalloc(&s.d_frame_skips, fc * sizeof(int)));
+  VS_CUDA(cudaMalloc(&s.d_hdr, sizeof(BatchHeader)));
+  VS_CUDA(cudaMallocHost(&s.h_hdr, sizeof(BatchHeader)));
+  VS_CUDA(cudaMallocHost(&s.h_hdr_init, sizeof(BatchHeader)));
+  return VS_OK;
+}
+
+int ensure_host_frames(vs_ctx* ctx, Slot& s, size_t need) {
+  if (need <= s.h_frames_cap) return VS_OK;
+  size_t cap = std::max<size_t>(need, std::max<size_t>(kEagerFrames, s.h_frames_cap * 2));
+  cudaFreeHost(s.h_frame_first);
+  cudaFreeHost(s.h_frame_start);
+  cudaFreeHost(s.h_frame_meta_pkt);
+  cudaFreeHost(s.h_frame_meta_time);
+  cudaFreeHost(s.h_frame_skips);
+  cudaFreeHost(s.h_frame_counts);
+  s.h_frames_cap = 0;
+  VS_CUDA(cudaMallocHost(&s.h_frame_first, cap * sizeof(long long)));
+  VS_CUDA(cudaMallocHost(&s.h_frame_start, cap * sizeof(int)));
+  VS_CUDA(cudaMallocHost(&s.h_frame_meta_pkt, cap * sizeof(int)));
+  VS_CUDA(cudaMallocHost(&s.h_frame_meta_time, cap * sizeof(long long)));
+  VS_CUDA(cudaMallocHost(&s.h_frame_skips, cap * sizeof(int)));
+  VS_CUDA(cudaMallocHost(&s.h_frame_counts, cap * kMaxLasers * sizeof(unsigned)));
+  s.h_frames_cap = cap;
+  return VS_OK;
+}
+
+int copy_frame_rows(vs_ctx* ctx, Slot& s, size_t n_rows) {
+  VS_CUDA(cudaMemcpyAsync(s.h_frame_first, s.d_frame_first, n_rows * sizeof(long long),
+                          cudaMemcpyDeviceToHost, s.stream));
+  VS_CUDA(cudaMemcpyAsync(s.h_frame_start, s.d_frame_start, n_rows * sizeof(int),
+                          cudaMemcpyDeviceToHost, s.stream));
+  VS_CUDA(cudaMemcpyAsync(s.h_frame_meta_pkt, s.d_frame_meta_pkt, n_rows * sizeof(int),
+                          cudaMemcpyDeviceToHost, s.stream));
+  VS_CUDA(cudaMemcpyAsync(s.h_frame_meta_time, s.d_frame_meta_time, n_rows * sizeof(long long),
+                          cudaMemcpyDeviceToHost, s.stream));
+  VS_CUDA(cudaMemcpyAsync(s.h_frame_skips, s.d_frame_skips, n_rows * sizeof(int),
+                          cudaMemcpyDeviceToHost, s.stream));
+  VS_CUDA(cudaMemcpyAsync(s.h_frame_counts, s.d_frame_counts,
+                          n_rows * kMaxLasers * sizeof(unsigned), cudaMemcpyDeviceToHost,
+                          s.stream));
+  return VS_OK;
+}
+
+template <int ADJ, bool CROP>
+int launch_decode(vs_ctx* ctx, Slot& s, const DecParams& dp, size_t smem) {
+  static size_t cached_smem = 0;  // one process drives one GPU: cache per instantiation
+  static int per_sm = 0;
+  if (cached_smem != smem) {
+    VS_CUDA(cudaFuncSetAttribute(k_decode<ADJ, CROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode<ADJ, CROP>,
+                                                          kDecThreads, smem));
+    cached_smem = smem;
+  }
+  if (per_sm < 1) return fail(ctx, VS_ERR_CUDA, "k_decode does not fit on an SM");
+  int grid = ctx->sm_count * per_sm;
+  if (grid > dp.n_tiles) grid = dp.n_tiles;
+  k_decode<ADJ, CROP><<<grid, kDecThreads, smem, s.stream>>>(dp);
+  VS_CUDA(cudaGetLastError());
+  return VS_OK;
+}
+
+// frame table rows for the index-only path (vs_read_frame_information)
+__global__ void k_frame_index(const PktSeg* __restrict__ seg, int n, int* frame_start, int cap) {
+  const int P = blockIdx.x * blockDim.x + threadIdx.x;
+  if (P >= n) return;
+  const PktSeg r = seg[P];
+  int wm = (r.x >> 4) & 0xfff;
+  int f = r.y;
+  while (wm) {
+    const int j = __ffs(wm) - 1;
+    wm &= wm - 1;
+    ++f;
+    if (f < cap) frame_start[f] = P * 12 + j;
+  }
+}
+
+int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const int64_t* pkt_time,
+              int64_t n, int64_t halo, int mode, uint32_t flags, int64_t t_base,
+              const vs_carry* carry_in, bool index_only) {
+  const bool dev_in = (flags & VS_FLAG_DEVICE_INPUT) != 0;
+  const bool pcap_t = (flags & VS_FLAG_PCAP_TIMES) != 0;
+  const uint8_t* d_pkts = pkts;
+  const long long* d_time = reinterpret_cast<const long long*>(pkt_time);
+  const int64_t payload_bytes = (n - 1) * stride + kPacketBytes;
+  s.n_launches = 0;
+
+  if (!dev_in) {
+    // stage host packets (and the pcap record headers in front of them when asked)
+    const int64_t lead = pcap_t ? 64 : 0;  // keeps the payload 2-byte aligned, covers the 58 B
+    const size_t need = (size_t)(payload_bytes + lead + 64);
+    if (need > s.d_in_bytes) {
+      cudaFree(s.d_in);
+      s.d_in = nullptr;
+      s.d_in_bytes = 0;
+      const size_t want = std::max(need, (size_t)(ctx->max_packets * stride + 128));
+      VS_CUDA(cudaMalloc(&s.d_in, want));
+      s.d_in_bytes = want;
+    }
+    const int64_t src_lead = pcap_t ? 58 : 0;
+    VS_CUDA(cudaMemcpyAsync(s.d_in + lead - src_lead, pkts - src_lead,
+                            (size_t)(payload_bytes + src_lead), cudaMemcpyHostToDevice, s.stream));
+    d_pkts = s.d_in + lead;
+    if (!pcap_t) {
+      VS_CUDA(cudaMemcpyAsync(s.d_time, pkt_time, (size_t)n * sizeof(long long),
+                              cudaMemcpyHostToDevice, s.stream));
+      d_time = s.d_time;
+    }
+  }
+  if (pcap_t) d_time = s.d_time;
+
+  VS_CUDA(cudaEventRecord(s.ev_k0, s.stream));
+  // ---- per-batch resets ------------------------------------------------------------------
+  const int64_t seg_tiles = (n + kSegThreads - 1) / kSegThreads;
+  const int64_t n_dec = n - halo;
+  const int64_t dec_tiles = (n_dec + kTilePkts - 1) / kTilePkts;
+  const int64_t frames_possible = std::min<int64_t>(ctx->frame_cap, 12 * n + 1);
+  {
+    // zero only what this batch can touch
+    const size_t head = (size_t)((uint8_t*)s.d_frame_counts - s.d_zero);
+    VS_CUDA(cudaMemsetAsync(s.d_zero, 0,
+                            head + (size_t)frames_possible * kMaxLasers * sizeof(unsigned),
+                            s.stream));
+    VS_CUDA(cudaMemsetAsync(s.d_frame_first, 0xff, (size_t)frames_possible * 8, s.stream));
+    VS_CUDA(cudaMemsetAsync(s.d_frame_start, 0xff, (size_t)frames_possible * 4, s.stream));
+    BatchHeader& hi = *s.h_hdr_init;
+    std::memset(&hi, 0, sizeof(hi));
+    hi.first_upper_block = LLONG_MAX;
+    hi.first_const_pkt = INT_MAX;
+    hi.origin_at_halo = -1;
+    hi.last_origin_packet = -1;
+    VS_CUDA(cudaMemcpyAsync(s.d_hdr, s.h_hdr_init, sizeof(BatchHeader), cudaMemcpyHostToDevice,
+                            s.stream));
+  }
+  if (pcap_t) {
+    k_pcap_times<<<(unsigned)((n + 255) / 256), 256, 0, s.stream>>>(d_pkts, stride, (int)n,
+                                                                   s.d_time);
+    VS_CUDA(cudaGetLastError());
+    ++s.n_launches;
+  }
+
+  vs_carry cin;
+  if (halo > 0 || !carry_in)
+    vs_carry_init(&cin);  // state is rebuilt from the halo
+  else
+    cin = *carry_in;
+
+  SegParams sp;
+  sp.pkts = d_pkts;
+  sp.stride = stride;
+  sp.pkt_time = d_time;
+  sp.n = (int)n;
+  sp.halo = (int)halo;
+  sp.mode = mode;
+  sp.carry_last_az = cin.last_azimuth;
+  sp.carry_skip = cin.firing_skip;
+  sp.carry_meta_inited = cin.frame_meta_inited;
+  sp.pkt_seg = s.d_seg;
+  sp.st_map = s.d_st_map;
+  sp.st_wrap = s.d_st_wrap;
+  sp.tile_counter = s.d_counters + 0;
+  sp.hdr = s.d_hdr;
+  k_segment<<<(unsigned)seg_tiles, kSegThreads, 0, s.stream>>>(sp);
+  VS_CUDA(cudaGetLastError());
+  ++s.n_launches;
+
+  const int n_poses = (int)ctx->pose_t.size();
+  const bool pose_valid = n_poses >= 2;
+  if (!index_only) {
+    if (pose_valid) {
+      PoseParams pp;
+      pp.pkt_time = d_time;
+      pp.pkt_seg = s.d_seg;
+      pp.n = (int)n;
+      pp.mode = mode;
+      pp.pose_t = ctx->d_pose_t;
+      pp.pose_trv = ctx->d_pose_trv;
+      pp.n_poses = n_poses;
+      pp.carry_meta_inited = cin.frame_meta_inited;
+      for (int k = 0; k < 3; ++k) pp.carry_origin_T[k] = cin.origin_T[k];
+      pp.pose_mat = s.d_pose_mat;
+      pp.hdr = s.d_hdr;
+      k_pose<<<(unsigned)((n + 255) / 256), 256, 0, s.stream>>>(pp);
+      VS_CUDA(cudaGetLastError());
+      ++s.n_launches;
+    }
+
+    DecParams dp;
+    dp.pkts = d_pkts;
+    dp.stride = stride;
+    dp.total_bytes = payload_bytes;
+    dp.pkt_time = d_time;
+    dp.t_base = t_base;
+    dp.pkt_seg = s.d_seg;
+    dp.pose_mat = s.d_pose_mat;
+    dp.lut_sin = ctx->d_lut_sin;
+    dp.lut_cos = ctx->d_lut_cos;
+    dp.cfg = ctx->d_cfg;
+    dp.n = (int)n;
+    dp.halo = (int)halo;
+    dp.mode = mode;
+    dp.pose_valid = pose_valid ? 1 : 0;
+    dp.n_tiles = (int)dec_tiles;
+    dp.stage_bytes = (int)align_up((size_t)kTilePkts * stride + 32, 128);
+    dp.x = s.d_x;
+    dp.y = s.d_y;
+    dp.z = s.d_z;
+    dp.intensity = s.d_inten;
+    dp.laser = s.d_laser;
+    dp.azimuth = s.d_az;
+    dp.distance = s.d_dist;
+    dp.t_us = s.d_t;
+    dp.st_cnt = s.d_st_cnt;
+    dp.tile_counter = s.d_counters + 1;
+    dp.frame_first_point = s.d_frame_first;
+    dp.frame_start_block = s.d_frame_start;
+    dp.frame_laser_counts = s.d_frame_counts;
+    dp.frame_cap = (int)ctx->frame_cap;
+    dp.hdr = s.d_hdr;
+    const size_t smem = align_up(sizeof(DecShared), 128) + 2 * (size_t)dp.stage_bytes;
+    if (dec_tiles > 0) {
+      const int adj = ctx->h_cfg.adj_mode;
+      const bool crop = ctx->h_cfg.crop_returns != 0;
+      int rc;
+      if (adj == 0)
+        rc = crop ? launch_decode<0, true>(ctx, s, dp, smem) : launch_decode<0, false>(ctx, s, dp, smem);
+      else if (adj == 1)
+        rc = crop ? launch_decode<1, true>(ctx, s, dp, smem) : launch_decode<1, false>(ctx, s, dp, smem);
+      else
+        rc = crop ? launch_decode<2, true>(ctx, s, dp, smem) : launch_decode<2, false>(ctx, s, dp, smem);
+      if (rc != VS_OK) return rc;
+      ++s.n_launches;
+    }
+  } else {
+    k_frame_index<<<(unsigned)((n + 255) / 256), 256, 0, s.stream>>>(s.d_seg, (int)n,
+                                                                    s.d_frame_start,
+                                                                    (int)ctx->frame_cap);
+    VS_CUDA(cudaGetLastError());
+    ++s.n_launches;
+  }
+
+  {
+    // frame meta gather over every frame the batch can hold; rows beyond total_wraps are
+    // ignored by the host
+    FrameParams fp;
+    fp.pkt_seg = s.d_seg;
+    fp.pkt_time = d_time;
+    fp.frame_start_block = s.d_frame_start;
+    fp.n = (int)n;
+    fp.n_frames = (int)frames_possible;
+    fp.mode = mode;
+    fp.frame_meta_packet = s.d_frame_meta_pkt;
+    fp.frame_meta_time = s.d_frame_meta_time;
+    fp.frame_skips = s.d_frame_skips;
+    k_frames<<<(unsigned)((frames_possible + 255) / 256), 256, 0, s.stream>>>(fp);
+    VS_CUDA(cudaGetLastError());
+    ++s.n_launches;
+  }
+  VS_CUDA(cudaEventRecord(s.ev_k1, s.stream));
+
+  VS_CUDA(cudaMemcpyAsync(s.h_hdr, s.d_hdr, sizeof(BatchHeader), cudaMemcpyDeviceToHost, s.stream));
+  {
+    int rc = ensure_host_frames(ctx, s, kEagerFrames);
+    if (rc != VS_OK) return rc;
+    rc = copy_frame_rows(ctx, s, (size_t)std::min<int64_t>(kEagerFrames, frames_possible));
+    if (rc != VS_OK) return rc;
+  }
+  VS_CUDA(cudaEventRecord(s.ev_done, s.stream));
+
+  s.busy = true;
+  s.done = false;
+  s.d_time_used = d_time;
+  s.n = n;
+  s.halo = halo;
+  s.mode = mode;
+  s.flags = flags;
+  s.t_base = t_base;
+  s.carry_in = cin;
+  s.index_only = index_only;
+  return VS_OK;
+}
+
+int finish_batch(vs_ctx* ctx, Slot& s) {
+  VS_CUDA(cudaEventSynchronize(s.ev_done));
+  const BatchHeader& h = *s.h_hdr;
+  if (h.frame_overflow || (int64_t)h.total_wraps + 1 > ctx->frame_cap) {
+    s.busy = false;
+    return fail(ctx, VS_ERR_CAPACITY, "frame table capacity exceeded (too many azimuth wraps)");
+  }
+  const int W = h.total_wraps;
+  const int64_t frames_possible = std::min<int64_t>(ctx->frame_cap, 12 * s.n + 1);
+  if (W + 1 > kEagerFrames) {
+    int rc = ensure_host_frames(ctx, s, (size_t)W + 1);
+    if (rc != VS_OK) return rc;
+    rc = copy_frame_rows(ctx, s, (size_t)std::min<int64_t>(W + 1, frames_possible));
+    if (rc != VS_OK) return rc;
+    VS_CUDA(cudaStreamSynchronize(s.stream));
+  }
+  if (s.halo > 0) {
+    // the state entering the first decoded packet must not depend on what preceded the
+    // halo: a constant skip map and, after it, a wrap
+    const bool skip_ok = (s.mode == VS_MODE_OFFLINE) || h.first_const_pkt < s.halo;
+    const int need_after = (s.mode == VS_MODE_OFFLINE) ? 0 : h.first_const_pkt + 1;
+    const bool origin_ok = h.origin_at_halo > need_after;
+    if (!skip_ok || !origin_ok) {
+      s.busy = false;
+      return fail(ctx, VS_ERR_HALO, "halo holds no azimuth wrap: cannot resolve the frame origin");
+    }
+  }
+
+  const int f_lo = (s.halo > 0) ? h.frame_at_halo : 0;  // first frame with decoded points
+  const int n_frames = W - f_lo + 1;
+  s.frames.assign((size_t)n_frames, vs_frame());
+  const int64_t total_points = s.index_only ? 0 : h.total_points;
+  const bool any_upper_before = s.carry_in.is_hdl64 != 0;
+  for (int i = 0; i < n_frames; ++i) {
+    const int f = f_lo + i;
+    vs_frame& fr = s.frames[(size_t)i];
+    std::memset(&fr, 0, sizeof(fr));
+    long long first = s.h_frame_first[f];
+    int sb = s.h_frame_start[f];
+    if (i == 0) {
+      // continues from the carry / the halo (or is the stream's very first frame)
+      if (first < 0) first = 0;
+      if (s.halo > 0 || sb < 0) sb = -1;
+    }
+    fr.first_point = first;
+    long long next_first = total_points;
+    if (i + 1 < n_frames) next_first = s.h_frame_first[f + 1];
+    fr.n_points = s.index_only ? 0 : (next_first - first);
+    fr.start_packet = sb < 0 ? -1 : sb / 12;
+    fr.start_block = sb < 0 ? -1 : sb % 12;
+    fr.closed = (i + 1 < n_frames) ? 1 : 0;
+    if (fr.closed) {
+      const long long close_block = s.h_frame_start[f + 1];
+      fr.hdl64_order =
+          (any_upper_before || (h.first_upper_block <= close_block)) ? 1 : 0;
+    }
+    for (int l = 0; l < kMaxLasers; ++l) fr.laser_counts[l] = s.h_frame_counts[(size_t)f * 64 + l];
+
+    // meta: timestamp / skips / carpose
+    int mp = -2;
+    int64_t mt = VS_TIME_NONE;
+    int sk = -1;
+    if (i == 0 && (sb < 0)) {
+      if (s.halo == 0 && s.carry_in.frame_meta_inited) {
+        mp = -1;
+        fr.timestamp_us = s.carry_in.frame_timestamp_us;
+        fr.skips = s.carry_in.frame_skips;
+        fr.carpose_valid = s.carry_in.frame_carpose_valid;
+        std::memcpy(fr.carpose, s.carry_in.frame_carpose, sizeof(fr.carpose));
+        fr.meta_packet = -1;
+        continue;
+      }
+      // frame meta comes from the origin packet of the first decoded packet: packet 0 of a
+      // fresh stream, or (halo) the packet that re-initialised the meta inside the halo
+      mp = (s.halo > 0) ? h.origin_at_halo : 0;
+      sk = -1;  // filled below from the device rows when available
+      mt = VS_TIME_NONE;
+      // timestamps of halo/first packets are fetched lazily below
+      fr.meta_packet = mp;
+      fr.skips = (s.halo > 0) ? -1 : s.carry_in.firing_skip;
+      fr.timestamp_us = VS_TIME_NONE;  // patched by patch_first_frame()
+      continue;
+    }
+    mp = s.h_frame_meta_pkt[f];
+    mt = s.h_frame_meta_time[f];
+    sk = s.h_frame_skips[f];
+    if (mp >= 0) {
+      fr.meta_packet = mp;
+      fr.timestamp_us = mt;
+      fr.skips = sk;
+      bool found, valid;
+      host_interpolate(ctx, mt, fr.carpose, &found, &valid);
+      fr.carpose_valid = valid ? 1 : 0;
+    } else {
+      fr.meta_packet = (mp == -3) ? -2 : mp;  // pending meta: initialised by the next batch
+      fr.timestamp_us = VS_TIME_NONE;
+      fr.skips = -1;
+      fr.carpose_valid = 0;
+    }
+  }
+  return VS_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char* vs_version(void) { return "veloslam_b200 0.1.0 sm_100a"; }
+
+void vs_carry_init(vs_carry* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->last_azimuth = -1;   // HDLParser.cxx:157, 480
+  c->firing_skip = 0;     // :156
+  c->frame_meta_inited = 0;
+  c->is_hdl64 = 0;
+  c->frame_timestamp_us = VS_TIME_NONE;
+  c->frame_skips = -1;
+}
+
+int vs_create(int device, int64_t max_batch_packets, int64_t max_poses, int n_slots, vs_ctx** out) {
+  if (!out || max_batch_packets < 1 || max_batch_packets > (1ll << 26) || max_poses < 0 ||
+      n_slots < 1 || n_slots > 2)
+    return VS_ERR_INVALID_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return VS_ERR_NO_DEVICE;
+  }
+  vs_ctx* ctx = new (std::nothrow) vs_ctx;
+  if (!ctx) return VS_ERR_CAPACITY;
+  auto bail = [&](int rc) {
+    g_create_err = ctx->err;
+    vs_destroy(ctx);
+    return rc;
+  };
+  ctx->device = device;
+  ctx->max_packets = max_batch_packets;
+  ctx->max_poses = std::max<int64_t>(max_poses, 2);
+  ctx->n_slots = n_slots;
+  ctx->frame_cap = std::min<int64_t>(12 * max_batch_packets + 1,
+                                     std::max<int64_t>(4096, max_batch_packets / 64));
+  if (cudaSetDevice(device) != cudaSuccess) return bail(VS_ERR_CUDA);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(VS_ERR_CUDA);
+  if (prop.major < 10) {
+    ctx->err = "veloslam_b200 is built for sm_100a only";
+    return bail(VS_ERR_NO_DEVICE);
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  auto init = [&]() -> int {
+    VS_CUDA(cudaMalloc(&ctx->d_cfg, sizeof(DevConfig)));
+    VS_CUDA(cudaMalloc(&ctx->d_lut_sin, kLutSize * sizeof(double)));
+    VS_CUDA(cudaMalloc(&ctx->d_lut_cos, kLutSize * sizeof(double)));
+    VS_CUDA(cudaMalloc(&ctx->d_pose_t, ctx->max_poses * sizeof(long long)));
+    VS_CUDA(cudaMalloc(&ctx->d_pose_trv, ctx->max_poses * 9 * sizeof(double)));
+    // HDLParser::initLookUpTables (HDLParser.cxx:755-768), evaluated with the host libm so the
+    // rotCorrection == 0 branch is bit-identical to the reference's table
+    std::vector<double> ls(kLutSize), lc(kLutSize);
+    for (int i = 0; i < kLutSize; ++i) {
+      const double rad = to_radians_h(i / 100.0);
+      lc[i] = std::cos(rad);
+      ls[i] = std::sin(rad);
+    }
+    VS_CUDA(cudaMemcpy(ctx->d_lut_sin, ls.data(), kLutSize * sizeof(double), cudaMemcpyHostToDevice));
+    VS_CUDA(cudaMemcpy(ctx->d_lut_cos, lc.data(), kLutSize * sizeof(double), cudaMemcpyHostToDevice));
+    for (int i = 0; i < ctx->n_slots; ++i) {
+      int rc = alloc_slot(ctx, ctx->slots[i]);
+      if (rc != VS_OK) return rc;
+    }
+    return VS_OK;
+  };
+  std::memset(&ctx->h_cfg, 0, sizeof(ctx->h_cfg));
+  ctx->h_cfg.laser_mask = ~0ull;  // HDLParser.cxx:172
+  int rc = init();
+  if (rc != VS_OK) return bail(rc);
+  *out = ctx;
+  return VS_OK;
+}
+
+void vs_destroy(vs_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->slots[i].stream) {
+      cudaStreamSynchronize(ctx->slots[i].stream);
+      free_slot(ctx->slots[i]);
+    }
+  cudaFree(ctx->d_cfg);
+  cudaFree(ctx->d_lut_sin);
+  cudaFree(ctx->d_lut_cos);
+  cudaFree(ctx->d_pose_t);
+  cudaFree(ctx->d_pose_trv);
+  delete ctx;
+}
+
+const char* vs_last_error(vs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int vs_set_calibration(vs_ctx* ctx, const vs_laser_corr* corr, int n_rows, int n_lasers_enabled) {
+  if (!ctx || !corr || n_rows < 0 || n_rows > kMaxLasers || n_lasers_enabled < 0 ||
+      n_lasers_enabled > kMaxLasers)
+    return fail(ctx, VS_ERR_INVALID_ARG, "vs_set_calibration: bad arguments");
+  DevConfig& c = ctx->h_cfg;
+  for (int i = 0; i < kMaxLasers; ++i) {
+    // rows the file does not define: the reference leaves them indeterminate; match the
+    // oracle's zero fill (azimuthCorrection 0 -> LUT branch, every other field 0)
+    c.cal[0][i] = 1.0;
+    c.cal[1][i] = 0.0;
+    for (int k = 2; k < 7; ++k) c.cal[k][i] = 0.0;
+  }
+  for (int i = 0; i < n_rows; ++i) {
+    // HDLParser.cxx:835-842
+    c.cal[0][i] = std::cos(to_radians_h(corr[i].rot_correction_deg));
+    c.cal[1][i] = std::sin(to_radians_h(corr[i].rot_correction_deg));
+    c.cal[2][i] = corr[i].dist_correction_cm / 100.0;
+    c.cal[3][i] = std::cos(to_radians_h(corr[i].vert_correction_deg));
+    c.cal[4][i] = std::sin(to_radians_h(corr[i].vert_correction_deg));
+    c.cal[5][i] = corr[i].vert_offset_correction_cm / 100.0;
+    c.cal[6][i] = corr[i].horiz_offset_correction_cm / 100.0;
+  }
+  c.n_enabled = n_lasers_enabled;
+  c.adj_mode = (n_lasers_enabled == 32) ? 1 : (n_lasers_enabled == 16 ? 2 : 0);
+  for (int j = 0; j < kBlocks; ++j) {
+    for (int dsr = 0; dsr < kReturns; ++dsr) {
+      // HDLParser.cxx:946-962 with the reference's operation order (no FMA on the host:
+      // this file is compiled with -ffp-contract=off)
+      double ta = 0.0, b0 = 0.0, nb = 1.0;
+      if (c.adj_mode == 1) {
+        ta = (j * 46.08) + (dsr * 1.152);
+        nb = ((j + 1) * 46.08) + (0 * 1.152);
+        b0 = (j * 46.08) + (0 * 1.152);
+      } else if (c.adj_mode == 2) {
+        const int laser = dsr >= 16 ? dsr - 16 : dsr;
+        const int fwb = dsr >= 16 ? 1 : 0;
+        ta = (j * 110.592) + (laser * 2.304) + (fwb * 55.296);
+        nb = ((j + 1) * 110.592) + (0 * 2.304) + (0 * 55.296);
+        b0 = (j * 110.592) + (0 * 2.304) + (0 * 55.296);
+      }
+      c.az_ratio[j][dsr] = (ta - b0) / (nb - b0);
+      c.tadj[j][dsr] = (uint16_t)std::round(ta);
+    }
+  }
+  cudaSetDevice(ctx->device);
+  VS_CUDA(cudaMemcpy(ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), cudaMemcpyHostToDevice));
+  ctx->calibrated = true;
+  return VS_OK;
+}
+
+int vs_set_filters(vs_ctx* ctx, const vs_filters* f) {
+  if (!ctx || !f || f->points_skip < 0)
+    return fail(ctx, VS_ERR_INVALID_ARG, "vs_set_filters: bad arguments");
+  DevConfig& c = ctx->h_cfg;
+  c.laser_mask = f->laser_mask;
+  c.points_skip = f->points_skip;
+  c.crop_returns = f->crop_returns ? 1 : 0;
+  c.crop_inside = f->crop_inside ? 1 : 0;
+  for (int i = 0; i < 6; ++i) c.crop[i] = f->crop_region[i];
+  cudaSetDevice(ctx->device);
+  VS_CUDA(cudaMemcpy(ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), cudaMemcpyHostToDevice));
+  return VS_OK;
+}
+
+int vs_set_poses(vs_ctx* ctx, const int64_t* t_us, const double* trv, int64_t n) {
+  if (!ctx || n < 0 || (n > 0 && (!t_us || !trv)))
+    return fail(ctx, VS_ERR_INVALID_ARG, "vs_set_poses: bad arguments");
+  if (n > ctx->max_poses) return fail(ctx, VS_ERR_CAPACITY, "vs_set_poses: more than max_poses");
+  for (int64_t i = 1; i < n; ++i)
+    if (t_us[i] <= t_us[i - 1])
+      return fail(ctx, VS_ERR_INVALID_ARG, "vs_set_poses: times must be strictly increasing");
+  ctx->pose_t.assign(t_us, t_us + n);
+  ctx->pose_trv.assign(trv, trv + n * 9);
+  cudaSetDevice(ctx->device);
+  if (n > 0) {
+    // pageable source: returns after the data is staged; ordered before later batch work
+    VS_CUDA(cudaMemcpy(ctx->d_pose_t, t_us, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice));
+    VS_CUDA(cudaMemcpy(ctx->d_pose_trv, trv, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return VS_OK;
+}
+
+int vs_interpolate(vs_ctx* ctx, int64_t t_us, double out_trv[9], int32_t* found, int32_t* valid) {
+  if (!ctx || !out_trv) return fail(ctx, VS_ERR_INVALID_ARG, "vs_interpolate: bad arguments");
+  bool f, v;
+  host_interpolate(ctx, t_us, out_trv, &f, &v);
+  if (found) *found = f ? 1 : 0;
+  if (valid) *valid = v ? 1 : 0;
+  return VS_OK;
+}
+
+static int submit_common(vs_ctx* ctx, const uint8_t* pkts, int64_t stride,
+                         const int64_t* pkt_time_us, int64_t n, int64_t n_halo, int mode,
+                         uint32_t flags, int64_t t_base_us, const vs_carry* carry_in,
+                         uint64_t* ticket, bool index_only) {
+  if (!ctx) return VS_ERR_INVALID_ARG;
+  if (!index_only && !ctx->calibrated)
+    return fail(ctx, VS_ERR_NOT_CALIBRATED, "corrections have not been set");
+  const bool dev_in = (flags & VS_FLAG_DEVICE_INPUT) != 0;
+  const bool pcap_t = (flags & VS_FLAG_PCAP_TIMES) != 0;
+  if (!pkts || n < 1 || n_halo < 0 || n_halo >= n || (mode != 0 && mode != 1) || !ticket ||
+      (!pcap_t && !pkt_time_us))
+    return fail(ctx, VS_ERR_INVALID_ARG, "vs_submit: bad arguments");
+  if (stride < kPacketBytes || stride > 1280 || (stride & 1) || (reinterpret_cast<uintptr_t>(pkts) & 1))
+    return fail(ctx, VS_ERR_INVALID_ARG,
+                "vs_submit: stride must be even and in [1206, 1280], packets 2-byte aligned");
+  if (n > ctx->max_packets) return fail(ctx, VS_ERR_CAPACITY, "vs_submit: batch exceeds max_batch_packets");
+  if (t_base_us == VS_TIME_NONE) {
+    if (dev_in) return fail(ctx, VS_ERR_INVALID_ARG, "vs_submit: device input needs an explicit t_base_us");
+    if (pcap_t) {
+      const uint8_t* h = pkts + n_halo * stride - 58;
+      uint32_t sec, usec;
+      std::memcpy(&sec, h, 4);
+      std::memcpy(&usec, h + 4, 4);
+      t_base_us = ((int64_t)sec + 8 * 3600) * 1000000ll + usec;
+    } else {
+      t_base_us = pkt_time_us[n_halo];
+    }
+  }
+  const uint64_t tk = ctx->next_ticket;
+  Slot& s = ctx->slots[tk % (uint64_t)ctx->n_slots];
+  if (s.busy && !s.done) {
+    // the slot still holds an unfinished batch: the caller must vs_wait it first
+    return fail(ctx, VS_ERR_STATE, "vs_submit: result slot busy (vs_wait the previous ticket)");
+  }
+  cudaSetDevice(ctx->device);
+  int rc = run_batch(ctx, s, pkts, stride, pkt_time_us, n, n_halo, mode, flags, t_base_us, carry_in,
+                     index_only);
+  if (rc != VS_OK) return rc;
+  s.ticket = tk;
+  ctx->next_ticket = tk + 1;
+  *ticket = tk;
+  return VS_OK;
+}
+
+int vs_submit(vs_ctx* ctx, const uint8_t* pkts, int64_t stride, const int64_t* pkt_time_us,
+              int64_t n, int64_t n_halo, int mode, uint32_t flags, int64_t t_base_us,
+              const vs_carry* carry_in, uint64_t* ticket) {
+  return submit_common(ctx, pkts, stride, pkt_time_us, n, n_halo, mode, flags, t_base_us, carry_in,
+                       ticket, false);
+}
+
+int vs_wait(vs_ctx* ctx, uint64_t ticket, vs_result* out) {
+  if (!ctx || !out) return fail(ctx, VS_ERR_INVALID_ARG, "vs_wait: bad arguments");
+  Slot& s = ctx->slots[ticket % (uint64_t)ctx->n_slots];
+  if (!s.busy || s.ticket != ticket) return fail(ctx, VS_ERR_STATE, "vs_wait: unknown ticket");
+  cudaSetDevice(ctx->device);
+  if (!s.done) {
+    int rc = finish_batch(ctx, s);
+    if (rc != VS_OK) return rc;
+    const BatchHeader& h = *s.h_hdr;
+    vs_result& r = s.result;
+    std::memset(&r, 0, sizeof(r));
+    r.n_packets = s.n - s.halo;
+    r.n_points = s.index_only ? 0 : h.total_points;
+    r.n_frames = (int32_t)s.frames.size();
+    r.n_closed = r.n_frames - 1;
+    r.x = s.d_x;
+    r.y = s.d_y;
+    r.z = s.d_z;
+    r.intensity = s.d_inten;
+    r.laser = s.d_laser;
+    r.azimuth = s.d_az;
+    r.distance = s.d_dist;
+    r.t_us = s.d_t;
+    r.t_base_us = s.t_base;
+    r.first_upper_block = (h.first_upper_block == LLONG_MAX) ? -1 : h.first_upper_block;
+    r.n_kernel_launches = s.n_launches;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
+    r.gpu_ms = ms;
+
+    // first frame of a fresh stream / of a halo shard: meta from a packet of this batch
+    vs_frame& f0 = s.frames[0];
+    if (f0.meta_packet >= 0 && f0.timestamp_us == VS_TIME_NONE) {
+      long long mt = VS_TIME_NONE;
+      VS_CUDA(cudaMemcpy(&mt, s.d_time_used + f0.meta_packet, sizeof(mt), cudaMemcpyDeviceToHost));
+      if (mt != VS_TIME_NONE) {
+        f0.timestamp_us = mt;
+        bool found, valid;
+        host_interpolate(ctx, mt, f0.carpose, &found, &valid);
+        f0.carpose_valid = valid ? 1 : 0;
+      }
+      if (s.halo > 0) {
+        PktSeg sg;
+        VS_CUDA(cudaMemcpy(&sg, s.d_seg + f0.meta_packet, sizeof(sg), cudaMemcpyDeviceToHost));
+        if (s.mode == VS_MODE_OFFLINE) {
+          const int wm = (sg.x >> 4) & 0xfff;  // the frame starts at the packet's last wrap
+          f0.skips = wm ? (31 - __builtin_clz((unsigned)wm)) : 0;
+        } else {
+          f0.skips = sg.x & 15;
+        }
+      }
+    }
+
+    // carry-out (HDLParser.cxx:196-216 state after the last packet)
+    vs_carry& co = r.carry_out;
+    co = s.carry_in;
+    co.last_azimuth = h.last_azimuth;
+    co.firing_skip = h.firing_skip_out;
+    co.is_hdl64 = (s.carry_in.is_hdl64 || h.first_upper_block != LLONG_MAX) ? 1 : 0;
+    const vs_frame& open = s.frames.back();
+    const bool pending = (s.mode == VS_MODE_STREAMING) && h.last_has_wrap;
+    co.frame_meta_inited = pending ? 0 : 1;
+    if (!pending) {
+      co.frame_timestamp_us = open.timestamp_us;
+      co.frame_skips = open.skips;
+      co.frame_carpose_valid = open.carpose_valid;
+      std::memcpy(co.frame_carpose, open.carpose, sizeof(co.frame_carpose));
+      if (ctx->pose_t.size() >= 2) {
+        // k_pose ran: it wrote the frame origin the last packet used (or, offline, started)
+        for (int k = 0; k < 3; ++k) co.origin_T[k] = h.carry_origin_T[k];
+      } else if (h.last_origin_packet >= 0) {
+        // fewer than two poses: carpose->T is what interpolateTransform wrote at the frame's
+        // meta packet (zeros, or the one-sample extrapolation)
+        double trv[9];
+        bool found, valid;
+        host_interpolate(ctx, h.last_origin_time, trv, &found, &valid);
+        for (int k = 0; k < 3; ++k) co.origin_T[k] = trv[k];
+      }
+    } else {
+      co.frame_timestamp_us = VS_TIME_NONE;
+      co.frame_skips = -1;
+      co.frame_carpose_valid = 0;
+      std::memset(co.frame_carpose, 0, sizeof(co.frame_carpose));
+    }
+    co.frames_closed = s.carry_in.frames_closed + r.n_closed;
+    co.points_emitted = s.carry_in.points_emitted + r.n_points;
+    co.packets_seen = s.carry_in.packets_seen + r.n_packets;
+    r.frames = s.frames.data();
+    s.done = true;
+  }
+  *out = s.result;
+  out->frames = s.frames.data();
+  return VS_OK;
+}
+
+int vs_fetch_points(vs_ctx* ctx, uint64_t ticket, int64_t first, int64_t count, float* x, float* y,
+                    float* z, uint8_t* intensity, uint8_t* laser, uint16_t* azimuth,
+                    uint16_t* distance, uint32_t* t_us) {
+  if (!ctx) return VS_ERR_INVALID_ARG;
+  Slot& s = ctx->slots[ticket % (uint64_t)ctx->n_slots];
+  if (!s.busy || !s.done || s.ticket != ticket)
+    return fail(ctx, VS_ERR_STATE, "vs_fetch_points: ticket not finished (vs_wait first)");
+  if (first < 0 || count < 0 || first + count > s.result.n_points)
+    return fail(ctx, VS_ERR_INVALID_ARG, "vs_fetch_points: range outside the batch");
+  if (count == 0) return VS_OK;
+  cudaSetDevice(ctx->device);
+  const size_t c = (size_t)count;
+  if (x) VS_CUDA(cudaMemcpyAsync(x, s.d_x + first, c * 4, cudaMemcpyDeviceToHost, s.stream));
+  if (y) VS_CUDA(cudaMemcpyAsync(y, s.d_y + first, c * 4, cudaMemcpyDeviceToHost, s.stream));
+  if (z) VS_CUDA(cudaMemcpyAsync(z, s.d_z + first, c * 4, cudaMemcpyDeviceToHost, s.stream));
+  if (intensity)
+    VS_CUDA(cudaMemcpyAsync(intensity, s.d_inten + first, c, cudaMemcpyDeviceToHost, s.stream));
+  if (laser) VS_CUDA(cudaMemcpyAsync(laser, s.d_laser + first, c, cudaMemcpyDeviceToHost, s.stream));
+  if (azimuth)
+    VS_CUDA(cudaMemcpyAsync(azimuth, s.d_az + first, c * 2, cudaMemcpyDeviceToHost, s.stream));
+  if (distance)
+    VS_CUDA(cudaMemcpyAsync(distance, s.d_dist + first, c * 2, cudaMemcpyDeviceToHost, s.stream));
+  if (t_us) VS_CUDA(cudaMemcpyAsync(t_us, s.d_t + first, c * 4, cudaMemcpyDeviceToHost, s.stream));
+  VS_CUDA(cudaStreamSynchronize(s.stream));
+  return VS_OK;
+}
+
+int vs_read_frame_information(vs_ctx* ctx, const uint8_t* pkts, int64_t stride,
+                              const int64_t* pkt_time_us, int64_t n, uint32_t flags,
+                              int32_t* start_packet, int32_t* skips, int64_t* timestamp_us,
+                              int32_t cap, int32_t* n_frames) {
+  if (!ctx || !n_frames || cap < 0)
+    return fail(ctx, VS_ERR_INVALID_ARG, "vs_read_frame_information: bad arguments");
+  uint64_t tk = 0;
+  vs_carry c;
+  vs_carry_init(&c);
+  int rc = submit_common(ctx, pkts, stride, pkt_time_us, n, 0, VS_MODE_OFFLINE, flags, 0, &c, &tk,
+                         true);
+  if (rc != VS_OK) return rc;
+  vs_result r;
+  rc = vs_wait(ctx, tk, &r);
+  if (rc != VS_OK) return rc;
+  *n_frames = r.n_frames;
+  for (int i = 0; i < r.n_frames && i < cap; ++i) {
+    const vs_frame& f = r.frames[i];
+    start_packet[i] = (i == 0) ? 0 : f.start_packet;
+    skips[i] = (i == 0) ? 0 : f.start_block;
+    timestamp_us[i] = f.timestamp_us;
+  }
+  return VS_OK;
+}
+
+void* vs_stream(vs_ctx* ctx) { return ctx ? (void*)ctx->slots[0].stream : nullptr; }
+
+}  // extern "C"
