@@ -252,11 +252,15 @@ class Oracle:
                                             _p(sk, C.c_int32), _p(ts, C.c_int64), cap)
         return sp[:n].copy(), sk[:n].copy(), ts[:n].copy()
 
-    def get_frame(self, pkts_u8, t_us, start_packet, skip):
+    def get_frame(self, pkts_u8, t_us, start_packet, skip, first=False):
+        """HDLParser::getFrame.  The reference hands back frames.back() (HDLParser.cxx:531): when
+        the packet that closes the frame holds several wraps that is the LAST frame closed by
+        that packet, not the one asked for; first=True returns the first closed frame instead
+        (identical whenever a packet holds at most one wrap, i.e. for real sensor data)."""
         d = np.ascontiguousarray(pkts_u8, dtype=np.uint8)
         t = np.ascontiguousarray(t_us, dtype=np.int64)
         ok = self._L.vo_get_frame(self._h, _p(d, C.c_uint8), d.shape[0], d.shape[1],
                                   _p(t, C.c_int64), int(start_packet), int(skip))
         if not ok:
             return None
-        return self.frame(self.num_frames() - 1)
+        return self.frame(0 if first else self.num_frames() - 1)

@@ -43,7 +43,7 @@ def make_ctx(calib, poses=None, laser_selection=None, points_skip=0, crop=None,
 def gpu_stream(ctx, pk_bytes, t_us, splits=(), mode=capi.MODE_STREAMING, t_base=None):
     """Decode in batches cut at `splits`, chaining the carry.  Returns [(result, cols)]."""
     n = pk_bytes.shape[0]
-    cuts = [0] + [s for s in splits if 0 < s < n] + [n]
+    cuts = [0] + sorted({int(s) for s in splits if 0 < s < n}) + [n]
     carry = capi.carry_init()
     out = []
     t_base = int(t_us[0]) if t_base is None else t_base
