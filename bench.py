@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py -- decoded+deskewed points/sec of the VeloSLAM ingest hot path on B200.
+
+A "step" is one pass of the hot path (segmentation + per-packet pose + decode/calibrate/
+transform/compaction + frame table) over one batch of synthetic HDL-64E S2 packets with a
+100 Hz INS timeline (BASELINE.json configs[2], the decode+deskew configuration the metric is
+quoted on).  `value` is measured with the packets already resident in HBM; `e2e` goes through
+the same C ABI with HOST buffers (pinned), H2D of packets/times and D2H of every point column
+inside the timed region.  N > 1: one process per GPU (torchrun), contiguous packet-range shards
+of one long recording with a one-rotation halo, no data-path collective (weak scaling); the
+frame-index all-gather runs once after the timed loop.
+
+`--impl reference` times the reference's CPU algorithm (oracle/_ref when the reference compiled
+here, else the oracle port) on the host cores with all threads it can use.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decoded+deskewed points/sec"
+UNIT = "points/s"
+BYTES_PER_POINT_OUT = 22          # x,y,z f32 + intensity u8 + laser u8 + azimuth u16 + distance u16 + t u32
+HBM_FALLBACK_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--packets", type=int, default=1 << 20, help="packets per GPU per step")
+    ap.add_argument("--e2e-chunk", type=int, default=1 << 16, help="packets per host->device chunk")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu), "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+        except Exception:
+            return out
+        sm, reasons, smax = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = smax
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline / reference arm
+# ------------------------------------------------------------------------------------------
+def load_cpu_reference():
+    """(kind, factory): oracle/_ref (the reference's own sources) when built, else the port."""
+    try:
+        from oracle import ref as ref_mod
+        if ref_mod.available():
+            return "reference", ref_mod.RefParser
+    except Exception:
+        pass
+    from oracle.oracle import Oracle
+    return "port", Oracle
+
+
+def cpu_make_parser(factory, calib, poses):
+    o = factory()
+    o.set_calibration(calib)
+    o.add_poses(poses[0], poses[1])
+    return o
+
+
+def cpu_time_threads(factory, calib, poses, pk_bytes, t_us, n_threads):
+    """Packet-range shards over n_threads host threads (each its own parser, like one
+    reference process per shard); returns (seconds, slots)."""
+    n = pk_bytes.shape[0]
+    cuts = [(n * i) // n_threads for i in range(n_threads + 1)]
+    parsers = [cpu_make_parser(factory, calib, poses) for _ in range(n_threads)]
+    threads = []
+
+    def work(i):
+        a, b = cuts[i], cuts[i + 1]
+        if b > a:
+            parsers[i].process_packets(pk_bytes[a:b], t_us[a:b])
+
+    t0 = time.perf_counter()
+    for i in range(n_threads):
+        th = threading.Thread(target=work, args=(i,))
+        th.start()
+        threads.append(th)
+    for th in threads:
+        th.join()
+    dt = time.perf_counter() - t0
+    return dt, n * 384
+
+
+def count_points(pk_struct):
+    return int(np.count_nonzero(pk_struct["blocks"]["returns"]["distance"]))
+
+
+def run_cpu_baseline(calib, poses, budget_s):
+    """Single-thread oracle on a bounded sample of the same workload."""
+    from veloslam_b200 import synth
+    kind, factory = load_cpu_reference()
+    probe_n = 8192
+    pk, t = synth.hdl64_stream_tiled(probe_n)
+    dt, _ = cpu_time_threads(factory, calib, poses, synth.as_bytes(pk), t, 1)
+    rate = probe_n / dt
+    n = int(max(probe_n, min(rate * budget_s, 1 << 19)))
+    pk, t = synth.hdl64_stream_tiled(n)
+    dt, slots = cpu_time_threads(factory, calib, poses, synth.as_bytes(pk), t, 1)
+    pts = count_points(pk)
+    return {"value": pts / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"{n} HDL-64E packets ({slots} return slots, {pts} points emitted) of the "
+                      f"bench workload, single thread, {dt:.2f} s",
+            "slots_per_s": slots / dt}
+
+
+def run_reference_arm(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from veloslam_b200 import synth
+    kind, factory = load_cpu_reference()
+    calib = synth.calib_hdl64()
+    n_threads = os.cpu_count() or 1
+    # bounded sample per step: ~ cpu-seconds / (steps + warmup) of work on all threads
+    probe_n = 4096 * n_threads
+    pk, t = synth.hdl64_stream_tiled(probe_n)
+    poses = synth.ins_trajectory(int(probe_n * 288e-6 * 100) + 40)
+    dt, _ = cpu_time_threads(factory, calib, poses, synth.as_bytes(pk), t, n_threads)
+    rate = probe_n / dt
+    total_steps = args.steps + args.warmup
+    per_step_s = min(10.0, max(1.0, 120.0 / total_steps))
+    n = int(max(probe_n, min(rate * per_step_s, 1 << 21)))
+    pk, t = synth.hdl64_stream_tiled(n)
+    poses = synth.ins_trajectory(int(n * 288e-6 * 100) + 40)
+    b = synth.as_bytes(pk)
+    pts = count_points(pk)
+    for _ in range(args.warmup):
+        cpu_time_threads(factory, calib, poses, b, t, n_threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_time_threads(factory, calib, poses, b, t, n_threads)
+    dt = time.perf_counter() - t0
+    value = pts * args.steps / dt
+    sample = (f"{n} HDL-64E packets per step ({n * 384} slots, {pts} points), "
+              f"{n_threads} threads over packet-range shards")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "HDL-64E S2 decode + per-packet deskew against a 100 Hz INS "
+                               "timeline (BASELINE.json configs[2]), CPU reference path",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from veloslam_b200 import capi, sharding, synth
+
+    rank, world, local = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    n_per = args.packets
+    halo = sharding.HALO_HDL64 if rank > 0 else 0
+    first = rank * n_per
+    pk, t = synth.hdl64_stream_tiled(n_per + halo, first_packet=first - halo)
+    b = synth.as_bytes(pk)
+    n_sub = n_per + halo
+    t_base = int(synth.T0_US)
+    calib = synth.calib_hdl64()
+    span_s = (world * n_per + 64) * 288e-6
+    poses = synth.ins_trajectory(int(span_s * 100) + 40)
+    n_emitted_expected = None
+
+    ctx = capi.Context(local, max_batch_packets=n_sub, max_poses=len(poses[0]) + 8, n_slots=1)
+    ctx.set_calibration(calib)
+    ctx.set_poses(poses[0], poses[1])
+    d_pk = torch.from_numpy(b).to(dev)
+    d_t = torch.from_numpy(np.ascontiguousarray(t)).to(dev)
+    torch.cuda.synchronize()
+
+    ext = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+
+    def step():
+        tk = ctx.submit(d_pk, d_t, n=n_sub, stride=1206, n_halo=halo, mode=capi.MODE_STREAMING,
+                        flags=capi.FLAG_DEVICE_INPUT, t_base_us=t_base)
+        return ctx.wait(tk, frames=False)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        r = step()
+    n_emitted = r.n_points
+    launches_per_step = r.n_kernel_launches
+
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    dec_ms, step_ms = [], []
+    with torch.cuda.stream(ext):
+        e0.record(ext)
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = step()
+        dec_ms.append(r.decode_ms)
+        step_ms.append(r.gpu_ms)
+    with torch.cuda.stream(ext):
+        e1.record(ext)
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        elapsed_ms = float(tt.item())
+        pts = torch.tensor([n_emitted], dtype=torch.int64, device=dev)
+        torch.distributed.all_reduce(pts)
+        total_emitted = int(pts.item())
+    else:
+        total_emitted = n_emitted
+    ms_per_step = elapsed_ms / args.steps
+    value = total_emitted / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_decode), this rank ------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = HBM_FALLBACK_GBS, "fallback"
+    try:
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "measured"
+    except Exception:
+        pass
+    alg_bytes = 1206 * n_per + BYTES_PER_POINT_OUT * n_emitted
+    dec_avg_ms = float(np.mean(dec_ms))
+    achieved = alg_bytes / (dec_avg_ms * 1e-3) / 1e9
+    step_avg_ms = float(np.mean(step_ms))
+    roofline = {"bound": "hbm", "kernel": "k_decode", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_ms": dec_avg_ms, "step_kernels_ms": step_avg_ms,
+                "frac_all_kernels_of_step": alg_bytes / (step_avg_ms * 1e-3) / 1e9 / peak}
+
+    # ---- frame index exchange (off the timed loop) ------------------------------------------
+    rr = step()
+    tab = sharding.local_table(rr.frame_table, rank, first, halo)
+    if world > 1:
+        tables = sharding.all_gather_tables(tab)
+    else:
+        tables = [tab]
+    frames = sharding.stitch(tables)
+    n_global_frames = len(frames)
+    mism = sum(1 for f in frames if "timestamp_mismatch" in f)
+
+    # ---- e2e through the C ABI with host buffers ---------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, ctx_args=(local, calib, poses), b=b[halo:], t=t[halo:], t_base=t_base,
+                      world=world, dev=dev)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = run_cpu_baseline(calib, poses, args.cpu_seconds)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "HDL-64E S2 decode + rotation segmentation + per-packet deskew against "
+                            "a 100 Hz INS timeline (BASELINE.json configs[2]; N>1: configs[3] "
+                            "packet-range shards with a 512-packet halo)",
+                "packets_per_gpu_per_step": n_per, "slots_per_gpu_per_step": n_per * 384,
+                "points_emitted_per_gpu_per_step": n_emitted, "mode": "streaming (reference parity)",
+                "input_bytes_per_gpu": n_sub * 1206,
+                "l2": "inputs (1.26 GB) and outputs (8.4 GB) per step exceed the 126 MB L2",
+                "slots_per_s": world * n_per * 384 / (ms_per_step * 1e-3),
+                "global_frames": n_global_frames, "stitch_timestamp_mismatches": mism,
+                "wall_ms_per_step": wall / args.steps * 1e3,
+            },
+            "roofline": roofline, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def run_e2e(args, ctx_args, b, t, t_base, world, dev):
+    """Host packets in, host point columns out, through vs_submit / vs_wait / vs_fetch_points
+    with two result slots so copies overlap the kernels."""
+    import torch
+    from veloslam_b200 import capi
+    local, calib, poses = ctx_args
+    chunk = min(args.e2e_chunk, b.shape[0])
+    n_chunks = b.shape[0] // chunk
+    ctx = capi.Context(local, max_batch_packets=chunk, max_poses=len(poses[0]) + 8, n_slots=2)
+    ctx.set_calibration(calib)
+    ctx.set_poses(poses[0], poses[1])
+    # pinned host input (the caller's ring) and pinned host output columns, one set per slot
+    h_pk = torch.from_numpy(b[:n_chunks * chunk]).pin_memory()
+    h_t = torch.from_numpy(np.ascontiguousarray(t[:n_chunks * chunk])).pin_memory()
+    cap = chunk * 384
+    outs = []
+    for _ in range(2):
+        cols = [torch.empty(cap, dtype=dt).pin_memory() for dt in
+                (torch.float32, torch.float32, torch.float32, torch.uint8, torch.uint8,
+                 torch.int16, torch.int16, torch.int32)]
+        outs.append(cols)
+
+    def one_pass():
+        carry = capi.carry_init()
+        pending = None
+        total = 0
+        h2d = d2h = 0
+        for c in range(n_chunks):
+            a = c * chunk
+            # the carry of chunk c is known only after chunk c-1 finished (a 72-byte state);
+            # its kernels are short next to the copies, so wait c-1 first, then overlap the
+            # D2H of c-1 with the H2D + kernels of c
+            if pending is not None:
+                rprev = ctx.wait(pending[0], frames=False)
+                carry = rprev.carry_out
+            tk = ctx.submit(h_pk[a:a + chunk], h_t[a:a + chunk], n=chunk, stride=1206,
+                            mode=capi.MODE_STREAMING, flags=0, t_base_us=t_base, carry=carry)
+            h2d += chunk * (1206 + 8)
+            if pending is not None:
+                ptrs = [x.data_ptr() for x in outs[pending[1]]]
+                ctx.fetch_into(pending[0], 0, rprev.n_points, ptrs)
+                total += rprev.n_points
+                d2h += rprev.n_points * BYTES_PER_POINT_OUT
+            pending = (tk, c % 2)
+        rprev = ctx.wait(pending[0], frames=False)
+        ptrs = [x.data_ptr() for x in outs[pending[1]]]
+        ctx.fetch_into(pending[0], 0, rprev.n_points, ptrs)
+        total += rprev.n_points
+        d2h += rprev.n_points * BYTES_PER_POINT_OUT
+        return total, h2d, d2h
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    one_pass()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        total, h2d, d2h = one_pass()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        dt = float(tt.item())
+        pts = torch.tensor([total], dtype=torch.int64, device=dev)
+        torch.distributed.all_reduce(pts)
+        total = int(pts.item())
+    ctx.close()
+    return {"value": total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+            "chunk_packets": chunk, "note": "host pinned packets -> vs_submit/vs_wait -> "
+            "vs_fetch_points into pinned host columns (all 8 columns, 22 B/point); PCIe-bound"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -143,7 +143,9 @@ typedef struct vs_result {
   int64_t t_base_us;
   int64_t first_upper_block;  /* first decoded 0xddff block (packet*12+block), -1 none */
   float   gpu_ms;             /* device time of the batch's kernels (CUDA events)  */
+  float   decode_ms;          /* device time of the decode kernel alone            */
   int32_t n_kernel_launches;
+  int32_t reserved;
 } vs_result;
 
 typedef struct vs_ctx vs_ctx;

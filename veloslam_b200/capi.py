@@ -60,7 +60,8 @@ class Result(C.Structure):
                 ("intensity", C.c_void_p), ("laser", C.c_void_p), ("azimuth", C.c_void_p),
                 ("distance", C.c_void_p), ("t_us", C.c_void_p), ("frames", C.POINTER(Frame)),
                 ("carry_out", Carry), ("t_base_us", C.c_int64), ("first_upper_block", C.c_int64),
-                ("gpu_ms", C.c_float), ("n_kernel_launches", C.c_int32)]
+                ("gpu_ms", C.c_float), ("decode_ms", C.c_float), ("n_kernel_launches", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class VeloError(RuntimeError):
@@ -153,19 +154,26 @@ class FrameView:
         self.laser_counts = np.array(list(f.laser_counts), dtype=np.int64)
 
 
+FRAME_TABLE_DTYPE = np.dtype(Frame)   # vs_frame rows as a numpy structured array
+
+
 class BatchResult:
-    def __init__(self, ctx, ticket, r):
+    def __init__(self, ctx, ticket, r, frames=True):
         self._ctx = ctx
         self.ticket = ticket
         self.n_packets = int(r.n_packets)
         self.n_points = int(r.n_points)
         self.n_frames = int(r.n_frames)
         self.n_closed = int(r.n_closed)
-        self.frames = [FrameView(r.frames[i]) for i in range(r.n_frames)]
+        self.frames = [FrameView(r.frames[i]) for i in range(r.n_frames)] if frames else None
+        # the same rows as one structured array (copied out of the context-owned buffer)
+        self.frame_table = np.ctypeslib.as_array(r.frames, shape=(r.n_frames,)).copy() \
+            if r.n_frames > 0 else np.zeros(0, dtype=FRAME_TABLE_DTYPE)
         self.carry_out = Carry.from_buffer_copy(r.carry_out)
         self.t_base_us = int(r.t_base_us)
         self.first_upper_block = int(r.first_upper_block)
         self.gpu_ms = float(r.gpu_ms)
+        self.decode_ms = float(r.decode_ms)
         self.n_kernel_launches = int(r.n_kernel_launches)
         self.device_ptrs = {k: getattr(r, k) for k in
                             ("x", "y", "z", "intensity", "laser", "azimuth", "distance", "t_us")}
@@ -260,10 +268,10 @@ class Context:
         self._keepalive = (pkts, pkt_time_us)
         return tk.value
 
-    def wait(self, ticket):
+    def wait(self, ticket, frames=True):
         r = Result()
         self._check(self._L.vs_wait(self._h, ticket, C.byref(r)))
-        return BatchResult(self, ticket, r)
+        return BatchResult(self, ticket, r, frames)
 
     def decode(self, pkts, pkt_time_us, **kw):
         return self.wait(self.submit(pkts, pkt_time_us, **kw))

@@ -32,7 +32,7 @@ struct HostFrameRow {  // pinned mirror of the per-frame device tables
 
 struct Slot {
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr, ev_done = nullptr;
   // device
   uint8_t* d_in = nullptr;  // staged packets (host input path only, allocated lazily)
   size_t d_in_bytes = 0;
@@ -178,6 +178,8 @@ void free_slot(Slot& s) {
   cudaFreeHost(s.h_frame_counts);
   if (s.ev_k0) cudaEventDestroy(s.ev_k0);
   if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+  if (s.ev_d0) cudaEventDestroy(s.ev_d0);
+  if (s.ev_d1) cudaEventDestroy(s.ev_d1);
   if (s.ev_done) cudaEventDestroy(s.ev_done);
   if (s.stream) cudaStreamDestroy(s.stream);
   s = Slot();
@@ -192,6 +194,8 @@ int alloc_slot(vs_ctx* ctx, Slot& s) {
   VS_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
   VS_CUDA(cudaEventCreate(&s.ev_k0));
   VS_CUDA(cudaEventCreate(&s.ev_k1));
+  VS_CUDA(cudaEventCreate(&s.ev_d0));
+  VS_CUDA(cudaEventCreate(&s.ev_d1));
   VS_CUDA(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
   VS_CUDA(cudaMalloc(&s.d_time, np * sizeof(long long)));
   VS_CUDA(cudaMalloc(&s.d_seg, np * sizeof(PktSeg)));
@@ -451,6 +455,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     dp.frame_cap = (int)ctx->frame_cap;
     dp.hdr = s.d_hdr;
     const size_t smem = align_up(sizeof(DecShared), 128) + 2 * (size_t)dp.stage_bytes;
+    VS_CUDA(cudaEventRecord(s.ev_d0, s.stream));
     if (dec_tiles > 0) {
       const int adj = ctx->h_cfg.adj_mode;
       const bool crop = ctx->h_cfg.crop_returns != 0;
@@ -464,6 +469,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
       if (rc != VS_OK) return rc;
       ++s.n_launches;
     }
+    VS_CUDA(cudaEventRecord(s.ev_d1, s.stream));
   } else {
     k_frame_index<<<(unsigned)((n + 255) / 256), 256, 0, s.stream>>>(s.d_seg, (int)n,
                                                                     s.d_frame_start,
@@ -885,6 +891,9 @@ int vs_wait(vs_ctx* ctx, uint64_t ticket, vs_result* out) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
     r.gpu_ms = ms;
+    ms = 0.f;
+    if (!s.index_only) cudaEventElapsedTime(&ms, s.ev_d0, s.ev_d1);
+    r.decode_ms = ms;
 
     // first frame of a fresh stream / of a halo shard: meta from a packet of this batch
     vs_frame& f0 = s.frames[0];

@@ -174,3 +174,20 @@ def ins_trajectory(n_poses, t0_us=T0_US - 50_000, dt_us=10_000, seed=7, yaw_amp_
     T += np.array([431000.0, 3391000.0, 12.0])[None, :] * 0.001  # a non-zero ENU origin offset
     trv = np.concatenate([T, np.stack([roll, pitch, yaw], axis=1), v], axis=1)
     return t_us, np.ascontiguousarray(trv, dtype=np.float64)
+
+
+def hdl64_stream_tiled(n_packets, first_packet=0, base_packets=16384, seed=0xC0FFEE, az0=12345.0,
+                       t0_us=T0_US, zero_frac=0.05):
+    """A long HDL-64E stream built quickly: azimuths and times are those of packets
+    [first_packet, first_packet + n) of the infinite stream; the returns repeat a seeded base
+    block of `base_packets` packets (phase-locked to the global packet index, so two shards of
+    the same stream agree where they overlap)."""
+    base, _ = hdl64_packets(base_packets, seed=seed, zero_frac=zero_frac)
+    idx = np.arange(first_packet, first_packet + n_packets, dtype=np.int64)
+    pk = np.take(as_bytes(base), idx % base_packets, axis=0).view(PACKET_DTYPE).reshape(-1)
+    pair = idx[:, None] * 6 + np.arange(6)[None, :]
+    az = np.floor(az0 + pair * HDL64_TICKS_PER_PAIR).astype(np.int64) % 36000
+    pk["blocks"]["azimuth"] = np.repeat(az, 2, axis=1).astype(np.uint16)
+    t_us = t0_us + idx * HDL64_US_PER_PACKET
+    pk["gps"] = (t_us % 3_600_000_000).astype(np.uint32)
+    return pk, t_us
