@@ -439,15 +439,18 @@ struct DecParams {
 };
 
 constexpr int kTilePkts = 32;
+constexpr int kTileBlocks = kTilePkts * kBlocks;  // 384
 constexpr int kDecThreads = 256;
 constexpr int kDecWarps = kDecThreads / 32;
-constexpr int kPktsPerWarp = kTilePkts / kDecWarps;  // 4
 
 struct DecShared {
   DevConfig cfg;
   uint64_t full[2];
+  unsigned mask[kTileBlocks];  // ballot of emitted return slots per firing block
+  unsigned offs[kTileBlocks];  // exclusive prefix of popc(mask) inside the tile
+  PktSeg seg[kTilePkts];
+  unsigned tpk[kTilePkts];     // packet time - t_base
   unsigned hist[2][kMaxLasers];
-  unsigned warp_cnt[kDecWarps];
   unsigned long long tile_base;
   int tile_id[2];
 };
@@ -457,56 +460,45 @@ __device__ __forceinline__ unsigned ld_smem_u16(const uint8_t* p) {
   return *reinterpret_cast<const unsigned short*>(p);
 }
 
-template <int ADJ, bool CROP>
-__device__ __forceinline__ bool decode_point(const DecShared& sh, const double* __restrict__ lut_sin,
-                                             const double* __restrict__ lut_cos, int j, int lane,
-                                             int row, unsigned rot, unsigned dist, int azdiff,
-                                             const double* __restrict__ M, bool pose_valid,
-                                             bool t_zero, float& fx, float& fy, float& fz,
-                                             unsigned& az_out) {
+// Per-laser calibration row held in registers (reloaded only when the bank changes).
+struct CalRow {
+  double cC, sC, dc, cV, sV, vo, ho;
+};
+__device__ __forceinline__ void load_cal(const DevConfig& c, int row, CalRow& r) {
+  r.cC = c.cal[0][row];
+  r.sC = c.cal[1][row];
+  r.dc = c.cal[2][row];
+  r.cV = c.cal[3][row];
+  r.sV = c.cal[4][row];
+  r.vo = c.cal[5][row];
+  r.ho = c.cal[6][row];
+}
+
+// Sensor-frame position of one return (HDLParser.cxx:597-623).  `az` is already adjusted and
+// reduced mod 36000.  All arithmetic in separate IEEE mul/add, reference operation order.
+__device__ __forceinline__ void sensor_point(const CalRow& c, double sA, double cA, unsigned dist,
+                                             double& px, double& py, double& pz) {
+  // sin/cos(rad(az/100) - rad(rotCorrection)); with rotCorrection == 0 (cC=1, sC=0) this is
+  // exactly the reference's LUT branch (:602-606)
+  const double sinAz = __dsub_rn(__dmul_rn(sA, c.cC), __dmul_rn(cA, c.sC));
+  const double cosAz = __dadd_rn(__dmul_rn(cA, c.cC), __dmul_rn(sA, c.sC));
+  const double dM = __dadd_rn(__dmul_rn((double)dist, 0.002), c.dc);  // :614
+  const double xy = __dmul_rn(dM, c.cV);                              // :615
+  px = __dsub_rn(__dmul_rn(xy, sinAz), __dmul_rn(c.ho, cosAz));       // :620
+  py = __dadd_rn(__dmul_rn(xy, cosAz), __dmul_rn(c.ho, sinAz));       // :621
+  pz = __dadd_rn(__dmul_rn(dM, c.sV), c.vo);                          // :622
+}
+
+template <int ADJ>
+__device__ __forceinline__ unsigned adjusted_azimuth(const DevConfig& c, unsigned rot, int azdiff,
+                                                     int j, int lane) {
   unsigned az = rot;
   if (ADJ != 0) {
     // HDLParser.cxx:961: std::round (half away from zero) of azimuthDiff * ratio
-    const int adj = (int)round(__dmul_rn((double)azdiff, sh.cfg.az_ratio[j][lane]));
+    const int adj = (int)round(__dmul_rn((double)azdiff, c.az_ratio[j][lane]));
     az = (unsigned)(unsigned short)(rot + adj);  // passed as unsigned short, :968
   }
-  az %= 36000u;  // :597
-  az_out = az;
-  const double sA = __ldg(&lut_sin[az]);
-  const double cA = __ldg(&lut_cos[az]);
-  const double cC = sh.cfg.cal[0][row], sC = sh.cfg.cal[1][row];
-  // sin/cos(rad(az/100) - rad(rotCorrection)); with rotCorrection == 0 (cC=1, sC=0) this is
-  // exactly the reference's LUT branch (:602-606)
-  const double sinAz = __dsub_rn(__dmul_rn(sA, cC), __dmul_rn(cA, sC));
-  const double cosAz = __dadd_rn(__dmul_rn(cA, cC), __dmul_rn(sA, sC));
-  const double dM = __dadd_rn(__dmul_rn((double)dist, 0.002), sh.cfg.cal[2][row]);  // :614
-  const double xy = __dmul_rn(dM, sh.cfg.cal[3][row]);                              // :615
-  const double ho = sh.cfg.cal[6][row];
-  double px = __dsub_rn(__dmul_rn(xy, sinAz), __dmul_rn(ho, cosAz));  // :620
-  double py = __dadd_rn(__dmul_rn(xy, cosAz), __dmul_rn(ho, sinAz));  // :621
-  double pz = __dadd_rn(__dmul_rn(dM, sh.cfg.cal[4][row]), sh.cfg.cal[5][row]);  // :622
-  if (CROP) {
-    const bool in_box = px >= sh.cfg.crop[0] && px <= sh.cfg.crop[1] && py >= sh.cfg.crop[2] &&
-                        py <= sh.cfg.crop[3] && pz >= sh.cfg.crop[4] && pz <= sh.cfg.crop[5];
-    if (in_box != (sh.cfg.crop_inside != 0)) return false;  // :634-638
-  }
-  if (pose_valid) {
-    // type_defs.h:160-166: row sums left to right, translation last
-    const double tx = t_zero ? 0.0 : M[3], ty = t_zero ? 0.0 : M[7], tz = t_zero ? 0.0 : M[11];
-    const double qx = __dadd_rn(
-        __dadd_rn(__dadd_rn(__dmul_rn(M[0], px), __dmul_rn(M[1], py)), __dmul_rn(M[2], pz)), tx);
-    const double qy = __dadd_rn(
-        __dadd_rn(__dadd_rn(__dmul_rn(M[4], px), __dmul_rn(M[5], py)), __dmul_rn(M[6], pz)), ty);
-    const double qz = __dadd_rn(
-        __dadd_rn(__dadd_rn(__dmul_rn(M[8], px), __dmul_rn(M[9], py)), __dmul_rn(M[10], pz)), tz);
-    px = qx;
-    py = qy;
-    pz = qz;
-  }
-  fx = (float)px;
-  fy = (float)py;
-  fz = (float)pz;
-  return true;
+  return az % 36000u;  // :597
 }
 
 // Byte span of a tile in the input array: [a0, a1) are the bytes the tile's packets occupy,
@@ -532,12 +524,17 @@ __device__ __forceinline__ TileSpan tile_span(long long in_base, long long strid
   return t;
 }
 
+// Work split inside a tile: warp w owns the packets {w/2 + 4k} and, inside them, the firing
+// blocks of parity w&1.  On HDL-64 data block parity == laser bank (0xeeff / 0xddff), so a
+// warp keeps one calibration bank in registers; the pose matrix is loaded once per packet.
 template <int ADJ, bool CROP>
 __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   DecShared& sh = *reinterpret_cast<DecShared*>(smem_raw);
   uint8_t* stage0 = smem_raw + ((sizeof(DecShared) + 127) & ~127);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int par = warp & 1, pk0 = warp >> 1;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
   // ---- one-time CTA setup -------------------------------------------------------------------
   {
@@ -580,6 +577,10 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
   const unsigned long long lmask = sh.cfg.laser_mask;
   const int pskip = sh.cfg.points_skip;
   const int n_enabled = sh.cfg.n_enabled;
+  const bool pose_valid = p.pose_valid != 0;
+
+  CalRow cal;
+  int cal_bank = -1;
 
   while (true) {
     const int tile = sh.tile_id[cur];
@@ -590,12 +591,24 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
       sh.tile_id[cur ^ 1] = tn;
       if (tn < p.n_tiles) issue(tn, cur ^ 1);
     }
-    if (tid < 2 * kMaxLasers) (&sh.hist[0][0])[tid] = 0;
-
     const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, p.halo, tile);
     const long long first = (long long)p.halo + (long long)tile * kTilePkts;
     const int npk = sp.npk;
     uint8_t* stage = stage0 + (size_t)cur * p.stage_bytes;
+
+    // per-packet records of this tile (overlaps the TMA wait)
+    if (tid < kTilePkts) {
+      PktSeg sg = make_int4(0, 0, 0, 0);
+      unsigned tp = 0;
+      if (tid < npk) {
+        sg = p.pkt_seg[first + tid];
+        tp = (unsigned)(__ldg(&p.pkt_time[first + tid]) - p.t_base);
+      }
+      sh.seg[tid] = sg;
+      sh.tpk[tid] = tp;
+    } else if (tid < kTilePkts + 2 * kMaxLasers) {
+      (&sh.hist[0][0])[tid - kTilePkts] = 0;
+    }
 
     mbar_wait(&sh.full[cur], phase[cur]);
     phase[cur] ^= 1u;
@@ -603,65 +616,99 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
       // tail bytes the bulk copy could not cover (unaligned end of the caller's buffer)
       for (long long a = sp.s1 + tid; a < sp.a1; a += kDecThreads)
         stage[a - sp.s0] = *reinterpret_cast<const uint8_t*>(a);
-      __syncthreads();
     }
+    __syncthreads();
     const uint8_t* tile_smem = stage + (sp.a0 - sp.s0);
-    const int tile_f0 = p.pkt_seg[first].y;
 
-    // ---- pass 1: count the points each block emits ---------------------------------------
-    unsigned cnt_reg[kPktsPerWarp];  // lane j (0..11) holds the count of block j
-    unsigned warp_total = 0;
-#pragma unroll
-    for (int k = 0; k < kPktsPerWarp; ++k) {
-      cnt_reg[k] = 0;
-      const int lp = warp * kPktsPerWarp + k;
-      if (lp >= npk) continue;
-      const long long P = first + lp;
-      const PktSeg seg = p.pkt_seg[P];
+    // ---- pass 1: which return slots of each firing block are emitted ---------------------
+#pragma unroll 1
+    for (int lp = pk0; lp < kTilePkts; lp += 4) {
+      const PktSeg seg = sh.seg[lp];
       const int skip_in = seg.x & 15;
       const uint8_t* pk = tile_smem + (size_t)lp * p.stride;
-#pragma unroll 1
-      for (int j = skip_in; j < kBlocks; ++j) {
-        if (pskip != 0 && (j % (pskip + 1)) != 0) continue;
-        const uint8_t* blk = pk + 100 * j;
-        const int off = (ld_smem_u16(blk) == 0xeeffu) ? 0 : 32;
-        const unsigned dist = blk[4 + 3 * lane] | (blk[5 + 3 * lane] << 8);
-        int laser_id = lane + off;
-        if (ADJ == 2 && laser_id >= 16) laser_id -= 16;
-        bool valid = dist != 0 && ((lmask >> laser_id) & 1ull) && laser_id < n_enabled;
-        if (CROP) {
-          if (valid) {
-            float fx, fy, fz;
-            unsigned azo;
-            valid = decode_point<ADJ, true>(sh, p.lut_sin, p.lut_cos, j, lane, lane + off,
-                                            ld_smem_u16(blk + 2), dist, seg.w, nullptr, false,
-                                            false, fx, fy, fz, azo);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int j = par + 2 * i;
+        unsigned m = 0;
+        if (lp < npk && j >= skip_in && (pskip == 0 || (j % (pskip + 1)) == 0)) {
+          const uint8_t* blk = pk + 100 * j;
+          const int off = (ld_smem_u16(blk) == 0xeeffu) ? 0 : 32;
+          const unsigned dist = blk[4 + 3 * lane] | (blk[5 + 3 * lane] << 8);
+          int laser_id = lane + off;
+          if (ADJ == 2 && laser_id >= 16) laser_id -= 16;
+          bool valid = dist != 0 && ((lmask >> laser_id) & 1ull) && laser_id < n_enabled;
+          if (CROP) {
+            // the crop test is on the sensor-frame position, before the transform (:629-639)
+            CalRow c;
+            load_cal(sh.cfg, lane + off, c);
+            const unsigned az = adjusted_azimuth<ADJ>(sh.cfg, ld_smem_u16(blk + 2), seg.w, j, lane);
+            double px, py, pz;
+            sensor_point(c, __ldg(&p.lut_sin[az]), __ldg(&p.lut_cos[az]), dist, px, py, pz);
+            const bool in_box = px >= sh.cfg.crop[0] && px <= sh.cfg.crop[1] &&
+                                py >= sh.cfg.crop[2] && py <= sh.cfg.crop[3] &&
+                                pz >= sh.cfg.crop[4] && pz <= sh.cfg.crop[5];
+            valid = valid && (in_box == (sh.cfg.crop_inside != 0));  // :634-638
           }
+          m = __ballot_sync(0xffffffffu, valid);
         }
-        const unsigned c = __popc(__ballot_sync(0xffffffffu, valid));
-        if (lane == j) cnt_reg[k] = c;
-        warp_total += c;
+        if (lane == 0) sh.mask[lp * kBlocks + j] = m;
       }
     }
-    if (lane == 0) sh.warp_cnt[warp] = warp_total;
     __syncthreads();
 
-    // ---- tile base through the decoupled look-back ------------------------------------------
+    // ---- scan (warp 0: lane == packet) + tile base through the decoupled look-back ----------
     if (warp == 0) {
-      unsigned long long agg = 0;
+      unsigned c[kBlocks];
+      unsigned tot = 0;
 #pragma unroll
-      for (int w = 0; w < kDecWarps; ++w) agg += sh.warp_cnt[w];
+      for (int j = 0; j < kBlocks; ++j) {
+        c[j] = tot;
+        tot += __popc(sh.mask[lane * kBlocks + j]);
+      }
+      unsigned inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      const unsigned pk_excl = inc - tot;
+#pragma unroll
+      for (int j = 0; j < kBlocks; ++j) sh.offs[lane * kBlocks + j] = pk_excl + c[j];
+      const unsigned long long agg = __shfl_sync(0xffffffffu, inc, 31);
       const unsigned long long ex = lookback_exclusive<SumTraits>(p.st_cnt, tile, agg);
       if (lane == 0) {
         sh.tile_base = ex;
         if (tile == p.n_tiles - 1) p.hdr->total_points = (long long)(ex + agg);
       }
+      // frame-start records: a wrap block opens frame f before it is decoded (:1035-1039)
+      const PktSeg seg = sh.seg[lane];
+      int wm = (seg.x >> 4) & 0xfff;
+      while (wm) {
+        const int j = __ffs(wm) - 1;
+        wm &= wm - 1;
+        const int f = seg.y + __popc(((seg.x >> 4) & 0xfff) & ((2 << j) - 1));
+        if (f < p.frame_cap) {
+          p.frame_first_point[f] = (long long)(ex + pk_excl + c[j]);
+          p.frame_start_block[f] = (int)((first + lane) * 12 + j);
+        } else {
+          p.hdr->frame_overflow = 1;
+        }
+      }
     }
     __syncthreads();
-    unsigned long long out = sh.tile_base;
-    for (int w = 0; w < warp; ++w) out += sh.warp_cnt[w];
 
-    // ---- pass 2: decode, transform, store ----------------------------------------------------
+    // ---- pass 2: decode, calibrate, transform, store ----------------------------------------
+    const unsigned long long tb = sh.tile_base;
+    float* const xt = p.x + tb;
+    float* const yt = p.y + tb;
+    float* const zt = p.z + tb;
+    uint32_t* const tt = p.t_us + tb;
+    uint16_t* const at = p.azimuth + tb;
+    uint16_t* const dt = p.distance + tb;
+    uint8_t* const it = p.intensity + tb;
+    uint8_t* const lt = p.laser + tb;
+    const int tile_f0 = sh.seg[0].y;
+
     unsigned cnt_lo = 0, cnt_hi = 0;  // per-lane emitted counts for the lower / upper laser bank
     int warp_frame = -1;
     auto flush_counts = [&](int f) {
@@ -682,75 +729,85 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
       cnt_lo = cnt_hi = 0;
     };
 
-#pragma unroll
-    for (int k = 0; k < kPktsPerWarp; ++k) {
-      const int lp = warp * kPktsPerWarp + k;
-      if (lp >= npk) continue;
-      const long long P = first + lp;
-      const PktSeg seg = p.pkt_seg[P];
-      const int skip_in = seg.x & 15;
+#pragma unroll 1
+    for (int lp = pk0; lp < npk; lp += 4) {
+      const PktSeg seg = sh.seg[lp];
       const int wrapmask = (seg.x >> 4) & 0xfff;
       const int first_wrap = wrapmask ? (__ffs(wrapmask) - 1) : 12;
       const uint8_t* pk = tile_smem + (size_t)lp * p.stride;
+      const unsigned tpk = sh.tpk[lp];
       double M[12];  // [L | t] of this packet, warp-uniform
-      if (p.pose_valid) {
+      if (pose_valid) {
+        const double* mp = p.pose_mat + (first + lp) * 12;
 #pragma unroll
-        for (int q = 0; q < 12; ++q) M[q] = __ldg(&p.pose_mat[P * 12 + q]);
+        for (int q = 0; q < 12; ++q) M[q] = __ldg(&mp[q]);
       }
-      const uint32_t tpk = (uint32_t)(__ldg(&p.pkt_time[P]) - p.t_base);
-#pragma unroll 1
-      for (int j = skip_in; j < kBlocks; ++j) {
-        const int f = seg.y + __popc(wrapmask & ((2 << j) - 1));
-        if ((wrapmask >> j) & 1) {
-          // this block opens frame f (HDLParser.cxx:1035-1039: split before it is decoded)
-          if (lane == 0) {
-            if (f < p.frame_cap) {
-              p.frame_first_point[f] = (long long)out;
-              p.frame_start_block[f] = (int)(P * 12 + j);
-            } else {
-              p.hdr->frame_overflow = 1;
-            }
+      if (wrapmask == 0 && seg.y != warp_frame) {
+        flush_counts(warp_frame);
+        warp_frame = seg.y;
+      }
+#pragma unroll 2
+      for (int i = 0; i < 6; ++i) {
+        const int j = par + 2 * i;
+        const int b = lp * kBlocks + j;
+        const unsigned m = sh.mask[b];
+        if (m == 0) continue;
+        if (wrapmask) {
+          const int f = seg.y + __popc(wrapmask & ((2 << j) - 1));
+          if (f != warp_frame) {
+            flush_counts(warp_frame);
+            warp_frame = f;
           }
         }
-        if (pskip != 0 && (j % (pskip + 1)) != 0) continue;
-        if (f != warp_frame) {
-          flush_counts(warp_frame);
-          warp_frame = f;
-        }
+        const unsigned o = sh.offs[b] + __popc(m & lt_mask);
+        const bool valid = (m >> lane) & 1u;
         const uint8_t* blk = pk + 100 * j;
         const int off = (ld_smem_u16(blk) == 0xeeffu) ? 0 : 32;
+        if (off != cal_bank) {
+          load_cal(sh.cfg, lane + off, cal);
+          cal_bank = off;
+        }
         const unsigned rot = ld_smem_u16(blk + 2);
         const unsigned dist = blk[4 + 3 * lane] | (blk[5 + 3 * lane] << 8);
         const unsigned inten = blk[6 + 3 * lane];
         int laser_id = lane + off;
         if (ADJ == 2 && laser_id >= 16) laser_id -= 16;
-        bool valid = dist != 0 && ((lmask >> laser_id) & 1ull) && laser_id < n_enabled;
-        float fx = 0.f, fy = 0.f, fz = 0.f;
-        unsigned azo = 0;
-        if (valid) {
+        const unsigned az = adjusted_azimuth<ADJ>(sh.cfg, rot, seg.w, j, lane);
+        double px, py, pz;
+        sensor_point(cal, __ldg(&p.lut_sin[az]), __ldg(&p.lut_cos[az]), dist, px, py, pz);
+        if (pose_valid) {
           // offline: blocks at/after the packet's first wrap start a frame whose origin is
-          // this very packet -> zero translation
+          // this very packet -> zero translation.  type_defs.h:160-166: row sums left to
+          // right, translation last.
           const bool t_zero = (p.mode == 1) && (j >= first_wrap);
-          valid = decode_point<ADJ, CROP>(sh, p.lut_sin, p.lut_cos, j, lane, lane + off, rot, dist,
-                                          seg.w, M, p.pose_valid != 0, t_zero, fx, fy, fz, azo);
+          const double tx = t_zero ? 0.0 : M[3], ty = t_zero ? 0.0 : M[7], tz = t_zero ? 0.0 : M[11];
+          const double qx = __dadd_rn(
+              __dadd_rn(__dadd_rn(__dmul_rn(M[0], px), __dmul_rn(M[1], py)), __dmul_rn(M[2], pz)),
+              tx);
+          const double qy = __dadd_rn(
+              __dadd_rn(__dadd_rn(__dmul_rn(M[4], px), __dmul_rn(M[5], py)), __dmul_rn(M[6], pz)),
+              ty);
+          const double qz = __dadd_rn(
+              __dadd_rn(__dadd_rn(__dmul_rn(M[8], px), __dmul_rn(M[9], py)), __dmul_rn(M[10], pz)),
+              tz);
+          px = qx;
+          py = qy;
+          pz = qz;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, valid);
         if (valid) {
-          const unsigned long long o = out + __popc(bal & ((1u << lane) - 1u));
-          p.x[o] = fx;
-          p.y[o] = fy;
-          p.z[o] = fz;
-          p.intensity[o] = (uint8_t)inten;
-          p.laser[o] = (uint8_t)laser_id;
-          p.azimuth[o] = (uint16_t)azo;
-          p.distance[o] = (uint16_t)dist;
-          p.t_us[o] = tpk + (ADJ != 0 ? (uint32_t)sh.cfg.tadj[j][lane] : 0u);
+          xt[o] = (float)px;
+          yt[o] = (float)py;
+          zt[o] = (float)pz;
+          tt[o] = tpk + (ADJ != 0 ? (uint32_t)sh.cfg.tadj[j][lane] : 0u);
+          at[o] = (uint16_t)az;
+          dt[o] = (uint16_t)dist;
+          it[o] = (uint8_t)inten;
+          lt[o] = (uint8_t)laser_id;
           if (off)
             ++cnt_hi;
           else
             ++cnt_lo;
         }
-        out += __popc(bal);
       }
     }
     flush_counts(warp_frame);
@@ -761,7 +818,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
       if (c && f < p.frame_cap)
         atomicAdd(&p.frame_laser_counts[(long long)f * kMaxLasers + (tid & 63)], c);
     }
-    __syncthreads();  // stage `cur` and hist are free again
+    __syncthreads();  // stage `cur`, masks and hist are free again
     cur ^= 1;
   }
 }
