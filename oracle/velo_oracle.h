@@ -7,14 +7,18 @@
  * cpu_baseline / --impl reference legs of bench.py may load it.  The product
  * (libveloslam_b200.so) never links, loads or calls anything in oracle/.
  *
- * Parity pin: the reference ships no golden vectors or known-answer tests for this
- * path, so the restatement is pinned two ways:
- *   1. hand-derived known-answer tests (tests/test_oracle_kat.py);
- *   2. oracle/_ref -- the reference's own HDLParser.cxx / TransformManager.cxx /
- *      TimeLine.h / type_defs.* compiled verbatim against shim headers
- *      (oracle/ref_shim/, see oracle/build_ref.py) and compared output-for-output
- *      (tests/test_oracle_vs_ref.py).  Where oracle/_ref is not built the header
- *      of that test says so and parity is "unpinned" beyond (1).
+ * Parity pin: the reference ships no golden vectors or known-answer tests for this path
+ * (SURVEY.md section 4).  The restatement is pinned three ways:
+ *   1. oracle/_ref -- the reference's own HDLParser.cxx / TransformManager.cxx / TimeLine.h /
+ *      type_defs.* / HDLFrame.cxx / vtkPacketFileWriter.cxx compiled verbatim, where they lie
+ *      under /root/reference, against stand-in third-party headers (oracle/ref_shim, recipe
+ *      oracle/build_ref.py) and compared output-for-output, bit-exact
+ *      (tests/test_oracle_vs_ref.py);
+ *   2. golden fixtures generated from oracle/_ref and committed under tests/golden/
+ *      (tests/golden/make_golden.py, tests/test_golden.py);
+ *   3. hand-derived known-answer tests (tests/test_oracle_kat.py).
+ * What (1) cannot pin is the third-party arithmetic itself (Eigen's AngleAxis/3x3 product
+ * rounding order, Boost's time arithmetic): those are restated in oracle/ref_shim.
  *
  * Time: boost::posix_time::ptime (microsecond resolution) is restated as
  * int64 microseconds since the Unix epoch.

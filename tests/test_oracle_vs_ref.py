@@ -1,0 +1,219 @@
+"""Pins the CPU oracle to the reference itself: oracle/_ref is /root/reference's own
+HDLParser.cxx / TransformManager.cxx / TimeLine.h / type_defs.* / HDLFrame.cxx /
+vtkPacketFileWriter.cxx compiled verbatim against stand-in third-party headers
+(oracle/ref_shim).  Every comparison here is exact (bit-for-bit floats included).
+
+Skipped when oracle/_ref is not built (no /root/reference and no prebuilt library); the
+committed fixtures under tests/golden/ (generated from oracle/_ref by
+tests/golden/make_golden.py) still pin the oracle in that case (test_golden.py).
+"""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from oracle import ref
+from oracle.oracle import Oracle
+from veloslam_b200 import pcapio, synth
+
+from helpers import make_packet
+
+# vtkPacketFileWriter stamps records with mktime(): make "local time" UTC for the byte compare
+os.environ["TZ"] = "UTC"
+time.tzset()
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref is not built")
+
+
+def both(calib, poses=None, sel=None, skip=0, crop=None):
+    out = []
+    for cls in (ref.RefParser, Oracle):
+        o = cls()
+        o.set_calibration(calib)
+        if sel is not None:
+            o.set_laser_selection(sel)
+        o.set_points_skip(skip)
+        if crop is not None:
+            o.set_crop(1, crop[0], crop[1])
+        if poses is not None:
+            o.add_poses(poses[0], poses[1])
+        out.append(o)
+    return out
+
+
+def assert_same_frames(r, o, force_split=True):
+    if force_split:
+        r.split_frame()
+        o.split_frame()
+    fr, fo = r.frames(), o.frames()
+    assert len(fr) == len(fo)
+    for a, b in zip(fr, fo):
+        assert a.n_points == b.n_points
+        assert a.timestamp_us == b.timestamp_us
+        # HDLFrame::skips is an uninitialised uint8_t in frames that never get their meta
+        if b.skips >= 0:
+            assert a.skips == b.skips
+        assert a.n_packets == b.n_packets
+        assert np.array_equal(a.laser_counts, b.laser_counts)
+        assert np.array_equal(a.xyzi.view(np.uint32), b.xyzi.view(np.uint32))
+        assert np.array_equal(a.azimuth, b.azimuth)
+        assert np.array_equal(a.distance.view(np.uint32), b.distance.view(np.uint32))
+        assert np.array_equal(a.carpose_TRV.view(np.uint64), b.carpose_TRV.view(np.uint64))
+        assert a.carpose_valid == b.carpose_valid
+    assert r.state() == o.state()
+    return len(fr)
+
+
+def test_hdl64_decode_deskew():
+    pk, t = synth.hdl64_packets(2500)
+    r, o = both(synth.calib_hdl64(), synth.ins_trajectory(90))
+    for p in (r, o):
+        p.process_packets(synth.as_bytes(pk), t)
+    assert assert_same_frames(r, o) == 8
+
+
+def test_hdl32_with_mid_packet_wraps():
+    pk, t = synth.hdl32_packets(2000, az0=123.0)
+    r, o = both(synth.calib_hdl32(), synth.ins_trajectory(130))
+    for p in (r, o):
+        p.process_packets(synth.as_bytes(pk), t)
+    assert assert_same_frames(r, o) >= 10
+
+
+def test_vlp16_mode():
+    pk, t = synth.hdl32_packets(300, seed=16)
+    c = synth.calib_hdl32()
+    c.n_enabled = 16
+    r, o = both(c)
+    for p in (r, o):
+        p.process_packets(synth.as_bytes(pk), t)
+    assert r.num_channels() == 16
+    assert_same_frames(r, o)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_azimuths(seed):
+    """Several wraps per packet, non-constant skip chains, frames that never get their meta."""
+    pk, t = synth.random_packets(700, seed)
+    r, o = both(synth.calib_hdl64(), synth.ins_trajectory(40))
+    for p in (r, o):
+        p.process_packets(synth.as_bytes(pk), t)
+    assert assert_same_frames(r, o) > 100
+
+
+def test_filters_and_crop():
+    pk, t = synth.hdl64_packets(900)
+    sel = np.ones(64, np.int32)
+    sel[[1, 17, 40]] = 0
+    region = (-20.0, 20.0, -30.0, 30.0, -5.0, 5.0)
+    for inside in (0, 1):
+        r, o = both(synth.calib_hdl64(), synth.ins_trajectory(40), sel=sel, skip=2,
+                    crop=(inside, region))
+        for p in (r, o):
+            p.process_packets(synth.as_bytes(pk), t)
+        assert_same_frames(r, o)
+
+
+def test_wrong_size_packets_are_dropped():
+    pk, t = synth.hdl64_packets(400)
+    b = synth.as_bytes(pk)
+    lengths = np.full(400, 1206, np.int32)
+    lengths[[3, 77, 200]] = [512, 1205, 0]
+    r, o = both(synth.calib_hdl64())
+    r.process_packets(b, t, lengths)
+    for i in range(400):
+        o.process_packet(b[i], t[i], length=int(lengths[i]))
+    assert_same_frames(r, o)
+
+
+def test_identity_kats_hold_for_the_reference_too():
+    r, _ = both(synth.calib_identity(64))
+    d = np.zeros((12, 32), np.uint16)
+    d[0, 3] = 5000
+    r.process_packets(synth.as_bytes(make_packet(9000 + 10 * np.arange(12), None, d)),
+                      np.array([synth.T0_US]))
+    r.split_frame()
+    f = r.frames()[0]
+    assert np.allclose(f.xyzi[0, :3], (10.0, 0.0, 0.0), atol=2e-6)
+
+
+def test_timeline_interpolation_everywhere():
+    rng = np.random.default_rng(5)
+    n = 300
+    ts = synth.T0_US + np.cumsum(rng.integers(2_000, 30_000, n)).astype(np.int64)
+    trv = rng.normal(size=(n, 9)) * 50
+    r, o = both(synth.calib_identity(64), (ts, trv))
+    q = np.concatenate([ts, ts[:-1] + 1, ts[1:] - 1, [ts[0] - 5_000, ts[-1] + 123_456],
+                        rng.integers(ts[0] - 1000, ts[-1] + 1000, 500)])
+    for t in q:
+        a, b = r.interpolate(int(t)), o.interpolate(int(t))
+        assert a[0] == b[0] and a[2] == b[2]
+        assert np.array_equal(a[1].view(np.uint64), b[1].view(np.uint64)), t
+
+
+def test_timeline_out_of_order_and_duplicates():
+    r, o = both(synth.calib_identity(64))
+    rng = np.random.default_rng(8)
+    order = rng.permutation(40)
+    for k in list(order) + [5, 17, 39]:
+        trv = rng.normal(size=(1, 9))
+        for p in (r, o):
+            p.add_poses([synth.T0_US + 10_000 * int(k)], trv)
+    assert r.num_poses() == o.num_poses()
+    for t in range(synth.T0_US - 20_000, synth.T0_US + 420_000, 3_333):
+        a, b = r.interpolate(t), o.interpolate(t)
+        assert a[0] == b[0] and np.array_equal(a[1].view(np.uint64), b[1].view(np.uint64)), t
+
+
+@pytest.mark.parametrize("n_poses", [0, 1])
+def test_short_timelines(n_poses):
+    pt, trv = synth.ins_trajectory(1)
+    r, o = both(synth.calib_hdl64(), (pt[:n_poses], trv[:n_poses]))
+    a, b = r.interpolate(synth.T0_US + 1_234_567), o.interpolate(synth.T0_US + 1_234_567)
+    assert a[0] == b[0] and a[2] == b[2] and np.array_equal(a[1], b[1])
+    pk, t = synth.hdl64_packets(500)
+    for p in (r, o):
+        p.process_packets(synth.as_bytes(pk), t)
+    assert_same_frames(r, o)
+
+
+def test_pose_matrix():
+    rng = np.random.default_rng(2)
+    for _ in range(50):
+        trv = rng.uniform(-180, 180, 9)
+        a, b = ref.RefParser.pose_matrix(trv), Oracle.pose_matrix(trv)
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def test_offline_index_and_get_frame_through_a_pcap_file(tmp_path):
+    pk, t = synth.hdl64_packets(1200)
+    b = synth.as_bytes(pk)
+    path = str(tmp_path / "20160701T000000.pcap")      # an ISO name: the reference renames others
+    pcapio.write_pcap(path, b, t)
+    calib = synth.calib_hdl64()
+    r, o = both(calib, synth.ins_trajectory(50))
+    pos, sk, ts = r.read_frame_information(path)
+    sp, sk2, ts2 = Oracle.read_frame_information(b, t)
+    assert np.array_equal(pos, pcapio.GLOBAL_HEADER_BYTES + sp.astype(np.int64) * pcapio.RECORD_BYTES)
+    assert np.array_equal(sk, sk2) and np.array_equal(ts, ts2)
+    for i in range(len(pos)):
+        fr = r.get_frame(path, pos[i], sk[i])
+        fo = o.get_frame(b, t, sp[i], sk2[i])
+        assert fr.n_points == fo.n_points
+        assert np.array_equal(fr.xyzi.view(np.uint32), fo.xyzi.view(np.uint32))
+        assert np.array_equal(fr.laser_counts, fo.laser_counts)
+    assert os.path.exists(path)
+
+
+def test_pcap_writer_matches_the_reference_byte_for_byte(tmp_path):
+    pk, t = synth.hdl64_packets(37)
+    b = synth.as_bytes(pk)
+    path = str(tmp_path / "ref.pcap")
+    # the reference stamps mktime(to_tm(t)) (local time, UTC here); its reader adds 8 hours
+    assert ref.RefParser.write_pcap(path, b, t - pcapio.TZ_SHIFT_US)
+    theirs = np.fromfile(path, dtype=np.uint8)
+    ours = pcapio.write_pcap_image(b, t)
+    assert theirs.shape == ours.shape and np.array_equal(theirs, ours)
+    back, tb = pcapio.read_pcap_image(theirs)
+    assert np.array_equal(back, b) and np.array_equal(tb, t)
