@@ -201,6 +201,11 @@ VS_API int vs_read_frame_information(vs_ctx* ctx, const uint8_t* pkts, int64_t s
                               int32_t* start_packet, int32_t* skips, int64_t* timestamp_us,
                               int32_t cap, int32_t* n_frames);
 
+/* Page-locked host memory for packet rings / result buffers (cudaHostAlloc / cudaFreeHost),
+ * so that callers above the ABI need no CUDA headers. */
+VS_API int vs_host_alloc(uint64_t bytes, void** out);
+VS_API void vs_host_free(void* p);
+
 /* The CUDA stream the context launches on (cudaStream_t), for callers that time or order
  * work against it. */
 VS_API void* vs_stream(vs_ctx* ctx);

@@ -1,0 +1,79 @@
+"""The C++ facade (HDLParser / HDLFrame / TransformManager with the reference's names) driven
+like the reference's consumers, on the GPU, against the oracle: laser-major frame contents."""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from veloslam_b200 import calibxml, pcapio, synth
+
+import facade_util as F
+import parity as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _driver():
+    F.build()
+
+
+def compare(frames, oracle_frames, tol):
+    assert len(frames) == len(oracle_frames)
+    for a, b in zip(frames, oracle_frames):
+        assert a.n_points == b.n_points
+        assert a.timestamp_us == b.timestamp_us and a.skips == b.skips
+        assert a.n_packets == b.n_packets
+        assert a.carpose_valid == b.carpose_valid
+        assert np.allclose(a.carpose_TRV, b.carpose_TRV, rtol=0, atol=1e-9)
+        assert np.array_equal(a.laser_counts, b.laser_counts)
+        assert np.array_equal(a.azimuth, b.azimuth)
+        assert np.array_equal(a.distance, b.distance)
+        assert np.array_equal(a.xyzi[:, 3], b.xyzi[:, 3])
+        d = np.abs(a.xyzi[:, :3].astype(np.float64) - b.xyzi[:, :3])
+        assert d.size == 0 or d.max() <= tol
+
+
+@pytest.mark.parametrize("sensor,batch", [("hdl64", 4096), ("hdl64", 100), ("hdl32", 4096)])
+def test_streaming_like_hdlsource(tmp_path, sensor, batch):
+    if sensor == "hdl64":
+        pk, t = synth.hdl64_packets(1500)
+        calib = synth.calib_hdl64()
+    else:
+        pk, t = synth.hdl32_packets(1200, az0=123.0)
+        calib = synth.calib_hdl32()
+    poses = synth.ins_trajectory(80)
+    b = synth.as_bytes(pk)
+    b.tofile(tmp_path / "pk.bin")
+    t.astype("<i8").tofile(tmp_path / "t.bin")
+    F.write_poses(tmp_path / "poses.bin", *poses)
+    calibxml.write_db_xml(str(tmp_path / "db.xml"), calib)
+    r = F.run(["stream", tmp_path / "db.xml", tmp_path / "pk.bin", tmp_path / "t.bin",
+               tmp_path / "poses.bin", tmp_path / "out.bin", batch])
+    assert r.returncode == 0, r.stderr
+    o = P.make_oracle(calib, poses)
+    o.process_packets(b, t)
+    compare(F.read_frames(tmp_path / "out.bin"), o.frames(), P.TOL_DESKEW)
+
+
+def test_offline_like_hdlmanager(tmp_path):
+    pk, t = synth.hdl64_packets(1300)
+    calib = synth.calib_hdl64()
+    poses = synth.ins_trajectory(60)
+    b = synth.as_bytes(pk)
+    path = tmp_path / "20160701T000000.pcap"
+    pcapio.write_pcap(str(path), b, t)
+    F.write_poses(tmp_path / "poses.bin", *poses)
+    calibxml.write_db_xml(str(tmp_path / "db.xml"), calib)
+    r = F.run(["offline", tmp_path / "db.xml", path, tmp_path / "poses.bin", tmp_path / "out.bin"])
+    assert r.returncode == 0, r.stderr
+    frames = F.read_frames(tmp_path / "out.bin")
+    o = P.make_oracle(calib, poses)
+    sp, sk, ts = Oracle.read_frame_information(b, t)
+    assert len(frames) == len(sp)
+    for i, f in enumerate(frames):
+        want = o.get_frame(b, t, sp[i], sk[i])
+        assert f.n_points == want.n_points and f.timestamp_us == ts[i] and f.skips == sk[i]
+        assert np.array_equal(f.laser_counts, want.laser_counts)
+        assert np.array_equal(f.azimuth, want.azimuth)
+        d = np.abs(f.xyzi[:, :3].astype(np.float64) - want.xyzi[:, :3])
+        assert d.max() <= P.TOL_DESKEW

@@ -42,5 +42,34 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+FACADE_DIR = os.path.join(HERE, "cpp")
+FACADE_LIB = os.path.join(HERE, "libveloslam_facade.so")
+FACADE_SOURCES = ["type_defs.cpp", "TransformManager.cpp", "vtkPacketFile.cpp",
+                  "CalibrationFile.cpp", "HDLParser.cpp"]
+DRIVER_SRC = os.path.join(os.path.dirname(HERE), "tests", "cpp", "facade_driver.cpp")
+DRIVER_EXE = os.path.join(os.path.dirname(HERE), "tests", "cpp", "facade_driver")
+CXXFLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-Wall"]
+
+
+def build_facade(force=False):
+    """C++ facade (HDLParser / HDLFrame / TransformManager / TimeLine with the reference's
+    names) over the C ABI, plus the test driver executable."""
+    build_library()
+    srcs = [os.path.join(FACADE_DIR, s) for s in FACADE_SOURCES]
+    deps = srcs + [os.path.join(FACADE_DIR, f) for f in os.listdir(FACADE_DIR)] + [LIB]
+    if (force or not os.path.exists(FACADE_LIB)
+            or os.path.getmtime(FACADE_LIB) < max(os.path.getmtime(d) for d in deps)):
+        subprocess.check_call(["g++"] + CXXFLAGS + ["-shared", "-o", FACADE_LIB] + srcs +
+                              ["-L", HERE, "-lveloslam_b200", "-Wl,-rpath,$ORIGIN"])
+    if (force or not os.path.exists(DRIVER_EXE)
+            or os.path.getmtime(DRIVER_EXE) < max(os.path.getmtime(DRIVER_SRC),
+                                                  os.path.getmtime(FACADE_LIB))):
+        subprocess.check_call(["g++"] + CXXFLAGS + ["-o", DRIVER_EXE, DRIVER_SRC, "-I", FACADE_DIR,
+                               "-L", HERE, "-lveloslam_facade", "-lveloslam_b200",
+                               "-Wl,-rpath,$ORIGIN/../../veloslam_b200"])
+    return FACADE_LIB
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))
+    print(build_facade(force=True))

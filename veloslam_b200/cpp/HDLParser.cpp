@@ -1,0 +1,540 @@
+// HDLParser.cpp -- host side of the drop-in facade: batching into a pinned ring, GPU decode
+// through the C ABI, and assembly of reference-shaped HDLFrames from the stream-order columns.
+#include "HDLParser.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+
+#include "../../include/veloslam_b200.h"
+#include "CalibrationFile.h"
+#include "vtkPacketFile.h"
+
+namespace {
+// HDL-64 beam re-order applied when a frame is closed on HDL-64 data: new[i] = old[LUT[i]]
+// (sensor manual ordering, reference HDLParser.cxx:179-182)
+const int kHDL64BeamLUT[64] = {38, 39, 42, 43, 32, 33, 36, 37, 40, 41, 46, 47, 50, 51, 54, 55,
+                               44, 45, 48, 49, 52, 53, 58, 59, 62, 63, 34, 35, 56, 57, 60, 61,
+                               6,  7,  10, 11, 0,  1,  4,  5,  8,  9,  14, 15, 18, 19, 22, 23,
+                               12, 13, 16, 17, 20, 21, 26, 27, 30, 31, 2,  3,  24, 25, 28, 29};
+}  // namespace
+
+class HDLParser::vsInternal {
+ public:
+  vsInternal()
+      : ctx(nullptr), device(0), batchPackets(4096), storePackets(true), pinnedPkts(nullptr),
+        pinnedTimes(nullptr), pending(0), pendingWrap(false), hostLastAz(-1),
+        correctionsInitialized(false), calibFileReportedNumLasers(64), numberOfTrailingFrames(0),
+        applyTransform(0), pointsSkip(0), shouldCropReturns(false), shouldCropInside(false),
+        dualReturnFilter(0), configDirty(true), poseVersion(0), warnedNoCalib(false) {
+    for (int i = 0; i < 6; ++i) cropRegion[i] = 0.0;
+    for (int i = 0; i < HDL_MAX_NUM_LASERS; ++i) laserSelections[i] = 1;
+    std::memset(&calib, 0, sizeof(calib));
+    vs_carry_init(&carry);
+  }
+  ~vsInternal() {
+    if (ctx) vs_destroy(ctx);
+    vs_host_free(pinnedPkts);
+    vs_host_free(pinnedTimes);
+  }
+
+  bool ensureContext() {
+    if (ctx) return true;
+    const int rc = vs_create(device, batchPackets, 1 << 20, 1, &ctx);
+    if (rc != VS_OK) {
+      error = std::string("vs_create failed: ") + vs_last_error(nullptr) +
+              " (status " + std::to_string(rc) + "; there is no CPU fallback)";
+      std::cerr << error << std::endl;
+      ctx = nullptr;
+      return false;
+    }
+    if (vs_host_alloc((uint64_t)batchPackets * VS_PACKET_BYTES, (void**)&pinnedPkts) != VS_OK ||
+        vs_host_alloc((uint64_t)batchPackets * sizeof(int64_t), (void**)&pinnedTimes) != VS_OK) {
+      error = "pinned host allocation failed for the packet ring";
+      return false;
+    }
+    configDirty = true;
+    return true;
+  }
+
+  bool syncConfig() {
+    if (configDirty) {
+      if (correctionsInitialized) {
+        if (vs_set_calibration(ctx, calib.rows, calib.n_rows, calibFileReportedNumLasers) != VS_OK) {
+          error = vs_last_error(ctx);
+          return false;
+        }
+      }
+      vs_filters f;
+      std::memset(&f, 0, sizeof(f));
+      for (int i = 0; i < 64; ++i)
+        if (laserSelections[i]) f.laser_mask |= 1ull << i;
+      f.points_skip = pointsSkip;
+      f.crop_returns = shouldCropReturns ? 1 : 0;
+      f.crop_inside = shouldCropInside ? 1 : 0;
+      for (int i = 0; i < 6; ++i) f.crop_region[i] = cropRegion[i];
+      if (vs_set_filters(ctx, &f) != VS_OK) {
+        error = vs_last_error(ctx);
+        return false;
+      }
+      configDirty = false;
+    }
+    const uint64_t v = transMgr ? transMgr->version() : 0;
+    if (v != poseVersion) {
+      std::vector<int64_t> t;
+      std::vector<double> trv;
+      if (transMgr) transMgr->snapshot(&t, &trv);
+      if (vs_set_poses(ctx, t.data(), trv.data(), (int64_t)t.size()) != VS_OK) {
+        error = vs_last_error(ctx);
+        return false;
+      }
+      poseVersion = v;
+    }
+    return true;
+  }
+
+  std::shared_ptr<HDLFrame> createHDLFrame() {
+    std::shared_ptr<HDLFrame> f(new HDLFrame);
+    f->points.resize(calibFileReportedNumLasers);
+    f->pointsMeta.resize(calibFileReportedNumLasers);
+    for (int i = 0; i < calibFileReportedNumLasers; ++i) {
+      f->points[i] = pcl::PointCloud<pcl::PointXYZI>::Ptr(new pcl::PointCloud<pcl::PointXYZI>);
+      f->points[i]->points.reserve(HDL_MAX_PTS_PER_LASER);
+      f->pointsMeta[i] = std::shared_ptr<std::vector<PointMeta> >(new std::vector<PointMeta>);
+      f->pointsMeta[i]->reserve(HDL_MAX_PTS_PER_LASER);
+    }
+    f->isInMemory = true;
+    return f;
+  }
+
+  // close a frame the way splitFrame does (reference HDLParser.cxx:867-897)
+  void closeFrame(std::shared_ptr<HDLFrame>& f, bool hdl64Order) {
+    for (auto& cloud : f->points) {
+      cloud->width = (uint32_t)cloud->points.size();
+      cloud->height = 1;
+    }
+    if (hdl64Order) {
+      std::vector<pcl::PointCloud<pcl::PointXYZI>::Ptr> pts(64);
+      std::vector<std::shared_ptr<std::vector<PointMeta> > > ptm(64);
+      for (int i = 0; i < 64; ++i) {
+        const size_t src = (size_t)kHDL64BeamLUT[i];
+        if (src < f->points.size()) {
+          pts[i] = f->points[src];
+          ptm[i] = f->pointsMeta[src];
+        } else {
+          pts[i] = pcl::PointCloud<pcl::PointXYZI>::Ptr(new pcl::PointCloud<pcl::PointXYZI>);
+          ptm[i] = std::shared_ptr<std::vector<PointMeta> >(new std::vector<PointMeta>);
+        }
+      }
+      f->points = std::move(pts);
+      f->pointsMeta = std::move(ptm);
+    }
+  }
+
+  void applyMeta(HDLFrame& f, const vs_frame& e) {
+    f.timestamp = ptime(e.timestamp_us);
+    if (e.skips >= 0) f.skips = (uint8_t)e.skips;
+    for (int k = 0; k < 3; ++k) {
+      f.carpose->T[k] = e.carpose[k];
+      f.carpose->R[k] = e.carpose[3 + k];
+      f.carpose->V[k] = e.carpose[6 + k];
+    }
+    f.carpose->seconds_pos = e.carpose_valid ? 0 : -1;
+    f.carpose->timestamp = f.timestamp;
+  }
+
+  // Decode the buffered packets and distribute the points over currentFrame / new frames.
+  // mode / carryIn are those of the streaming parser; returns false on a GPU error.
+  bool decodePending(std::deque<std::shared_ptr<HDLFrame> >* closedOut) {
+    if (pending == 0) return true;
+    if (!ensureContext() || !syncConfig()) return false;
+    uint64_t ticket = 0;
+    vs_result r;
+    int rc = vs_submit(ctx, pinnedPkts, VS_PACKET_BYTES, pinnedTimes, pending, 0, VS_MODE_STREAMING,
+                       0, pinnedTimes[0], &carry, &ticket);
+    if (rc == VS_OK) rc = vs_wait(ctx, ticket, &r);
+    if (rc != VS_OK) {
+      error = vs_last_error(ctx);
+      std::cerr << "HDLParser: GPU decode failed: " << error << std::endl;
+      pending = 0;
+      pendingWrap = false;
+      return false;
+    }
+    error.clear();
+    const size_t n = (size_t)r.n_points;
+    hx.resize(n);
+    hy.resize(n);
+    hz.resize(n);
+    hi.resize(n);
+    hl.resize(n);
+    ha.resize(n);
+    hd.resize(n);
+    if (n) {
+      rc = vs_fetch_points(ctx, ticket, 0, r.n_points, hx.data(), hy.data(), hz.data(), hi.data(),
+                           hl.data(), ha.data(), hd.data(), nullptr);
+      if (rc != VS_OK) {
+        error = vs_last_error(ctx);
+        return false;
+      }
+    }
+    for (int i = 0; i < r.n_frames; ++i) {
+      const vs_frame& e = r.frames[i];
+      if (i > 0) currentFrame = createHDLFrame();
+      HDLFrame& f = *currentFrame;
+      if (e.meta_packet >= 0) applyMeta(f, e);  // -1: carried (already applied), -2: never
+      // raw packets: a packet is stored in the frame that is current when it arrives; the
+      // frame's first packet is stored twice (reference HDLParser.cxx:999 + 1009)
+      if (storePackets) {
+        const int first = (i == 0) ? 0 : e.start_packet + 1;
+        const int last = (i + 1 < r.n_frames) ? r.frames[i + 1].start_packet : (int)pending - 1;
+        for (int p = first; p <= last; ++p) {
+          const std::string raw(reinterpret_cast<const char*>(pinnedPkts) + (size_t)p * VS_PACKET_BYTES,
+                                VS_PACKET_BYTES);
+          if (p == e.meta_packet) f.packets.push_back(std::make_pair(ptime(pinnedTimes[p]), raw));
+          f.packets.push_back(std::make_pair(ptime(pinnedTimes[p]), raw));
+        }
+      }
+      const size_t nl = f.points.size();
+      for (int64_t k = e.first_point; k < e.first_point + e.n_points; ++k) {
+        const unsigned laser = hl[k];
+        if (laser >= nl) continue;
+        pcl::PointXYZI p;
+        p.x = hx[k];
+        p.y = hy[k];
+        p.z = hz[k];
+        p.intensity = hi[k];
+        f.points[laser]->points.push_back(p);
+        PointMeta m;
+        m.azimuth = ha[k];
+        // PointMeta::distance = float(dist * 0.002 + distanceCorrection) (HDLParser.cxx:614,747)
+        m.distance = (float)(hd[k] * 0.002 + calib.rows[laser].dist_correction_cm / 100.0);
+        m.intensityFlag = m.distanceFlag = m.flags = 0;
+        f.pointsMeta[laser]->push_back(m);
+      }
+      if (e.closed) {
+        closeFrame(currentFrame, e.hdl64_order != 0);
+        closedOut->push_back(currentFrame);
+        closedBy.push_back(packetBase + r.frames[i + 1].start_packet);  // packet holding the wrap
+      }
+    }
+    if (r.n_frames > 0 && r.frames[r.n_frames - 1].closed) currentFrame = createHDLFrame();
+    carry = r.carry_out;
+    packetBase += pending;
+    pending = 0;
+    pendingWrap = false;
+    return true;
+  }
+
+  vs_ctx* ctx;
+  int device;
+  int batchPackets;
+  bool storePackets;
+  uint8_t* pinnedPkts;
+  int64_t* pinnedTimes;
+  int64_t pending;
+  bool pendingWrap;
+  int hostLastAz;
+  vs_carry carry;
+  int64_t packetBase = 0;            // packets decoded since unloadData
+  std::vector<int64_t> closedBy;     // for each frame closed since unloadData: the closing packet
+
+  std::deque<std::shared_ptr<HDLFrame> > frames;
+  std::shared_ptr<HDLFrame> currentFrame;
+  std::shared_ptr<TransformManager> transMgr;
+  std::shared_ptr<HDLManager> hdlMgr;
+
+  CalibrationFile calib;
+  bool correctionsInitialized;
+  int calibFileReportedNumLasers;
+  int numberOfTrailingFrames;
+  int applyTransform;
+  int pointsSkip;
+  bool shouldCropReturns;
+  bool shouldCropInside;
+  double cropRegion[6];
+  int laserSelections[HDL_MAX_NUM_LASERS];
+  unsigned int dualReturnFilter;
+  bool configDirty;
+  uint64_t poseVersion;
+  bool warnedNoCalib;
+  std::string error;
+
+  std::vector<float> hx, hy, hz;
+  std::vector<uint8_t> hi, hl;
+  std::vector<uint16_t> ha, hd;
+};
+
+// ---------------------------------------------------------------------------------------------
+HDLParser::HDLParser() {
+  this->internal_ = new vsInternal;
+  this->unloadData();
+}
+HDLParser::~HDLParser() { delete this->internal_; }
+
+const std::string& HDLParser::getDirName() { return this->dirName; }
+void HDLParser::setDirName(const std::string& filename) {
+  if (filename == this->dirName) return;
+  this->dirName = filename;
+  this->unloadData();
+}
+
+const std::string& HDLParser::getCorrectionsFile() { return this->correctionsFile; }
+void HDLParser::setCorrectionsFile(const std::string& file) {
+  if (file == this->correctionsFile) return;
+  CalibrationFile c;
+  std::string err;
+  if (!c.load(file, &err)) {
+    std::cerr << "Invalid sensor configuration file" << file << std::endl;
+    return;
+  }
+  this->flush();  // packets buffered so far were received under the old calibration
+  this->internal_->calib = c;
+  this->internal_->calibFileReportedNumLasers = c.n_enabled;
+  this->internal_->correctionsInitialized = true;
+  this->internal_->configDirty = true;
+  this->correctionsFile = file;
+  this->unloadData();
+}
+
+void HDLParser::setNumberOfTrailingFrames(int n) { this->internal_->numberOfTrailingFrames = n; }
+
+void HDLParser::setLaserSelection(int x00, int x01, int x02, int x03, int x04, int x05, int x06, int x07,
+                                  int x08, int x09, int x10, int x11, int x12, int x13, int x14, int x15,
+                                  int x16, int x17, int x18, int x19, int x20, int x21, int x22, int x23,
+                                  int x24, int x25, int x26, int x27, int x28, int x29, int x30, int x31,
+                                  int x32, int x33, int x34, int x35, int x36, int x37, int x38, int x39,
+                                  int x40, int x41, int x42, int x43, int x44, int x45, int x46, int x47,
+                                  int x48, int x49, int x50, int x51, int x52, int x53, int x54, int x55,
+                                  int x56, int x57, int x58, int x59, int x60, int x61, int x62, int x63) {
+  int mask[64] = {x00, x01, x02, x03, x04, x05, x06, x07, x08, x09, x10, x11, x12, x13, x14, x15,
+                  x16, x17, x18, x19, x20, x21, x22, x23, x24, x25, x26, x27, x28, x29, x30, x31,
+                  x32, x33, x34, x35, x36, x37, x38, x39, x40, x41, x42, x43, x44, x45, x46, x47,
+                  x48, x49, x50, x51, x52, x53, x54, x55, x56, x57, x58, x59, x60, x61, x62, x63};
+  this->setLaserSelection(mask);
+}
+void HDLParser::setLaserSelection(int sel[64]) {
+  this->flush();
+  for (int i = 0; i < 64; ++i) this->internal_->laserSelections[i] = sel[i] ? 1 : 0;
+  this->internal_->configDirty = true;
+}
+void HDLParser::getLaserSelection(int sel[64]) {
+  for (int i = 0; i < 64; ++i) sel[i] = this->internal_->laserSelections[i];
+}
+void HDLParser::getVerticalCorrections(double v[64]) {
+  for (int i = 0; i < 64; ++i) v[i] = this->internal_->calib.rows[i].vert_correction_deg;
+}
+
+unsigned int HDLParser::getDualReturnFilter() const { return this->internal_->dualReturnFilter; }
+void HDLParser::setDualReturnFilter(unsigned int f) { this->internal_->dualReturnFilter = f; }
+void HDLParser::setPointsSkip(int pr) {
+  this->flush();
+  this->internal_->pointsSkip = pr < 0 ? 0 : pr;
+  this->internal_->configDirty = true;
+}
+void HDLParser::setCropReturns(int crop) {
+  this->flush();
+  this->internal_->shouldCropReturns = !!crop;
+  this->internal_->configDirty = true;
+}
+void HDLParser::setCropInside(int crop) {
+  this->flush();
+  this->internal_->shouldCropInside = !!crop;
+  this->internal_->configDirty = true;
+}
+void HDLParser::setCropRegion(double region[6]) {
+  this->flush();
+  std::copy(region, region + 6, this->internal_->cropRegion);
+  this->internal_->configDirty = true;
+}
+void HDLParser::setCropRegion(double xl, double xu, double yl, double yu, double zl, double zu) {
+  double r[6] = {xl, xu, yl, yu, zl, zu};
+  this->setCropRegion(r);
+}
+
+int HDLParser::getNumberOfChannels() { return this->internal_->calibFileReportedNumLasers; }
+
+void HDLParser::unloadData() {
+  vsInternal* in = this->internal_;
+  in->pending = 0;
+  in->pendingWrap = false;
+  in->hostLastAz = -1;
+  const int skip = in->carry.firing_skip;  // unloadData does not reset firingSkip (HDLParser.cxx:478-486)
+  vs_carry_init(&in->carry);
+  in->carry.firing_skip = skip;
+  in->frames.clear();
+  in->closedBy.clear();
+  in->packetBase = 0;
+  in->currentFrame = in->createHDLFrame();
+}
+
+void HDLParser::processHDLPacket(unsigned char* data, unsigned int bytesReceived, ptime t) {
+  if (bytesReceived != 1206) return;  // reference HDLParser.cxx:982-985
+  vsInternal* in = this->internal_;
+  if (!in->correctionsInitialized) {
+    // the reference decodes with indeterminate corrections here; this facade refuses
+    if (!in->warnedNoCalib) {
+      std::cerr << "Corrections have not been set" << std::endl;
+      in->warnedNoCalib = true;
+    }
+    in->error = "Corrections have not been set";
+    return;
+  }
+  if (!in->ensureContext()) return;
+  std::memcpy(in->pinnedPkts + (size_t)in->pending * VS_PACKET_BYTES, data, VS_PACKET_BYTES);
+  in->pinnedTimes[in->pending] = t.us;
+  ++in->pending;
+  // an azimuth decrease anywhere in the packet is the only thing that can close a frame
+  for (int j = 0; j < HDL_FIRING_PER_PKT; ++j) {
+    const int az = data[100 * j + 2] | (data[100 * j + 3] << 8);
+    if (az < in->hostLastAz) in->pendingWrap = true;
+    in->hostLastAz = az;
+  }
+  if (in->pending >= in->batchPackets) this->flush();
+}
+
+void HDLParser::flush() {
+  vsInternal* in = this->internal_;
+  if (in->pending == 0) return;
+  in->decodePending(&in->frames);
+}
+
+std::deque<std::shared_ptr<HDLFrame> > HDLParser::getAllFrames() {
+  if (this->internal_->pendingWrap) this->flush();
+  return this->internal_->frames;
+}
+void HDLParser::clearAllFrames() { this->internal_->frames.clear(); }
+std::shared_ptr<HDLFrame> HDLParser::createHDLFrame() { return this->internal_->createHDLFrame(); }
+
+bool HDLParser::getFrame(std::shared_ptr<HDLFrame>& dest, const std::string& filename,
+                         int64_t& startPos, const int& skip) {
+  vsInternal* in = this->internal_;
+  this->unloadData();
+  vtkPacketFileReader reader;
+  if (!reader.open(filename)) {
+    std::cerr << "failed to open packets file: " << filename << std::endl;
+    return false;
+  }
+  if (!in->correctionsInitialized) {
+    std::cerr << "Corrections have not been set" << std::endl;
+    return false;
+  }
+  if (!in->ensureContext()) return false;
+  reader.setFilePosition(&startPos);
+  in->carry.firing_skip = skip;
+  const unsigned char* data = nullptr;
+  unsigned int len = 0;
+  ptime t;
+  std::deque<std::shared_ptr<HDLFrame> > closed;
+  bool eof = false;
+  while (closed.empty() && !eof) {
+    // one chunk: enough for a rotation of either sensor, decoded in one launch
+    const int chunk = std::min(in->batchPackets, 512);
+    while (in->pending < chunk) {
+      if (!reader.nextPacket(data, len, t)) {
+        eof = true;
+        break;
+      }
+      if (len != 1206) continue;
+      std::memcpy(in->pinnedPkts + (size_t)in->pending * VS_PACKET_BYTES, data, VS_PACKET_BYTES);
+      in->pinnedTimes[in->pending] = t.us;
+      ++in->pending;
+    }
+    if (in->pending == 0) break;
+    if (!in->decodePending(&closed)) return false;
+  }
+  if (!closed.empty()) {
+    // the reference stops at the first packet that closes a frame and hands back
+    // frames.back(): the last frame that packet closed (HDLParser.cxx:529-537)
+    std::shared_ptr<HDLFrame> pick = closed.front();
+    for (size_t i = 1; i < closed.size() && in->closedBy[i] == in->closedBy[0]; ++i) pick = closed[i];
+    dest->points = std::move(pick->points);
+    dest->pointsMeta = std::move(pick->pointsMeta);
+    this->unloadData();
+    return true;
+  }
+  // end of file: force the split (HDLParser.cxx:540-543)
+  in->closeFrame(in->currentFrame, in->carry.is_hdl64 != 0);
+  dest.swap(in->currentFrame);
+  this->unloadData();
+  return true;
+}
+
+std::vector<std::shared_ptr<HDLFrame> > HDLParser::readFrameInformation(const std::string& name,
+                                                                       bool touchOnly) {
+  std::vector<std::shared_ptr<HDLFrame> > result;
+  vtkPacketFileReader reader;
+  if (!reader.open(name)) {
+    std::cerr << "Failed to open packet file: " << name << std::endl << reader.getLastError() << std::endl;
+    return result;
+  }
+  // file names are the ISO string of the first packet's time; others get renamed below
+  std::string stem = name;
+  const size_t slash = stem.find_last_of('/');
+  const std::string dir = slash == std::string::npos ? std::string(".") : stem.substr(0, slash);
+  if (slash != std::string::npos) stem = stem.substr(slash + 1);
+  const size_t dot = stem.find_last_of('.');
+  if (dot != std::string::npos) stem = stem.substr(0, dot);
+  ptime nameTime;
+  const bool nameIsTime = from_iso_string(stem, &nameTime);
+  if (!nameIsTime)
+    std::cout << "Filename is not a valid ptime string, I'll convert it into a ptime string.\n";
+
+  const unsigned char* data = nullptr;
+  unsigned int len = 0;
+  ptime packetTime, filenameTime;
+  unsigned int lastAzimuth = 0;
+  int64_t lastFilePosition = 0;
+  result.push_back(std::shared_ptr<HDLFrame>(new HDLFrame));
+  reader.getFilePosition(&lastFilePosition);
+  result.back()->fileStartPos = lastFilePosition;
+  result.back()->skips = 0;
+  result.back()->isOnHardDrive = true;
+  while (reader.nextPacket(data, len, packetTime)) {
+    if (len != 1206) continue;
+    if (filenameTime.is_special()) {
+      filenameTime = packetTime;
+      result.back()->timestamp = packetTime;
+      if (touchOnly) break;
+    }
+    for (int i = 0; i < HDL_FIRING_PER_PKT; ++i) {
+      const unsigned int rot = data[100 * i + 2] | (data[100 * i + 3] << 8);
+      if (rot < lastAzimuth) {
+        result.push_back(std::shared_ptr<HDLFrame>(new HDLFrame));
+        result.back()->fileStartPos = lastFilePosition;
+        result.back()->skips = (uint8_t)i;
+        result.back()->isOnHardDrive = true;
+        result.back()->timestamp = packetTime;
+      }
+      lastAzimuth = rot;
+    }
+    reader.getFilePosition(&lastFilePosition);
+  }
+  for (auto& f : result) f->filenameTime = filenameTime;
+  reader.close();
+  if (!nameIsTime && !filenameTime.is_special()) {
+    const std::string newname = dir + "/" + to_iso_string(filenameTime) + ".pcap";
+    if (std::rename(name.c_str(), newname.c_str()) == 0)
+      std::cout << "The original filename: '" << name << "' was converted to: '" << newname << '\''
+                << std::endl;
+  }
+  return result;
+}
+
+void HDLParser::setHDLManager(std::shared_ptr<HDLManager> p) { this->internal_->hdlMgr = p; }
+
+std::shared_ptr<TransformManager> HDLParser::getTransformMgr() const { return this->internal_->transMgr; }
+void HDLParser::setTransformMgr(std::shared_ptr<TransformManager> mgr) {
+  this->flush();
+  this->internal_->transMgr = mgr;
+  this->internal_->poseVersion = ~0ull;
+}
+int HDLParser::getApplyTransform() { return this->internal_->applyTransform; }
+void HDLParser::setApplyTransform(int apply) { this->internal_->applyTransform = apply; }
+
+void HDLParser::setDevice(int d) { this->internal_->device = d; }
+void HDLParser::setBatchPackets(int n) {
+  if (!this->internal_->ctx && n > 0) this->internal_->batchPackets = n;
+}
+void HDLParser::setStorePackets(bool s) { this->internal_->storePackets = s; }
+const std::string& HDLParser::lastError() const { return this->internal_->error; }

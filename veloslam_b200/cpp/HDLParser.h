@@ -1,0 +1,114 @@
+// HDLParser.h -- drop-in facade with the reference's HDLParser interface
+// (/root/reference/HDLParser.h:84-147) over the B200 C ABI (include/veloslam_b200.h).
+//
+// Same method names, argument meaning and error behaviour as the reference; the differences
+// forced by the missing third-party libraries are: boost::shared_ptr -> std::shared_ptr,
+// boost::posix_time::ptime -> ptime (type_defs.h), fpos_t -> int64_t byte offset.
+//
+// processHDLPacket() appends the packet to a pinned host ring; the ring is decoded on the GPU
+// (segmentation + pose + decode/deskew kernels) when it is full, or when getAllFrames() is
+// called and the buffered packets contain an azimuth decrease -- the only event that can
+// close a frame -- so callers that poll getAllFrames() after every packet (HDLSource.cxx:
+// 209-225) see each frame right after the packet that closes it, as with the reference.
+// There is no CPU decode path: without a CUDA device every decode call reports an error.
+#ifndef VELOSLAM_B200_HDLPARSER_H
+#define VELOSLAM_B200_HDLPARSER_H
+
+#include <deque>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "HDLFrame.h"
+#include "TransformManager.h"
+#include "type_defs.h"
+
+class HDLManager;
+
+class HDLParser {
+ public:
+  enum DualFlag {
+    DUAL_DISTANCE_NEAR = 0x1,
+    DUAL_DISTANCE_FAR = 0x2,
+    DUAL_INTENSITY_HIGH = 0x4,
+    DUAL_INTENSITY_LOW = 0x8,
+    DUAL_DOUBLED = 0xf,
+    DUAL_DISTANCE_MASK = 0x3,
+    DUAL_INTENSITY_MASK = 0xc,
+  };
+
+  HDLParser();
+  ~HDLParser();
+
+  const std::string& getDirName();
+  void setDirName(const std::string& filename);
+
+  const std::string& getCorrectionsFile();
+  // reads the db.xml calibration; an unreadable file prints "Invalid sensor configuration
+  // file" and leaves the parser unchanged (reference HDLParser.cxx:458-475)
+  void setCorrectionsFile(const std::string& correctionsFile);
+
+  void setNumberOfTrailingFrames(int numberTrailing);
+  void setLaserSelection(int, int, int, int, int, int, int, int, int, int, int, int, int, int, int, int,
+                         int, int, int, int, int, int, int, int, int, int, int, int, int, int, int, int,
+                         int, int, int, int, int, int, int, int, int, int, int, int, int, int, int, int,
+                         int, int, int, int, int, int, int, int, int, int, int, int, int, int, int, int);
+  void setLaserSelection(int LaserSelection[64]);
+  void getLaserSelection(int LaserSelection[64]);
+  void getVerticalCorrections(double LaserAngles[64]);
+
+  unsigned int getDualReturnFilter() const;
+  void setDualReturnFilter(unsigned int);
+  void setPointsSkip(int);
+  void setCropReturns(int);
+  void setCropInside(int);
+  void setCropRegion(double[6]);
+  void setCropRegion(double, double, double, double, double, double);
+
+  int getNumberOfChannels();
+
+  // offline index: one entry per rotation with fileStartPos / skips / timestamp
+  // (touchOnly: only make sure the file is named after its first packet's time)
+  std::vector<std::shared_ptr<HDLFrame> > readFrameInformation(const std::string& name,
+                                                              bool touchOnly = false);
+  void setHDLManager(std::shared_ptr<HDLManager> p);
+
+  // decode one rotation from `filename` starting at byte offset startPos, skipping `skip`
+  // firing blocks of the first packet
+  bool getFrame(std::shared_ptr<HDLFrame>& dest, const std::string& filename, int64_t& startPos,
+                const int& skip);
+  void processHDLPacket(unsigned char* data, unsigned int bytesReceived, ptime t);
+  std::deque<std::shared_ptr<HDLFrame> > getAllFrames();
+  void clearAllFrames();
+  std::shared_ptr<HDLFrame> createHDLFrame();
+
+  std::shared_ptr<TransformManager> getTransformMgr() const;
+  void setTransformMgr(std::shared_ptr<TransformManager> mgr);
+  int getApplyTransform();
+  void setApplyTransform(int apply);
+
+  // ---- B200 controls (not in the reference) -------------------------------------------------
+  void setDevice(int cudaDevice);          // before the first packet; default 0
+  void setBatchPackets(int maxPackets);    // capacity of the pinned ring; default 4096
+  void setStorePackets(bool store);        // keep raw packets inside HDLFrame::packets; default on
+  void flush();                            // decode whatever is buffered now
+  const std::string& lastError() const;    // empty when the last GPU call succeeded
+
+ protected:
+  void unloadData();
+
+  std::string correctionsFile;
+  std::string dirName;
+
+  class vsInternal;
+  vsInternal* internal_;
+
+ private:
+  HDLParser(const HDLParser&);
+  void operator=(const HDLParser&);
+};
+
+// Names of the reference's earlier revisions of the same classes.
+typedef HDLParser HDLReader;
+
+#endif

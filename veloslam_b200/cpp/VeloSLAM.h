@@ -1,0 +1,10 @@
+// VeloSLAM.h -- umbrella header of the drop-in facade (the reference ships one of the same name).
+#ifndef VELOSLAM_B200_VELOSLAM_H
+#define VELOSLAM_B200_VELOSLAM_H
+#include "HDLFrame.h"
+#include "HDLParser.h"
+#include "TimeLine.h"
+#include "TransformManager.h"
+#include "type_defs.h"
+#include "vtkPacketFile.h"
+#endif

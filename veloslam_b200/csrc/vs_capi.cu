@@ -1012,6 +1012,15 @@ int vs_read_frame_information(vs_ctx* ctx, const uint8_t* pkts, int64_t stride,
   return VS_OK;
 }
 
+int vs_host_alloc(uint64_t bytes, void** out) {
+  if (!out) return VS_ERR_INVALID_ARG;
+  *out = nullptr;
+  return cudaMallocHost(out, (size_t)bytes) == cudaSuccess ? VS_OK : VS_ERR_CUDA;
+}
+void vs_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 void* vs_stream(vs_ctx* ctx) { return ctx ? (void*)ctx->slots[0].stream : nullptr; }
 
 }  // extern "C"
