@@ -39,6 +39,8 @@ struct Slot {
   long long* d_time = nullptr;
   const long long* d_time_used = nullptr;  // times of the batch in flight (may be caller-owned)
   PktSeg* d_seg = nullptr;
+  unsigned* d_masks = nullptr;            // 12 emission masks per packet (k_scan -> k_decode)
+  unsigned long long* d_pkt_off = nullptr;  // first emitted point of each packet (k_pose)
   double* d_pose_mat = nullptr;
   float *d_x = nullptr, *d_y = nullptr, *d_z = nullptr;
   uint8_t *d_inten = nullptr, *d_laser = nullptr;
@@ -121,6 +123,19 @@ int fail(vs_ctx* c, int code, const std::string& msg) {
 
 inline double to_radians_h(double x) { return (x * M_PI) / 180.0; }  // HDLParser.cxx:59
 
+// laser selection per return slot of a lower / upper block (see DevConfig::sel_lo)
+void update_selection(DevConfig& c) {
+  c.sel_lo = c.sel_hi = 0;
+  for (int bank = 0; bank < 2; ++bank) {
+    for (int lane = 0; lane < 32; ++lane) {
+      int id = lane + 32 * bank;
+      if (c.adj_mode == 2 && id >= 16) id -= 16;  // VLP-16 remap, HDLParser.cxx:935-943
+      const bool ok = ((c.laser_mask >> id) & 1ull) && id < c.n_enabled;
+      if (ok) (bank ? c.sel_hi : c.sel_lo) |= 1u << lane;
+    }
+  }
+}
+
 // TransformManager::interpolateTransform (TransformManager.cxx:149-177) over the sorted host
 // snapshot; bracket = clamp(lower_bound, 1, N-1) (TimeLine.h:384-468 net semantics).
 void host_interpolate(const vs_ctx* c, int64_t t, double out[9], bool* found, bool* valid) {
@@ -153,6 +168,8 @@ void free_slot(Slot& s) {
   cudaFree(s.d_in);
   cudaFree(s.d_time);
   cudaFree(s.d_seg);
+  cudaFree(s.d_masks);
+  cudaFree(s.d_pkt_off);
   cudaFree(s.d_pose_mat);
   cudaFree(s.d_x);
   cudaFree(s.d_y);
@@ -199,6 +216,8 @@ int alloc_slot(vs_ctx* ctx, Slot& s) {
   VS_CUDA(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
   VS_CUDA(cudaMalloc(&s.d_time, np * sizeof(long long)));
   VS_CUDA(cudaMalloc(&s.d_seg, np * sizeof(PktSeg)));
+  VS_CUDA(cudaMalloc(&s.d_masks, np * kBlocks * sizeof(unsigned)));
+  VS_CUDA(cudaMalloc(&s.d_pkt_off, np * sizeof(unsigned long long)));
   VS_CUDA(cudaMalloc(&s.d_pose_mat, np * 12 * sizeof(double)));
   VS_CUDA(cudaMalloc(&s.d_x, pts * sizeof(float)));
   VS_CUDA(cudaMalloc(&s.d_y, pts * sizeof(float)));
@@ -209,15 +228,15 @@ int alloc_slot(vs_ctx* ctx, Slot& s) {
   VS_CUDA(cudaMalloc(&s.d_dist, pts * sizeof(uint16_t)));
   VS_CUDA(cudaMalloc(&s.d_t, pts * sizeof(uint32_t)));
   // zeroed-per-batch block: [st_map | st_wrap | st_cnt | counters | frame_counts]
-  const size_t seg_tiles = (size_t)((np + kSegThreads - 1) / kSegThreads);
-  const size_t dec_tiles = (size_t)((np + kTilePkts - 1) / kTilePkts);
+  const size_t scan_tiles = (size_t)((np + kTilePkts - 1) / kTilePkts);
+  const size_t pose_tiles = (size_t)((np + kPoseThreads - 1) / kPoseThreads);
   size_t off = 0;
   const size_t o_map = off;
-  off += align_up(seg_tiles * 8, 256);
+  off += align_up(scan_tiles * 8, 256);
   const size_t o_wrap = off;
-  off += align_up(seg_tiles * 8, 256);
+  off += align_up(pose_tiles * 8, 256);
   const size_t o_cnt = off;
-  off += align_up(dec_tiles * 8, 256);
+  off += align_up(pose_tiles * 8, 256);
   const size_t o_ctr = off;
   off += 256;
   const size_t o_fc = off;
@@ -278,38 +297,41 @@ int copy_frame_rows(vs_ctx* ctx, Slot& s, size_t n_rows) {
   return VS_OK;
 }
 
-template <int ADJ, bool CROP>
+template <int ADJ>
 int launch_decode(vs_ctx* ctx, Slot& s, const DecParams& dp, size_t smem) {
   static size_t cached_smem = 0;  // one process drives one GPU: cache per instantiation
   static int per_sm = 0;
   if (cached_smem != smem) {
-    VS_CUDA(cudaFuncSetAttribute(k_decode<ADJ, CROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VS_CUDA(cudaFuncSetAttribute(k_decode<ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode<ADJ, CROP>,
-                                                          kDecThreads, smem));
+    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode<ADJ>, kDecThreads, smem));
     cached_smem = smem;
   }
   if (per_sm < 1) return fail(ctx, VS_ERR_CUDA, "k_decode does not fit on an SM");
   int grid = ctx->sm_count * per_sm;
   if (grid > dp.n_tiles) grid = dp.n_tiles;
-  k_decode<ADJ, CROP><<<grid, kDecThreads, smem, s.stream>>>(dp);
+  k_decode<ADJ><<<grid, kDecThreads, smem, s.stream>>>(dp);
   VS_CUDA(cudaGetLastError());
   return VS_OK;
 }
 
-// frame table rows for the index-only path (vs_read_frame_information)
-__global__ void k_frame_index(const PktSeg* __restrict__ seg, int n, int* frame_start, int cap) {
-  const int P = blockIdx.x * blockDim.x + threadIdx.x;
-  if (P >= n) return;
-  const PktSeg r = seg[P];
-  int wm = (r.x >> 4) & 0xfff;
-  int f = r.y;
-  while (wm) {
-    const int j = __ffs(wm) - 1;
-    wm &= wm - 1;
-    ++f;
-    if (f < cap) frame_start[f] = P * 12 + j;
+template <int ADJ, bool CROP>
+int launch_scan(vs_ctx* ctx, Slot& s, const ScanParams& sp, size_t smem) {
+  static size_t cached_smem = 0;
+  static int per_sm = 0;
+  if (cached_smem != smem) {
+    VS_CUDA(cudaFuncSetAttribute(k_scan<ADJ, CROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<ADJ, CROP>, kScanThreads,
+                                                          smem));
+    cached_smem = smem;
   }
+  if (per_sm < 1) return fail(ctx, VS_ERR_CUDA, "k_scan does not fit on an SM");
+  int grid = ctx->sm_count * per_sm;
+  if (grid > sp.n_tiles) grid = sp.n_tiles;
+  k_scan<ADJ, CROP><<<grid, kScanThreads, smem, s.stream>>>(sp);
+  VS_CUDA(cudaGetLastError());
+  return VS_OK;
 }
 
 int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const int64_t* pkt_time,
@@ -348,7 +370,8 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
 
   VS_CUDA(cudaEventRecord(s.ev_k0, s.stream));
   // ---- per-batch resets ------------------------------------------------------------------
-  const int64_t seg_tiles = (n + kSegThreads - 1) / kSegThreads;
+  const int64_t scan_tiles = (n + kTilePkts - 1) / kTilePkts;
+  const int64_t pose_tiles = (n + kPoseThreads - 1) / kPoseThreads;
   const int64_t n_dec = n - halo;
   const int64_t dec_tiles = (n_dec + kTilePkts - 1) / kTilePkts;
   const int64_t frames_possible = std::min<int64_t>(ctx->frame_cap, 12 * n + 1);
@@ -382,53 +405,77 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
   else
     cin = *carry_in;
 
-  SegParams sp;
-  sp.pkts = d_pkts;
-  sp.stride = stride;
-  sp.pkt_time = d_time;
-  sp.n = (int)n;
-  sp.halo = (int)halo;
-  sp.mode = mode;
-  sp.carry_last_az = cin.last_azimuth;
-  sp.carry_skip = cin.firing_skip;
-  sp.carry_meta_inited = cin.frame_meta_inited;
-  sp.pkt_seg = s.d_seg;
-  sp.st_map = s.d_st_map;
-  sp.st_wrap = s.d_st_wrap;
-  sp.tile_counter = s.d_counters + 0;
-  sp.hdr = s.d_hdr;
-  k_segment<<<(unsigned)seg_tiles, kSegThreads, 0, s.stream>>>(sp);
-  VS_CUDA(cudaGetLastError());
-  ++s.n_launches;
-
   const int n_poses = (int)ctx->pose_t.size();
   const bool pose_valid = n_poses >= 2;
+  const int adj = ctx->h_cfg.adj_mode;
+  const bool crop = ctx->h_cfg.crop_returns != 0 && !index_only;
+  {
+    ScanParams sp;
+    sp.pkts = d_pkts;
+    sp.stride = stride;
+    sp.total_bytes = payload_bytes;
+    sp.cfg = ctx->d_cfg;
+    sp.lut_sin = ctx->d_lut_sin;
+    sp.lut_cos = ctx->d_lut_cos;
+    sp.n = (int)n;
+    sp.mode = mode;
+    sp.halo = (int)halo;
+    sp.carry_last_az = cin.last_azimuth;
+    sp.carry_skip = cin.firing_skip;
+    sp.n_tiles = (int)scan_tiles;
+    sp.stage_bytes = (int)align_up((size_t)kTilePkts * stride + kLead + 48, 128);
+    sp.pkt_seg = s.d_seg;
+    sp.masks = s.d_masks;
+    sp.st_map = s.d_st_map;
+    sp.tile_counter = s.d_counters + 0;
+    sp.hdr = s.d_hdr;
+    const size_t smem = align_up(sizeof(ScanShared), 128) + align_up(sizeof(DevConfig), 128) +
+                        2 * (size_t)sp.stage_bytes;
+    int rc;
+    if (adj == 0)
+      rc = crop ? launch_scan<0, true>(ctx, s, sp, smem) : launch_scan<0, false>(ctx, s, sp, smem);
+    else if (adj == 1)
+      rc = crop ? launch_scan<1, true>(ctx, s, sp, smem) : launch_scan<1, false>(ctx, s, sp, smem);
+    else
+      rc = crop ? launch_scan<2, true>(ctx, s, sp, smem) : launch_scan<2, false>(ctx, s, sp, smem);
+    if (rc != VS_OK) return rc;
+    ++s.n_launches;
+  }
+  {
+    PoseParams pp;
+    pp.pkt_time = d_time;
+    pp.pkt_seg = s.d_seg;
+    pp.masks = s.d_masks;
+    pp.pkt_off = s.d_pkt_off;
+    pp.st_wrap = s.d_st_wrap;
+    pp.st_cnt = s.d_st_cnt;
+    pp.tile_counter = s.d_counters + 1;
+    pp.n = (int)n;
+    pp.halo = (int)halo;
+    pp.mode = mode;
+    pp.n_poses = index_only ? 0 : n_poses;
+    pp.carry_meta_inited = cin.frame_meta_inited;
+    pp.t_base = t_base;
+    pp.pose_t = ctx->d_pose_t;
+    pp.pose_trv = ctx->d_pose_trv;
+    for (int k = 0; k < 3; ++k) pp.carry_origin_T[k] = cin.origin_T[k];
+    pp.pose_mat = s.d_pose_mat;
+    pp.frame_first_point = s.d_frame_first;
+    pp.frame_start_block = s.d_frame_start;
+    pp.frame_cap = (int)ctx->frame_cap;
+    pp.hdr = s.d_hdr;
+    k_pose<<<(unsigned)pose_tiles, kPoseThreads, 0, s.stream>>>(pp);
+    VS_CUDA(cudaGetLastError());
+    ++s.n_launches;
+  }
   if (!index_only) {
-    if (pose_valid) {
-      PoseParams pp;
-      pp.pkt_time = d_time;
-      pp.pkt_seg = s.d_seg;
-      pp.n = (int)n;
-      pp.mode = mode;
-      pp.pose_t = ctx->d_pose_t;
-      pp.pose_trv = ctx->d_pose_trv;
-      pp.n_poses = n_poses;
-      pp.carry_meta_inited = cin.frame_meta_inited;
-      for (int k = 0; k < 3; ++k) pp.carry_origin_T[k] = cin.origin_T[k];
-      pp.pose_mat = s.d_pose_mat;
-      pp.hdr = s.d_hdr;
-      k_pose<<<(unsigned)((n + 255) / 256), 256, 0, s.stream>>>(pp);
-      VS_CUDA(cudaGetLastError());
-      ++s.n_launches;
-    }
-
     DecParams dp;
     dp.pkts = d_pkts;
     dp.stride = stride;
     dp.total_bytes = payload_bytes;
-    dp.pkt_time = d_time;
-    dp.t_base = t_base;
     dp.pkt_seg = s.d_seg;
+    dp.masks = s.d_masks;
+    dp.pkt_off = s.d_pkt_off;
     dp.pose_mat = s.d_pose_mat;
     dp.lut_sin = ctx->d_lut_sin;
     dp.lut_cos = ctx->d_lut_cos;
@@ -438,7 +485,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     dp.mode = mode;
     dp.pose_valid = pose_valid ? 1 : 0;
     dp.n_tiles = (int)dec_tiles;
-    dp.stage_bytes = (int)align_up((size_t)kTilePkts * stride + 32, 128);
+    dp.stage_bytes = (int)align_up((size_t)kMaskBytes + kSegBytes + (size_t)kTilePkts * stride + 48, 128);
     dp.x = s.d_x;
     dp.y = s.d_y;
     dp.z = s.d_z;
@@ -447,35 +494,23 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     dp.azimuth = s.d_az;
     dp.distance = s.d_dist;
     dp.t_us = s.d_t;
-    dp.st_cnt = s.d_st_cnt;
-    dp.tile_counter = s.d_counters + 1;
-    dp.frame_first_point = s.d_frame_first;
-    dp.frame_start_block = s.d_frame_start;
+    dp.tile_counter = s.d_counters + 2;
     dp.frame_laser_counts = s.d_frame_counts;
     dp.frame_cap = (int)ctx->frame_cap;
-    dp.hdr = s.d_hdr;
     const size_t smem = align_up(sizeof(DecShared), 128) + 2 * (size_t)dp.stage_bytes;
     VS_CUDA(cudaEventRecord(s.ev_d0, s.stream));
     if (dec_tiles > 0) {
-      const int adj = ctx->h_cfg.adj_mode;
-      const bool crop = ctx->h_cfg.crop_returns != 0;
       int rc;
       if (adj == 0)
-        rc = crop ? launch_decode<0, true>(ctx, s, dp, smem) : launch_decode<0, false>(ctx, s, dp, smem);
+        rc = launch_decode<0>(ctx, s, dp, smem);
       else if (adj == 1)
-        rc = crop ? launch_decode<1, true>(ctx, s, dp, smem) : launch_decode<1, false>(ctx, s, dp, smem);
+        rc = launch_decode<1>(ctx, s, dp, smem);
       else
-        rc = crop ? launch_decode<2, true>(ctx, s, dp, smem) : launch_decode<2, false>(ctx, s, dp, smem);
+        rc = launch_decode<2>(ctx, s, dp, smem);
       if (rc != VS_OK) return rc;
       ++s.n_launches;
     }
     VS_CUDA(cudaEventRecord(s.ev_d1, s.stream));
-  } else {
-    k_frame_index<<<(unsigned)((n + 255) / 256), 256, 0, s.stream>>>(s.d_seg, (int)n,
-                                                                    s.d_frame_start,
-                                                                    (int)ctx->frame_cap);
-    VS_CUDA(cudaGetLastError());
-    ++s.n_launches;
   }
 
   {
@@ -696,8 +731,12 @@ int vs_create(int device, int64_t max_batch_packets, int64_t max_poses, int n_sl
   };
   std::memset(&ctx->h_cfg, 0, sizeof(ctx->h_cfg));
   ctx->h_cfg.laser_mask = ~0ull;  // HDLParser.cxx:172
+  ctx->h_cfg.n_enabled = 64;      // :170
+  update_selection(ctx->h_cfg);
   int rc = init();
   if (rc != VS_OK) return bail(rc);
+  if (cudaMemcpy(ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), cudaMemcpyHostToDevice) != cudaSuccess)
+    return bail(VS_ERR_CUDA);
   *out = ctx;
   return VS_OK;
 }
@@ -764,6 +803,7 @@ int vs_set_calibration(vs_ctx* ctx, const vs_laser_corr* corr, int n_rows, int n
       c.tadj[j][dsr] = (uint16_t)std::round(ta);
     }
   }
+  update_selection(c);
   cudaSetDevice(ctx->device);
   VS_CUDA(cudaMemcpy(ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), cudaMemcpyHostToDevice));
   ctx->calibrated = true;
@@ -779,6 +819,7 @@ int vs_set_filters(vs_ctx* ctx, const vs_filters* f) {
   c.crop_returns = f->crop_returns ? 1 : 0;
   c.crop_inside = f->crop_inside ? 1 : 0;
   for (int i = 0; i < 6; ++i) c.crop[i] = f->crop_region[i];
+  update_selection(c);
   cudaSetDevice(ctx->device);
   VS_CUDA(cudaMemcpy(ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), cudaMemcpyHostToDevice));
   return VS_OK;

@@ -30,20 +30,25 @@ struct DevConfig {
   uint16_t tadj[kBlocks][kReturns];
   double crop[6];
   unsigned long long laser_mask;
+  // laser selection folded per return slot: bit l of sel_lo / sel_hi == "slot l of a 0xeeff /
+  // 0xddff block is emitted" (laserSelections[laserId] && laserId < calibFileReportedNumLasers,
+  // with the VLP-16 id remap of HDLParser.cxx:935-943)
+  unsigned sel_lo;
+  unsigned sel_hi;
   int points_skip;
   int crop_returns;
   int crop_inside;
   int n_enabled;   // calibFileReportedNumLasers
   int adj_mode;    // 0 none (HDL-64 / other), 1 HDL-32, 2 VLP-16
-  int pad;
 };
 
 // Per-packet segmentation record written by k_segment, read by k_pose / k_decode.
 //   x: bits 0-3 skip_in (firingSkip entering the packet), bits 4-15 wrap mask over the
-//      iterated blocks, bits 16-27 mask of 0xddff ("upper") blocks
-//   y: number of wraps before this packet (frame id at the packet's first block)
-//   z: origin packet (whose pose T is the frame origin for this packet), -1 = carry-in
-//   w: azimuthDiff = 7th smallest of the 11 block-to-block azimuth deltas
+//      iterated blocks, bits 16-31 azimuthDiff (7th smallest of the 11 azimuth deltas)
+//   y: k_scan: emitted-point count; after k_pose: number of wraps before this packet
+//      (frame id at the packet's first block)
+//   z: after k_pose: packet time - t_base (microseconds, u32)
+//   w: unused
 typedef int4 PktSeg;
 
 // Batch header: written by the kernels, copied to the host with the frame tables.

@@ -1,10 +1,11 @@
 // vs_kernels.cuh -- the sm_100a kernels of the ingest hot path.
 //
 //   k_pcap_times  pcap record headers -> packet times           (vtkPacketFileReader.h:166-197)
-//   k_segment     azimuth-wrap segmentation, firingSkip chain   (HDLParser.cxx:1013-1054)
-//   k_pose        per-packet pose bracket + lerp + Ry.Rx.Rz     (TransformManager.cxx:149-177,
-//                                                                 type_defs.h:134-146)
-//   k_decode      decode + calibrate + transform + compaction   (HDLParser.cxx:587-752, 900-977)
+//   k_scan        azimuth-wrap segmentation, firingSkip chain,   (HDLParser.cxx:1013-1054,
+//                 emission masks per firing block                 964, 629-639)
+//   k_pose        frame ids / origins / point offsets (scans),   (TransformManager.cxx:149-177,
+//                 per-packet pose bracket + lerp + Ry.Rx.Rz       type_defs.h:134-146)
+//   k_decode      decode + calibrate + transform + SoA stores    (HDLParser.cxx:587-752, 900-977)
 //   k_frames      frame table gather (meta packet time / skips)  (HDLParser.cxx:993-1001)
 //
 // All FP64 arithmetic that feeds an output uses __dmul_rn/__dadd_rn/__dsub_rn so that nvcc
@@ -31,255 +32,425 @@ __global__ void k_pcap_times(const uint8_t* __restrict__ pkts, long long stride,
 }
 
 // =========================================================================================
-// k_segment
+// Tiles: both streaming kernels (k_scan, k_decode) walk the packet array in tiles of 32
+// packets (384 firing blocks, 12 288 return slots, 38.6 KB) staged into shared memory with
+// one TMA bulk copy per tile, double buffered.
 // =========================================================================================
-struct SegParams {
+constexpr int kTilePkts = 32;
+constexpr int kTileBlocks = kTilePkts * kBlocks;  // 384
+constexpr int kLead = 192;  // bytes in front of a tile that hold the previous packet's last
+                            // azimuth (stride - 1102 <= 178 for stride <= 1280), 16-B multiple
+
+// Byte span of a tile in the input array: [a0, a1) are the bytes the tile's packets occupy,
+// [s0, s1) the 16-byte-granular span the bulk copy moves (optionally `lead` bytes earlier).
+// When rounding a1 up would read past the bytes the caller owns, the copy stops at the last
+// full granule and the (< 16) tail bytes are fetched with plain loads.
+struct TileSpan {
+  long long a0, a1, s0, s1;
+  int npk;
+};
+__device__ __forceinline__ TileSpan tile_span(long long in_base, long long stride,
+                                              long long total_bytes, int n, long long first,
+                                              int lead) {
+  TileSpan t;
+  t.npk = n - (int)first;
+  if (t.npk > kTilePkts) t.npk = kTilePkts;
+  t.a0 = in_base + first * stride;
+  t.a1 = t.a0 + (long long)(t.npk - 1) * stride + kPacketBytes;
+  long long b = t.a0 - lead;
+  if (b < in_base) b = in_base;
+  t.s0 = b & ~15ll;
+  t.s1 = (t.a1 + 15) & ~15ll;
+  if (t.s1 > in_base + total_bytes) t.s1 = t.a1 & ~15ll;
+  if (t.s1 < t.s0) t.s1 = t.s0;
+  return t;
+}
+
+__device__ __forceinline__ unsigned ld_smem_u16(const uint8_t* p) {
+  // packets are only guaranteed 2-byte aligned (1206 = 2 * 603)
+  return *reinterpret_cast<const unsigned short*>(p);
+}
+
+// Per-laser calibration row held in registers.
+struct CalRow {
+  double cC, sC, dc, cV, sV, vo, ho;
+};
+__device__ __forceinline__ void load_cal(const DevConfig& c, int row, CalRow& r) {
+  r.cC = c.cal[0][row];
+  r.sC = c.cal[1][row];
+  r.dc = c.cal[2][row];
+  r.cV = c.cal[3][row];
+  r.sV = c.cal[4][row];
+  r.vo = c.cal[5][row];
+  r.ho = c.cal[6][row];
+}
+
+// Sensor-frame position of one return (HDLParser.cxx:597-623).  `az` is already adjusted and
+// reduced mod 36000.  Separate IEEE mul/add in the reference's operation order.
+__device__ __forceinline__ void sensor_point(const CalRow& c, double sA, double cA, unsigned dist,
+                                             double& px, double& py, double& pz) {
+  // sin/cos(rad(az/100) - rad(rotCorrection)); with rotCorrection == 0 (cC=1, sC=0) this is
+  // exactly the reference's LUT branch (:602-606)
+  const double sinAz = __dsub_rn(__dmul_rn(sA, c.cC), __dmul_rn(cA, c.sC));
+  const double cosAz = __dadd_rn(__dmul_rn(cA, c.cC), __dmul_rn(sA, c.sC));
+  const double dM = __dadd_rn(__dmul_rn((double)dist, 0.002), c.dc);  // :614
+  const double xy = __dmul_rn(dM, c.cV);                              // :615
+  px = __dsub_rn(__dmul_rn(xy, sinAz), __dmul_rn(c.ho, cosAz));       // :620
+  py = __dadd_rn(__dmul_rn(xy, cosAz), __dmul_rn(c.ho, sinAz));       // :621
+  pz = __dadd_rn(__dmul_rn(dM, c.sV), c.vo);                          // :622
+}
+
+template <int ADJ>
+__device__ __forceinline__ unsigned adjusted_azimuth(const DevConfig& c, unsigned rot, int azdiff,
+                                                     int j, int lane) {
+  unsigned az = rot;
+  if (ADJ != 0) {
+    // HDLParser.cxx:961: std::round (half away from zero) of azimuthDiff * ratio
+    const int adj = (int)round(__dmul_rn((double)azdiff, c.az_ratio[j][lane]));
+    az = (unsigned)(unsigned short)(rot + adj);  // passed as unsigned short, :968
+  }
+  return az % 36000u;  // :597
+}
+
+// =========================================================================================
+// k_scan: segmentation + emission masks in one streaming pass over the packets.
+//   per packet : firingSkip entering it, wrap mask over the iterated blocks, azimuthDiff,
+//                emitted-point count                                  -> PktSeg
+//   per block  : 32-bit mask of the return slots the reference emits -> masks[n*12]
+// The firingSkip recurrence is a scan of 12-entry maps; across tiles it is resolved with a
+// look-back that stops at the first constant composed map.
+// =========================================================================================
+struct ScanParams {
   const uint8_t* pkts;
   long long stride;
-  const long long* pkt_time;
-  int n;     // packets including the halo
-  int halo;  // index of the first decoded packet
+  long long total_bytes;
+  const DevConfig* cfg;
+  const double* lut_sin;
+  const double* lut_cos;
+  int n;
   int mode;  // 0 streaming, 1 offline
+  int halo;
   int carry_last_az;
   int carry_skip;
-  int carry_meta_inited;
+  int n_tiles;
+  int stage_bytes;
   PktSeg* pkt_seg;
-  unsigned long long* st_map;  // look-back state, one word per tile
-  unsigned long long* st_wrap;
+  unsigned* masks;
+  unsigned long long* st_map;
   int* tile_counter;
   BatchHeader* hdr;
 };
 
-constexpr int kSegThreads = 512;  // one packet per thread, one tile per CTA
+constexpr int kScanThreads = 256;
 
-__global__ void __launch_bounds__(kSegThreads) k_segment(const SegParams p) {
-  __shared__ unsigned long long s_incl[kSegThreads];
-  __shared__ unsigned long long s_warp[kSegThreads / 32];
-  __shared__ int s_tile;
-  __shared__ int s_skip_in;
-  __shared__ unsigned long long s_wrap_prefix;
+struct ScanShared {
+  uint64_t full[2];
+  unsigned nz[kTileBlocks];  // raw "distance != 0" (or crop-tested) bits per block
+  int skip[kTilePkts];
+  int tile_id[2];
+};
 
+template <int ADJ, bool CROP>
+__global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  ScanShared& sh = *reinterpret_cast<ScanShared*>(smem_raw);
+  DevConfig* cfg_s = reinterpret_cast<DevConfig*>(smem_raw + ((sizeof(ScanShared) + 127) & ~127));
+  uint8_t* stage0 = reinterpret_cast<uint8_t*>(cfg_s) + ((sizeof(DevConfig) + 127) & ~127);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
-  __syncthreads();
-  const int tile = s_tile;
-  const int P = tile * kSegThreads + tid;
-  const bool live = P < p.n;
 
-  // ---- block headers: 12 x (id, azimuth) ------------------------------------------------
-  int az11 = 0;
-  unsigned wm = 0;  // bit j (1..11): az[j] < az[j-1]
-  unsigned em = 0;  // bit s (0..11): az[s] < lastAzimuth entering the packet
-  unsigned um = 0;  // bit j: block id != 0xeeff
-  int azdiff = 0;
-  if (live) {
-    const uint8_t* pk = p.pkts + (long long)P * p.stride;
-    int az[12];
-#pragma unroll
-    for (int j = 0; j < 12; ++j) {
-      const unsigned short id = __ldg(reinterpret_cast<const unsigned short*>(pk + 100 * j));
-      az[j] = __ldg(reinterpret_cast<const unsigned short*>(pk + 100 * j + 2));
-      if (id != 0xeeff) um |= 1u << j;
-    }
-    const int prev11 =
-        (P > 0) ? (int)__ldg(reinterpret_cast<const unsigned short*>(pk - p.stride + 1102))
-                : p.carry_last_az;
-#pragma unroll
-    for (int j = 1; j < 12; ++j)
-      if (az[j] < az[j - 1]) wm |= 1u << j;
-#pragma unroll
-    for (int j = 0; j < 12; ++j)
-      if (az[j] < prev11) em |= 1u << j;
-    az11 = az[11];
-    // azimuthDiff: element of rank 6 among the 11 modular deltas (nth_element, :1016-1026)
-    int d[11];
-#pragma unroll
-    for (int i = 0; i < 11; ++i) d[i] = (36000 + az[i + 1] - az[i]) % 36000;
-#pragma unroll
-    for (int i = 0; i < 11; ++i) {
-      int rank = 0;
-#pragma unroll
-      for (int k = 0; k < 11; ++k) rank += (d[k] < d[i]) || (d[k] == d[i] && k < i);
-      if (rank == 6) azdiff = d[i];
-    }
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.cfg);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(cfg_s);
+    for (int i = tid; i < (int)(sizeof(DevConfig) / 4); i += kScanThreads) dst[i] = __ldg(&src[i]);
   }
-
-  // ---- skip map of this packet (streaming only; offline never skips) --------------------
-  unsigned long long m = kMapIdentity;
-  if (live) {
-    m = 0;
-    if (p.mode == 0) {
-#pragma unroll
-      for (int s = 0; s < 12; ++s) {
-        const unsigned hi = wm & ~((2u << s) - 1u);
-        const int out = hi ? (31 - __clz(hi)) : (((em >> s) & 1u) ? s : 0);
-        m |= (unsigned long long)out << (4 * s);
-      }
-    }
-    if (P < p.halo && map_is_const(m)) atomicMin(&p.hdr->first_const_pkt, P);
-  }
-
-  // ---- inclusive scan of maps over the tile ------------------------------------------------
-  unsigned long long inc = m;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned long long prev = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc = map_compose(prev, inc);
-  }
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    unsigned long long w = (lane < kSegThreads / 32) ? s_warp[lane] : kMapIdentity;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-      const unsigned long long prev = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w = map_compose(prev, w);
-    }
-    if (lane < kSegThreads / 32) s_warp[lane] = w;
-  }
-  __syncthreads();
-  if (warp > 0) inc = map_compose(s_warp[warp - 1], inc);
-  s_incl[tid] = inc;
-  __syncthreads();
-
-  // ---- look-back #1: firingSkip entering the tile ------------------------------------------
-  // Serial walk by one thread; it stops at the first constant composed map, which for real
-  // sensor data is the previous tile's aggregate.
   if (tid == 0) {
-    const unsigned long long agg = s_incl[kSegThreads - 1];
-    int skip_in;
-    if (tile == 0) {
-      skip_in = p.carry_skip;
+    mbar_init(&sh.full[0], 1);
+    mbar_init(&sh.full[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const DevConfig& cfg = *cfg_s;
+  const long long in_base = reinterpret_cast<long long>(p.pkts);
+
+  auto issue = [&](int t, int b) {
+    const long long first = (long long)t * kTilePkts;
+    const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, kLead);
+    const uint32_t bytes = (uint32_t)(sp.s1 - sp.s0);
+    fence_proxy_async();
+    if (bytes) {
+      mbar_expect_tx(&sh.full[b], bytes);
+      bulk_g2s(stage0 + (size_t)b * p.stage_bytes, reinterpret_cast<const void*>(sp.s0), bytes,
+               &sh.full[b]);
     } else {
-      st_release_u64(&p.st_map[tile], kFlagAgg | agg);
-      unsigned long long acc = kMapIdentity;  // maps of tiles (idx, tile) composed
-      int idx = tile - 1;
-      while (true) {
-        unsigned long long v;
-        do {
-          v = ld_acquire_u64(&p.st_map[idx]);
-        } while ((v >> 62) == 0);
-        if ((v >> 62) == 2) {
-          skip_in = map_apply(acc, (int)(v & 15ull));
-          break;
+      mbar_arrive(&sh.full[b]);
+    }
+  };
+  if (tid == 0) {
+    const int t = atomicAdd(p.tile_counter, 1);
+    sh.tile_id[0] = t;
+    if (t < p.n_tiles) issue(t, 0);
+  }
+  __syncthreads();
+
+  uint32_t phase[2] = {0u, 0u};
+  int cur = 0;
+  while (true) {
+    const int tile = sh.tile_id[cur];
+    if (tile >= p.n_tiles) break;
+    if (tid == 0) {
+      const int tn = atomicAdd(p.tile_counter, 1);
+      sh.tile_id[cur ^ 1] = tn;
+      if (tn < p.n_tiles) issue(tn, cur ^ 1);
+    }
+    const long long first = (long long)tile * kTilePkts;
+    const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, kLead);
+    const int npk = sp.npk;
+    uint8_t* stage = stage0 + (size_t)cur * p.stage_bytes;
+    mbar_wait(&sh.full[cur], phase[cur]);
+    phase[cur] ^= 1u;
+    if (sp.s1 < sp.a1) {
+      for (long long a = sp.s1 + tid; a < sp.a1; a += kScanThreads)
+        stage[a - sp.s0] = *reinterpret_cast<const uint8_t*>(a);
+      __syncthreads();
+    }
+    const uint8_t* tile_smem = stage + (sp.a0 - sp.s0);
+
+    // ---- phase A (warp 0, lane == packet): headers, skip maps, look-back -------------------
+    unsigned wm = 0, em = 0, um = 0, wrapmask = 0;
+    int azdiff = 0, s_in = 0, az11 = 0;
+    unsigned long long m = kMapIdentity;
+    if (warp == 0) {
+      const bool live = lane < npk;
+      int az[12];
+      if (live) {
+        const uint8_t* pk = tile_smem + (size_t)lane * p.stride;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+          if (ld_smem_u16(pk + 100 * j) != 0xeeffu) um |= 1u << j;
+          az[j] = (int)ld_smem_u16(pk + 100 * j + 2);
         }
-        acc = map_compose(v & kPayloadMask, acc);
-        if (map_is_const(acc)) {
-          skip_in = (int)(acc & 15ull);
-          break;
+        az11 = az[11];
+      }
+      // lastAzimuth entering the packet: block 11 of the previous packet (always iterated)
+      int prev11 = __shfl_up_sync(0xffffffffu, az11, 1);
+      if (lane == 0)
+        prev11 = (first > 0) ? (int)ld_smem_u16(tile_smem - p.stride + 1102) : p.carry_last_az;
+      if (live) {
+#pragma unroll
+        for (int j = 1; j < 12; ++j)
+          if (az[j] < az[j - 1]) wm |= 1u << j;
+#pragma unroll
+        for (int j = 0; j < 12; ++j)
+          if (az[j] < prev11) em |= 1u << j;
+        if (ADJ != 0) {
+          // azimuthDiff: element of rank 6 among the 11 modular deltas (nth_element, :1016-1026)
+          int d[11];
+#pragma unroll
+          for (int i = 0; i < 11; ++i) d[i] = (36000 + az[i + 1] - az[i]) % 36000;
+#pragma unroll
+          for (int i = 0; i < 11; ++i) {
+            int rank = 0;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) rank += (d[k] < d[i]) || (d[k] == d[i] && k < i);
+            if (rank == 6) azdiff = d[i];
+          }
         }
-        if (--idx < 0) {
-          skip_in = map_apply(acc, p.carry_skip);
-          break;
+        m = 0;
+        if (p.mode == 0) {
+#pragma unroll
+          for (int s = 0; s < 12; ++s) {
+            const unsigned hi = wm & ~((2u << s) - 1u);
+            const int out = hi ? (31 - __clz(hi)) : (((em >> s) & 1u) ? s : 0);
+            m |= (unsigned long long)out << (4 * s);
+          }
         }
+        if (first + lane < p.halo && map_is_const(m))
+          atomicMin(&p.hdr->first_const_pkt, (int)(first + lane));
+      }
+      unsigned long long inc = m;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long prev = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = map_compose(prev, inc);
+      }
+      const unsigned long long agg = __shfl_sync(0xffffffffu, inc, 31);
+      int skip_tile = 0;
+      if (lane == 0) {
+        if (tile == 0) {
+          skip_tile = p.carry_skip;
+        } else {
+          st_release_u64(&p.st_map[tile], kFlagAgg | agg);
+          unsigned long long acc = kMapIdentity;  // maps of tiles (idx, tile) composed
+          int idx = tile - 1;
+          while (true) {
+            unsigned long long v;
+            do {
+              v = ld_acquire_u64(&p.st_map[idx]);
+            } while ((v >> 62) == 0);
+            if ((v >> 62) == 2) {
+              skip_tile = map_apply(acc, (int)(v & 15ull));
+              break;
+            }
+            acc = map_compose(v & kPayloadMask, acc);
+            if (map_is_const(acc)) {
+              skip_tile = (int)(acc & 15ull);
+              break;
+            }
+            if (--idx < 0) {
+              skip_tile = map_apply(acc, p.carry_skip);
+              break;
+            }
+          }
+        }
+        st_release_u64(&p.st_map[tile], kFlagPrefix | (unsigned long long)map_apply(agg, skip_tile));
+      }
+      skip_tile = __shfl_sync(0xffffffffu, skip_tile, 0);
+      unsigned long long excl = __shfl_up_sync(0xffffffffu, inc, 1);
+      if (lane == 0) excl = kMapIdentity;
+      s_in = (p.mode == 0) ? map_apply(excl, skip_tile) : 0;
+      if (live) wrapmask = (wm & ~((2u << s_in) - 1u)) | (((em >> s_in) & 1u) << s_in);
+      sh.skip[lane] = s_in;
+    }
+
+    // ---- phase B1: which return slots of each block could be emitted ------------------------
+    if (!CROP) {
+      // lane per block: scan the 32 distance fields of a block with 16-bit loads (the 100-byte
+      // block stride makes the lanes of a warp hit distinct banks)
+      for (int b = tid; b < kTileBlocks; b += kScanThreads) {
+        const int lp = b / kBlocks, j = b - lp * kBlocks;
+        unsigned bits = 0;
+        if (lp < npk) {
+          const uint8_t* blk = tile_smem + (size_t)lp * p.stride + 100 * j;
+          unsigned h[50];
+#pragma unroll
+          for (int k = 2; k < 50; ++k) h[k] = ld_smem_u16(blk + 2 * k);
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const int o = 4 + 3 * r;  // byte offset of the distance field
+            unsigned d;
+            if ((o & 1) == 0)
+              d = h[o >> 1];
+            else
+              d = (h[o >> 1] & 0xff00u) | (h[(o >> 1) + 1] & 0x00ffu);
+            bits |= (d != 0u ? 1u : 0u) << r;
+          }
+        }
+        sh.nz[b] = bits;
+      }
+    } else {
+      // crop test needs the sensor-frame position (HDLParser.cxx:629-639): warp per block
+      for (int b = warp; b < kTileBlocks; b += kScanThreads / 32) {
+        const int lp = b / kBlocks, j = b - lp * kBlocks;
+        unsigned bits = 0;
+        if (lp < npk) {
+          const uint8_t* pk = tile_smem + (size_t)lp * p.stride;
+          const uint8_t* blk = pk + 100 * j;
+          const int off = (ld_smem_u16(blk) == 0xeeffu) ? 0 : 32;
+          const unsigned dist = blk[4 + 3 * lane] | (blk[5 + 3 * lane] << 8);
+          int ad = 0;
+          if (ADJ != 0) {
+            int d[11];
+#pragma unroll
+            for (int i = 0; i < 11; ++i)
+              d[i] = (36000 + (int)ld_smem_u16(pk + 100 * (i + 1) + 2) - (int)ld_smem_u16(pk + 100 * i + 2)) % 36000;
+#pragma unroll
+            for (int i = 0; i < 11; ++i) {
+              int rank = 0;
+#pragma unroll
+              for (int k = 0; k < 11; ++k) rank += (d[k] < d[i]) || (d[k] == d[i] && k < i);
+              if (rank == 6) ad = d[i];
+            }
+          }
+          CalRow c;
+          load_cal(cfg, lane + off, c);
+          const unsigned az = adjusted_azimuth<ADJ>(cfg, ld_smem_u16(blk + 2), ad, j, lane);
+          double px, py, pz;
+          sensor_point(c, __ldg(&p.lut_sin[az]), __ldg(&p.lut_cos[az]), dist, px, py, pz);
+          const bool in_box = px >= cfg.crop[0] && px <= cfg.crop[1] && py >= cfg.crop[2] &&
+                              py <= cfg.crop[3] && pz >= cfg.crop[4] && pz <= cfg.crop[5];
+          bits = __ballot_sync(0xffffffffu, dist != 0 && (in_box == (cfg.crop_inside != 0)));
+        }
+        if (lane == 0) sh.nz[b] = bits;
       }
     }
-    st_release_u64(&p.st_map[tile], kFlagPrefix | (unsigned long long)map_apply(agg, skip_in));
-    s_skip_in = skip_in;
-  }
-  __syncthreads();
-  const int s = (p.mode == 0)
-                    ? map_apply(tid == 0 ? kMapIdentity : s_incl[tid - 1], s_skip_in)
-                    : 0;
+    __syncthreads();
 
-  // ---- wraps over the iterated blocks -------------------------------------------------------
-  unsigned wrapmask = 0;
-  if (live) wrapmask = (wm & ~((2u << s) - 1u)) | (((em >> s) & 1u) << s);
-  const int nw = __popc(wrapmask);
-  // origin marker: streaming -> the packet after the wrap re-initialises the frame meta
-  // (F4b); offline -> the wrap packet itself.  marker - 1 == origin packet index.
-  const unsigned marker = nw ? (unsigned)(P + (p.mode == 0 ? 2 : 1)) : 0u;
-  const unsigned long long v2 = ((unsigned long long)nw << 32) | marker;
-
-  unsigned long long inc2 = v2;
+    // ---- phase B2: final masks (iterated, gated, selected lasers) ---------------------------
+    const int pskip = cfg.points_skip;
+    for (int b = tid; b < kTileBlocks; b += kScanThreads) {
+      const int lp = b / kBlocks, j = b - lp * kBlocks;
+      if (lp < npk) {
+        unsigned mk = 0;
+        if (j >= sh.skip[lp] && (pskip == 0 || (j % (pskip + 1)) == 0)) {
+          const bool upper = ld_smem_u16(tile_smem + (size_t)lp * p.stride + 100 * j) != 0xeeffu;
+          mk = sh.nz[b] & (upper ? cfg.sel_hi : cfg.sel_lo);
+        }
+        sh.nz[b] = mk;
+        p.masks[(first + lp) * kBlocks + j] = mk;
+      }
+    }
+    __syncthreads();
+    if (warp == 0 && lane < npk) {
+      unsigned cnt = 0;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned long long prev = __shfl_up_sync(0xffffffffu, inc2, o);
-    if (lane >= o) inc2 = WrapTraits::combine(prev, inc2);
-  }
-  __syncthreads();  // s_warp reuse
-  if (lane == 31) s_warp[warp] = inc2;
-  __syncthreads();
-  if (warp == 0) {
-    unsigned long long w = (lane < kSegThreads / 32) ? s_warp[lane] : 0ull;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-      const unsigned long long prev = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w = WrapTraits::combine(prev, w);
+      for (int j = 0; j < kBlocks; ++j) cnt += __popc(sh.nz[lane * kBlocks + j]);
+      const long long P = first + lane;
+      PktSeg r;
+      r.x = s_in | (int)(wrapmask << 4) | (azdiff << 16);
+      r.y = (int)cnt;
+      r.z = 0;
+      r.w = 0;
+      p.pkt_seg[P] = r;
+      const unsigned ium = um & ~((1u << s_in) - 1u);
+      if (ium) {
+        const long long fu = P * 12 + (__ffs(ium) - 1);
+        // tiles run in order: after the first one almost every packet fails this test
+        if (fu < *reinterpret_cast<volatile long long*>(&p.hdr->first_upper_block))
+          atomicMin(reinterpret_cast<unsigned long long*>(&p.hdr->first_upper_block),
+                    (unsigned long long)fu);
+      }
+      if (P == p.n - 1) {
+        p.hdr->last_azimuth = az11;
+        p.hdr->firing_skip_out = (p.mode == 0) ? map_apply(m, s_in) : 0;
+      }
     }
-    if (lane < kSegThreads / 32) s_warp[lane] = w;
-  }
-  __syncthreads();
-  if (warp > 0) inc2 = WrapTraits::combine(s_warp[warp - 1], inc2);
-  // look-back #2 (warp 0): wraps and origin marker before this tile
-  if (warp == 0) {
-    const unsigned long long agg = s_warp[kSegThreads / 32 - 1];
-    unsigned long long ex = lookback_exclusive<WrapTraits>(p.st_wrap, tile, agg);
-    if (lane == 0) s_wrap_prefix = ex;
-  }
-  __syncthreads();
-  unsigned long long excl = __shfl_up_sync(0xffffffffu, inc2, 1);
-  if (lane == 0) excl = (warp > 0) ? s_warp[warp - 1] : 0ull;
-  // (s_warp[warp-1] is the inclusive value of the previous warp's last thread)
-  excl = WrapTraits::combine(s_wrap_prefix, excl);
-  // seed: with no frame meta carried in, packet 0 is the origin until the first wrap
-  if (!p.carry_meta_inited) excl = WrapTraits::combine(excl, 1ull);
-
-  if (live) {
-    const int frame_base = (int)(excl >> 32);
-    const int origin = (int)(unsigned)excl - 1;
-    PktSeg r;
-    r.x = s | (int)(wrapmask << 4) | (int)(um << 16);
-    r.y = frame_base;
-    r.z = origin;
-    r.w = azdiff;
-    p.pkt_seg[P] = r;
-
-    const unsigned ium = um & ~((1u << s) - 1u);
-    if (ium) {
-      const long long fu = (long long)P * 12 + (__ffs(ium) - 1);
-      // monotone tile order: after the first tile almost every packet fails this test
-      if (fu < *reinterpret_cast<volatile long long*>(&p.hdr->first_upper_block))
-        atomicMin(reinterpret_cast<unsigned long long*>(&p.hdr->first_upper_block),
-                  (unsigned long long)fu);
-    }
-    if (P == p.halo) {
-      p.hdr->origin_at_halo = origin;
-      p.hdr->frame_at_halo = frame_base;
-    }
-    if (P == p.n - 1) {
-      p.hdr->total_wraps = frame_base + nw;
-      p.hdr->last_azimuth = az11;
-      p.hdr->firing_skip_out = (p.mode == 0) ? map_apply(m, s) : 0;
-      p.hdr->last_has_wrap = nw > 0;
-      int lo;
-      if (p.mode == 0)
-        lo = nw ? -2 : origin;  // -2: frame meta not initialised yet
-      else
-        lo = nw ? P : origin;
-      p.hdr->last_origin_packet = lo;
-      p.hdr->last_origin_time = (lo >= 0) ? p.pkt_time[lo] : 0;
-    }
+    __syncthreads();  // stage `cur`, nz and skip are free again
+    cur ^= 1;
   }
 }
 
 // =========================================================================================
-// k_pose: one thread per packet.  Output 12 doubles per packet, row-major [L | t] with
-// t = T(packet) - T(origin packet).  Launched only when the snapshot holds >= 2 poses.
+// k_pose: one thread per packet.
+//   (1) scans over packets (decoupled look-back): wraps -> frame id, last wrap -> origin
+//       packet, emitted counts -> point offset; frame-start records of the frame table;
+//   (2) pose bracket + lerp + Ry.Rx.Rz and T(packet) - T(origin) when the snapshot has >= 2
+//       poses: 12 doubles per packet, row-major [L | t].
 // =========================================================================================
 struct PoseParams {
   const long long* pkt_time;
-  const PktSeg* pkt_seg;
+  PktSeg* pkt_seg;           // in: x, y = count; out: y = frame id, z = time - t_base
+  const unsigned* masks;
+  unsigned long long* pkt_off;  // out: index of the packet's first emitted point
+  unsigned long long* st_wrap;
+  unsigned long long* st_cnt;
+  int* tile_counter;
   int n;
+  int halo;
   int mode;
-  const long long* pose_t;
-  const double* pose_trv;  // n_poses x 9
   int n_poses;
   int carry_meta_inited;
+  long long t_base;
+  const long long* pose_t;
+  const double* pose_trv;  // n_poses x 9
   double carry_origin_T[3];
   double* pose_mat;  // n x 12
+  long long* frame_first_point;
+  int* frame_start_block;
+  int frame_cap;
   BatchHeader* hdr;
 };
+
+constexpr int kPoseThreads = 256;
 
 __device__ __forceinline__ double to_radians(double x) {
   return __ddiv_rn(__dmul_rn(x, 3.14159265358979323846), 180.0);
@@ -357,15 +528,137 @@ __device__ __forceinline__ void rotate_by(double L[3][3], double angle, int axis
     for (int j = 0; j < 3; ++j) L[i][j] = out[i][j];
 }
 
-__global__ void __launch_bounds__(256) k_pose(const PoseParams p) {
-  const int P = blockIdx.x * blockDim.x + threadIdx.x;
-  if (P >= p.n) return;
+__global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
+  __shared__ unsigned long long s_w[kPoseThreads / 32];
+  __shared__ unsigned long long s_c[kPoseThreads / 32];
+  __shared__ unsigned long long s_wrap_prefix, s_cnt_prefix;
+  __shared__ int s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  const int P = tile * kPoseThreads + tid;
+  const bool live = P < p.n;
+
+  PktSeg seg = make_int4(0, 0, 0, 0);
+  if (live) seg = p.pkt_seg[P];
+  const unsigned wrapmask = (seg.x >> 4) & 0xfff;
+  const int nw = __popc(wrapmask);
+  // origin marker: streaming -> the packet after the wrap re-initialises the frame meta
+  // (F4b); offline -> the wrap packet itself.  marker - 1 == origin packet index.
+  const unsigned marker = nw ? (unsigned)(P + (p.mode == 0 ? 2 : 1)) : 0u;
+  const unsigned long long v2 = ((unsigned long long)nw << 32) | marker;
+  const unsigned long long cnt = (live && P >= p.halo) ? (unsigned long long)(unsigned)seg.y : 0ull;
+
+  unsigned long long inc2 = v2, incc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long a = __shfl_up_sync(0xffffffffu, inc2, o);
+    const unsigned long long b = __shfl_up_sync(0xffffffffu, incc, o);
+    if (lane >= o) {
+      inc2 = WrapTraits::combine(a, inc2);
+      incc += b;
+    }
+  }
+  if (lane == 31) {
+    s_w[warp] = inc2;
+    s_c[warp] = incc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = (lane < kPoseThreads / 32) ? s_w[lane] : 0ull;
+    unsigned long long c = (lane < kPoseThreads / 32) ? s_c[lane] : 0ull;
+#pragma unroll
+    for (int o = 1; o < kPoseThreads / 32; o <<= 1) {
+      const unsigned long long a = __shfl_up_sync(0xffffffffu, w, o);
+      const unsigned long long b = __shfl_up_sync(0xffffffffu, c, o);
+      if (lane >= o) {
+        w = WrapTraits::combine(a, w);
+        c += b;
+      }
+    }
+    if (lane < kPoseThreads / 32) {
+      s_w[lane] = w;
+      s_c[lane] = c;
+    }
+  }
+  __syncthreads();
+  // two look-backs side by side: warp 0 wraps/origin, warp 1 point counts
+  if (warp == 0) {
+    const unsigned long long ex =
+        lookback_exclusive<WrapTraits>(p.st_wrap, tile, s_w[kPoseThreads / 32 - 1]);
+    if (lane == 0) s_wrap_prefix = ex;
+  } else if (warp == 1) {
+    const unsigned long long ex =
+        lookback_exclusive<SumTraits>(p.st_cnt, tile, s_c[kPoseThreads / 32 - 1]);
+    if (lane == 0) s_cnt_prefix = ex;
+  }
+  __syncthreads();
+  unsigned long long ex2 = __shfl_up_sync(0xffffffffu, inc2, 1);
+  unsigned long long exc = __shfl_up_sync(0xffffffffu, incc, 1);
+  if (lane == 0) {
+    ex2 = 0ull;
+    exc = 0ull;
+  }
+  if (warp > 0) {
+    ex2 = WrapTraits::combine(s_w[warp - 1], ex2);
+    exc += s_c[warp - 1];
+  }
+  ex2 = WrapTraits::combine(s_wrap_prefix, ex2);
+  exc += s_cnt_prefix;
+  // seed: with no frame meta carried in, packet 0 is the origin until the first wrap
+  if (!p.carry_meta_inited) ex2 = WrapTraits::combine(ex2, 1ull);
+  if (!live) return;
+
+  const int frame_base = (int)(ex2 >> 32);
+  const int origin = (int)(unsigned)ex2 - 1;
   const long long t = __ldg(&p.pkt_time[P]);
-  const PktSeg seg = p.pkt_seg[P];
+  seg.y = frame_base;
+  seg.z = (int)(unsigned)(t - p.t_base);
+  p.pkt_seg[P] = seg;
+  p.pkt_off[P] = exc;
+
+  // frame table: a wrap block opens frame f before it is decoded (HDLParser.cxx:1035-1039)
+  if (wrapmask && P >= p.halo) {
+    unsigned wm = wrapmask;
+    unsigned before = 0;
+    int jprev = 0;
+    int f = frame_base;
+    while (wm) {
+      const int j = __ffs(wm) - 1;
+      wm &= wm - 1;
+      for (int q = jprev; q < j; ++q) before += __popc(__ldg(&p.masks[(long long)P * kBlocks + q]));
+      jprev = j;
+      ++f;
+      if (f < p.frame_cap) {
+        p.frame_first_point[f] = (long long)(exc + before);
+        p.frame_start_block[f] = P * 12 + j;
+      } else {
+        p.hdr->frame_overflow = 1;
+      }
+    }
+  }
+  if (P == p.halo) {
+    p.hdr->origin_at_halo = origin;
+    p.hdr->frame_at_halo = frame_base;
+  }
+  if (P == p.n - 1) {
+    p.hdr->total_wraps = frame_base + nw;
+    p.hdr->last_has_wrap = nw > 0;
+    p.hdr->total_points = (long long)(exc + cnt);
+    int lo;
+    if (p.mode == 0)
+      lo = nw ? -2 : origin;  // -2: frame meta not initialised yet
+    else
+      lo = nw ? P : origin;
+    p.hdr->last_origin_packet = lo;
+    p.hdr->last_origin_time = (lo >= 0) ? p.pkt_time[lo] : 0;
+  }
+
+  if (p.n_poses < 2) return;
   double T[3], R[3];
   interp_pose(p.pose_t, p.pose_trv, p.n_poses, t, T, R, true);
   double To[3];
-  const int origin = seg.z;
   if (origin < 0) {
     To[0] = p.carry_origin_T[0];
     To[1] = p.carry_origin_T[1];
@@ -391,8 +684,6 @@ __global__ void __launch_bounds__(256) k_pose(const PoseParams p) {
     o[4 * r + 3] = __dsub_rn(T[r], To[r]);  // reprojectToFrameBeginning, HDLParser.cxx:1057
   }
   if (P == p.n - 1) {
-    // frame origin inherited by the next batch
-    const int nw = __popc((seg.x >> 4) & 0xfff);
     const bool self = (p.mode == 1) && nw;  // offline: the wrap packet is its frame's origin
 #pragma unroll
     for (int k = 0; k < 3; ++k) p.hdr->carry_origin_T[k] = self ? T[k] : To[k];
@@ -400,17 +691,21 @@ __global__ void __launch_bounds__(256) k_pose(const PoseParams p) {
 }
 
 // =========================================================================================
-// k_decode: persistent CTAs, tiles of kTilePkts packets staged into shared memory with TMA
-// bulk copies (double-buffered), one warp per 100-byte firing block (lane == return slot),
-// stream-order compaction through a decoupled look-back on the emitted-point count.
+// k_decode: decode + calibrate + transform + compacted SoA stores.  No inter-CTA dependency:
+// emission masks and point offsets come from k_scan / k_pose.  Persistent CTAs (2 per SM),
+// tiles staged by TMA bulk copies (packets, masks, segment records), one warp per 100-byte
+// firing block with lane == return slot.
+// Work split inside a tile: warp w owns the packets {w/2 + 4k} and, inside them, the firing
+// blocks of parity w&1.  On HDL-64 data block parity == laser bank (0xeeff / 0xddff), so a
+// warp keeps one calibration bank in registers; the pose row is loaded once per packet.
 // =========================================================================================
 struct DecParams {
   const uint8_t* pkts;  // first packet of the submitted array (halo included)
   long long stride;
-  long long total_bytes;  // n * stride: bytes that may be read from pkts
-  const long long* pkt_time;
-  long long t_base;
+  long long total_bytes;  // bytes that may be read from pkts
   const PktSeg* pkt_seg;
+  const unsigned* masks;
+  const unsigned long long* pkt_off;
   const double* pose_mat;
   const double* lut_sin;
   const double* lut_cos;
@@ -420,7 +715,7 @@ struct DecParams {
   int mode;
   int pose_valid;
   int n_tiles;
-  int stage_bytes;  // bytes per shared-memory stage (multiple of 16)
+  int stage_bytes;  // bytes per shared-memory stage (multiple of 128)
   float* x;
   float* y;
   float* z;
@@ -429,105 +724,25 @@ struct DecParams {
   uint16_t* azimuth;
   uint16_t* distance;
   uint32_t* t_us;
-  unsigned long long* st_cnt;
   int* tile_counter;
-  long long* frame_first_point;
-  int* frame_start_block;
   unsigned* frame_laser_counts;  // frame_cap x 64
   int frame_cap;
-  BatchHeader* hdr;
 };
 
-constexpr int kTilePkts = 32;
-constexpr int kTileBlocks = kTilePkts * kBlocks;  // 384
 constexpr int kDecThreads = 256;
 constexpr int kDecWarps = kDecThreads / 32;
+constexpr int kMaskBytes = kTileBlocks * 4;           // 1536
+constexpr int kSegBytes = kTilePkts * (int)sizeof(PktSeg);  // 512
 
 struct DecShared {
   DevConfig cfg;
   uint64_t full[2];
-  unsigned mask[kTileBlocks];  // ballot of emitted return slots per firing block
-  unsigned offs[kTileBlocks];  // exclusive prefix of popc(mask) inside the tile
-  PktSeg seg[kTilePkts];
-  unsigned tpk[kTilePkts];     // packet time - t_base
+  unsigned long long off[2][kTilePkts];
   unsigned hist[2][kMaxLasers];
-  unsigned long long tile_base;
   int tile_id[2];
 };
 
-__device__ __forceinline__ unsigned ld_smem_u16(const uint8_t* p) {
-  // packets are only guaranteed 2-byte aligned (1206 = 2 * 603)
-  return *reinterpret_cast<const unsigned short*>(p);
-}
-
-// Per-laser calibration row held in registers (reloaded only when the bank changes).
-struct CalRow {
-  double cC, sC, dc, cV, sV, vo, ho;
-};
-__device__ __forceinline__ void load_cal(const DevConfig& c, int row, CalRow& r) {
-  r.cC = c.cal[0][row];
-  r.sC = c.cal[1][row];
-  r.dc = c.cal[2][row];
-  r.cV = c.cal[3][row];
-  r.sV = c.cal[4][row];
-  r.vo = c.cal[5][row];
-  r.ho = c.cal[6][row];
-}
-
-// Sensor-frame position of one return (HDLParser.cxx:597-623).  `az` is already adjusted and
-// reduced mod 36000.  All arithmetic in separate IEEE mul/add, reference operation order.
-__device__ __forceinline__ void sensor_point(const CalRow& c, double sA, double cA, unsigned dist,
-                                             double& px, double& py, double& pz) {
-  // sin/cos(rad(az/100) - rad(rotCorrection)); with rotCorrection == 0 (cC=1, sC=0) this is
-  // exactly the reference's LUT branch (:602-606)
-  const double sinAz = __dsub_rn(__dmul_rn(sA, c.cC), __dmul_rn(cA, c.sC));
-  const double cosAz = __dadd_rn(__dmul_rn(cA, c.cC), __dmul_rn(sA, c.sC));
-  const double dM = __dadd_rn(__dmul_rn((double)dist, 0.002), c.dc);  // :614
-  const double xy = __dmul_rn(dM, c.cV);                              // :615
-  px = __dsub_rn(__dmul_rn(xy, sinAz), __dmul_rn(c.ho, cosAz));       // :620
-  py = __dadd_rn(__dmul_rn(xy, cosAz), __dmul_rn(c.ho, sinAz));       // :621
-  pz = __dadd_rn(__dmul_rn(dM, c.sV), c.vo);                          // :622
-}
-
 template <int ADJ>
-__device__ __forceinline__ unsigned adjusted_azimuth(const DevConfig& c, unsigned rot, int azdiff,
-                                                     int j, int lane) {
-  unsigned az = rot;
-  if (ADJ != 0) {
-    // HDLParser.cxx:961: std::round (half away from zero) of azimuthDiff * ratio
-    const int adj = (int)round(__dmul_rn((double)azdiff, c.az_ratio[j][lane]));
-    az = (unsigned)(unsigned short)(rot + adj);  // passed as unsigned short, :968
-  }
-  return az % 36000u;  // :597
-}
-
-// Byte span of a tile in the input array: [a0, a1) are the bytes the tile's packets occupy,
-// [s0, s1) the 16-byte-granular span the TMA bulk copy moves.  When rounding a1 up would
-// read past the bytes the caller owns, the copy stops at the last full granule and the
-// (< 16) tail bytes are fetched with plain loads.
-struct TileSpan {
-  long long a0, a1, s0, s1;
-  int npk;
-};
-__device__ __forceinline__ TileSpan tile_span(long long in_base, long long stride,
-                                              long long total_bytes, int n, int halo, int tile) {
-  TileSpan t;
-  const long long first = (long long)halo + (long long)tile * kTilePkts;
-  t.npk = n - (int)first;
-  if (t.npk > kTilePkts) t.npk = kTilePkts;
-  t.a0 = in_base + first * stride;
-  t.a1 = t.a0 + (long long)(t.npk - 1) * stride + kPacketBytes;
-  t.s0 = t.a0 & ~15ll;
-  t.s1 = (t.a1 + 15) & ~15ll;
-  if (t.s1 > in_base + total_bytes) t.s1 = t.a1 & ~15ll;
-  if (t.s1 < t.s0) t.s1 = t.s0;
-  return t;
-}
-
-// Work split inside a tile: warp w owns the packets {w/2 + 4k} and, inside them, the firing
-// blocks of parity w&1.  On HDL-64 data block parity == laser bank (0xeeff / 0xddff), so a
-// warp keeps one calibration bank in registers; the pose matrix is loaded once per packet.
-template <int ADJ, bool CROP>
 __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   DecShared& sh = *reinterpret_cast<DecShared*>(smem_raw);
@@ -536,7 +751,6 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
   const int par = warp & 1, pk0 = warp >> 1;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  // ---- one-time CTA setup -------------------------------------------------------------------
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.cfg);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.cfg);
@@ -550,219 +764,156 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
   __syncthreads();
 
   const long long in_base = reinterpret_cast<long long>(p.pkts);
-
-  // issue the staged load of tile `t` into buffer `b` (thread 0 only)
+  // stage layout: [masks 1536 B | seg 512 B | packets]
   auto issue = [&](int t, int b) {
-    const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, p.halo, t);
+    const long long first = (long long)p.halo + (long long)t * kTilePkts;
+    const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, 0);
+    uint8_t* st = stage0 + (size_t)b * p.stage_bytes;
     const uint32_t bytes = (uint32_t)(sp.s1 - sp.s0);
+    const uint32_t mbytes = (uint32_t)sp.npk * kBlocks * 4u;
+    const uint32_t sbytes = (uint32_t)sp.npk * (uint32_t)sizeof(PktSeg);
     fence_proxy_async();
-    if (bytes) {
-      mbar_expect_tx(&sh.full[b], bytes);
-      bulk_g2s(stage0 + (size_t)b * p.stage_bytes, reinterpret_cast<const void*>(sp.s0), bytes,
-               &sh.full[b]);
-    } else {
-      mbar_arrive(&sh.full[b]);
-    }
+    mbar_expect_tx(&sh.full[b], bytes + mbytes + sbytes);
+    bulk_g2s(st, p.masks + first * kBlocks, mbytes, &sh.full[b]);
+    bulk_g2s(st + kMaskBytes, p.pkt_seg + first, sbytes, &sh.full[b]);
+    if (bytes) bulk_g2s(st + kMaskBytes + kSegBytes, reinterpret_cast<const void*>(sp.s0), bytes, &sh.full[b]);
   };
 
+  unsigned long long next_off = 0;  // threads 0..31: point offset of packet `tid` of the next tile
   if (tid == 0) {
     const int t = atomicAdd(p.tile_counter, 1);
     sh.tile_id[0] = t;
     if (t < p.n_tiles) issue(t, 0);
   }
   __syncthreads();
+  {
+    const int t0 = sh.tile_id[0];
+    if (tid < kTilePkts && t0 < p.n_tiles) {
+      const long long P = (long long)p.halo + (long long)t0 * kTilePkts + tid;
+      sh.off[0][tid] = __ldg(&p.pkt_off[P < p.n ? P : p.n - 1]);
+    }
+  }
 
   uint32_t phase[2] = {0u, 0u};
   int cur = 0;
-  const unsigned long long lmask = sh.cfg.laser_mask;
-  const int pskip = sh.cfg.points_skip;
-  const int n_enabled = sh.cfg.n_enabled;
   const bool pose_valid = p.pose_valid != 0;
-
   CalRow cal;
   int cal_bank = -1;
 
   while (true) {
     const int tile = sh.tile_id[cur];
     if (tile >= p.n_tiles) break;
-    // prefetch the next tile into the other buffer
     if (tid == 0) {
       const int tn = atomicAdd(p.tile_counter, 1);
       sh.tile_id[cur ^ 1] = tn;
       if (tn < p.n_tiles) issue(tn, cur ^ 1);
     }
-    const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, p.halo, tile);
+    if (tid >= 128 && tid < 128 + 2 * kMaxLasers) (&sh.hist[0][0])[tid - 128] = 0;
     const long long first = (long long)p.halo + (long long)tile * kTilePkts;
+    const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, 0);
     const int npk = sp.npk;
     uint8_t* stage = stage0 + (size_t)cur * p.stage_bytes;
-
-    // per-packet records of this tile (overlaps the TMA wait)
-    if (tid < kTilePkts) {
-      PktSeg sg = make_int4(0, 0, 0, 0);
-      unsigned tp = 0;
-      if (tid < npk) {
-        sg = p.pkt_seg[first + tid];
-        tp = (unsigned)(__ldg(&p.pkt_time[first + tid]) - p.t_base);
-      }
-      sh.seg[tid] = sg;
-      sh.tpk[tid] = tp;
-    } else if (tid < kTilePkts + 2 * kMaxLasers) {
-      (&sh.hist[0][0])[tid - kTilePkts] = 0;
-    }
+    const unsigned* s_mask = reinterpret_cast<const unsigned*>(stage);
+    const PktSeg* s_seg = reinterpret_cast<const PktSeg*>(stage + kMaskBytes);
+    uint8_t* s_pk = stage + kMaskBytes + kSegBytes;
 
     mbar_wait(&sh.full[cur], phase[cur]);
     phase[cur] ^= 1u;
     if (sp.s1 < sp.a1) {
-      // tail bytes the bulk copy could not cover (unaligned end of the caller's buffer)
       for (long long a = sp.s1 + tid; a < sp.a1; a += kDecThreads)
-        stage[a - sp.s0] = *reinterpret_cast<const uint8_t*>(a);
+        s_pk[a - sp.s0] = *reinterpret_cast<const uint8_t*>(a);
     }
-    __syncthreads();
-    const uint8_t* tile_smem = stage + (sp.a0 - sp.s0);
-
-    // ---- pass 1: which return slots of each firing block are emitted ---------------------
-#pragma unroll 1
-    for (int lp = pk0; lp < kTilePkts; lp += 4) {
-      const PktSeg seg = sh.seg[lp];
-      const int skip_in = seg.x & 15;
-      const uint8_t* pk = tile_smem + (size_t)lp * p.stride;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int j = par + 2 * i;
-        unsigned m = 0;
-        if (lp < npk && j >= skip_in && (pskip == 0 || (j % (pskip + 1)) == 0)) {
-          const uint8_t* blk = pk + 100 * j;
-          const int off = (ld_smem_u16(blk) == 0xeeffu) ? 0 : 32;
-          const unsigned dist = blk[4 + 3 * lane] | (blk[5 + 3 * lane] << 8);
-          int laser_id = lane + off;
-          if (ADJ == 2 && laser_id >= 16) laser_id -= 16;
-          bool valid = dist != 0 && ((lmask >> laser_id) & 1ull) && laser_id < n_enabled;
-          if (CROP) {
-            // the crop test is on the sensor-frame position, before the transform (:629-639)
-            CalRow c;
-            load_cal(sh.cfg, lane + off, c);
-            const unsigned az = adjusted_azimuth<ADJ>(sh.cfg, ld_smem_u16(blk + 2), seg.w, j, lane);
-            double px, py, pz;
-            sensor_point(c, __ldg(&p.lut_sin[az]), __ldg(&p.lut_cos[az]), dist, px, py, pz);
-            const bool in_box = px >= sh.cfg.crop[0] && px <= sh.cfg.crop[1] &&
-                                py >= sh.cfg.crop[2] && py <= sh.cfg.crop[3] &&
-                                pz >= sh.cfg.crop[4] && pz <= sh.cfg.crop[5];
-            valid = valid && (in_box == (sh.cfg.crop_inside != 0));  // :634-638
-          }
-          m = __ballot_sync(0xffffffffu, valid);
-        }
-        if (lane == 0) sh.mask[lp * kBlocks + j] = m;
+    __syncthreads();  // tile_id[cur^1], off[cur], hist and the tail bytes are visible
+    // point offsets of the next tile: loaded now, parked in a register until the switch
+    {
+      const int tn = sh.tile_id[cur ^ 1];
+      if (tid < kTilePkts && tn < p.n_tiles) {
+        const long long P = (long long)p.halo + (long long)tn * kTilePkts + tid;
+        next_off = __ldg(&p.pkt_off[P < p.n ? P : p.n - 1]);
       }
     }
-    __syncthreads();
+    const uint8_t* tile_smem = s_pk + (sp.a0 - sp.s0);
+    const unsigned long long tb = sh.off[cur][0];
+    // per-tile column pointers, kept opaque so every store is base + 32-bit index
+    float* xt = p.x + tb;
+    float* yt = p.y + tb;
+    float* zt = p.z + tb;
+    uint32_t* tt = p.t_us + tb;
+    uint16_t* at = p.azimuth + tb;
+    uint16_t* dt = p.distance + tb;
+    uint8_t* it = p.intensity + tb;
+    uint8_t* lt = p.laser + tb;
+    asm volatile("" : "+l"(xt), "+l"(yt), "+l"(zt), "+l"(tt));
+    asm volatile("" : "+l"(at), "+l"(dt), "+l"(it), "+l"(lt));
+    const int tile_f0 = s_seg[0].y;
 
-    // ---- scan (warp 0: lane == packet) + tile base through the decoupled look-back ----------
-    if (warp == 0) {
-      unsigned c[kBlocks];
-      unsigned tot = 0;
-#pragma unroll
-      for (int j = 0; j < kBlocks; ++j) {
-        c[j] = tot;
-        tot += __popc(sh.mask[lane * kBlocks + j]);
+    unsigned cnt = 0;  // emitted points of (cnt_frame, cnt_bank) seen by this lane
+    int cnt_frame = -1, cnt_bank = 0;
+    auto flush_counts = [&]() {
+      if (cnt) {
+        int l = lane + cnt_bank;
+        if (ADJ == 2 && l >= 16) l -= 16;
+        const int d = cnt_frame - tile_f0;
+        if (d == 0 || d == 1)
+          atomicAdd(&sh.hist[d][l], cnt);
+        else if (cnt_frame < p.frame_cap)
+          atomicAdd(&p.frame_laser_counts[(long long)cnt_frame * kMaxLasers + l], cnt);
+        cnt = 0;
       }
-      unsigned inc = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-      }
-      const unsigned pk_excl = inc - tot;
-#pragma unroll
-      for (int j = 0; j < kBlocks; ++j) sh.offs[lane * kBlocks + j] = pk_excl + c[j];
-      const unsigned long long agg = __shfl_sync(0xffffffffu, inc, 31);
-      const unsigned long long ex = lookback_exclusive<SumTraits>(p.st_cnt, tile, agg);
-      if (lane == 0) {
-        sh.tile_base = ex;
-        if (tile == p.n_tiles - 1) p.hdr->total_points = (long long)(ex + agg);
-      }
-      // frame-start records: a wrap block opens frame f before it is decoded (:1035-1039)
-      const PktSeg seg = sh.seg[lane];
-      int wm = (seg.x >> 4) & 0xfff;
-      while (wm) {
-        const int j = __ffs(wm) - 1;
-        wm &= wm - 1;
-        const int f = seg.y + __popc(((seg.x >> 4) & 0xfff) & ((2 << j) - 1));
-        if (f < p.frame_cap) {
-          p.frame_first_point[f] = (long long)(ex + pk_excl + c[j]);
-          p.frame_start_block[f] = (int)((first + lane) * 12 + j);
-        } else {
-          p.hdr->frame_overflow = 1;
-        }
-      }
-    }
-    __syncthreads();
-
-    // ---- pass 2: decode, calibrate, transform, store ----------------------------------------
-    const unsigned long long tb = sh.tile_base;
-    float* const xt = p.x + tb;
-    float* const yt = p.y + tb;
-    float* const zt = p.z + tb;
-    uint32_t* const tt = p.t_us + tb;
-    uint16_t* const at = p.azimuth + tb;
-    uint16_t* const dt = p.distance + tb;
-    uint8_t* const it = p.intensity + tb;
-    uint8_t* const lt = p.laser + tb;
-    const int tile_f0 = sh.seg[0].y;
-
-    unsigned cnt_lo = 0, cnt_hi = 0;  // per-lane emitted counts for the lower / upper laser bank
-    int warp_frame = -1;
-    auto flush_counts = [&](int f) {
-      if (f < 0) return;
-      const int d = f - tile_f0;
-      int l_lo = lane, l_hi = lane + 32;
-      if (ADJ == 2) {
-        l_lo = lane >= 16 ? lane - 16 : lane;
-        l_hi = lane + 16;
-      }
-      if (d == 0 || d == 1) {
-        if (cnt_lo) atomicAdd(&sh.hist[d][l_lo], cnt_lo);
-        if (cnt_hi) atomicAdd(&sh.hist[d][l_hi], cnt_hi);
-      } else if (f < p.frame_cap) {
-        if (cnt_lo) atomicAdd(&p.frame_laser_counts[(long long)f * kMaxLasers + l_lo], cnt_lo);
-        if (cnt_hi) atomicAdd(&p.frame_laser_counts[(long long)f * kMaxLasers + l_hi], cnt_hi);
-      }
-      cnt_lo = cnt_hi = 0;
     };
 
 #pragma unroll 1
     for (int lp = pk0; lp < npk; lp += 4) {
-      const PktSeg seg = sh.seg[lp];
+      const PktSeg seg = s_seg[lp];
       const int wrapmask = (seg.x >> 4) & 0xfff;
-      const int first_wrap = wrapmask ? (__ffs(wrapmask) - 1) : 12;
+      const int azdiff = (seg.x >> 16) & 0xffff;
       const uint8_t* pk = tile_smem + (size_t)lp * p.stride;
-      const unsigned tpk = sh.tpk[lp];
+      const unsigned tpk = (unsigned)seg.z;
+      // exclusive prefix of the packet's 12 block counts (lanes 0..11)
+      unsigned mymask = (lane < kBlocks) ? s_mask[lp * kBlocks + lane] : 0u;
+      unsigned pre = __popc(mymask);
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += v;
+      }
+      pre -= __popc(mymask);
+      const unsigned pkt_rel = (unsigned)(sh.off[cur][lp] - tb);
       double M[12];  // [L | t] of this packet, warp-uniform
       if (pose_valid) {
         const double* mp = p.pose_mat + (first + lp) * 12;
 #pragma unroll
         for (int q = 0; q < 12; ++q) M[q] = __ldg(&mp[q]);
       }
-      if (wrapmask == 0 && seg.y != warp_frame) {
-        flush_counts(warp_frame);
-        warp_frame = seg.y;
+      int frame = seg.y;
+      if (wrapmask == 0 && (frame != cnt_frame)) {
+        flush_counts();
+        cnt_frame = frame;
       }
 #pragma unroll 2
       for (int i = 0; i < 6; ++i) {
         const int j = par + 2 * i;
-        const int b = lp * kBlocks + j;
-        const unsigned m = sh.mask[b];
+        const unsigned m = __shfl_sync(0xffffffffu, mymask, j);
+        const unsigned boff = __shfl_sync(0xffffffffu, pre, j);
         if (m == 0) continue;
-        if (wrapmask) {
-          const int f = seg.y + __popc(wrapmask & ((2 << j) - 1));
-          if (f != warp_frame) {
-            flush_counts(warp_frame);
-            warp_frame = f;
-          }
-        }
-        const unsigned o = sh.offs[b] + __popc(m & lt_mask);
-        const bool valid = (m >> lane) & 1u;
         const uint8_t* blk = pk + 100 * j;
         const int off = (ld_smem_u16(blk) == 0xeeffu) ? 0 : 32;
+        if (wrapmask) {
+          // rare: a frame boundary inside the packet
+          frame = seg.y + __popc(wrapmask & ((2 << j) - 1));
+          if (p.mode == 1 && pose_valid && ((wrapmask & ((2 << j) - 1)) != 0)) {
+            // offline: blocks at/after the packet's first wrap start a frame whose origin is
+            // this very packet -> zero translation
+            M[3] = 0.0;
+            M[7] = 0.0;
+            M[11] = 0.0;
+          }
+        }
+        if (frame != cnt_frame || off != cnt_bank) {
+          flush_counts();
+          cnt_frame = frame;
+          cnt_bank = off;
+        }
         if (off != cal_bank) {
           load_cal(sh.cfg, lane + off, cal);
           cal_bank = off;
@@ -772,29 +923,26 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
         const unsigned inten = blk[6 + 3 * lane];
         int laser_id = lane + off;
         if (ADJ == 2 && laser_id >= 16) laser_id -= 16;
-        const unsigned az = adjusted_azimuth<ADJ>(sh.cfg, rot, seg.w, j, lane);
+        const unsigned az = adjusted_azimuth<ADJ>(sh.cfg, rot, azdiff, j, lane);
         double px, py, pz;
         sensor_point(cal, __ldg(&p.lut_sin[az]), __ldg(&p.lut_cos[az]), dist, px, py, pz);
         if (pose_valid) {
-          // offline: blocks at/after the packet's first wrap start a frame whose origin is
-          // this very packet -> zero translation.  type_defs.h:160-166: row sums left to
-          // right, translation last.
-          const bool t_zero = (p.mode == 1) && (j >= first_wrap);
-          const double tx = t_zero ? 0.0 : M[3], ty = t_zero ? 0.0 : M[7], tz = t_zero ? 0.0 : M[11];
+          // type_defs.h:160-166: row sums left to right, translation last
           const double qx = __dadd_rn(
               __dadd_rn(__dadd_rn(__dmul_rn(M[0], px), __dmul_rn(M[1], py)), __dmul_rn(M[2], pz)),
-              tx);
+              M[3]);
           const double qy = __dadd_rn(
               __dadd_rn(__dadd_rn(__dmul_rn(M[4], px), __dmul_rn(M[5], py)), __dmul_rn(M[6], pz)),
-              ty);
+              M[7]);
           const double qz = __dadd_rn(
               __dadd_rn(__dadd_rn(__dmul_rn(M[8], px), __dmul_rn(M[9], py)), __dmul_rn(M[10], pz)),
-              tz);
+              M[11]);
           px = qx;
           py = qy;
           pz = qz;
         }
-        if (valid) {
+        if ((m >> lane) & 1u) {
+          const unsigned o = pkt_rel + boff + __popc(m & lt_mask);
           xt[o] = (float)px;
           yt[o] = (float)py;
           zt[o] = (float)pz;
@@ -803,14 +951,11 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
           dt[o] = (uint16_t)dist;
           it[o] = (uint8_t)inten;
           lt[o] = (uint8_t)laser_id;
-          if (off)
-            ++cnt_hi;
-          else
-            ++cnt_lo;
+          ++cnt;
         }
       }
     }
-    flush_counts(warp_frame);
+    flush_counts();
     __syncthreads();
     if (tid < 2 * kMaxLasers) {
       const unsigned c = (&sh.hist[0][0])[tid];
@@ -818,7 +963,8 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
       if (c && f < p.frame_cap)
         atomicAdd(&p.frame_laser_counts[(long long)f * kMaxLasers + (tid & 63)], c);
     }
-    __syncthreads();  // stage `cur`, masks and hist are free again
+    if (tid < kTilePkts) sh.off[cur ^ 1][tid] = next_off;
+    __syncthreads();  // stage `cur` and hist are free again; off[cur^1] is published
     cur ^= 1;
   }
 }
