@@ -485,7 +485,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     dp.mode = mode;
     dp.pose_valid = pose_valid ? 1 : 0;
     dp.n_tiles = (int)dec_tiles;
-    dp.stage_bytes = (int)align_up((size_t)kMaskBytes + kSegBytes + (size_t)kTilePkts * stride + 48, 128);
+    dp.stage_bytes = (int)align_up((size_t)kMaskBytes + kSegBytes + kPoseBytes + (size_t)kTilePkts * stride + 48, 128);
     dp.x = s.d_x;
     dp.y = s.d_y;
     dp.z = s.d_z;

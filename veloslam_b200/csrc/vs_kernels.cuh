@@ -734,8 +734,12 @@ constexpr int kDecWarps = kDecThreads / 32;
 constexpr int kMaskBytes = kTileBlocks * 4;           // 1536
 constexpr int kSegBytes = kTilePkts * (int)sizeof(PktSeg);  // 512
 
+constexpr int kPoseBytes = kTilePkts * 12 * 8;              // 3072
+
 struct DecShared {
   DevConfig cfg;
+  double sn[kTileBlocks];  // sin / cos of each firing block's azimuth (ADJ == 0), gathered
+  double cs[kTileBlocks];  //   from the LUT once per tile so the block loop has no global loads
   uint64_t full[2];
   unsigned long long off[2][kTilePkts];
   unsigned hist[2][kMaxLasers];
@@ -764,7 +768,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
   __syncthreads();
 
   const long long in_base = reinterpret_cast<long long>(p.pkts);
-  // stage layout: [masks 1536 B | seg 512 B | packets]
+  // stage layout: [masks 1536 B | seg 512 B | pose rows 3072 B | packets]
   auto issue = [&](int t, int b) {
     const long long first = (long long)p.halo + (long long)t * kTilePkts;
     const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, 0);
@@ -773,10 +777,14 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
     const uint32_t mbytes = (uint32_t)sp.npk * kBlocks * 4u;
     const uint32_t sbytes = (uint32_t)sp.npk * (uint32_t)sizeof(PktSeg);
     fence_proxy_async();
-    mbar_expect_tx(&sh.full[b], bytes + mbytes + sbytes);
+    const uint32_t pbytes = p.pose_valid ? (uint32_t)sp.npk * 96u : 0u;
+    mbar_expect_tx(&sh.full[b], bytes + mbytes + sbytes + pbytes);
     bulk_g2s(st, p.masks + first * kBlocks, mbytes, &sh.full[b]);
     bulk_g2s(st + kMaskBytes, p.pkt_seg + first, sbytes, &sh.full[b]);
-    if (bytes) bulk_g2s(st + kMaskBytes + kSegBytes, reinterpret_cast<const void*>(sp.s0), bytes, &sh.full[b]);
+    if (pbytes) bulk_g2s(st + kMaskBytes + kSegBytes, p.pose_mat + first * 12, pbytes, &sh.full[b]);
+    if (bytes)
+      bulk_g2s(st + kMaskBytes + kSegBytes + kPoseBytes, reinterpret_cast<const void*>(sp.s0), bytes,
+               &sh.full[b]);
   };
 
   unsigned long long next_off = 0;  // threads 0..31: point offset of packet `tid` of the next tile
@@ -815,7 +823,8 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
     uint8_t* stage = stage0 + (size_t)cur * p.stage_bytes;
     const unsigned* s_mask = reinterpret_cast<const unsigned*>(stage);
     const PktSeg* s_seg = reinterpret_cast<const PktSeg*>(stage + kMaskBytes);
-    uint8_t* s_pk = stage + kMaskBytes + kSegBytes;
+    const double* s_pose = reinterpret_cast<const double*>(stage + kMaskBytes + kSegBytes);
+    uint8_t* s_pk = stage + kMaskBytes + kSegBytes + kPoseBytes;
 
     mbar_wait(&sh.full[cur], phase[cur]);
     phase[cur] ^= 1u;
@@ -824,6 +833,16 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
         s_pk[a - sp.s0] = *reinterpret_cast<const uint8_t*>(a);
     }
     __syncthreads();  // tile_id[cur^1], off[cur], hist and the tail bytes are visible
+    if (ADJ == 0) {
+      // sin/cos of every block azimuth of the tile: independent gathers, one round trip
+      const uint8_t* base = s_pk + (sp.a0 - sp.s0);
+      for (int b = tid; b < npk * kBlocks; b += kDecThreads) {
+        const int lp = b / kBlocks, j = b - lp * kBlocks;
+        const unsigned az = ld_smem_u16(base + (size_t)lp * p.stride + 100 * j + 2) % 36000u;
+        sh.sn[b] = __ldg(&p.lut_sin[az]);
+        sh.cs[b] = __ldg(&p.lut_cos[az]);
+      }
+    }
     // point offsets of the next tile: loaded now, parked in a register until the switch
     {
       const int tn = sh.tile_id[cur ^ 1];
@@ -846,6 +865,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
     asm volatile("" : "+l"(xt), "+l"(yt), "+l"(zt), "+l"(tt));
     asm volatile("" : "+l"(at), "+l"(dt), "+l"(it), "+l"(lt));
     const int tile_f0 = s_seg[0].y;
+    if (ADJ == 0) __syncthreads();  // sn / cs are complete
 
     unsigned cnt = 0;  // emitted points of (cnt_frame, cnt_bank) seen by this lane
     int cnt_frame = -1, cnt_bank = 0;
@@ -881,9 +901,8 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
       const unsigned pkt_rel = (unsigned)(sh.off[cur][lp] - tb);
       double M[12];  // [L | t] of this packet, warp-uniform
       if (pose_valid) {
-        const double* mp = p.pose_mat + (first + lp) * 12;
 #pragma unroll
-        for (int q = 0; q < 12; ++q) M[q] = __ldg(&mp[q]);
+        for (int q = 0; q < 12; ++q) M[q] = s_pose[lp * 12 + q];
       }
       int frame = seg.y;
       if (wrapmask == 0 && (frame != cnt_frame)) {
@@ -925,7 +944,15 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
         if (ADJ == 2 && laser_id >= 16) laser_id -= 16;
         const unsigned az = adjusted_azimuth<ADJ>(sh.cfg, rot, azdiff, j, lane);
         double px, py, pz;
-        sensor_point(cal, __ldg(&p.lut_sin[az]), __ldg(&p.lut_cos[az]), dist, px, py, pz);
+        double sA, cA;
+        if (ADJ == 0) {
+          sA = sh.sn[lp * kBlocks + j];
+          cA = sh.cs[lp * kBlocks + j];
+        } else {
+          sA = __ldg(&p.lut_sin[az]);
+          cA = __ldg(&p.lut_cos[az]);
+        }
+        sensor_point(cal, sA, cA, dist, px, py, pz);
         if (pose_valid) {
           // type_defs.h:160-166: row sums left to right, translation last
           const double qx = __dadd_rn(
