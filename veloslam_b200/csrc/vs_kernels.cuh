@@ -71,6 +71,24 @@ __device__ __forceinline__ unsigned ld_smem_u16(const uint8_t* p) {
   return *reinterpret_cast<const unsigned short*>(p);
 }
 
+// Loads through explicit 32-bit shared-window addresses (no generic->shared conversion in the
+// block loop).
+__device__ __forceinline__ unsigned lds_u8(uint32_t a) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned lds_u16(uint32_t a) {
+  unsigned v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+
 // Per-laser calibration row held in registers.
 struct CalRow {
   double cC, sC, dc, cV, sV, vo, ho;
@@ -399,7 +417,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
       r.x = s_in | (int)(wrapmask << 4) | (azdiff << 16);
       r.y = (int)cnt;
       r.z = 0;
-      r.w = 0;
+      r.w = (int)um;
       p.pkt_seg[P] = r;
       const unsigned ium = um & ~((1u << s_in) - 1u);
       if (ium) {
@@ -881,16 +899,72 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
         cnt = 0;
       }
     };
+    // 32-bit shared-window addresses, kept opaque so they stay in registers
+    uint32_t tile_a = smem_u32(tile_smem) + 3u * (unsigned)lane;
+    uint32_t sn_a = smem_u32(&sh.sn[0]);
+    asm volatile("" : "+r"(tile_a), "+r"(sn_a));
+    const unsigned pm = par ? 0xaaau : 0x555u;  // the blocks of this warp
+
+    // one firing block: loads from shared memory, FP64 math, predicated SoA stores
+    auto do_block = [&](const int lp, const int j, const unsigned m, const unsigned boff,
+                        const int off, const int laser_id, const unsigned pkt_rel,
+                        const unsigned tpk, const int azdiff, const uint32_t pk_a,
+                        const double* M) {
+      const uint32_t blk_a = pk_a + 100u * (unsigned)j;
+      const unsigned rot = lds_u16(blk_a + 2u - 3u * (unsigned)lane);
+      const unsigned dist = lds_u8(blk_a + 4u) | (lds_u8(blk_a + 5u) << 8);
+      const unsigned inten = lds_u8(blk_a + 6u);
+      const unsigned az = adjusted_azimuth<ADJ>(sh.cfg, rot, azdiff, j, lane);
+      double sA, cA;
+      if (ADJ == 0) {
+        const uint32_t q = sn_a + 8u * (unsigned)(lp * kBlocks + j);
+        sA = lds_f64(q);
+        cA = lds_f64(q + (uint32_t)(kTileBlocks * 8));
+      } else {
+        sA = __ldg(&p.lut_sin[az]);
+        cA = __ldg(&p.lut_cos[az]);
+      }
+      double px, py, pz;
+      sensor_point(cal, sA, cA, dist, px, py, pz);
+      if (pose_valid) {
+        // type_defs.h:160-166: row sums left to right, translation last
+        const double qx = __dadd_rn(
+            __dadd_rn(__dadd_rn(__dmul_rn(M[0], px), __dmul_rn(M[1], py)), __dmul_rn(M[2], pz)),
+            M[3]);
+        const double qy = __dadd_rn(
+            __dadd_rn(__dadd_rn(__dmul_rn(M[4], px), __dmul_rn(M[5], py)), __dmul_rn(M[6], pz)),
+            M[7]);
+        const double qz = __dadd_rn(
+            __dadd_rn(__dadd_rn(__dmul_rn(M[8], px), __dmul_rn(M[9], py)), __dmul_rn(M[10], pz)),
+            M[11]);
+        px = qx;
+        py = qy;
+        pz = qz;
+      }
+      if ((m >> lane) & 1u) {
+        const unsigned o = pkt_rel + boff + __popc(m & lt_mask);
+        xt[o] = (float)px;
+        yt[o] = (float)py;
+        zt[o] = (float)pz;
+        tt[o] = tpk + (ADJ != 0 ? (uint32_t)sh.cfg.tadj[j][lane] : 0u);
+        at[o] = (uint16_t)az;
+        dt[o] = (uint16_t)dist;
+        it[o] = (uint8_t)inten;
+        lt[o] = (uint8_t)laser_id;
+        ++cnt;
+      }
+    };
 
 #pragma unroll 1
     for (int lp = pk0; lp < npk; lp += 4) {
       const PktSeg seg = s_seg[lp];
       const int wrapmask = (seg.x >> 4) & 0xfff;
       const int azdiff = (seg.x >> 16) & 0xffff;
-      const uint8_t* pk = tile_smem + (size_t)lp * p.stride;
+      const unsigned um = (unsigned)seg.w & 0xfffu;
+      const uint32_t pk_a = tile_a + (unsigned)lp * (unsigned)p.stride;
       const unsigned tpk = (unsigned)seg.z;
       // exclusive prefix of the packet's 12 block counts (lanes 0..11)
-      unsigned mymask = (lane < kBlocks) ? s_mask[lp * kBlocks + lane] : 0u;
+      const unsigned mymask = (lane < kBlocks) ? s_mask[lp * kBlocks + lane] : 0u;
       unsigned pre = __popc(mymask);
 #pragma unroll
       for (int o = 1; o < 16; o <<= 1) {
@@ -904,22 +978,38 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
 #pragma unroll
         for (int q = 0; q < 12; ++q) M[q] = s_pose[lp * 12 + q];
       }
-      int frame = seg.y;
-      if (wrapmask == 0 && (frame != cnt_frame)) {
-        flush_counts();
-        cnt_frame = frame;
-      }
+      const unsigned ub = um & pm;
+      if (wrapmask == 0 && (ub == 0u || ub == pm)) {
+        // fast path (every packet of a real stream but the ~0.3 % that hold a wrap): one
+        // frame, one laser bank for all blocks of this warp
+        const int off = ub ? 32 : 0;
+        if (seg.y != cnt_frame || off != cnt_bank) {
+          flush_counts();
+          cnt_frame = seg.y;
+          cnt_bank = off;
+        }
+        if (off != cal_bank) {
+          load_cal(sh.cfg, lane + off, cal);
+          cal_bank = off;
+        }
+        int laser_id = lane + off;
+        if (ADJ == 2 && laser_id >= 16) laser_id -= 16;
 #pragma unroll 2
-      for (int i = 0; i < 6; ++i) {
-        const int j = par + 2 * i;
-        const unsigned m = __shfl_sync(0xffffffffu, mymask, j);
-        const unsigned boff = __shfl_sync(0xffffffffu, pre, j);
-        if (m == 0) continue;
-        const uint8_t* blk = pk + 100 * j;
-        const int off = (ld_smem_u16(blk) == 0xeeffu) ? 0 : 32;
-        if (wrapmask) {
-          // rare: a frame boundary inside the packet
-          frame = seg.y + __popc(wrapmask & ((2 << j) - 1));
+        for (int i = 0; i < 6; ++i) {
+          const int j = par + 2 * i;
+          const unsigned m = __shfl_sync(0xffffffffu, mymask, j);
+          const unsigned boff = __shfl_sync(0xffffffffu, pre, j);
+          if (m != 0u) do_block(lp, j, m, boff, off, laser_id, pkt_rel, tpk, azdiff, pk_a, M);
+        }
+      } else {
+#pragma unroll 1
+        for (int i = 0; i < 6; ++i) {
+          const int j = par + 2 * i;
+          const unsigned m = __shfl_sync(0xffffffffu, mymask, j);
+          const unsigned boff = __shfl_sync(0xffffffffu, pre, j);
+          if (m == 0u) continue;
+          const int off = ((um >> j) & 1u) ? 32 : 0;
+          const int frame = seg.y + __popc(wrapmask & ((2 << j) - 1));
           if (p.mode == 1 && pose_valid && ((wrapmask & ((2 << j) - 1)) != 0)) {
             // offline: blocks at/after the packet's first wrap start a frame whose origin is
             // this very packet -> zero translation
@@ -927,58 +1017,18 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
             M[7] = 0.0;
             M[11] = 0.0;
           }
-        }
-        if (frame != cnt_frame || off != cnt_bank) {
-          flush_counts();
-          cnt_frame = frame;
-          cnt_bank = off;
-        }
-        if (off != cal_bank) {
-          load_cal(sh.cfg, lane + off, cal);
-          cal_bank = off;
-        }
-        const unsigned rot = ld_smem_u16(blk + 2);
-        const unsigned dist = blk[4 + 3 * lane] | (blk[5 + 3 * lane] << 8);
-        const unsigned inten = blk[6 + 3 * lane];
-        int laser_id = lane + off;
-        if (ADJ == 2 && laser_id >= 16) laser_id -= 16;
-        const unsigned az = adjusted_azimuth<ADJ>(sh.cfg, rot, azdiff, j, lane);
-        double px, py, pz;
-        double sA, cA;
-        if (ADJ == 0) {
-          sA = sh.sn[lp * kBlocks + j];
-          cA = sh.cs[lp * kBlocks + j];
-        } else {
-          sA = __ldg(&p.lut_sin[az]);
-          cA = __ldg(&p.lut_cos[az]);
-        }
-        sensor_point(cal, sA, cA, dist, px, py, pz);
-        if (pose_valid) {
-          // type_defs.h:160-166: row sums left to right, translation last
-          const double qx = __dadd_rn(
-              __dadd_rn(__dadd_rn(__dmul_rn(M[0], px), __dmul_rn(M[1], py)), __dmul_rn(M[2], pz)),
-              M[3]);
-          const double qy = __dadd_rn(
-              __dadd_rn(__dadd_rn(__dmul_rn(M[4], px), __dmul_rn(M[5], py)), __dmul_rn(M[6], pz)),
-              M[7]);
-          const double qz = __dadd_rn(
-              __dadd_rn(__dadd_rn(__dmul_rn(M[8], px), __dmul_rn(M[9], py)), __dmul_rn(M[10], pz)),
-              M[11]);
-          px = qx;
-          py = qy;
-          pz = qz;
-        }
-        if ((m >> lane) & 1u) {
-          const unsigned o = pkt_rel + boff + __popc(m & lt_mask);
-          xt[o] = (float)px;
-          yt[o] = (float)py;
-          zt[o] = (float)pz;
-          tt[o] = tpk + (ADJ != 0 ? (uint32_t)sh.cfg.tadj[j][lane] : 0u);
-          at[o] = (uint16_t)az;
-          dt[o] = (uint16_t)dist;
-          it[o] = (uint8_t)inten;
-          lt[o] = (uint8_t)laser_id;
-          ++cnt;
+          if (frame != cnt_frame || off != cnt_bank) {
+            flush_counts();
+            cnt_frame = frame;
+            cnt_bank = off;
+          }
+          if (off != cal_bank) {
+            load_cal(sh.cfg, lane + off, cal);
+            cal_bank = off;
+          }
+          int laser_id = lane + off;
+          if (ADJ == 2 && laser_id >= 16) laser_id -= 16;
+          do_block(lp, j, m, boff, off, laser_id, pkt_rel, tpk, azdiff, pk_a, M);
         }
       }
     }
