@@ -423,14 +423,13 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     sp.carry_last_az = cin.last_azimuth;
     sp.carry_skip = cin.firing_skip;
     sp.n_tiles = (int)scan_tiles;
-    sp.stage_bytes = (int)align_up((size_t)kTilePkts * stride + kLead + 48, 128);
+    sp.stage_bytes = (int)align_up((size_t)(kTilePkts + 1) * stride + kLead + 48, 128);
     sp.pkt_seg = s.d_seg;
     sp.masks = s.d_masks;
     sp.st_map = s.d_st_map;
     sp.tile_counter = s.d_counters + 0;
     sp.hdr = s.d_hdr;
-    const size_t smem = align_up(sizeof(ScanShared), 128) + align_up(sizeof(DevConfig), 128) +
-                        2 * (size_t)sp.stage_bytes;
+    const size_t smem = align_up(sizeof(ScanShared), 128) + (size_t)sp.stage_bytes;
     int rc;
     if (adj == 0)
       rc = crop ? launch_scan<0, true>(ctx, s, sp, smem) : launch_scan<0, false>(ctx, s, sp, smem);

@@ -162,70 +162,80 @@ struct ScanParams {
 constexpr int kScanThreads = 256;
 
 struct ScanShared {
-  uint64_t full[2];
+  uint64_t full;
   unsigned nz[kTileBlocks];  // raw "distance != 0" (or crop-tested) bits per block
   int skip[kTilePkts];
-  int tile_id[2];
+  int tile_id;
 };
 
+// 12-entry skip map of one packet from its block azimuths and the azimuth that precedes it.
+__device__ __forceinline__ unsigned long long packet_skip_map(const int az[12], int prev11,
+                                                              unsigned& wm, unsigned& em) {
+  wm = 0;
+  em = 0;
+#pragma unroll
+  for (int j = 1; j < 12; ++j)
+    if (az[j] < az[j - 1]) wm |= 1u << j;
+#pragma unroll
+  for (int j = 0; j < 12; ++j)
+    if (az[j] < prev11) em |= 1u << j;
+  unsigned long long m = 0;
+#pragma unroll
+  for (int s = 0; s < 12; ++s) {
+    const unsigned hi = wm & ~((2u << s) - 1u);
+    const int out = hi ? (31 - __clz(hi)) : (((em >> s) & 1u) ? s : 0);
+    m |= (unsigned long long)out << (4 * s);
+  }
+  return m;
+}
+
+// One stage per CTA, 4-5 CTAs per SM: the TMA latency of one CTA is hidden by the others.
+// The tile's lead bytes hold the whole previous packet, so the firingSkip entering the tile is
+// known locally whenever that packet's skip map is constant (always, on sensor data); only
+// otherwise does the tile fall back to the look-back over the published tile maps.
 template <int ADJ, bool CROP>
 __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   ScanShared& sh = *reinterpret_cast<ScanShared*>(smem_raw);
-  DevConfig* cfg_s = reinterpret_cast<DevConfig*>(smem_raw + ((sizeof(ScanShared) + 127) & ~127));
-  uint8_t* stage0 = reinterpret_cast<uint8_t*>(cfg_s) + ((sizeof(DevConfig) + 127) & ~127);
+  uint8_t* stage = smem_raw + ((sizeof(ScanShared) + 127) & ~127);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const DevConfig& cfg = *p.cfg;  // few uniform fields; the CROP variant reads the rows too
 
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.cfg);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(cfg_s);
-    for (int i = tid; i < (int)(sizeof(DevConfig) / 4); i += kScanThreads) dst[i] = __ldg(&src[i]);
-  }
   if (tid == 0) {
-    mbar_init(&sh.full[0], 1);
-    mbar_init(&sh.full[1], 1);
+    mbar_init(&sh.full, 1);
     fence_mbar_init();
   }
   __syncthreads();
-  const DevConfig& cfg = *cfg_s;
   const long long in_base = reinterpret_cast<long long>(p.pkts);
+  const int lead = (int)p.stride + kLead;
+  const unsigned sel_lo = cfg.sel_lo, sel_hi = cfg.sel_hi;
+  const int pskip = cfg.points_skip;
 
-  auto issue = [&](int t, int b) {
-    const long long first = (long long)t * kTilePkts;
-    const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, kLead);
-    const uint32_t bytes = (uint32_t)(sp.s1 - sp.s0);
-    fence_proxy_async();
-    if (bytes) {
-      mbar_expect_tx(&sh.full[b], bytes);
-      bulk_g2s(stage0 + (size_t)b * p.stage_bytes, reinterpret_cast<const void*>(sp.s0), bytes,
-               &sh.full[b]);
-    } else {
-      mbar_arrive(&sh.full[b]);
-    }
-  };
-  if (tid == 0) {
-    const int t = atomicAdd(p.tile_counter, 1);
-    sh.tile_id[0] = t;
-    if (t < p.n_tiles) issue(t, 0);
-  }
-  __syncthreads();
-
-  uint32_t phase[2] = {0u, 0u};
-  int cur = 0;
+  uint32_t phase = 0u;
   while (true) {
-    const int tile = sh.tile_id[cur];
-    if (tile >= p.n_tiles) break;
     if (tid == 0) {
-      const int tn = atomicAdd(p.tile_counter, 1);
-      sh.tile_id[cur ^ 1] = tn;
-      if (tn < p.n_tiles) issue(tn, cur ^ 1);
+      const int t = atomicAdd(p.tile_counter, 1);
+      sh.tile_id = t;
+      if (t < p.n_tiles) {
+        const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, (long long)t * kTilePkts, lead);
+        const uint32_t bytes = (uint32_t)(sp.s1 - sp.s0);
+        fence_proxy_async();
+        if (bytes) {
+          mbar_expect_tx(&sh.full, bytes);
+          bulk_g2s(stage, reinterpret_cast<const void*>(sp.s0), bytes, &sh.full);
+        } else {
+          mbar_arrive(&sh.full);
+        }
+      }
     }
+    __syncthreads();
+    const int tile = sh.tile_id;
+    if (tile >= p.n_tiles) break;
     const long long first = (long long)tile * kTilePkts;
-    const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, kLead);
+    const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, lead);
     const int npk = sp.npk;
-    uint8_t* stage = stage0 + (size_t)cur * p.stage_bytes;
-    mbar_wait(&sh.full[cur], phase[cur]);
-    phase[cur] ^= 1u;
+    mbar_wait(&sh.full, phase);
+    phase ^= 1u;
     if (sp.s1 < sp.a1) {
       for (long long a = sp.s1 + tid; a < sp.a1; a += kScanThreads)
         stage[a - sp.s0] = *reinterpret_cast<const uint8_t*>(a);
@@ -233,13 +243,15 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
     }
     const uint8_t* tile_smem = stage + (sp.a0 - sp.s0);
 
-    // ---- phase A (warp 0, lane == packet): headers, skip maps, look-back -------------------
+    // ---- phase A (warp 0, lane == packet): headers, skip maps, firingSkip per packet --------
     unsigned wm = 0, em = 0, um = 0, wrapmask = 0;
     int azdiff = 0, s_in = 0, az11 = 0;
     unsigned long long m = kMapIdentity;
     if (warp == 0) {
       const bool live = lane < npk;
       int az[12];
+#pragma unroll
+      for (int j = 0; j < 12; ++j) az[j] = 0;
       if (live) {
         const uint8_t* pk = tile_smem + (size_t)lane * p.stride;
 #pragma unroll
@@ -254,12 +266,8 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
       if (lane == 0)
         prev11 = (first > 0) ? (int)ld_smem_u16(tile_smem - p.stride + 1102) : p.carry_last_az;
       if (live) {
-#pragma unroll
-        for (int j = 1; j < 12; ++j)
-          if (az[j] < az[j - 1]) wm |= 1u << j;
-#pragma unroll
-        for (int j = 0; j < 12; ++j)
-          if (az[j] < prev11) em |= 1u << j;
+        m = packet_skip_map(az, prev11, wm, em);
+        if (p.mode != 0) m = 0;
         if (ADJ != 0) {
           // azimuthDiff: element of rank 6 among the 11 modular deltas (nth_element, :1016-1026)
           int d[11];
@@ -273,23 +281,20 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
             if (rank == 6) azdiff = d[i];
           }
         }
-        m = 0;
-        if (p.mode == 0) {
-#pragma unroll
-          for (int s = 0; s < 12; ++s) {
-            const unsigned hi = wm & ~((2u << s) - 1u);
-            const int out = hi ? (31 - __clz(hi)) : (((em >> s) & 1u) ? s : 0);
-            m |= (unsigned long long)out << (4 * s);
-          }
-        }
         if (first + lane < p.halo && map_is_const(m))
           atomicMin(&p.hdr->first_const_pkt, (int)(first + lane));
       }
+      // inclusive scan of the maps; trivial when no packet of the tile can skip
       unsigned long long inc = m;
+      const bool all_zero = __all_sync(0xffffffffu, m == 0ull || !live);
+      if (!all_zero) {
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long prev = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc = map_compose(prev, inc);
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned long long prev = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc = map_compose(prev, inc);
+        }
+      } else if (!live) {
+        inc = 0ull;  // dead lanes follow a constant-0 packet
       }
       const unsigned long long agg = __shfl_sync(0xffffffffu, inc, 31);
       int skip_tile = 0;
@@ -298,25 +303,45 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
           skip_tile = p.carry_skip;
         } else {
           st_release_u64(&p.st_map[tile], kFlagAgg | agg);
-          unsigned long long acc = kMapIdentity;  // maps of tiles (idx, tile) composed
-          int idx = tile - 1;
-          while (true) {
-            unsigned long long v;
-            do {
-              v = ld_acquire_u64(&p.st_map[idx]);
-            } while ((v >> 62) == 0);
-            if ((v >> 62) == 2) {
-              skip_tile = map_apply(acc, (int)(v & 15ull));
-              break;
+          // the previous packet's own map, from the lead bytes
+          bool known = false;
+          if (p.mode != 0) {
+            known = true;
+            skip_tile = 0;
+          } else {
+            int paz[12];
+            const uint8_t* pp = tile_smem - p.stride;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) paz[j] = (int)ld_smem_u16(pp + 100 * j + 2);
+            const int pprev = (first > 1) ? (int)ld_smem_u16(pp - p.stride + 1102) : p.carry_last_az;
+            unsigned w2, e2;
+            const unsigned long long pmap = packet_skip_map(paz, pprev, w2, e2);
+            if (map_is_const(pmap)) {
+              known = true;
+              skip_tile = (int)(pmap & 15ull);
             }
-            acc = map_compose(v & kPayloadMask, acc);
-            if (map_is_const(acc)) {
-              skip_tile = (int)(acc & 15ull);
-              break;
-            }
-            if (--idx < 0) {
-              skip_tile = map_apply(acc, p.carry_skip);
-              break;
+          }
+          if (!known) {
+            unsigned long long acc = kMapIdentity;  // maps of tiles (idx, tile) composed
+            int idx = tile - 1;
+            while (true) {
+              unsigned long long v;
+              do {
+                v = ld_acquire_u64(&p.st_map[idx]);
+              } while ((v >> 62) == 0);
+              if ((v >> 62) == 2) {
+                skip_tile = map_apply(acc, (int)(v & 15ull));
+                break;
+              }
+              acc = map_compose(v & kPayloadMask, acc);
+              if (map_is_const(acc)) {
+                skip_tile = (int)(acc & 15ull);
+                break;
+              }
+              if (--idx < 0) {
+                skip_tile = map_apply(acc, p.carry_skip);
+                break;
+              }
             }
           }
         }
@@ -333,7 +358,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
     // ---- phase B1: which return slots of each block could be emitted ------------------------
     if (!CROP) {
       // lane per block: scan the 32 distance fields of a block with 16-bit loads (the 100-byte
-      // block stride makes the lanes of a warp hit distinct banks)
+      // block stride spreads the lanes of a warp over the banks)
       for (int b = tid; b < kTileBlocks; b += kScanThreads) {
         const int lp = b / kBlocks, j = b - lp * kBlocks;
         unsigned bits = 0;
@@ -370,7 +395,8 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
             int d[11];
 #pragma unroll
             for (int i = 0; i < 11; ++i)
-              d[i] = (36000 + (int)ld_smem_u16(pk + 100 * (i + 1) + 2) - (int)ld_smem_u16(pk + 100 * i + 2)) % 36000;
+              d[i] = (36000 + (int)ld_smem_u16(pk + 100 * (i + 1) + 2) -
+                      (int)ld_smem_u16(pk + 100 * i + 2)) % 36000;
 #pragma unroll
             for (int i = 0; i < 11; ++i) {
               int rank = 0;
@@ -380,7 +406,13 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
             }
           }
           CalRow c;
-          load_cal(cfg, lane + off, c);
+          c.cC = __ldg(&cfg.cal[0][lane + off]);
+          c.sC = __ldg(&cfg.cal[1][lane + off]);
+          c.dc = __ldg(&cfg.cal[2][lane + off]);
+          c.cV = __ldg(&cfg.cal[3][lane + off]);
+          c.sV = __ldg(&cfg.cal[4][lane + off]);
+          c.vo = __ldg(&cfg.cal[5][lane + off]);
+          c.ho = __ldg(&cfg.cal[6][lane + off]);
           const unsigned az = adjusted_azimuth<ADJ>(cfg, ld_smem_u16(blk + 2), ad, j, lane);
           double px, py, pz;
           sensor_point(c, __ldg(&p.lut_sin[az]), __ldg(&p.lut_cos[az]), dist, px, py, pz);
@@ -394,14 +426,13 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
     __syncthreads();
 
     // ---- phase B2: final masks (iterated, gated, selected lasers) ---------------------------
-    const int pskip = cfg.points_skip;
     for (int b = tid; b < kTileBlocks; b += kScanThreads) {
       const int lp = b / kBlocks, j = b - lp * kBlocks;
       if (lp < npk) {
         unsigned mk = 0;
         if (j >= sh.skip[lp] && (pskip == 0 || (j % (pskip + 1)) == 0)) {
           const bool upper = ld_smem_u16(tile_smem + (size_t)lp * p.stride + 100 * j) != 0xeeffu;
-          mk = sh.nz[b] & (upper ? cfg.sel_hi : cfg.sel_lo);
+          mk = sh.nz[b] & (upper ? sel_hi : sel_lo);
         }
         sh.nz[b] = mk;
         p.masks[(first + lp) * kBlocks + j] = mk;
@@ -432,8 +463,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
         p.hdr->firing_skip_out = (p.mode == 0) ? map_apply(m, s_in) : 0;
       }
     }
-    __syncthreads();  // stage `cur`, nz and skip are free again
-    cur ^= 1;
+    __syncthreads();  // stage, nz, skip and tile_id are free again
   }
 }
 
