@@ -209,6 +209,8 @@ VS_API void vs_host_free(void* p);
 /* The CUDA stream the context launches on (cudaStream_t), for callers that time or order
  * work against it. */
 VS_API void* vs_stream(vs_ctx* ctx);
+/* Each result slot launches on its own stream (ticket t uses slot t % n_slots). */
+VS_API void* vs_slot_stream(vs_ctx* ctx, int slot);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ STATUS = {0: "VS_OK", 1: "VS_ERR_INVALID_ARG", 2: "VS_ERR_NOT_CALIBRATED", 3: "V
 EXPORTS = ["vs_version", "vs_create", "vs_destroy", "vs_last_error", "vs_set_calibration",
            "vs_set_filters", "vs_set_poses", "vs_interpolate", "vs_carry_init", "vs_submit",
            "vs_wait", "vs_fetch_points", "vs_read_frame_information", "vs_host_alloc",
-           "vs_host_free", "vs_stream"]
+           "vs_host_free", "vs_stream", "vs_slot_stream"]
 
 
 class LaserCorr(C.Structure):
@@ -114,6 +114,8 @@ def load_library():
                                             C.POINTER(i32)]
     L.vs_stream.restype = vp
     L.vs_stream.argtypes = [vp]
+    L.vs_slot_stream.restype = vp
+    L.vs_slot_stream.argtypes = [vp, C.c_int]
     _lib = L
     return L
 
@@ -168,8 +170,8 @@ class BatchResult:
         self.n_closed = int(r.n_closed)
         self.frames = [FrameView(r.frames[i]) for i in range(r.n_frames)] if frames else None
         # the same rows as one structured array (copied out of the context-owned buffer)
-        self.frame_table = np.ctypeslib.as_array(r.frames, shape=(r.n_frames,)).copy() \
-            if r.n_frames > 0 else np.zeros(0, dtype=FRAME_TABLE_DTYPE)
+        self._raw_frames = (r.frames, r.n_frames)
+        self._frame_table = None
         self.carry_out = Carry.from_buffer_copy(r.carry_out)
         self.t_base_us = int(r.t_base_us)
         self.first_upper_block = int(r.first_upper_block)
@@ -178,6 +180,16 @@ class BatchResult:
         self.n_kernel_launches = int(r.n_kernel_launches)
         self.device_ptrs = {k: getattr(r, k) for k in
                             ("x", "y", "z", "intensity", "laser", "azimuth", "distance", "t_us")}
+
+    @property
+    def frame_table(self):
+        """vs_frame rows as one structured array (copied out of the context-owned buffer; call
+        before the slot's next submit)."""
+        if self._frame_table is None:
+            ptr, n = self._raw_frames
+            self._frame_table = np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n > 0 else \
+                np.zeros(0, dtype=FRAME_TABLE_DTYPE)
+        return self._frame_table
 
     def fetch(self, first=0, count=None, columns=None):
         """Copy point columns to host numpy arrays."""
@@ -306,5 +318,5 @@ class Context:
             _ptr(ts), cap, C.byref(nf)))
         return sp[:nf.value].copy(), sk[:nf.value].copy(), ts[:nf.value].copy()
 
-    def stream(self):
-        return self._L.vs_stream(self._h)
+    def stream(self, slot=0):
+        return self._L.vs_slot_stream(self._h, slot)

@@ -23,7 +23,7 @@ using namespace vsd;
 
 namespace {
 
-constexpr int kEagerFrames = 64;  // frame-table rows copied back with the header
+constexpr int kEagerFrames = 64;  // minimum frame-table rows copied back with the header
 
 struct HostFrameRow {  // pinned mirror of the per-frame device tables
   std::vector<long long> first;
@@ -78,6 +78,7 @@ struct Slot {
   int64_t t_base = 0;
   vs_carry carry_in;
   int n_launches = 0;
+  int64_t eager_rows = 0;
   bool index_only = false;
   std::vector<vs_frame> frames;
   vs_result result;
@@ -533,9 +534,11 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
 
   VS_CUDA(cudaMemcpyAsync(s.h_hdr, s.d_hdr, sizeof(BatchHeader), cudaMemcpyDeviceToHost, s.stream));
   {
-    int rc = ensure_host_frames(ctx, s, kEagerFrames);
+    // rows copied back right away: enough for ~3 frames per sensor rotation of the batch
+    s.eager_rows = std::min<int64_t>(frames_possible, std::max<int64_t>(kEagerFrames, n / 100 + 8));
+    int rc = ensure_host_frames(ctx, s, (size_t)s.eager_rows);
     if (rc != VS_OK) return rc;
-    rc = copy_frame_rows(ctx, s, (size_t)std::min<int64_t>(kEagerFrames, frames_possible));
+    rc = copy_frame_rows(ctx, s, (size_t)s.eager_rows);
     if (rc != VS_OK) return rc;
   }
   VS_CUDA(cudaEventRecord(s.ev_done, s.stream));
@@ -562,7 +565,7 @@ int finish_batch(vs_ctx* ctx, Slot& s) {
   }
   const int W = h.total_wraps;
   const int64_t frames_possible = std::min<int64_t>(ctx->frame_cap, 12 * s.n + 1);
-  if (W + 1 > kEagerFrames) {
+  if (W + 1 > s.eager_rows) {
     int rc = ensure_host_frames(ctx, s, (size_t)W + 1);
     if (rc != VS_OK) return rc;
     rc = copy_frame_rows(ctx, s, (size_t)std::min<int64_t>(W + 1, frames_possible));
@@ -1062,5 +1065,8 @@ void vs_host_free(void* p) {
 }
 
 void* vs_stream(vs_ctx* ctx) { return ctx ? (void*)ctx->slots[0].stream : nullptr; }
+void* vs_slot_stream(vs_ctx* ctx, int slot) {
+  return (ctx && slot >= 0 && slot < ctx->n_slots) ? (void*)ctx->slots[slot].stream : nullptr;
+}
 
 }  // extern "C"
