@@ -83,6 +83,37 @@ __device__ __forceinline__ unsigned lds_u16(uint32_t a) {
   asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ unsigned lds_u32(uint32_t a) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int4 lds_v4(uint32_t a) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(a));
+  return v;
+}
+// Streaming stores: explicit global space (the column pointers are kept opaque to pin them in
+// registers, which would otherwise degrade the stores to generic ST).
+__device__ __forceinline__ void stg_f32(float* p, float v) {
+  asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void stg_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stg_u16(uint16_t* p, unsigned v) {
+  asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void stg_u8(uint8_t* p, unsigned v) {
+  asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ double lds_f64(uint32_t a) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
@@ -869,9 +900,10 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
     const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, 0);
     const int npk = sp.npk;
     uint8_t* stage = stage0 + (size_t)cur * p.stage_bytes;
-    const unsigned* s_mask = reinterpret_cast<const unsigned*>(stage);
-    const PktSeg* s_seg = reinterpret_cast<const PktSeg*>(stage + kMaskBytes);
-    const double* s_pose = reinterpret_cast<const double*>(stage + kMaskBytes + kSegBytes);
+    const uint32_t mask_a = smem_u32(stage);
+    const uint32_t seg_a = mask_a + kMaskBytes;
+    const uint32_t pose_a = seg_a + kSegBytes;
+    const uint32_t off_a = smem_u32(&sh.off[cur][0]);
     uint8_t* s_pk = stage + kMaskBytes + kSegBytes + kPoseBytes;
 
     mbar_wait(&sh.full[cur], phase[cur]);
@@ -900,7 +932,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
       }
     }
     const uint8_t* tile_smem = s_pk + (sp.a0 - sp.s0);
-    const unsigned long long tb = sh.off[cur][0];
+    const unsigned long long tb = lds_u64(off_a);
     // per-tile column pointers, kept opaque so every store is base + 32-bit index
     float* xt = p.x + tb;
     float* yt = p.y + tb;
@@ -912,7 +944,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
     uint8_t* lt = p.laser + tb;
     asm volatile("" : "+l"(xt), "+l"(yt), "+l"(zt), "+l"(tt));
     asm volatile("" : "+l"(at), "+l"(dt), "+l"(it), "+l"(lt));
-    const int tile_f0 = s_seg[0].y;
+    const int tile_f0 = lds_v4(seg_a).y;
     if (ADJ == 0) __syncthreads();  // sn / cs are complete
 
     unsigned cnt = 0;  // emitted points of (cnt_frame, cnt_bank) seen by this lane
@@ -973,28 +1005,29 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
       }
       if ((m >> lane) & 1u) {
         const unsigned o = pkt_rel + boff + __popc(m & lt_mask);
-        xt[o] = (float)px;
-        yt[o] = (float)py;
-        zt[o] = (float)pz;
-        tt[o] = tpk + (ADJ != 0 ? (uint32_t)sh.cfg.tadj[j][lane] : 0u);
-        at[o] = (uint16_t)az;
-        dt[o] = (uint16_t)dist;
-        it[o] = (uint8_t)inten;
-        lt[o] = (uint8_t)laser_id;
+        stg_f32(xt + o, (float)px);
+        stg_f32(yt + o, (float)py);
+        stg_f32(zt + o, (float)pz);
+        stg_u32(tt + o, tpk + (ADJ != 0 ? (uint32_t)sh.cfg.tadj[j][lane] : 0u));
+        stg_u16(at + o, az);
+        stg_u16(dt + o, dist);
+        stg_u8(it + o, inten);
+        stg_u8(lt + o, (unsigned)laser_id);
         ++cnt;
       }
     };
 
 #pragma unroll 1
     for (int lp = pk0; lp < npk; lp += 4) {
-      const PktSeg seg = s_seg[lp];
+      const PktSeg seg = lds_v4(seg_a + 16u * (unsigned)lp);
       const int wrapmask = (seg.x >> 4) & 0xfff;
       const int azdiff = (seg.x >> 16) & 0xffff;
       const unsigned um = (unsigned)seg.w & 0xfffu;
       const uint32_t pk_a = tile_a + (unsigned)lp * (unsigned)p.stride;
       const unsigned tpk = (unsigned)seg.z;
       // exclusive prefix of the packet's 12 block counts (lanes 0..11)
-      const unsigned mymask = (lane < kBlocks) ? s_mask[lp * kBlocks + lane] : 0u;
+      const unsigned mymask =
+          (lane < kBlocks) ? lds_u32(mask_a + 4u * (unsigned)(lp * kBlocks + lane)) : 0u;
       unsigned pre = __popc(mymask);
 #pragma unroll
       for (int o = 1; o < 16; o <<= 1) {
@@ -1002,11 +1035,11 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
         if (lane >= o) pre += v;
       }
       pre -= __popc(mymask);
-      const unsigned pkt_rel = (unsigned)(sh.off[cur][lp] - tb);
+      const unsigned pkt_rel = (unsigned)(lds_u64(off_a + 8u * (unsigned)lp) - tb);
       double M[12];  // [L | t] of this packet, warp-uniform
       if (pose_valid) {
 #pragma unroll
-        for (int q = 0; q < 12; ++q) M[q] = s_pose[lp * 12 + q];
+        for (int q = 0; q < 12; ++q) M[q] = lds_f64(pose_a + 8u * (unsigned)(lp * 12 + q));
       }
       const unsigned ub = um & pm;
       if (wrapmask == 0 && (ub == 0u || ub == pm)) {
