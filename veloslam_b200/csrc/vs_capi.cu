@@ -39,7 +39,7 @@ struct Slot {
   long long* d_time = nullptr;
   const long long* d_time_used = nullptr;  // times of the batch in flight (may be caller-owned)
   PktSeg* d_seg = nullptr;
-  unsigned* d_masks = nullptr;            // 12 emission masks per packet (k_scan -> k_decode)
+  BlkRec* d_recs = nullptr;               // 12 block records per packet (k_scan -> k_decode)
   unsigned long long* d_pkt_off = nullptr;  // first emitted point of each packet (k_pose)
   double* d_pose_mat = nullptr;
   float *d_x = nullptr, *d_y = nullptr, *d_z = nullptr;
@@ -169,7 +169,7 @@ void free_slot(Slot& s) {
   cudaFree(s.d_in);
   cudaFree(s.d_time);
   cudaFree(s.d_seg);
-  cudaFree(s.d_masks);
+  cudaFree(s.d_recs);
   cudaFree(s.d_pkt_off);
   cudaFree(s.d_pose_mat);
   cudaFree(s.d_x);
@@ -217,8 +217,8 @@ int alloc_slot(vs_ctx* ctx, Slot& s) {
   VS_CUDA(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
   VS_CUDA(cudaMalloc(&s.d_time, np * sizeof(long long)));
   VS_CUDA(cudaMalloc(&s.d_seg, np * sizeof(PktSeg)));
-  VS_CUDA(cudaMalloc(&s.d_masks, np * kBlocks * sizeof(unsigned)));
-  VS_CUDA(cudaMalloc(&s.d_pkt_off, np * sizeof(unsigned long long)));
+  VS_CUDA(cudaMalloc(&s.d_recs, np * kBlocks * sizeof(BlkRec)));
+  VS_CUDA(cudaMalloc(&s.d_pkt_off, (np + 2) * sizeof(unsigned long long)));  // k_decode copies even-aligned pairs
   VS_CUDA(cudaMalloc(&s.d_pose_mat, np * 12 * sizeof(double)));
   VS_CUDA(cudaMalloc(&s.d_x, pts * sizeof(float)));
   VS_CUDA(cudaMalloc(&s.d_y, pts * sizeof(float)));
@@ -299,7 +299,8 @@ int copy_frame_rows(vs_ctx* ctx, Slot& s, size_t n_rows) {
 }
 
 template <int ADJ>
-int launch_decode(vs_ctx* ctx, Slot& s, const DecParams& dp, size_t smem) {
+int launch_decode(vs_ctx* ctx, Slot& s, const DecParams& dp) {
+  const size_t smem = (size_t)DecLayout<ADJ>::kStages + kDecStages * (size_t)dp.stage_bytes;
   static size_t cached_smem = 0;  // one process drives one GPU: cache per instantiation
   static int per_sm = 0;
   if (cached_smem != smem) {
@@ -374,7 +375,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
   const int64_t scan_tiles = (n + kTilePkts - 1) / kTilePkts;
   const int64_t pose_tiles = (n + kPoseThreads - 1) / kPoseThreads;
   const int64_t n_dec = n - halo;
-  const int64_t dec_tiles = (n_dec + kTilePkts - 1) / kTilePkts;
+  const int64_t dec_tiles = (n_dec + kDecTile - 1) / kDecTile;
   const int64_t frames_possible = std::min<int64_t>(ctx->frame_cap, 12 * n + 1);
   {
     // zero only what this batch can touch
@@ -426,7 +427,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     sp.n_tiles = (int)scan_tiles;
     sp.stage_bytes = (int)align_up((size_t)(kTilePkts + 1) * stride + kLead + 48, 128);
     sp.pkt_seg = s.d_seg;
-    sp.masks = s.d_masks;
+    sp.recs = s.d_recs;
     sp.st_map = s.d_st_map;
     sp.tile_counter = s.d_counters + 0;
     sp.hdr = s.d_hdr;
@@ -445,7 +446,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     PoseParams pp;
     pp.pkt_time = d_time;
     pp.pkt_seg = s.d_seg;
-    pp.masks = s.d_masks;
+    pp.recs = s.d_recs;
     pp.pkt_off = s.d_pkt_off;
     pp.st_wrap = s.d_st_wrap;
     pp.st_cnt = s.d_st_cnt;
@@ -474,7 +475,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     dp.stride = stride;
     dp.total_bytes = payload_bytes;
     dp.pkt_seg = s.d_seg;
-    dp.masks = s.d_masks;
+    dp.recs = s.d_recs;
     dp.pkt_off = s.d_pkt_off;
     dp.pose_mat = s.d_pose_mat;
     dp.lut_sin = ctx->d_lut_sin;
@@ -485,7 +486,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     dp.mode = mode;
     dp.pose_valid = pose_valid ? 1 : 0;
     dp.n_tiles = (int)dec_tiles;
-    dp.stage_bytes = (int)align_up((size_t)kMaskBytes + kSegBytes + kPoseBytes + (size_t)kTilePkts * stride + 48, 128);
+    dp.stage_bytes = (int)align_up((size_t)kDPkts + (size_t)kDecTile * stride + 48, 128);
     dp.x = s.d_x;
     dp.y = s.d_y;
     dp.z = s.d_z;
@@ -494,19 +495,17 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     dp.azimuth = s.d_az;
     dp.distance = s.d_dist;
     dp.t_us = s.d_t;
-    dp.tile_counter = s.d_counters + 2;
     dp.frame_laser_counts = s.d_frame_counts;
     dp.frame_cap = (int)ctx->frame_cap;
-    const size_t smem = align_up(sizeof(DecShared), 128) + 2 * (size_t)dp.stage_bytes;
     VS_CUDA(cudaEventRecord(s.ev_d0, s.stream));
     if (dec_tiles > 0) {
       int rc;
       if (adj == 0)
-        rc = launch_decode<0>(ctx, s, dp, smem);
+        rc = launch_decode<0>(ctx, s, dp);
       else if (adj == 1)
-        rc = launch_decode<1>(ctx, s, dp, smem);
+        rc = launch_decode<1>(ctx, s, dp);
       else
-        rc = launch_decode<2>(ctx, s, dp, smem);
+        rc = launch_decode<2>(ctx, s, dp);
       if (rc != VS_OK) return rc;
       ++s.n_launches;
     }

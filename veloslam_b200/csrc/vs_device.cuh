@@ -48,8 +48,16 @@ struct DevConfig {
 //   y: k_scan: emitted-point count; after k_pose: number of wraps before this packet
 //      (frame id at the packet's first block)
 //   z: after k_pose: packet time - t_base (microseconds, u32)
-//   w: unused
+//   w: bits 0-11 mask of the 0xddff ("upper") blocks, bits 12-20 emitted points of the packet
 typedef int4 PktSeg;
+
+// Per-block record written by k_scan, read by k_pose / k_decode.
+//   x: mask of the return slots the reference emits (iterated block, distance != 0, selected
+//      laser, crop)
+//   y: bits 0-15 block azimuth (mod 36000 when no per-return adjustment applies, else raw),
+//      bits 16-24 emitted points of the packet in front of this block, bit 25 0xddff block,
+//      bits 26-29 wraps of the packet up to and including this block
+typedef uint2 BlkRec;
 
 // Batch header: written by the kernels, copied to the host with the frame tables.
 struct BatchHeader {

@@ -51,10 +51,10 @@ struct TileSpan {
 };
 __device__ __forceinline__ TileSpan tile_span(long long in_base, long long stride,
                                               long long total_bytes, int n, long long first,
-                                              int lead) {
+                                              int lead, int tile_pkts = kTilePkts) {
   TileSpan t;
   t.npk = n - (int)first;
-  if (t.npk > kTilePkts) t.npk = kTilePkts;
+  if (t.npk > tile_pkts) t.npk = tile_pkts;
   t.a0 = in_base + first * stride;
   t.a1 = t.a0 + (long long)(t.npk - 1) * stride + kPacketBytes;
   long long b = t.a0 - lead;
@@ -165,7 +165,8 @@ __device__ __forceinline__ unsigned adjusted_azimuth(const DevConfig& c, unsigne
 // k_scan: segmentation + emission masks in one streaming pass over the packets.
 //   per packet : firingSkip entering it, wrap mask over the iterated blocks, azimuthDiff,
 //                emitted-point count                                  -> PktSeg
-//   per block  : 32-bit mask of the return slots the reference emits -> masks[n*12]
+//   per block  : BlkRec {mask of the return slots the reference emits, azimuth, points of the
+//                packet in front of the block, laser bank, wraps up to the block} -> recs[n*12]
 // The firingSkip recurrence is a scan of 12-entry maps; across tiles it is resolved with a
 // look-back that stops at the first constant composed map.
 // =========================================================================================
@@ -184,7 +185,7 @@ struct ScanParams {
   int n_tiles;
   int stage_bytes;
   PktSeg* pkt_seg;
-  unsigned* masks;
+  BlkRec* recs;
   unsigned long long* st_map;
   int* tile_counter;
   BatchHeader* hdr;
@@ -196,6 +197,7 @@ struct ScanShared {
   uint64_t full;
   unsigned nz[kTileBlocks];  // raw "distance != 0" (or crop-tested) bits per block
   int skip[kTilePkts];
+  unsigned wrap[kTilePkts];  // wrap mask over the iterated blocks of each packet
   int tile_id;
 };
 
@@ -384,6 +386,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
       s_in = (p.mode == 0) ? map_apply(excl, skip_tile) : 0;
       if (live) wrapmask = (wm & ~((2u << s_in) - 1u)) | (((em >> s_in) & 1u) << s_in);
       sh.skip[lane] = s_in;
+      sh.wrap[lane] = wrapmask;
     }
 
     // ---- phase B1: which return slots of each block could be emitted ------------------------
@@ -466,10 +469,26 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
           mk = sh.nz[b] & (upper ? sel_hi : sel_lo);
         }
         sh.nz[b] = mk;
-        p.masks[(first + lp) * kBlocks + j] = mk;
       }
     }
     __syncthreads();
+    // ---- phase B3: block records -------------------------------------------------------------
+    for (int b = tid; b < kTileBlocks; b += kScanThreads) {
+      const int lp = b / kBlocks, j = b - lp * kBlocks;
+      if (lp < npk) {
+        const uint8_t* blk = tile_smem + (size_t)lp * p.stride + 100 * j;
+        unsigned pre = 0;
+        for (int q = 0; q < j; ++q) pre += __popc(sh.nz[lp * kBlocks + q]);
+        const unsigned upper = ld_smem_u16(blk) != 0xeeffu ? 1u : 0u;
+        const unsigned wb = __popc(sh.wrap[lp] & ((2u << j) - 1u));
+        unsigned az = ld_smem_u16(blk + 2);
+        if (ADJ == 0) az %= 36000u;  // HDLParser.cxx:597 (ADJ != 0: adjusted per return later)
+        BlkRec r;
+        r.x = sh.nz[b];
+        r.y = az | (pre << 16) | (upper << 25) | (wb << 26);
+        p.recs[(first + lp) * kBlocks + j] = r;
+      }
+    }
     if (warp == 0 && lane < npk) {
       unsigned cnt = 0;
 #pragma unroll
@@ -479,7 +498,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
       r.x = s_in | (int)(wrapmask << 4) | (azdiff << 16);
       r.y = (int)cnt;
       r.z = 0;
-      r.w = (int)um;
+      r.w = (int)(um | (cnt << 12));
       p.pkt_seg[P] = r;
       const unsigned ium = um & ~((1u << s_in) - 1u);
       if (ium) {
@@ -508,7 +527,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
 struct PoseParams {
   const long long* pkt_time;
   PktSeg* pkt_seg;           // in: x, y = count; out: y = frame id, z = time - t_base
-  const unsigned* masks;
+  const BlkRec* recs;
   unsigned long long* pkt_off;  // out: index of the packet's first emitted point
   unsigned long long* st_wrap;
   unsigned long long* st_cnt;
@@ -700,14 +719,11 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
   // frame table: a wrap block opens frame f before it is decoded (HDLParser.cxx:1035-1039)
   if (wrapmask && P >= p.halo) {
     unsigned wm = wrapmask;
-    unsigned before = 0;
-    int jprev = 0;
     int f = frame_base;
     while (wm) {
       const int j = __ffs(wm) - 1;
       wm &= wm - 1;
-      for (int q = jprev; q < j; ++q) before += __popc(__ldg(&p.masks[(long long)P * kBlocks + q]));
-      jprev = j;
+      const unsigned before = (__ldg(&p.recs[(long long)P * kBlocks + j].y) >> 16) & 0x1ffu;
       ++f;
       if (f < p.frame_cap) {
         p.frame_first_point[f] = (long long)(exc + before);
@@ -771,20 +787,42 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
 
 // =========================================================================================
 // k_decode: decode + calibrate + transform + compacted SoA stores.  No inter-CTA dependency:
-// emission masks and point offsets come from k_scan / k_pose.  Persistent CTAs (2 per SM),
-// tiles staged by TMA bulk copies (packets, masks, segment records), one warp per 100-byte
-// firing block with lane == return slot.
-// Work split inside a tile: warp w owns the packets {w/2 + 4k} and, inside them, the firing
-// blocks of parity w&1.  On HDL-64 data block parity == laser bank (0xeeff / 0xddff), so a
-// warp keeps one calibration bank in registers; the pose row is loaded once per packet.
+// block records (emission masks, azimuths, in-packet offsets) come from k_scan, frame ids,
+// point offsets and pose rows from k_pose.
+//
+// Input side.  Persistent CTAs (2 per SM, 8 warps), tiles of 8 packets dealt round-robin to the
+// CTAs.  A tile (block records, segment records, point offsets, pose rows and the packet bytes:
+// five TMA bulk copies on one mbarrier) moves through a 3-stage shared-memory ring.  There is
+// no block-wide barrier in the tile loop: every warp waits on the stage's "full" mbarrier by
+// itself, and the warp that releases a stage last (shared-memory counter) re-arms it.
+//
+// Work split.  The warp pair (2q, 2q+1) owns the packets 2q, 2q+1 of a tile and warp w the
+// firing blocks of parity w&1 inside them (lane == return slot).  On HDL-64 data block parity ==
+// laser bank (0xeeff / 0xddff), so a warp keeps one calibration bank in registers.  Per tile a
+// warp first expands the records of the 12 firing blocks it owns (lane == block) to 32 bytes:
+// mask, staging position of the block's first point, azimuth, laser bank, frame id and sin/cos
+// of the azimuth gathered from the LUT.  The block loop then reads everything warp-uniform
+// with two broadcast LDS.128 and runs two blocks at a time as one straight-line body
+// (independent FP64 chains, predicated stores, no branches).
+//
+// Output side.  Compaction makes the per-block output ranges start at arbitrary element
+// offsets; written straight to HBM that is two partial 32-byte sectors per block and column,
+// and partial-sector writes cost the B200 L2 about 3x (measured: 8 compacted columns reach
+// 2.2-2.7 TB/s against 6.0-6.9 TB/s for sector-aligned ones).  So a pair stages the points of
+// its two packets (<= 768 x 22 B) in shared memory at the same 16-element phase as their global
+// position, and after a pair barrier every column leaves as ONE TMA bulk store of whole
+// 16-element granules (cp.async.bulk.global.shared::cta); only the < 16 leading / trailing
+// elements go out as scalar stores.  The bulk reads overlap the next tile's wait + record
+// expansion; a second pair barrier in front of the next tile's first staging write closes the
+// loop.
 // =========================================================================================
 struct DecParams {
   const uint8_t* pkts;  // first packet of the submitted array (halo included)
   long long stride;
   long long total_bytes;  // bytes that may be read from pkts
   const PktSeg* pkt_seg;
-  const unsigned* masks;
-  const unsigned long long* pkt_off;
+  const BlkRec* recs;
+  const unsigned long long* pkt_off;  // n + 2 entries allocated
   const double* pose_mat;
   const double* lut_sin;
   const double* lut_cos;
@@ -794,7 +832,7 @@ struct DecParams {
   int mode;
   int pose_valid;
   int n_tiles;
-  int stage_bytes;  // bytes per shared-memory stage (multiple of 128)
+  int stage_bytes;  // bytes per shared-memory input stage (multiple of 128)
   float* x;
   float* y;
   float* z;
@@ -803,310 +841,418 @@ struct DecParams {
   uint16_t* azimuth;
   uint16_t* distance;
   uint32_t* t_us;
-  int* tile_counter;
   unsigned* frame_laser_counts;  // frame_cap x 64
   int frame_cap;
 };
 
+constexpr int kDecTile = 8;  // packets per tile
+constexpr int kDecStages = 3;
 constexpr int kDecThreads = 256;
 constexpr int kDecWarps = kDecThreads / 32;
-constexpr int kMaskBytes = kTileBlocks * 4;           // 1536
-constexpr int kSegBytes = kTilePkts * (int)sizeof(PktSeg);  // 512
+constexpr int kDecPairs = kDecWarps / 2;
+constexpr int kDecPktsPerWarp = kDecTile / kDecPairs;  // 2
+constexpr int kDecRecs = kDecPktsPerWarp * 6;          // firing blocks per warp and tile
+// input stage layout (byte offsets, all multiples of 16)
+constexpr int kDRec = 0;                            // 12 BlkRec per packet
+constexpr int kDSeg = kDRec + kDecTile * 96;        // PktSeg per packet
+constexpr int kDOff = kDSeg + kDecTile * 16;        // u64 point offset per packet (+2 pad)
+constexpr int kDPose = kDOff + (kDecTile + 2) * 8;  // 12 doubles per packet
+constexpr int kDPkts = kDPose + kDecTile * 96;      // packet bytes (16-byte granular span)
+static_assert(kDPose % 16 == 0 && kDPkts % 16 == 0, "stage sections must be 16-byte aligned");
+static_assert(kDecRecs <= 32, "one lane per block record");
+// output staging of one pair: its packets' points + 16 elements of phase, column after column
+constexpr int kOutCap = kDecPktsPerWarp * 384 + 16;
+constexpr int kOX = 0, kOY = 4 * kOutCap, kOZ = 8 * kOutCap, kOT = 12 * kOutCap;
+constexpr int kOAz = 16 * kOutCap, kODist = 18 * kOutCap;
+constexpr int kOInt = 20 * kOutCap, kOLas = 21 * kOutCap;
+constexpr int kOutBytes = (22 * kOutCap + 127) & ~127;
+static_assert(kOutCap % 16 == 0, "column bases must stay 16-byte aligned");
 
-constexpr int kPoseBytes = kTilePkts * 12 * 8;              // 3072
-
-struct DecShared {
-  DevConfig cfg;
-  double sn[kTileBlocks];  // sin / cos of each firing block's azimuth (ADJ == 0), gathered
-  double cs[kTileBlocks];  //   from the LUT once per tile so the block loop has no global loads
-  uint64_t full[2];
-  unsigned long long off[2][kTilePkts];
-  unsigned hist[2][kMaxLasers];
-  int tile_id[2];
+struct DecCtl {
+  uint64_t full[kDecStages];
+  int released[kDecStages];  // warps that are done with the stage
 };
+
+// dynamic shared memory: [DecCtl | block records | DevConfig (ADJ != 0) | staging | stages]
+template <int ADJ>
+struct DecLayout {
+  static constexpr int kRec = 128;
+  static constexpr int kCfg = kRec + kDecWarps * kDecRecs * 32;
+  static constexpr int kOut = kCfg + ((ADJ == 0) ? 0 : (((int)sizeof(DevConfig) + 127) & ~127));
+  static constexpr int kStages = kOut + kDecPairs * kOutBytes;
+};
+static_assert(sizeof(DecCtl) <= 128, "DecCtl must fit its slot");
+
+__device__ __forceinline__ void lds_v2f64(uint32_t a, double& v0, double& v1) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(a));
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, unsigned x, unsigned y, unsigned z, unsigned w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w)
+               : "memory");
+}
+__device__ __forceinline__ void sts_v2f64(uint32_t a, double v0, double v1) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v0), "d"(v1) : "memory");
+}
+// TMA bulk copy shared -> global (16-byte granules), tracked by the thread's bulk async-group.
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void pair_barrier(int pair) {
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+}
+
+// The eight column values of one point into the pair's staging buffer under one predicate
+// (no branch in the block body).  a4 / a2 / a1: addresses of the point in the 4-, 2- and
+// 1-byte column groups; the columns of a group sit at fixed distances.
+__device__ __forceinline__ void stage_point(unsigned pred, uint32_t a4, uint32_t a2, uint32_t a1,
+                                            float vx, float vy, float vz, unsigned vt, unsigned va,
+                                            unsigned vd, unsigned vi, unsigned vl) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %11, 0;\n"
+      "@p st.shared.f32 [%0], %3;\n"
+      "@p st.shared.f32 [%0+%12], %4;\n"
+      "@p st.shared.f32 [%0+%13], %5;\n"
+      "@p st.shared.u32 [%0+%14], %6;\n"
+      "@p st.shared.u16 [%1], %7;\n"
+      "@p st.shared.u16 [%1+%15], %8;\n"
+      "@p st.shared.u8 [%2], %9;\n"
+      "@p st.shared.u8 [%2+%16], %10;\n"
+      "}\n" ::"r"(a4),
+      "r"(a2), "r"(a1), "f"(vx), "f"(vy), "f"(vz), "r"(vt), "r"(va), "r"(vd), "r"(vi), "r"(vl),
+      "r"(pred), "n"(kOY - kOX), "n"(kOZ - kOX), "n"(kOT - kOX), "n"(kODist - kOAz),
+      "n"(kOLas - kOInt)
+      : "memory");
+}
+
+// type_defs.h:160-166: row sums left to right, translation last.
+__device__ __forceinline__ void rigid(const double* M, double& px, double& py, double& pz) {
+  const double qx = __dadd_rn(
+      __dadd_rn(__dadd_rn(__dmul_rn(M[0], px), __dmul_rn(M[1], py)), __dmul_rn(M[2], pz)), M[3]);
+  const double qy = __dadd_rn(
+      __dadd_rn(__dadd_rn(__dmul_rn(M[4], px), __dmul_rn(M[5], py)), __dmul_rn(M[6], pz)), M[7]);
+  const double qz = __dadd_rn(
+      __dadd_rn(__dadd_rn(__dmul_rn(M[8], px), __dmul_rn(M[9], py)), __dmul_rn(M[10], pz)), M[11]);
+  px = qx;
+  py = qy;
+  pz = qz;
+}
 
 template <int ADJ>
 __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
+  typedef DecLayout<ADJ> L;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  DecShared& sh = *reinterpret_cast<DecShared*>(smem_raw);
-  uint8_t* stage0 = smem_raw + ((sizeof(DecShared) + 127) & ~127);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int par = warp & 1, pk0 = warp >> 1;
+  DecCtl& sh = *reinterpret_cast<DecCtl*>(smem_raw);
+  const DevConfig& cfg =
+      (ADJ == 0) ? *p.cfg : *reinterpret_cast<const DevConfig*>(smem_raw + L::kCfg);
+  uint8_t* stage0 = smem_raw + L::kStages;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
+  const int par = warp & 1, pair = warp >> 1;
   const unsigned lt_mask = (1u << lane) - 1u;
+  const long long in_base = reinterpret_cast<long long>(p.pkts);
 
-  {
+  // start the copies of tile t into stage s (one thread); t >= n_tiles: nothing left
+  auto produce = [&](int s, int t) {
+    if (t >= p.n_tiles) {
+      mbar_arrive(&sh.full[s]);
+      return;
+    }
+    const long long first = (long long)p.halo + (long long)t * kDecTile;
+    const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, 0, kDecTile);
+    uint8_t* st = stage0 + (size_t)s * p.stage_bytes;
+    for (long long a = sp.s1; a < sp.a1; ++a)  // < 16 bytes, last tile of the array only
+      st[kDPkts + (a - sp.s0)] = *reinterpret_cast<const uint8_t*>(a);
+    const uint32_t bytes = (uint32_t)(sp.s1 - sp.s0);
+    const uint32_t rbytes = (uint32_t)sp.npk * 96u;
+    const uint32_t sbytes = (uint32_t)sp.npk * 16u;
+    const int odd = (int)(first & 1);  // the offsets are copied from an even index
+    const uint32_t obytes = (uint32_t)((sp.npk + odd + 1) & ~1) * 8u;
+    const uint32_t pbytes = p.pose_valid ? (uint32_t)sp.npk * 96u : 0u;
+    fence_proxy_async();
+    mbar_expect_tx(&sh.full[s], bytes + rbytes + sbytes + obytes + pbytes);
+    bulk_g2s(st + kDRec, p.recs + first * kBlocks, rbytes, &sh.full[s]);
+    bulk_g2s(st + kDSeg, p.pkt_seg + first, sbytes, &sh.full[s]);
+    bulk_g2s(st + kDOff, p.pkt_off + (first - odd), obytes, &sh.full[s]);
+    if (pbytes) bulk_g2s(st + kDPose, p.pose_mat + first * 12, pbytes, &sh.full[s]);
+    if (bytes) bulk_g2s(st + kDPkts, reinterpret_cast<const void*>(sp.s0), bytes, &sh.full[s]);
+  };
+
+  if (ADJ != 0) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.cfg);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.cfg);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw + L::kCfg);
     for (int i = tid; i < (int)(sizeof(DevConfig) / 4); i += kDecThreads) dst[i] = __ldg(&src[i]);
   }
   if (tid == 0) {
-    mbar_init(&sh.full[0], 1);
-    mbar_init(&sh.full[1], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  const long long in_base = reinterpret_cast<long long>(p.pkts);
-  // stage layout: [masks 1536 B | seg 512 B | pose rows 3072 B | packets]
-  auto issue = [&](int t, int b) {
-    const long long first = (long long)p.halo + (long long)t * kTilePkts;
-    const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, 0);
-    uint8_t* st = stage0 + (size_t)b * p.stage_bytes;
-    const uint32_t bytes = (uint32_t)(sp.s1 - sp.s0);
-    const uint32_t mbytes = (uint32_t)sp.npk * kBlocks * 4u;
-    const uint32_t sbytes = (uint32_t)sp.npk * (uint32_t)sizeof(PktSeg);
-    fence_proxy_async();
-    const uint32_t pbytes = p.pose_valid ? (uint32_t)sp.npk * 96u : 0u;
-    mbar_expect_tx(&sh.full[b], bytes + mbytes + sbytes + pbytes);
-    bulk_g2s(st, p.masks + first * kBlocks, mbytes, &sh.full[b]);
-    bulk_g2s(st + kMaskBytes, p.pkt_seg + first, sbytes, &sh.full[b]);
-    if (pbytes) bulk_g2s(st + kMaskBytes + kSegBytes, p.pose_mat + first * 12, pbytes, &sh.full[b]);
-    if (bytes)
-      bulk_g2s(st + kMaskBytes + kSegBytes + kPoseBytes, reinterpret_cast<const void*>(sp.s0), bytes,
-               &sh.full[b]);
-  };
-
-  unsigned long long next_off = 0;  // threads 0..31: point offset of packet `tid` of the next tile
-  if (tid == 0) {
-    const int t = atomicAdd(p.tile_counter, 1);
-    sh.tile_id[0] = t;
-    if (t < p.n_tiles) issue(t, 0);
-  }
-  __syncthreads();
-  {
-    const int t0 = sh.tile_id[0];
-    if (tid < kTilePkts && t0 < p.n_tiles) {
-      const long long P = (long long)p.halo + (long long)t0 * kTilePkts + tid;
-      sh.off[0][tid] = __ldg(&p.pkt_off[P < p.n ? P : p.n - 1]);
+#pragma unroll
+    for (int s = 0; s < kDecStages; ++s) {
+      mbar_init(&sh.full[s], 1);
+      sh.released[s] = 0;
     }
+    fence_mbar_init();
+#pragma unroll 1
+    for (int s = 0; s < kDecStages; ++s) produce(s, (int)blockIdx.x + s * (int)gridDim.x);
   }
+  __syncthreads();
 
-  uint32_t phase[2] = {0u, 0u};
-  int cur = 0;
   const bool pose_valid = p.pose_valid != 0;
   CalRow cal;
   int cal_bank = -1;
-
-  while (true) {
-    const int tile = sh.tile_id[cur];
-    if (tile >= p.n_tiles) break;
-    if (tid == 0) {
-      const int tn = atomicAdd(p.tile_counter, 1);
-      sh.tile_id[cur ^ 1] = tn;
-      if (tn < p.n_tiles) issue(tn, cur ^ 1);
+  unsigned cnt = 0;  // emitted points of (cnt_frame, cnt_bank) seen by this lane
+  int cnt_frame = -1, cnt_bank = 0;
+  auto flush_counts = [&]() {
+    if (cnt) {
+      int l = lane + cnt_bank;
+      if (ADJ == 2 && l >= 16) l -= 16;
+      if (cnt_frame < p.frame_cap)
+        atomicAdd(&p.frame_laser_counts[(long long)cnt_frame * kMaxLasers + l], cnt);
+      cnt = 0;
     }
-    if (tid >= 128 && tid < 128 + 2 * kMaxLasers) (&sh.hist[0][0])[tid - 128] = 0;
-    const long long first = (long long)p.halo + (long long)tile * kTilePkts;
-    const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, 0);
-    const int npk = sp.npk;
-    uint8_t* stage = stage0 + (size_t)cur * p.stage_bytes;
-    const uint32_t mask_a = smem_u32(stage);
-    const uint32_t seg_a = mask_a + kMaskBytes;
-    const uint32_t pose_a = seg_a + kSegBytes;
-    const uint32_t off_a = smem_u32(&sh.off[cur][0]);
-    uint8_t* s_pk = stage + kMaskBytes + kSegBytes + kPoseBytes;
+  };
+  const uint32_t smem_a = smem_u32(smem_raw);
+  const uint32_t rec_a = smem_a + L::kRec + (uint32_t)warp * (kDecRecs * 32);
+  const uint32_t out_a = smem_a + L::kOut + (uint32_t)pair * kOutBytes;
+  const uint32_t stage_a0 = smem_a + L::kStages;
+  const unsigned stride = (unsigned)p.stride;
 
-    mbar_wait(&sh.full[cur], phase[cur]);
-    phase[cur] ^= 1u;
-    if (sp.s1 < sp.a1) {
-      for (long long a = sp.s1 + tid; a < sp.a1; a += kDecThreads)
-        s_pk[a - sp.s0] = *reinterpret_cast<const uint8_t*>(a);
-    }
-    __syncthreads();  // tile_id[cur^1], off[cur], hist and the tail bytes are visible
+  // one firing block: everything after the shared-memory loads
+  auto finish_block = [&](const int4 r, const double sn, const double cs, const unsigned d0,
+                          const unsigned d1, const unsigned inten, const int j, const int laser_id,
+                          const unsigned tpk, const int azdiff, const double* M) {
+    const unsigned m = (unsigned)r.x;
+    const unsigned dist = d0 | (d1 << 8);
+    unsigned az;
+    double sA, cA;
     if (ADJ == 0) {
-      // sin/cos of every block azimuth of the tile: independent gathers, one round trip
-      const uint8_t* base = s_pk + (sp.a0 - sp.s0);
-      for (int b = tid; b < npk * kBlocks; b += kDecThreads) {
-        const int lp = b / kBlocks, j = b - lp * kBlocks;
-        const unsigned az = ld_smem_u16(base + (size_t)lp * p.stride + 100 * j + 2) % 36000u;
-        sh.sn[b] = __ldg(&p.lut_sin[az]);
-        sh.cs[b] = __ldg(&p.lut_cos[az]);
-      }
+      az = (unsigned)r.z & 0xffffu;
+      sA = sn;
+      cA = cs;
+    } else {
+      az = adjusted_azimuth<ADJ>(cfg, (unsigned)r.z & 0xffffu, azdiff, j, lane);
+      sA = __ldg(&p.lut_sin[az]);
+      cA = __ldg(&p.lut_cos[az]);
     }
-    // point offsets of the next tile: loaded now, parked in a register until the switch
-    {
-      const int tn = sh.tile_id[cur ^ 1];
-      if (tid < kTilePkts && tn < p.n_tiles) {
-        const long long P = (long long)p.halo + (long long)tn * kTilePkts + tid;
-        next_off = __ldg(&p.pkt_off[P < p.n ? P : p.n - 1]);
-      }
+    double px, py, pz;
+    sensor_point(cal, sA, cA, dist, px, py, pz);
+    if (pose_valid) rigid(M, px, py, pz);
+    const unsigned pred = (m >> lane) & 1u;
+    const unsigned o = (unsigned)r.y + __popc(m & lt_mask);  // position in the pair's staging
+    stage_point(pred, out_a + kOX + 4u * o, out_a + kOAz + 2u * o, out_a + kOInt + o, (float)px,
+                (float)py, (float)pz, tpk + (ADJ != 0 ? (uint32_t)cfg.tadj[j][lane] : 0u), az, dist,
+                inten, (unsigned)laser_id);
+    cnt += pred;
+  };
+
+  const int lp0 = kDecPktsPerWarp * pair;  // first packet of the pair inside a tile
+#pragma unroll 1
+  for (int it = 0;; ++it) {
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    if (tile >= p.n_tiles) break;
+    const int s = it % kDecStages;
+    mbar_wait(&sh.full[s], (uint32_t)(it / kDecStages) & 1u);
+    const long long first = (long long)p.halo + (long long)tile * kDecTile;
+    const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, 0, kDecTile);
+    const int npk = sp.npk;
+    const uint32_t st_a = stage_a0 + (uint32_t)s * (uint32_t)p.stage_bytes;
+    const uint32_t brec_a = st_a + kDRec;
+    const uint32_t seg_a = st_a + kDSeg;
+    const uint32_t off_a = st_a + kDOff + 8u * (unsigned)(first & 1);
+    const uint32_t pose_a = st_a + kDPose;
+    const uint32_t pkt_a = st_a + kDPkts + (uint32_t)(sp.a0 - sp.s0);
+    // global index of the pair's first point and the number of points of its packets
+    unsigned long long P0 = 0;
+    unsigned tot = 0;
+    if (lp0 < npk) {
+      P0 = lds_u64(off_a + 8u * (unsigned)lp0);
+#pragma unroll
+      for (int k = 0; k < kDecPktsPerWarp; ++k)
+        if (lp0 + k < npk) tot += (lds_u32(seg_a + 16u * (unsigned)(lp0 + k) + 12u) >> 12) & 0x1ffu;
     }
-    const uint8_t* tile_smem = s_pk + (sp.a0 - sp.s0);
-    const unsigned long long tb = lds_u64(off_a);
-    // per-tile column pointers, kept opaque so every store is base + 32-bit index
-    float* xt = p.x + tb;
-    float* yt = p.y + tb;
-    float* zt = p.z + tb;
-    uint32_t* tt = p.t_us + tb;
-    uint16_t* at = p.azimuth + tb;
-    uint16_t* dt = p.distance + tb;
-    uint8_t* it = p.intensity + tb;
-    uint8_t* lt = p.laser + tb;
-    asm volatile("" : "+l"(xt), "+l"(yt), "+l"(zt), "+l"(tt));
-    asm volatile("" : "+l"(at), "+l"(dt), "+l"(it), "+l"(lt));
-    const int tile_f0 = lds_v4(seg_a).y;
-    if (ADJ == 0) __syncthreads();  // sn / cs are complete
+    const unsigned ph = (unsigned)P0 & 15u;
 
-    unsigned cnt = 0;  // emitted points of (cnt_frame, cnt_bank) seen by this lane
-    int cnt_frame = -1, cnt_bank = 0;
-    auto flush_counts = [&]() {
-      if (cnt) {
-        int l = lane + cnt_bank;
-        if (ADJ == 2 && l >= 16) l -= 16;
-        const int d = cnt_frame - tile_f0;
-        if (d == 0 || d == 1)
-          atomicAdd(&sh.hist[d][l], cnt);
-        else if (cnt_frame < p.frame_cap)
-          atomicAdd(&p.frame_laser_counts[(long long)cnt_frame * kMaxLasers + l], cnt);
-        cnt = 0;
+    // ---- expand the block records of this warp (lane == block) -----------------------------
+    if (lane < kDecRecs) {
+      const int k = lane / 6, i = lane - 6 * k;
+      const int lp = lp0 + k, j = par + 2 * i;
+      unsigned m = 0, off = 0, azf = 0;
+      int frame = 0;
+      double sn = 0.0, cs = 0.0;
+      if (lp < npk) {
+        const unsigned long long br = lds_u64(brec_a + 8u * (unsigned)(lp * kBlocks + j));
+        m = (unsigned)br;
+        const unsigned info = (unsigned)(br >> 32);
+        const unsigned wb = (info >> 26) & 15u;
+        frame = (int)lds_u32(seg_a + 16u * (unsigned)lp + 4u) + (int)wb;
+        off = ph + (lds_u32(off_a + 8u * (unsigned)lp) - (unsigned)P0) + ((info >> 16) & 0x1ffu);
+        // bits 0-15 azimuth, 16 laser bank, 17 zero translation (offline, at/after a wrap)
+        azf = (info & 0xffffu) | (((info >> 25) & 1u) << 16) |
+              ((p.mode == 1 && wb != 0u) ? (1u << 17) : 0u);
+        if (ADJ == 0) {
+          sn = __ldg(&p.lut_sin[info & 0xffffu]);
+          cs = __ldg(&p.lut_cos[info & 0xffffu]);
+        }
       }
-    };
-    // 32-bit shared-window addresses, kept opaque so they stay in registers
-    uint32_t tile_a = smem_u32(tile_smem) + 3u * (unsigned)lane;
-    uint32_t sn_a = smem_u32(&sh.sn[0]);
-    asm volatile("" : "+r"(tile_a), "+r"(sn_a));
-    const unsigned pm = par ? 0xaaau : 0x555u;  // the blocks of this warp
-
-    // one firing block: loads from shared memory, FP64 math, predicated SoA stores
-    auto do_block = [&](const int lp, const int j, const unsigned m, const unsigned boff,
-                        const int off, const int laser_id, const unsigned pkt_rel,
-                        const unsigned tpk, const int azdiff, const uint32_t pk_a,
-                        const double* M) {
-      const uint32_t blk_a = pk_a + 100u * (unsigned)j;
-      const unsigned rot = lds_u16(blk_a + 2u - 3u * (unsigned)lane);
-      const unsigned dist = lds_u8(blk_a + 4u) | (lds_u8(blk_a + 5u) << 8);
-      const unsigned inten = lds_u8(blk_a + 6u);
-      const unsigned az = adjusted_azimuth<ADJ>(sh.cfg, rot, azdiff, j, lane);
-      double sA, cA;
-      if (ADJ == 0) {
-        const uint32_t q = sn_a + 8u * (unsigned)(lp * kBlocks + j);
-        sA = lds_f64(q);
-        cA = lds_f64(q + (uint32_t)(kTileBlocks * 8));
-      } else {
-        sA = __ldg(&p.lut_sin[az]);
-        cA = __ldg(&p.lut_cos[az]);
-      }
-      double px, py, pz;
-      sensor_point(cal, sA, cA, dist, px, py, pz);
-      if (pose_valid) {
-        // type_defs.h:160-166: row sums left to right, translation last
-        const double qx = __dadd_rn(
-            __dadd_rn(__dadd_rn(__dmul_rn(M[0], px), __dmul_rn(M[1], py)), __dmul_rn(M[2], pz)),
-            M[3]);
-        const double qy = __dadd_rn(
-            __dadd_rn(__dadd_rn(__dmul_rn(M[4], px), __dmul_rn(M[5], py)), __dmul_rn(M[6], pz)),
-            M[7]);
-        const double qz = __dadd_rn(
-            __dadd_rn(__dadd_rn(__dmul_rn(M[8], px), __dmul_rn(M[9], py)), __dmul_rn(M[10], pz)),
-            M[11]);
-        px = qx;
-        py = qy;
-        pz = qz;
-      }
-      if ((m >> lane) & 1u) {
-        const unsigned o = pkt_rel + boff + __popc(m & lt_mask);
-        stg_f32(xt + o, (float)px);
-        stg_f32(yt + o, (float)py);
-        stg_f32(zt + o, (float)pz);
-        stg_u32(tt + o, tpk + (ADJ != 0 ? (uint32_t)sh.cfg.tadj[j][lane] : 0u));
-        stg_u16(at + o, az);
-        stg_u16(dt + o, dist);
-        stg_u8(it + o, inten);
-        stg_u8(lt + o, (unsigned)laser_id);
-        ++cnt;
-      }
-    };
+      sts_v4(rec_a + 32u * (unsigned)lane, m, off, azf, (unsigned)frame);
+      sts_v2f64(rec_a + 32u * (unsigned)lane + 16u, sn, cs);
+    }
+    __syncwarp();
+    // staging is free once both warps' bulk stores of the previous tile have read it
+    if (it > 0) {
+      if (lane == 0) bulk_wait_read0();
+      pair_barrier(pair);
+    }
 
 #pragma unroll 1
-    for (int lp = pk0; lp < npk; lp += 4) {
+    for (int k = 0; k < kDecPktsPerWarp; ++k) {
+      const int lp = lp0 + k;
+      if (lp >= npk) break;
       const PktSeg seg = lds_v4(seg_a + 16u * (unsigned)lp);
-      const int wrapmask = (seg.x >> 4) & 0xfff;
+      const unsigned wrapmask = ((unsigned)seg.x >> 4) & 0xfffu;
       const int azdiff = (seg.x >> 16) & 0xffff;
       const unsigned um = (unsigned)seg.w & 0xfffu;
-      const uint32_t pk_a = tile_a + (unsigned)lp * (unsigned)p.stride;
       const unsigned tpk = (unsigned)seg.z;
-      // exclusive prefix of the packet's 12 block counts (lanes 0..11)
-      const unsigned mymask =
-          (lane < kBlocks) ? lds_u32(mask_a + 4u * (unsigned)(lp * kBlocks + lane)) : 0u;
-      unsigned pre = __popc(mymask);
-#pragma unroll
-      for (int o = 1; o < 16; o <<= 1) {
-        const unsigned v = __shfl_up_sync(0xffffffffu, pre, o);
-        if (lane >= o) pre += v;
-      }
-      pre -= __popc(mymask);
-      const unsigned pkt_rel = (unsigned)(lds_u64(off_a + 8u * (unsigned)lp) - tb);
+      // lane's first return of block `par`: 3 bytes per return after the 4-byte block header
+      const uint32_t blk_a = pkt_a + (unsigned)lp * stride + 100u * (unsigned)par + 4u + 3u * (unsigned)lane;
+      const uint32_t rk_a = rec_a + 32u * 6u * (unsigned)k;
       double M[12];  // [L | t] of this packet, warp-uniform
       if (pose_valid) {
 #pragma unroll
-        for (int q = 0; q < 12; ++q) M[q] = lds_f64(pose_a + 8u * (unsigned)(lp * 12 + q));
+        for (int q = 0; q < 6; ++q) lds_v2f64(pose_a + 96u * (unsigned)lp + 16u * (unsigned)q, M[2 * q], M[2 * q + 1]);
       }
+      const unsigned pm = par ? 0xaaau : 0x555u;  // the blocks of this warp
       const unsigned ub = um & pm;
-      if (wrapmask == 0 && (ub == 0u || ub == pm)) {
+      if (wrapmask == 0u && (ub == 0u || ub == pm)) {
         // fast path (every packet of a real stream but the ~0.3 % that hold a wrap): one
         // frame, one laser bank for all blocks of this warp
-        const int off = ub ? 32 : 0;
-        if (seg.y != cnt_frame || off != cnt_bank) {
+        const int bank = ub ? 32 : 0;
+        if (seg.y != cnt_frame || bank != cnt_bank) {
           flush_counts();
           cnt_frame = seg.y;
-          cnt_bank = off;
+          cnt_bank = bank;
         }
-        if (off != cal_bank) {
-          load_cal(sh.cfg, lane + off, cal);
-          cal_bank = off;
+        if (bank != cal_bank) {
+          load_cal(cfg, lane + bank, cal);
+          cal_bank = bank;
         }
-        int laser_id = lane + off;
+        int laser_id = lane + bank;
         if (ADJ == 2 && laser_id >= 16) laser_id -= 16;
-#pragma unroll 2
-        for (int i = 0; i < 6; ++i) {
-          const int j = par + 2 * i;
-          const unsigned m = __shfl_sync(0xffffffffu, mymask, j);
-          const unsigned boff = __shfl_sync(0xffffffffu, pre, j);
-          if (m != 0u) do_block(lp, j, m, boff, off, laser_id, pkt_rel, tpk, azdiff, pk_a, M);
+#pragma unroll
+        for (int i = 0; i < 6; i += 2) {
+          // two blocks as one straight-line body: loads first, then both FP64 chains
+          const int4 ra = lds_v4(rk_a + 32u * (unsigned)i);
+          const int4 rb = lds_v4(rk_a + 32u * (unsigned)(i + 1));
+          double sna = 0.0, csa = 0.0, snb = 0.0, csb = 0.0;
+          if (ADJ == 0) {
+            lds_v2f64(rk_a + 32u * (unsigned)i + 16u, sna, csa);
+            lds_v2f64(rk_a + 32u * (unsigned)(i + 1) + 16u, snb, csb);
+          }
+          const uint32_t a0 = blk_a + 200u * (unsigned)i;
+          const unsigned a_d0 = lds_u8(a0), a_d1 = lds_u8(a0 + 1u), a_in = lds_u8(a0 + 2u);
+          const unsigned b_d0 = lds_u8(a0 + 200u), b_d1 = lds_u8(a0 + 201u), b_in = lds_u8(a0 + 202u);
+          finish_block(ra, sna, csa, a_d0, a_d1, a_in, par + 2 * i, laser_id, tpk, azdiff, M);
+          finish_block(rb, snb, csb, b_d0, b_d1, b_in, par + 2 * i + 2, laser_id, tpk, azdiff, M);
         }
       } else {
 #pragma unroll 1
         for (int i = 0; i < 6; ++i) {
-          const int j = par + 2 * i;
-          const unsigned m = __shfl_sync(0xffffffffu, mymask, j);
-          const unsigned boff = __shfl_sync(0xffffffffu, pre, j);
-          if (m == 0u) continue;
-          const int off = ((um >> j) & 1u) ? 32 : 0;
-          const int frame = seg.y + __popc(wrapmask & ((2 << j) - 1));
-          if (p.mode == 1 && pose_valid && ((wrapmask & ((2 << j) - 1)) != 0)) {
+          const int4 r = lds_v4(rk_a + 32u * (unsigned)i);
+          if (r.x == 0) continue;
+          double sn = 0.0, cs = 0.0;
+          if (ADJ == 0) lds_v2f64(rk_a + 32u * (unsigned)i + 16u, sn, cs);
+          const int bank = (((unsigned)r.z >> 16) & 1u) ? 32 : 0;
+          if (((unsigned)r.z >> 17) & 1u) {
             // offline: blocks at/after the packet's first wrap start a frame whose origin is
             // this very packet -> zero translation
             M[3] = 0.0;
             M[7] = 0.0;
             M[11] = 0.0;
           }
-          if (frame != cnt_frame || off != cnt_bank) {
+          if (r.w != cnt_frame || bank != cnt_bank) {
             flush_counts();
-            cnt_frame = frame;
-            cnt_bank = off;
+            cnt_frame = r.w;
+            cnt_bank = bank;
           }
-          if (off != cal_bank) {
-            load_cal(sh.cfg, lane + off, cal);
-            cal_bank = off;
+          if (bank != cal_bank) {
+            load_cal(cfg, lane + bank, cal);
+            cal_bank = bank;
           }
-          int laser_id = lane + off;
+          int laser_id = lane + bank;
           if (ADJ == 2 && laser_id >= 16) laser_id -= 16;
-          do_block(lp, j, m, boff, off, laser_id, pkt_rel, tpk, azdiff, pk_a, M);
+          const uint32_t a0 = blk_a + 200u * (unsigned)i;
+          const unsigned d0 = lds_u8(a0), d1 = lds_u8(a0 + 1u), in = lds_u8(a0 + 2u);
+          finish_block(r, sn, cs, d0, d1, in, par + 2 * i, laser_id, tpk, azdiff, M);
         }
       }
     }
-    flush_counts();
-    __syncthreads();
-    if (tid < 2 * kMaxLasers) {
-      const unsigned c = (&sh.hist[0][0])[tid];
-      const int f = tile_f0 + (tid >> 6);
-      if (c && f < p.frame_cap)
-        atomicAdd(&p.frame_laser_counts[(long long)f * kMaxLasers + (tid & 63)], c);
+    __syncwarp();  // every lane is done with the stage and with the records
+    if (lane == 0) {
+      const int old = atomicAdd(&sh.released[s], 1);
+      if (old == kDecWarps - 1) {
+        sh.released[s] = 0;
+        produce(s, tile + kDecStages * (int)gridDim.x);
+      }
     }
-    if (tid < kTilePkts) sh.off[cur ^ 1][tid] = next_off;
-    __syncthreads();  // stage `cur` and hist are free again; off[cur^1] is published
-    cur ^= 1;
+
+    // ---- the pair's points leave: one bulk store per column + scalar head / tail -----------
+    fence_proxy_async();  // this thread's staging writes -> async proxy
+    pair_barrier(pair);
+    {
+      const unsigned long long Pu =
+          ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(P0 >> 32), 0) << 32) |
+          __shfl_sync(0xffffffffu, (unsigned)P0, 0);
+      const unsigned totu = __shfl_sync(0xffffffffu, tot, 0);
+      if (totu != 0u) {
+        const unsigned phu = (unsigned)Pu & 15u;
+        const unsigned s1 = phu + totu;                   // staging range [phu, s1)
+        const unsigned b0 = (phu + 15u) & ~15u, b1 = s1 & ~15u;  // whole granules [b0, b1)
+        const unsigned long long g0 = Pu - phu;           // global index of staging element 0
+        if (b1 > b0 && lane == 0) {
+          // warp `par` stores two 4-byte columns, one 2-byte and one 1-byte column
+          const unsigned nb = b1 - b0;
+          const unsigned long long gb = g0 + b0;
+          if (par == 0) {
+            bulk_s2g(p.x + gb, out_a + kOX + 4u * b0, 4u * nb);
+            bulk_s2g(p.y + gb, out_a + kOY + 4u * b0, 4u * nb);
+            bulk_s2g(p.azimuth + gb, out_a + kOAz + 2u * b0, 2u * nb);
+            bulk_s2g(p.intensity + gb, out_a + kOInt + b0, nb);
+          } else {
+            bulk_s2g(p.z + gb, out_a + kOZ + 4u * b0, 4u * nb);
+            bulk_s2g(p.t_us + gb, out_a + kOT + 4u * b0, 4u * nb);
+            bulk_s2g(p.distance + gb, out_a + kODist + 2u * b0, 2u * nb);
+            bulk_s2g(p.laser + gb, out_a + kOLas + b0, nb);
+          }
+          bulk_commit();
+        }
+        // head (warp 0) / tail (warp 1): the elements outside the whole granules, all inside
+        // the first / last 16-element window of the range
+        if (lane < 16) {
+          const unsigned wf = phu & ~15u, wl = (s1 - 1u) & ~15u;
+          const unsigned e = (par ? wl : wf) + (unsigned)lane;
+          if (e >= phu && e < s1 && (e < b0 || e >= b1) && !(par && wl == wf)) {
+            const unsigned long long g = g0 + e;
+            p.x[g] = __uint_as_float(lds_u32(out_a + kOX + 4u * e));
+            p.y[g] = __uint_as_float(lds_u32(out_a + kOY + 4u * e));
+            p.z[g] = __uint_as_float(lds_u32(out_a + kOZ + 4u * e));
+            p.t_us[g] = lds_u32(out_a + kOT + 4u * e);
+            p.azimuth[g] = (uint16_t)lds_u16(out_a + kOAz + 2u * e);
+            p.distance[g] = (uint16_t)lds_u16(out_a + kODist + 2u * e);
+            p.intensity[g] = (uint8_t)lds_u8(out_a + kOInt + e);
+            p.laser[g] = (uint8_t)lds_u8(out_a + kOLas + e);
+          }
+        }
+      }
+    }
   }
+  flush_counts();
+  if (lane == 0) bulk_wait0();  // shared memory must outlive the bulk stores that read it
 }
 
 // =========================================================================================
