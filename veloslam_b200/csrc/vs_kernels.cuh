@@ -852,6 +852,7 @@ constexpr int kDecWarps = kDecThreads / 32;
 constexpr int kDecPairs = kDecWarps / 2;
 constexpr int kDecPktsPerWarp = kDecTile / kDecPairs;  // 2
 constexpr int kDecRecs = kDecPktsPerWarp * 6;          // firing blocks per warp and tile
+constexpr int kDecIlp = 2;  // firing blocks per straight-line body (divides 6)
 // input stage layout (byte offsets, all multiples of 16)
 constexpr int kDRec = 0;                            // 12 BlkRec per packet
 constexpr int kDSeg = kDRec + kDecTile * 96;        // PktSeg per packet
@@ -1052,6 +1053,8 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
   };
 
   const int lp0 = kDecPktsPerWarp * pair;  // first packet of the pair inside a tile
+  bool pf_ok = false;  // pf_sn / pf_cs hold the LUT values of this lane's block of the next tile
+  double pf_sn = 0.0, pf_cs = 0.0;
 #pragma unroll 1
   for (int it = 0;; ++it) {
     const int tile = (int)blockIdx.x + it * (int)gridDim.x;
@@ -1096,14 +1099,38 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
         azf = (info & 0xffffu) | (((info >> 25) & 1u) << 16) |
               ((p.mode == 1 && wb != 0u) ? (1u << 17) : 0u);
         if (ADJ == 0) {
-          sn = __ldg(&p.lut_sin[info & 0xffffu]);
-          cs = __ldg(&p.lut_cos[info & 0xffffu]);
+          if (pf_ok) {
+            sn = pf_sn;
+            cs = pf_cs;
+          } else {
+            sn = __ldg(&p.lut_sin[info & 0xffffu]);
+            cs = __ldg(&p.lut_cos[info & 0xffffu]);
+          }
         }
       }
       sts_v4(rec_a + 32u * (unsigned)lane, m, off, azf, (unsigned)frame);
       sts_v2f64(rec_a + 32u * (unsigned)lane + 16u, sn, cs);
     }
     __syncwarp();
+    // LUT gather of the NEXT tile's blocks, issued now so that its L2 round trip hides behind
+    // this tile's math (only when that tile has already landed; else it is gathered later)
+    pf_ok = false;
+    if (ADJ == 0 && tile + (int)gridDim.x < p.n_tiles) {
+      const int sn_ = (it + 1) % kDecStages;
+      pf_ok = __shfl_sync(0xffffffffu,
+                          (int)mbar_test(&sh.full[sn_], (uint32_t)((it + 1) / kDecStages) & 1u), 0) != 0;
+      if (pf_ok && lane < kDecRecs) {
+        const int k = lane / 6, i = lane - 6 * k;
+        const int lp = lp0 + k, j = par + 2 * i;
+        const long long first_n = first + (long long)gridDim.x * kDecTile;
+        if (first_n + lp < p.n) {
+          const unsigned info = lds_u32(stage_a0 + (uint32_t)sn_ * (uint32_t)p.stage_bytes + kDRec +
+                                        8u * (unsigned)(lp * kBlocks + j) + 4u);
+          pf_sn = __ldg(&p.lut_sin[info & 0xffffu]);
+          pf_cs = __ldg(&p.lut_cos[info & 0xffffu]);
+        }
+      }
+    }
     // staging is free once both warps' bulk stores of the previous tile have read it
     if (it > 0) {
       if (lane == 0) bulk_wait_read0();
@@ -1145,20 +1172,29 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
         int laser_id = lane + bank;
         if (ADJ == 2 && laser_id >= 16) laser_id -= 16;
 #pragma unroll
-        for (int i = 0; i < 6; i += 2) {
-          // two blocks as one straight-line body: loads first, then both FP64 chains
-          const int4 ra = lds_v4(rk_a + 32u * (unsigned)i);
-          const int4 rb = lds_v4(rk_a + 32u * (unsigned)(i + 1));
-          double sna = 0.0, csa = 0.0, snb = 0.0, csb = 0.0;
-          if (ADJ == 0) {
-            lds_v2f64(rk_a + 32u * (unsigned)i + 16u, sna, csa);
-            lds_v2f64(rk_a + 32u * (unsigned)(i + 1) + 16u, snb, csb);
+        for (int i = 0; i < 6; i += kDecIlp) {
+          // kDecIlp blocks as one straight-line body: loads first, then the FP64 chains
+          int4 r[kDecIlp];
+          double sn[kDecIlp], cs[kDecIlp];
+          unsigned d0[kDecIlp], d1[kDecIlp], in[kDecIlp];
+#pragma unroll
+          for (int u = 0; u < kDecIlp; ++u) {
+            r[u] = lds_v4(rk_a + 32u * (unsigned)(i + u));
+            sn[u] = 0.0;
+            cs[u] = 0.0;
+            if (ADJ == 0) lds_v2f64(rk_a + 32u * (unsigned)(i + u) + 16u, sn[u], cs[u]);
           }
-          const uint32_t a0 = blk_a + 200u * (unsigned)i;
-          const unsigned a_d0 = lds_u8(a0), a_d1 = lds_u8(a0 + 1u), a_in = lds_u8(a0 + 2u);
-          const unsigned b_d0 = lds_u8(a0 + 200u), b_d1 = lds_u8(a0 + 201u), b_in = lds_u8(a0 + 202u);
-          finish_block(ra, sna, csa, a_d0, a_d1, a_in, par + 2 * i, laser_id, tpk, azdiff, M);
-          finish_block(rb, snb, csb, b_d0, b_d1, b_in, par + 2 * i + 2, laser_id, tpk, azdiff, M);
+#pragma unroll
+          for (int u = 0; u < kDecIlp; ++u) {
+            const uint32_t a0 = blk_a + 200u * (unsigned)(i + u);
+            d0[u] = lds_u8(a0);
+            d1[u] = lds_u8(a0 + 1u);
+            in[u] = lds_u8(a0 + 2u);
+          }
+#pragma unroll
+          for (int u = 0; u < kDecIlp; ++u)
+            finish_block(r[u], sn[u], cs[u], d0[u], d1[u], in[u], par + 2 * (i + u), laser_id, tpk,
+                         azdiff, M);
         }
       } else {
 #pragma unroll 1
