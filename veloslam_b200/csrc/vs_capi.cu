@@ -50,6 +50,8 @@ struct Slot {
   size_t zero_bytes = 0;      //   per-frame laser counts
   unsigned long long *d_st_map = nullptr, *d_st_wrap = nullptr, *d_st_cnt = nullptr;
   int* d_counters = nullptr;
+  unsigned long long* d_grp_cnt = nullptr;  // per group of kGroupTiles scan tiles (atomics)
+  unsigned *d_grp_wsum = nullptr, *d_grp_wmax = nullptr;
   unsigned* d_frame_counts = nullptr;
   uint8_t* d_ff = nullptr;  // one allocation set to 0xff per batch: first_point / start_block
   long long* d_frame_first = nullptr;
@@ -228,18 +230,24 @@ int alloc_slot(vs_ctx* ctx, Slot& s) {
   VS_CUDA(cudaMalloc(&s.d_az, pts * sizeof(uint16_t)));
   VS_CUDA(cudaMalloc(&s.d_dist, pts * sizeof(uint16_t)));
   VS_CUDA(cudaMalloc(&s.d_t, pts * sizeof(uint32_t)));
-  // zeroed-per-batch block: [st_map | st_wrap | st_cnt | counters | frame_counts]
+  // zeroed-per-batch block: [st_map | st_wrap | st_cnt | counters | group aggregates | frame_counts]
   const size_t scan_tiles = (size_t)((np + kTilePkts - 1) / kTilePkts);
-  const size_t pose_tiles = (size_t)((np + kPoseThreads - 1) / kPoseThreads);
   size_t off = 0;
   const size_t o_map = off;
   off += align_up(scan_tiles * 8, 256);
   const size_t o_wrap = off;
-  off += align_up(pose_tiles * 8, 256);
+  off += align_up(scan_tiles * 8, 256);
   const size_t o_cnt = off;
-  off += align_up(pose_tiles * 8, 256);
+  off += align_up(scan_tiles * 8, 256);
   const size_t o_ctr = off;
   off += 256;
+  const size_t groups = scan_tiles / kGroupTiles + 1;
+  const size_t o_gc = off;
+  off += align_up(groups * 8, 256);
+  const size_t o_gs = off;
+  off += align_up(groups * 4, 256);
+  const size_t o_gm = off;
+  off += align_up(groups * 4, 256);
   const size_t o_fc = off;
   off += (size_t)fc * kMaxLasers * sizeof(unsigned);
   s.zero_bytes = off;
@@ -248,6 +256,9 @@ int alloc_slot(vs_ctx* ctx, Slot& s) {
   s.d_st_wrap = reinterpret_cast<unsigned long long*>(s.d_zero + o_wrap);
   s.d_st_cnt = reinterpret_cast<unsigned long long*>(s.d_zero + o_cnt);
   s.d_counters = reinterpret_cast<int*>(s.d_zero + o_ctr);
+  s.d_grp_cnt = reinterpret_cast<unsigned long long*>(s.d_zero + o_gc);
+  s.d_grp_wsum = reinterpret_cast<unsigned*>(s.d_zero + o_gs);
+  s.d_grp_wmax = reinterpret_cast<unsigned*>(s.d_zero + o_gm);
   s.d_frame_counts = reinterpret_cast<unsigned*>(s.d_zero + o_fc);
   VS_CUDA(cudaMalloc(&s.d_ff, (size_t)fc * 12));
   s.d_frame_first = reinterpret_cast<long long*>(s.d_ff);
@@ -429,6 +440,11 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     sp.pkt_seg = s.d_seg;
     sp.recs = s.d_recs;
     sp.st_map = s.d_st_map;
+    sp.agg_wrap = s.d_st_wrap;
+    sp.agg_cnt = s.d_st_cnt;
+    sp.grp_cnt = s.d_grp_cnt;
+    sp.grp_wsum = s.d_grp_wsum;
+    sp.grp_wmax = s.d_grp_wmax;
     sp.tile_counter = s.d_counters + 0;
     sp.hdr = s.d_hdr;
     const size_t smem = align_up(sizeof(ScanShared), 128) + (size_t)sp.stage_bytes;
@@ -448,9 +464,11 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     pp.pkt_seg = s.d_seg;
     pp.recs = s.d_recs;
     pp.pkt_off = s.d_pkt_off;
-    pp.st_wrap = s.d_st_wrap;
-    pp.st_cnt = s.d_st_cnt;
-    pp.tile_counter = s.d_counters + 1;
+    pp.agg_wrap = s.d_st_wrap;
+    pp.agg_cnt = s.d_st_cnt;
+    pp.grp_cnt = s.d_grp_cnt;
+    pp.grp_wsum = s.d_grp_wsum;
+    pp.grp_wmax = s.d_grp_wmax;
     pp.n = (int)n;
     pp.halo = (int)halo;
     pp.mode = mode;

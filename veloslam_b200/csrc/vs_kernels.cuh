@@ -187,11 +187,20 @@ struct ScanParams {
   PktSeg* pkt_seg;
   BlkRec* recs;
   unsigned long long* st_map;
+  unsigned long long* agg_wrap;  // per tile: (wraps << 32) | max origin marker
+  unsigned long long* agg_cnt;   // per tile: emitted points of the decoded packets
+  unsigned long long* grp_cnt;   // the same per group of kGroupTiles tiles (atomics)
+  unsigned* grp_wsum;
+  unsigned* grp_wmax;
   int* tile_counter;
   BatchHeader* hdr;
 };
 
 constexpr int kScanThreads = 256;
+// Two-level aggregates for the packet scans of k_pose: per tile (32 packets) and per group of
+// 256 tiles (8192 packets).  A k_pose CTA reduces the groups in front of its own and the tiles
+// of its group in front of it: no scan kernel and no look-back chain in between.
+constexpr int kGroupTiles = 256;
 
 struct ScanShared {
   uint64_t full;
@@ -489,28 +498,53 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
         p.recs[(first + lp) * kBlocks + j] = r;
       }
     }
-    if (warp == 0 && lane < npk) {
+    if (warp == 0) {
       unsigned cnt = 0;
+      if (lane < npk) {
 #pragma unroll
-      for (int j = 0; j < kBlocks; ++j) cnt += __popc(sh.nz[lane * kBlocks + j]);
-      const long long P = first + lane;
-      PktSeg r;
-      r.x = s_in | (int)(wrapmask << 4) | (azdiff << 16);
-      r.y = (int)cnt;
-      r.z = 0;
-      r.w = (int)(um | (cnt << 12));
-      p.pkt_seg[P] = r;
-      const unsigned ium = um & ~((1u << s_in) - 1u);
-      if (ium) {
-        const long long fu = P * 12 + (__ffs(ium) - 1);
-        // tiles run in order: after the first one almost every packet fails this test
-        if (fu < *reinterpret_cast<volatile long long*>(&p.hdr->first_upper_block))
-          atomicMin(reinterpret_cast<unsigned long long*>(&p.hdr->first_upper_block),
-                    (unsigned long long)fu);
+        for (int j = 0; j < kBlocks; ++j) cnt += __popc(sh.nz[lane * kBlocks + j]);
+        const long long P = first + lane;
+        PktSeg r;
+        r.x = s_in | (int)(wrapmask << 4) | (azdiff << 16);
+        r.y = (int)cnt;
+        r.z = 0;
+        r.w = (int)(um | (cnt << 12));
+        p.pkt_seg[P] = r;
+        const unsigned ium = um & ~((1u << s_in) - 1u);
+        if (ium) {
+          const long long fu = P * 12 + (__ffs(ium) - 1);
+          // tiles run in order: after the first one almost every packet fails this test
+          if (fu < *reinterpret_cast<volatile long long*>(&p.hdr->first_upper_block))
+            atomicMin(reinterpret_cast<unsigned long long*>(&p.hdr->first_upper_block),
+                      (unsigned long long)fu);
+        }
+        if (P == p.n - 1) {
+          p.hdr->last_azimuth = az11;
+          p.hdr->firing_skip_out = (p.mode == 0) ? map_apply(m, s_in) : 0;
+        }
       }
-      if (P == p.n - 1) {
-        p.hdr->last_azimuth = az11;
-        p.hdr->firing_skip_out = (p.mode == 0) ? map_apply(m, s_in) : 0;
+      // tile aggregates for the frame-id / origin / point-offset scans (k_tilescan, k_pose).
+      // Origin marker: streaming -> the packet after the wrap re-initialises the frame meta
+      // (F4b); offline -> the wrap packet itself.  marker - 1 == origin packet index.
+      const long long P = first + lane;
+      const unsigned nw = __popc(wrapmask);
+      unsigned long long aw =
+          ((unsigned long long)nw << 32) | (nw ? (unsigned)(P + (p.mode == 0 ? 2 : 1)) : 0u);
+      unsigned long long ac = (lane < npk && P >= p.halo) ? (unsigned long long)cnt : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        aw = WrapTraits::combine(aw, __shfl_xor_sync(0xffffffffu, aw, o));
+        ac += __shfl_xor_sync(0xffffffffu, ac, o);
+      }
+      if (lane == 0) {
+        p.agg_wrap[tile] = aw;
+        p.agg_cnt[tile] = ac;
+        const int g = tile / kGroupTiles;
+        if (ac) atomicAdd(&p.grp_cnt[g], ac);
+        if (aw) {
+          atomicAdd(&p.grp_wsum[g], (unsigned)(aw >> 32));
+          atomicMax(&p.grp_wmax[g], (unsigned)aw);
+        }
       }
     }
     __syncthreads();  // stage, nz, skip and tile_id are free again
@@ -519,8 +553,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
 
 // =========================================================================================
 // k_pose: one thread per packet.
-//   (1) scans over packets (decoupled look-back): wraps -> frame id, last wrap -> origin
-//       packet, emitted counts -> point offset; frame-start records of the frame table;
+//   (1) scans over packets (block scan on top of k_scan's tile / group aggregates): wraps -> frame
+//       id, last wrap -> origin packet, emitted counts -> point offset; frame-start records
+//       of the frame table;
 //   (2) pose bracket + lerp + Ry.Rx.Rz and T(packet) - T(origin) when the snapshot has >= 2
 //       poses: 12 doubles per packet, row-major [L | t].
 // =========================================================================================
@@ -529,9 +564,11 @@ struct PoseParams {
   PktSeg* pkt_seg;           // in: x, y = count; out: y = frame id, z = time - t_base
   const BlkRec* recs;
   unsigned long long* pkt_off;  // out: index of the packet's first emitted point
-  unsigned long long* st_wrap;
-  unsigned long long* st_cnt;
-  int* tile_counter;
+  const unsigned long long* agg_wrap;  // aggregates per 32-packet tile / per group (k_scan)
+  const unsigned long long* agg_cnt;
+  const unsigned long long* grp_cnt;
+  const unsigned* grp_wsum;
+  const unsigned* grp_wmax;
   int n;
   int halo;
   int mode;
@@ -556,17 +593,37 @@ __device__ __forceinline__ double to_radians(double x) {
 
 // TimeLine::getBoundaryData net semantics (TimeLine.h:384-468): i = clamp(lower_bound, 1, N-1),
 // bracket (i-1, i); then TransformManager.cxx:168-175 fore + (back - fore) * ratio.
+// The lower bound starts from an interpolated guess (INS poses are evenly sampled, so the guess
+// is the answer or next to it: two loads instead of log2 N dependent ones) and widens the
+// bracket geometrically when the guess is off; the result is the exact lower bound for any
+// strictly increasing pose times.
+__device__ __forceinline__ int pose_lower_bound(const long long* __restrict__ pt, int np, long long t) {
+  const long long t_first = __ldg(&pt[0]), t_last = __ldg(&pt[np - 1]);
+  if (t <= t_first) return 0;
+  if (t > t_last) return np;
+  int a = 0, b = np - 1;  // pt[a] < t <= pt[b]
+  int g = (int)((double)(t - t_first) / (double)(t_last - t_first) * (double)(np - 1));
+  g = g < 1 ? 1 : (g > np - 1 ? np - 1 : g);
+  for (int r = 1;; r *= 4) {
+    const int ph = min(g - 1 + r, np - 1), pl = max(g - r, 0);
+    const bool hi_ok = __ldg(&pt[ph]) >= t, lo_ok = __ldg(&pt[pl]) < t;
+    if (hi_ok) b = min(b, ph); else a = max(a, ph);
+    if (lo_ok) a = max(a, pl); else b = min(b, pl);
+    if (hi_ok && lo_ok) break;
+  }
+  while (b - a > 1) {
+    const int mid = (a + b) >> 1;
+    if (__ldg(&pt[mid]) < t)
+      a = mid;
+    else
+      b = mid;
+  }
+  return b;
+}
 __device__ __forceinline__ void interp_pose(const long long* __restrict__ pt,
                                             const double* __restrict__ trv, int np, long long t,
                                             double T[3], double R[3], bool want_R) {
-  int lo = 0, hi = np;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(&pt[mid]) < t)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
+  const int lo = pose_lower_bound(pt, np, t);
   int i = lo < 1 ? 1 : lo;
   if (i > np - 1) i = np - 1;
   const long long tf = __ldg(&pt[i - 1]), tb = __ldg(&pt[i]);
@@ -629,15 +686,11 @@ __device__ __forceinline__ void rotate_by(double L[3][3], double angle, int axis
 __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
   __shared__ unsigned long long s_w[kPoseThreads / 32];
   __shared__ unsigned long long s_c[kPoseThreads / 32];
-  __shared__ unsigned long long s_wrap_prefix, s_cnt_prefix;
-  __shared__ int s_tile;
+  __shared__ unsigned long long s_pw[kPoseThreads / 32], s_pc[kPoseThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
-  __syncthreads();
-  const int tile = s_tile;
+  const int tile = blockIdx.x;
   const int P = tile * kPoseThreads + tid;
   const bool live = P < p.n;
-
   PktSeg seg = make_int4(0, 0, 0, 0);
   if (live) seg = p.pkt_seg[P];
   const unsigned wrapmask = (seg.x >> 4) & 0xfff;
@@ -648,6 +701,29 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
   const unsigned long long v2 = ((unsigned long long)nw << 32) | marker;
   const unsigned long long cnt = (live && P >= p.halo) ? (unsigned long long)(unsigned)seg.y : 0ull;
 
+  // what precedes this CTA's 256 packets: the groups in front of its group + the tiles of its
+  // group in front of it (k_scan aggregates), reduced by the whole CTA
+  unsigned long long pw = 0ull, pc = 0ull;
+  {
+    static_assert(kPoseThreads % kTilePkts == 0, "a pose tile is a whole number of scan tiles");
+    const int my_tile = tile * (kPoseThreads / kTilePkts);  // first scan tile of this CTA
+    const int g = my_tile / kGroupTiles;
+    for (int q = tid; q < g; q += kPoseThreads) {
+      pw = WrapTraits::combine(pw, ((unsigned long long)__ldg(&p.grp_wsum[q]) << 32) | __ldg(&p.grp_wmax[q]));
+      pc += __ldg(&p.grp_cnt[q]);
+    }
+    static_assert(kGroupTiles <= kPoseThreads, "one thread per tile of a group");
+    const int f = g * kGroupTiles + tid;
+    if (tid < kGroupTiles && f < my_tile) {
+      pw = WrapTraits::combine(pw, __ldg(&p.agg_wrap[f]));
+      pc += __ldg(&p.agg_cnt[f]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      pw = WrapTraits::combine(pw, __shfl_xor_sync(0xffffffffu, pw, o));
+      pc += __shfl_xor_sync(0xffffffffu, pc, o);
+    }
+  }
   unsigned long long inc2 = v2, incc = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -661,6 +737,10 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
   if (lane == 31) {
     s_w[warp] = inc2;
     s_c[warp] = incc;
+  }
+  if (lane == 0) {
+    s_pw[warp] = pw;
+    s_pc[warp] = pc;
   }
   __syncthreads();
   if (warp == 0) {
@@ -681,17 +761,12 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
     }
   }
   __syncthreads();
-  // two look-backs side by side: warp 0 wraps/origin, warp 1 point counts
-  if (warp == 0) {
-    const unsigned long long ex =
-        lookback_exclusive<WrapTraits>(p.st_wrap, tile, s_w[kPoseThreads / 32 - 1]);
-    if (lane == 0) s_wrap_prefix = ex;
-  } else if (warp == 1) {
-    const unsigned long long ex =
-        lookback_exclusive<SumTraits>(p.st_cnt, tile, s_c[kPoseThreads / 32 - 1]);
-    if (lane == 0) s_cnt_prefix = ex;
+  unsigned long long s_wrap_prefix = 0ull, s_cnt_prefix = 0ull;
+#pragma unroll
+  for (int q = 0; q < kPoseThreads / 32; ++q) {
+    s_wrap_prefix = WrapTraits::combine(s_wrap_prefix, s_pw[q]);
+    s_cnt_prefix += s_pc[q];
   }
-  __syncthreads();
   unsigned long long ex2 = __shfl_up_sync(0xffffffffu, inc2, 1);
   unsigned long long exc = __shfl_up_sync(0xffffffffu, incc, 1);
   if (lane == 0) {
