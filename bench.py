@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 METRIC = "decoded+deskewed points/sec"
 UNIT = "points/s"
 BYTES_PER_POINT_OUT = 22          # x,y,z f32 + intensity u8 + laser u8 + azimuth u16 + distance u16 + t u32
+# What the reference-facing facade (veloslam_b200/cpp/HDLParser.cpp, decodePending) copies back
+# to build HDLFrame::points / pointsMeta: every column but t_us (HDLFrame has no per-point time).
+BYTES_PER_POINT_E2E = 18
 HBM_FALLBACK_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -45,6 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-online", action="store_true")
     return ap.parse_args()
 
 
@@ -418,6 +422,17 @@ def run_ours(args):
     if not args.no_e2e:
         e2e = run_e2e(args, ctx_args=(local, calib, poses), b=b[halo:], t=t[halo:], t_base=t_base,
                       world=world, dev=dev)
+    online = None
+    if not args.no_online:
+        online = run_online(local, calib, poses, b[halo:], t[halo:], t_base)
+        if world > 1:
+            allo = [None] * world
+            torch.distributed.all_gather_object(allo, online)
+            online = {"per_rank_p99_ms": [o["index_only"]["p99_ms"] for o in allo],
+                      "per_rank_p50_ms": [o["index_only"]["p50_ms"] for o in allo],
+                      "aggregate_points_per_s": sum(o["index_only"]["points_per_s"] for o in allo),
+                      "with_points_p99_ms": [o["with_points"]["p99_ms"] for o in allo],
+                      "streams": world, "note": allo[0]["note"]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = run_cpu_baseline(calib, poses, args.cpu_seconds)
@@ -445,6 +460,8 @@ def run_ours(args):
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if online is not None:
+            line["online"] = online
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
@@ -474,6 +491,10 @@ def run_e2e(args, ctx_args, b, t, t_base, world, dev):
                  torch.int16, torch.int16, torch.int32)]
         outs.append(cols)
 
+    def ptrs_of(slot):
+        # x, y, z, intensity, laser, azimuth, distance; t_us stays on the device (NULL)
+        return [x.data_ptr() for x in outs[slot][:7]] + [None]
+
     def one_pass():
         carry = capi.carry_init()
         pending = None
@@ -491,16 +512,14 @@ def run_e2e(args, ctx_args, b, t, t_base, world, dev):
                             mode=capi.MODE_STREAMING, flags=0, t_base_us=t_base, carry=carry)
             h2d += chunk * (1206 + 8)
             if pending is not None:
-                ptrs = [x.data_ptr() for x in outs[pending[1]]]
-                ctx.fetch_into(pending[0], 0, rprev.n_points, ptrs)
+                ctx.fetch_into(pending[0], 0, rprev.n_points, ptrs_of(pending[1]))
                 total += rprev.n_points
-                d2h += rprev.n_points * BYTES_PER_POINT_OUT
+                d2h += rprev.n_points * BYTES_PER_POINT_E2E
             pending = (tk, c % 2)
         rprev = ctx.wait(pending[0], frames=False)
-        ptrs = [x.data_ptr() for x in outs[pending[1]]]
-        ctx.fetch_into(pending[0], 0, rprev.n_points, ptrs)
+        ctx.fetch_into(pending[0], 0, rprev.n_points, ptrs_of(pending[1]))
         total += rprev.n_points
-        d2h += rprev.n_points * BYTES_PER_POINT_OUT
+        d2h += rprev.n_points * BYTES_PER_POINT_E2E
         return total, h2d, d2h
 
     def barrier():
@@ -526,7 +545,57 @@ def run_e2e(args, ctx_args, b, t, t_base, world, dev):
     return {"value": total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
             "chunk_packets": chunk, "note": "host pinned packets -> vs_submit/vs_wait -> "
-            "vs_fetch_points into pinned host columns (all 8 columns, 22 B/point); PCIe-bound"}
+            "vs_fetch_points into pinned host columns: the 7 columns the HDLFrame facade "
+            "consumes (x, y, z, intensity, laser, azimuth, distance = 18 B/point; t_us has no "
+            "counterpart in HDLFrame and stays on the device); PCIe D2H bound"}
+
+
+def run_online(local, calib, poses, b, t, t_base, rotations=300):
+    """BASELINE.json configs[4] on this rank's GPU: one stream, rotation-sized batches (347
+    packets, 133 k points), host packets in -> frame index table on the host, back to back.
+    Latency = wall time of vs_submit + vs_wait (H2D of the packets, the four kernels, D2H of the
+    batch header and frame rows); the second figure adds the D2H of the facade's 7 columns."""
+    import torch
+    from veloslam_b200 import capi
+    rot = 347
+    n_rot = min(rotations, b.shape[0] // rot)
+    ctx = capi.Context(local, max_batch_packets=512, max_poses=len(poses[0]) + 8, n_slots=1)
+    ctx.set_calibration(calib)
+    ctx.set_poses(poses[0], poses[1])
+    h_pk = torch.from_numpy(b[:n_rot * rot]).pin_memory()
+    h_t = torch.from_numpy(np.ascontiguousarray(t[:n_rot * rot])).pin_memory()
+    cols = [torch.empty(512 * 384, dtype=dt).pin_memory() for dt in
+            (torch.float32, torch.float32, torch.float32, torch.uint8, torch.uint8, torch.int16,
+             torch.int16)]
+    ptrs = [c.data_ptr() for c in cols] + [None]
+    out = {}
+    for with_points in (False, True):
+        carry = capi.carry_init()
+        lat = []
+        pts = 0
+        t_all0 = time.perf_counter()
+        for r in range(n_rot):
+            a = r * rot
+            t0 = time.perf_counter()
+            tk = ctx.submit(h_pk[a:a + rot], h_t[a:a + rot], n=rot, stride=1206,
+                            mode=capi.MODE_STREAMING, flags=0, t_base_us=t_base, carry=carry)
+            res = ctx.wait(tk, frames=False)
+            if with_points and res.n_points:
+                ctx.fetch_into(tk, 0, res.n_points, ptrs)
+            lat.append(time.perf_counter() - t0)
+            carry = res.carry_out
+            pts += res.n_points
+        dt_all = time.perf_counter() - t_all0
+        lat = np.array(lat[10:]) * 1e3  # first rotations warm the path up
+        out["with_points" if with_points else "index_only"] = {
+            "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
+            "max_ms": float(lat.max()), "points_per_s": pts / dt_all}
+    ctx.close()
+    out["rotations"] = n_rot
+    out["packets_per_rotation"] = rot
+    out["note"] = ("one HDL-64E stream on this GPU, rotation-sized batches back to back (a 10 Hz "
+                   "sensor leaves 100 ms per rotation); host wall clock around vs_submit+vs_wait")
+    return out
 
 
 def main():
