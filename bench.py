@@ -295,6 +295,27 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+NCU_FULL_CSV = os.path.join(ROOT, "profiles", "r1s_k_decode_ncu_full.csv")
+NCU_FULL_PACKETS = 1 << 20  # packets per launch of the captured k_decode
+
+
+def ncu_traffic(n_per):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_decode launch from the committed
+    `ncu --set full` capture (same workload and batch size), else None."""
+    if n_per != NCU_FULL_PACKETS or not os.path.exists(NCU_FULL_CSV):
+        return None, None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    try:
+        for line in open(NCU_FULL_CSV):
+            name, unit, val = line.strip().split(",")[:3]
+            if name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(val) * scale[unit]
+    except Exception:
+        return None, None
+    return (tot if tot > 0 else None), os.path.relpath(NCU_FULL_CSV, ROOT)
+
+
 def run_ours(args):
     import torch
     from veloslam_b200 import capi, sharding, synth
@@ -394,12 +415,14 @@ def run_ours(args):
     except Exception:
         pass
     alg_bytes = 1206 * n_per + BYTES_PER_POINT_OUT * n_emitted
+    traffic, traffic_src = ncu_traffic(n_per)
     dec_avg_ms = float(np.mean(dec_ms))
     achieved = alg_bytes / (dec_avg_ms * 1e-3) / 1e9
     step_avg_ms = float(np.mean(step_ms))
     roofline = {"bound": "hbm", "kernel": "k_decode", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": dec_avg_ms,
                 # every kernel, memset and gap of the step: algorithmic bytes / ms_per_step
                 "frac_whole_step": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
