@@ -187,6 +187,52 @@ def test_ragged_sizes(n):
     _run_streaming(pk, t, synth.calib_hdl64(), synth.ins_trajectory(10))
 
 
+# --- staged output of k_decode: whole 16-element granules by TMA bulk store, scalar head / tail ------
+@pytest.mark.parametrize("n", [3, 7, 8, 9, 15, 16, 17, 23, 24, 25, 40])
+def test_sizes_around_the_decode_tile(n):
+    """k_decode tiles are 8 packets, a warp pair owns 2 of them: every remainder."""
+    pk, t = synth.hdl64_packets(n, az0=35950.0, seed=n)
+    _run_streaming(pk, t, synth.calib_hdl64(), synth.ins_trajectory(10))
+
+
+@pytest.mark.parametrize("zero_frac", [0.5, 0.9, 0.97, 0.995])
+def test_sparse_returns_partial_granules(zero_frac):
+    """Few points per packet pair: ranges shorter than one 16-element granule (scalar stores
+    only), ranges that straddle one granule boundary, pairs and packets that emit nothing."""
+    pk, t = synth.hdl64_packets(700, zero_frac=zero_frac, seed=int(zero_frac * 1000))
+    d = pk["blocks"]["returns"]["distance"]
+    d[100:140] = 0          # whole packets without a point, inside and across tiles
+    d[333] = 0
+    _run_streaming(pk, t, synth.calib_hdl64(), synth.ins_trajectory(30), splits=(97, 98, 355))
+
+
+def test_sparse_hdl32_and_random_streams():
+    pk, t = synth.hdl32_packets(500, zero_frac=0.93, seed=93)
+    _run_streaming(pk, t, synth.calib_hdl32(), tol=0.0)
+    pk, t = synth.random_packets(300, seed=77, zero_frac=0.9)
+    _run_streaming(pk, t, synth.calib_hdl64(), synth.ins_trajectory(20))
+
+
+@pytest.mark.parametrize("halo", [349, 350, 351, 356])
+def test_odd_and_even_halos(halo):
+    """The point-offset column is copied from an even index: odd first packets shift it."""
+    pk, t = synth.hdl64_packets(1500, seed=halo)
+    b = synth.as_bytes(pk)
+    calib = synth.calib_hdl64()
+    poses = synth.ins_trajectory(60)
+    ctx = P.make_ctx(calib, poses)
+    whole = ctx.decode(b, t, t_base_us=int(t[0]))
+    wc = whole.fetch()
+    cut = 801
+    r = ctx.decode(np.ascontiguousarray(b[cut - halo:]), np.ascontiguousarray(t[cut - halo:]),
+                   n_halo=halo, t_base_us=int(t[0]))
+    c = r.fetch()
+    first = whole.n_points - r.n_points
+    for k in wc:
+        assert np.array_equal(wc[k][first:], c[k]), k
+    ctx.close()
+
+
 def test_all_zero_distances_emit_nothing():
     pk, t = synth.hdl64_packets(100, zero_frac=1.1)
     ctx = P.make_ctx(synth.calib_hdl64())
