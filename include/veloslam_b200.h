@@ -206,6 +206,14 @@ VS_API int vs_read_frame_information(vs_ctx* ctx, const uint8_t* pkts, int64_t s
 VS_API int vs_host_alloc(uint64_t bytes, void** out);
 VS_API void vs_host_free(void* p);
 
+/* Device buffers for callers above the ABI that keep a whole recording resident in HBM and
+ * decode rotations out of it on demand (HDLManager::loadOffline / prepareFrame,
+ * HDLManager.cxx:103-117, 195-211: the reference re-reads the pcap file for every frame it
+ * re-decodes).  Pointers returned here are what VS_FLAG_DEVICE_INPUT expects. */
+VS_API int vs_device_alloc(vs_ctx* ctx, uint64_t bytes, void** out_dev);
+VS_API void vs_device_free(vs_ctx* ctx, void* dev);
+VS_API int vs_device_upload(vs_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes);
+
 /* The CUDA stream the context launches on (cudaStream_t), for callers that time or order
  * work against it. */
 VS_API void* vs_stream(vs_ctx* ctx);

@@ -153,6 +153,98 @@ static int hostModes(int argc, char** argv) {
     os.write((const char*)vert, sizeof(vert));
     return 0;
   }
+  if (mode == "manager_host" && argc >= 4) {
+    // HDLManager host logic without a GPU: time queries, cache, hard-drive buffers written as
+    // pcap files, .hdlmeta round trip.  argv[2]: scratch directory, argv[3]: report file.
+    std::ofstream rep(argv[3]);
+    HDLManager mgr(100);
+    mgr.setBufferDir(argv[2], false);
+    const int64_t t0 = 1467331200000000ll;
+    std::vector<std::shared_ptr<HDLFrame> > made;
+    for (int i = 0; i < 10; ++i) {
+      std::shared_ptr<HDLFrame> f(new HDLFrame);
+      f->timestamp = ptime(t0 + 100000ll * i);
+      f->isInMemory = true;
+      f->points.resize(1);
+      f->points[0] = pcl::PointCloud<pcl::PointXYZI>::Ptr(new pcl::PointCloud<pcl::PointXYZI>);
+      f->points[0]->points.resize(5);
+      f->carpose->T[0] = i;
+      f->skips = (uint8_t)(i % 12);
+      for (int k = 0; k < 3; ++k) {  // three raw packets per frame
+        std::string raw(1206, (char)(i * 3 + k));
+        f->packets.push_back(std::make_pair(ptime(t0 + 100000ll * i + 288 * k), raw));
+      }
+      made.push_back(f);
+    }
+    // out-of-order insertion keeps the timeline sorted
+    mgr.addFrame(made[1]);
+    mgr.addFrame(made[0]);
+    for (int i = 2; i < 10; ++i) mgr.addFrame(made[i]);
+    rep << "frames " << mgr.getNumberOfFrames() << "\n";
+    ptime q(t0 + 300000);
+    HDLFramePtr at = mgr.getFrameAt(q);
+    rep << "at3 " << (at ? (int)at->carpose->T[0] : -1) << "\n";
+    ptime qn(t0 + 449999);
+    HDLFramePtr near = mgr.getFrameNear(qn);
+    rep << "near4 " << (near ? (int)near->carpose->T[0] : -1) << "\n";
+    ptime qm(t0 + 123);
+    rep << "at_missing " << (mgr.getFrameAt(qm) ? 1 : 0) << "\n";
+    ptime a(t0 + 200000), b(t0 + 500000);
+    rep << "range " << mgr.getRangeBetween(a, b).size() << "\n";
+    rep << "recent " << (int)mgr.getRecentFrame()->carpose->T[0] << "\n";
+    // a cache of 4 frames: older frames are cleared unless an end user still holds them
+    {
+      HDLManager small(4);
+      std::vector<std::shared_ptr<HDLFrame> > fr;
+      for (int i = 0; i < 10; ++i) {
+        std::shared_ptr<HDLFrame> f(new HDLFrame);
+        f->timestamp = ptime(t0 + 100000ll * i);
+        f->isInMemory = true;
+        f->points.resize(1);
+        fr.push_back(f);
+      }
+      for (int i = 0; i < 4; ++i) small.addFrame(fr[i]);
+      ptime t1(t0 + 100000);
+      HDLFramePtr held = small.getFrameAt(t1);
+      for (int i = 4; i < 10; ++i) small.addFrame(fr[i]);
+      int cleared = 0;
+      for (auto& f : fr) cleared += f->points.empty() ? 1 : 0;
+      rep << "cleared " << cleared << "\n";
+      rep << "held1_alive " << ((held && !fr[1]->points.empty()) ? 1 : 0) << "\n";
+      ptime t2(t0 + 200000);
+      rep << "cleared_not_on_disk " << (small.getFrameAt(t2) ? 1 : 0) << "\n";
+    }
+    // hard-drive buffers: 3 frames per pcap file
+    HDLManager disk(100);
+    disk.setBufferDir(argv[2], false);
+    disk.setBufferSize(3);
+    disk.startSwaping();
+    std::vector<std::shared_ptr<HDLFrame> > made2;
+    for (int i = 0; i < 7; ++i) {
+      std::shared_ptr<HDLFrame> f(new HDLFrame);
+      f->timestamp = ptime(t0 + 100000ll * i);
+      f->isInMemory = true;
+      for (int k = 0; k < 3; ++k) {
+        std::string raw(1206, (char)(i * 3 + k));
+        f->packets.push_back(std::make_pair(ptime(t0 + 100000ll * i + 288 * k), raw));
+      }
+      made2.push_back(f);
+      disk.addFrame(f);
+    }
+    disk.flushFileBuffer();
+    for (int i = 0; i < 7; ++i)
+      rep << "disk " << i << " " << (made2[i]->isOnHardDrive ? 1 : 0) << " " << made2[i]->fileStartPos
+          << " " << to_iso_string(made2[i]->filenameTime) << "\n";
+    rep << "savemeta " << (disk.saveHDLMeta() ? 1 : 0) << "\n";
+    HDLManager again(100);
+    again.setBufferDir(argv[2], false);
+    rep << "loadmeta " << (again.loadHDLMeta() ? 1 : 0) << " " << again.getNumberOfFrames() << "\n";
+    std::vector<std::shared_ptr<HDLFrame> > meta = again.getAllFrameMeta();
+    for (size_t i = 0; i < meta.size(); ++i)
+      rep << "meta " << i << " " << meta[i]->timestamp.us << " " << meta[i]->fileStartPos << " "
+          << (int)meta[i]->skips << " " << (meta[i]->isOnHardDrive ? 1 : 0) << "\n";
+    return 0;
+  }
   return -1;
 }
 
@@ -193,6 +285,48 @@ int main(int argc, char** argv) {
     const int32_t nf = (int32_t)all.size();
     os.write((const char*)&nf, 4);
     for (auto& f : all) dumpFrame(os, *f);
+    return 0;
+  }
+  if (mode == "manager" || mode == "manager_file") {
+    // HDLManager::loadOffline on a packet file, then every frame through getFrameAt
+    //   facade_driver manager <calib.xml> <file.pcap> <poses.bin|-> <out.bin>
+    // manager: rotations are decoded out of the recording resident in HBM;
+    // manager_file: the recording is dropped after the index, getFrame re-reads the file.
+    HDLManager mgr(8);
+    mgr.setCalibFile(argv[2]);
+    std::shared_ptr<TransformManager> poses = loadPoses(argv[4]);
+    std::vector<int64_t> pt;
+    std::vector<double> trv;
+    poses->snapshot(&pt, &trv);
+    for (size_t i = 0; i < pt.size(); ++i) {
+      std::shared_ptr<PoseTransform> p(new PoseTransform);
+      for (int k = 0; k < 3; ++k) {
+        p->T[k] = trv[9 * i + k];
+        p->R[k] = trv[9 * i + 3 + k];
+        p->V[k] = trv[9 * i + 6 + k];
+      }
+      p->timestamp = ptime(pt[i]);
+      p->seconds_pos = 0;
+      mgr.getTransformMgr()->addTransform(p);
+    }
+    mgr.loadOffline("-", argv[3]);  // "-": no INS text file, the poses above stay
+    const bool resident = mgr.getParser()->hasRecording(argv[3]);
+    std::cerr << "resident " << (resident ? 1 : 0) << std::endl;
+    if (mode == "manager_file") mgr.getParser()->unloadRecording();
+    std::vector<std::shared_ptr<HDLFrame> > meta = mgr.getAllFrameMeta();
+    std::ofstream os(argv[5], std::ios::binary);
+    const int32_t nf = (int32_t)meta.size();
+    os.write((const char*)&nf, 4);
+    for (auto& m : meta) {
+      ptime t = m->timestamp;
+      HDLFramePtr f = mgr.getFrameAt(t);
+      if (!f) return 1;
+      dumpFrame(os, *f);
+    }
+    if (!mgr.getParser()->lastError().empty()) {
+      std::cerr << "facade error: " << mgr.getParser()->lastError() << std::endl;
+      return 1;
+    }
     return 0;
   }
   if (mode == "offline") {

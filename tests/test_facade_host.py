@@ -83,3 +83,38 @@ def test_calibration_xml_reader(tmp_path):
     raw = open(tmp_path / "c.bin", "rb").read()
     assert int(np.frombuffer(raw, "<i4", 1)[0]) == 64
     assert np.array_equal(np.frombuffer(raw, "<f8", 64, 4), calib.vert_deg)
+
+
+# --- HDLManager host logic: TimeLine queries, cache, hard-drive buffers, meta ------
+def test_hdlmanager_host_logic(tmp_path):
+    d = tmp_path / "buf"
+    d.mkdir()
+    r = F.run(["manager_host", d, tmp_path / "report.txt"])
+    assert r.returncode == 0, r.stderr
+    rep = [l.split() for l in open(tmp_path / "report.txt")]
+    kv = {l[0]: l[1:] for l in rep if l[0] not in ("disk", "meta")}
+    assert kv["frames"] == ["10"]
+    assert kv["at3"] == ["3"] and kv["near4"] == ["4"] and kv["at_missing"] == ["0"]
+    assert kv["range"] == ["4"]            # [a, b] inclusive on both ends (HDLManager.h:148)
+    assert kv["recent"] == ["9"]
+    # cache of 4 (HDLManager.cxx:400-421): the held frame survives and keeps its cache slot
+    assert kv["cleared"] == ["6"] and kv["held1_alive"] == ["1"]
+    assert kv["cleared_not_on_disk"] == ["0"]
+    # hard-drive buffers of 3 frames x 3 packets: file names = first packet time, manual fpos
+    disk = [l for l in rep if l[0] == "disk"]
+    assert [int(l[3]) for l in disk] == [24, 24 + 3 * 1264, 24 + 6 * 1264] * 2 + [24]
+    assert all(l[2] == "1" for l in disk)
+    assert [l[4] for l in disk] == ["20160701T000000"] * 3 + ["20160701T000000.300000"] * 3 + \
+        ["20160701T000000.600000"]
+    # the files are what vtkPacketFileWriter writes: header + 1264-byte records, payload intact
+    img = np.fromfile(d / "20160701T000000.pcap", dtype=np.uint8)
+    assert img.size == 24 + 9 * 1264
+    rec = img[24:].reshape(9, 1264)
+    assert all(np.all(rec[k, 58:] == k) for k in range(9))
+    # .hdlmeta round trip into a fresh manager
+    assert kv["savemeta"] == ["1"] and kv["loadmeta"] == ["1", "7"]
+    meta = [l for l in rep if l[0] == "meta"]
+    assert [int(l[2]) for l in meta] == [synth.T0_US - synth.T0_US + 1467331200000000 + 100000 * i
+                                         for i in range(7)]
+    assert [int(l[3]) for l in meta] == [int(l[3]) for l in disk]
+    assert all(l[5] == "1" for l in meta)

@@ -77,3 +77,58 @@ def test_offline_like_hdlmanager(tmp_path):
         assert np.array_equal(f.azimuth, want.azimuth)
         d = np.abs(f.xyzi[:, :3].astype(np.float64) - want.xyzi[:, :3])
         assert d.max() <= P.TOL_DESKEW
+
+
+# --- HDLManager: loadOffline + getFrameAt, recording resident in HBM vs file ------
+@pytest.mark.parametrize("mode", ["manager", "manager_file"])
+def test_hdlmanager_load_offline_and_get_frame(tmp_path, mode):
+    pk, t = synth.hdl64_packets(1300, seed=64)
+    calib = synth.calib_hdl64()
+    poses = synth.ins_trajectory(60)
+    b = synth.as_bytes(pk)
+    path = tmp_path / "20160701T000000.pcap"
+    pcapio.write_pcap(str(path), b, t)
+    F.write_poses(tmp_path / "poses.bin", *poses)
+    calibxml.write_db_xml(str(tmp_path / "db.xml"), calib)
+    r = F.run([mode, tmp_path / "db.xml", path, tmp_path / "poses.bin", tmp_path / "out.bin"])
+    assert r.returncode == 0, r.stderr
+    assert "resident 1" in r.stderr        # fixed-stride packet file: uploaded to HBM once
+    frames = F.read_frames(tmp_path / "out.bin")
+    o = P.make_oracle(calib, poses)
+    sp, sk, ts = Oracle.read_frame_information(b, t)
+    assert len(frames) == len(sp)          # GPU index == reference index
+    for i, f in enumerate(frames):
+        want = o.get_frame(b, t, sp[i], sk[i])
+        assert f.n_points == want.n_points and f.timestamp_us == ts[i] and f.skips == sk[i]
+        ok, trv, spos = o.interpolate(int(ts[i]))     # HDLManager::loadOffline sets carpose
+        assert np.allclose(f.carpose_TRV, trv, rtol=0, atol=1e-12)
+        assert np.array_equal(f.laser_counts, want.laser_counts)
+        assert np.array_equal(f.azimuth, want.azimuth)
+        assert np.array_equal(f.xyzi[:, 3], want.xyzi[:, 3])
+        d = np.abs(f.xyzi[:, :3].astype(np.float64) - want.xyzi[:, :3])
+        assert d.max() <= P.TOL_DESKEW
+
+
+def test_hdlmanager_renames_recording_and_index_spans_batches(tmp_path):
+    """A file not named after its first packet is renamed (HDLParser.cxx:1150-1158) and keeps
+    being served from HBM; 9000 packets > the parser's 4096-packet batch: the GPU index runs in
+    chunks linked by the carry."""
+    pk, t = synth.hdl32_packets(9000, seed=5)
+    calib = synth.calib_hdl32()
+    b = synth.as_bytes(pk)
+    path = tmp_path / "drive.pcap"
+    pcapio.write_pcap(str(path), b, t)
+    calibxml.write_db_xml(str(tmp_path / "db.xml"), calib)
+    r = F.run(["manager", tmp_path / "db.xml", path, "-", tmp_path / "out.bin"])
+    assert r.returncode == 0, r.stderr
+    assert not path.exists() and len(list(tmp_path.glob("2016*T*.pcap"))) == 1
+    frames = F.read_frames(tmp_path / "out.bin")
+    sp, sk, ts = Oracle.read_frame_information(b, t)
+    assert len(frames) == len(sp) and len(sp) > 40
+    o = P.make_oracle(calib)
+    for i in (0, 1, len(sp) // 2, len(sp) - 1):
+        want = o.get_frame(b, t, sp[i], sk[i])
+        f = frames[i]
+        assert f.timestamp_us == ts[i] and f.skips == sk[i] and f.n_points == want.n_points
+        assert np.array_equal(f.azimuth, want.azimuth)
+        assert np.array_equal(f.xyzi.view(np.uint32), want.xyzi.view(np.uint32))

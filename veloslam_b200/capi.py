@@ -23,7 +23,8 @@ STATUS = {0: "VS_OK", 1: "VS_ERR_INVALID_ARG", 2: "VS_ERR_NOT_CALIBRATED", 3: "V
 EXPORTS = ["vs_version", "vs_create", "vs_destroy", "vs_last_error", "vs_set_calibration",
            "vs_set_filters", "vs_set_poses", "vs_interpolate", "vs_carry_init", "vs_submit",
            "vs_wait", "vs_fetch_points", "vs_read_frame_information", "vs_host_alloc",
-           "vs_host_free", "vs_stream", "vs_slot_stream"]
+           "vs_host_free", "vs_stream", "vs_slot_stream", "vs_device_alloc", "vs_device_free",
+           "vs_device_upload"]
 
 
 class LaserCorr(C.Structure):

@@ -1,0 +1,351 @@
+// HDLManager.cpp -- see HDLManager.h.  Host logic only; every decode goes through HDLParser
+// (C ABI -> sm_100a kernels).
+#include "HDLManager.h"
+
+#include <dirent.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+
+#include <algorithm>
+#include <chrono>
+#include <fstream>
+#include <iostream>
+
+namespace {
+ptime localTimeNow() {
+  timeval tv;
+  gettimeofday(&tv, nullptr);
+  return ptime((int64_t)tv.tv_sec * 1000000ll + tv.tv_usec);
+}
+bool isDirectory(const std::string& d) {
+  struct stat st;
+  return stat(d.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+std::string parentPath(const std::string& f) {
+  const size_t slash = f.find_last_of('/');
+  return slash == std::string::npos ? std::string(".") : f.substr(0, slash);
+}
+
+// .hdlmeta record (reference HDLFrame.cxx:160-190): timestamp, filenameTime, fileStartPos,
+// skips, isOnHardDrive, then the car pose as in .insmeta (type_defs.cxx:4-33)
+void writePoseRecord(std::ofstream& os, const PoseTransform& p) {
+  for (int i = 0; i < 3; ++i) {
+    os.write(reinterpret_cast<const char*>(p.T + i), sizeof(double));
+    os.write(reinterpret_cast<const char*>(p.R + i), sizeof(double));
+    os.write(reinterpret_cast<const char*>(p.V + i), sizeof(double));
+  }
+  os.write(reinterpret_cast<const char*>(&p.timestamp.us), sizeof(int64_t));
+  os.write(reinterpret_cast<const char*>(&p.week_number), sizeof(p.week_number));
+  os.write(reinterpret_cast<const char*>(&p.milliseconds), sizeof(p.milliseconds));
+  os.write(reinterpret_cast<const char*>(&p.week_number_pos), sizeof(p.week_number_pos));
+  os.write(reinterpret_cast<const char*>(&p.seconds_pos), sizeof(p.seconds_pos));
+}
+bool readPoseRecord(std::ifstream& is, PoseTransform& p) {
+  for (int i = 0; i < 3; ++i) {
+    is.read(reinterpret_cast<char*>(p.T + i), sizeof(double));
+    is.read(reinterpret_cast<char*>(p.R + i), sizeof(double));
+    is.read(reinterpret_cast<char*>(p.V + i), sizeof(double));
+  }
+  is.read(reinterpret_cast<char*>(&p.timestamp.us), sizeof(int64_t));
+  is.read(reinterpret_cast<char*>(&p.week_number), sizeof(p.week_number));
+  is.read(reinterpret_cast<char*>(&p.milliseconds), sizeof(p.milliseconds));
+  is.read(reinterpret_cast<char*>(&p.week_number_pos), sizeof(p.week_number_pos));
+  is.read(reinterpret_cast<char*>(&p.seconds_pos), sizeof(p.seconds_pos));
+  return (bool)is;
+}
+void writeFrameRecord(std::ofstream& os, const HDLFrame& f) {
+  os.write(reinterpret_cast<const char*>(&f.timestamp.us), sizeof(int64_t));
+  os.write(reinterpret_cast<const char*>(&f.filenameTime.us), sizeof(int64_t));
+  os.write(reinterpret_cast<const char*>(&f.fileStartPos), sizeof(f.fileStartPos));
+  os.write(reinterpret_cast<const char*>(&f.skips), sizeof(f.skips));
+  os.write(reinterpret_cast<const char*>(&f.isOnHardDrive), sizeof(f.isOnHardDrive));
+  writePoseRecord(os, *f.carpose);
+}
+bool readFrameRecord(std::ifstream& is, HDLFrame& f) {
+  is.read(reinterpret_cast<char*>(&f.timestamp.us), sizeof(int64_t));
+  is.read(reinterpret_cast<char*>(&f.filenameTime.us), sizeof(int64_t));
+  is.read(reinterpret_cast<char*>(&f.fileStartPos), sizeof(f.fileStartPos));
+  is.read(reinterpret_cast<char*>(&f.skips), sizeof(f.skips));
+  is.read(reinterpret_cast<char*>(&f.isOnHardDrive), sizeof(f.isOnHardDrive));
+  return readPoseRecord(is, *f.carpose);
+}
+}  // namespace
+
+HDLManager::HDLManager(int capacity)
+    : hardDriveBuffer(&hardDriveBuffer1), cacheCounter(0), hasNewData(false), bufferSize(100),
+      maxCacheSize((size_t)capacity), bufferDirName("/tmp/"), isUsingBuffer1(true),
+      writerIdle(true), fileBufferMode(false), packetWriter(new vtkPacketFileWriter),
+      transMgr(new TransformManager), hdlParser(new HDLParser), metaSerial(0) {
+  hdlParser->setTransformMgr(transMgr);
+}
+
+HDLManager::~HDLManager() { delete packetWriter; }
+
+void HDLManager::loadOffline(const std::string& insTxt, const std::string& pcapfile) {
+  frames.clear();
+  transMgr->loadFromTxtFile(insTxt, true);
+  std::cout << "Read " << transMgr->getNumberOfTransforms() << " transforms.\n";
+  // the whole recording goes to HBM once; when the file is not a fixed-stride packet file the
+  // parser falls back to reading it record by record, like the reference
+  hdlParser->loadRecording(pcapfile);
+  auto frameVec = hdlParser->readFrameInformation(pcapfile);
+  /* because readFrameInformation() can't determine carpose for each frame
+   * we need to ask transform manager */
+  for (auto& f : frameVec) {
+    transMgr->interpolateTransform(f->timestamp, f->carpose.get());
+    this->addFrame(f);
+  }
+  std::cout << "Read " << this->getNumberOfFrames() << " frames." << std::endl;
+  this->setBufferDir(parentPath(pcapfile), false);
+}
+
+void HDLManager::touchPcap(const std::string& pcapfile) { hdlParser->readFrameInformation(pcapfile, true); }
+
+int HDLManager::getNumberOfFrames() {
+  std::lock_guard<std::mutex> lock(framesMutex);
+  return (int)frames.size();
+}
+int HDLManager::getNumberOfTransforms() { return transMgr->getNumberOfTransforms(); }
+
+void HDLManager::scanBufferDir() {
+  DIR* d = opendir(bufferDirName.c_str());
+  if (!d) return;
+  while (dirent* e = readdir(d)) {
+    const std::string name = e->d_name;
+    const size_t dot = name.find_last_of('.');
+    if (dot == std::string::npos) continue;
+    const std::string ext = name.substr(dot);
+    if (ext == HDL_META_EXT_NAME)
+      hdlMetaNames.insert(bufferDirName + name);
+    else if (ext == INS_META_EXT_NAME)
+      insMetaNames.insert(bufferDirName + name);
+    else if (ext == ".pcap")
+      bufferFileNames.insert(name);
+  }
+  closedir(d);
+}
+
+void HDLManager::switchBuffer() {
+  {
+    std::lock_guard<std::mutex> lock(writerMutex);
+    hardDriveBuffer = isUsingBuffer1 ? &hardDriveBuffer2 : &hardDriveBuffer1;
+    isUsingBuffer1 = !isUsingBuffer1;
+    writerIdle = false;
+  }
+  // the reference wakes its writer thread here; this facade writes in place
+  writePackets();
+}
+
+void HDLManager::setCalibFile(std::string filename) { hdlParser->setCorrectionsFile(filename); }
+
+void HDLManager::addFrame(std::shared_ptr<HDLFrame> frame) {
+  {
+    std::lock_guard<std::mutex> lock(framesMutex);
+    frames.addData(frame);
+    hasNewData = true;
+    cond_.notify_one();
+  }
+  if (fileBufferMode && (!frame->isOnHardDrive)) {
+    hardDriveBuffer->push_back(frame);
+    if (hardDriveBuffer->size() == bufferSize && writerIdle) switchBuffer();
+  } else {
+    pushCache(frame);
+  }
+}
+
+HDLFramePtr HDLManager::prepareFrame(std::shared_ptr<HDLFrame> frame) {
+  if (!frame) return HDLFramePtr();
+  if (frame->isInMemory) {
+    return HDLFramePtr(frame.get());
+  } else if (frame->isOnHardDrive) {
+    const std::string filename = bufferDirName + to_iso_string(frame->filenameTime) + ".pcap";
+    if (hdlParser->getFrame(frame, filename, frame->fileStartPos, frame->skips)) {
+      frame->isInMemory = true;
+      this->pushCache(frame);
+      return HDLFramePtr(frame.get());
+    }
+    return HDLFramePtr();
+  }
+  return HDLFramePtr();
+}
+
+HDLFramePtr HDLManager::waitForFrame(int64_t micro) {
+  std::unique_lock<std::mutex> lock(framesMutex);
+  cond_.wait_for(lock, std::chrono::microseconds(micro), [this] { return hasNewData; });
+  if (hasNewData) {
+    hasNewData = false;
+    std::shared_ptr<HDLFrame> f = frames.back();
+    lock.unlock();
+    return prepareFrame(f);
+  }
+  return HDLFramePtr();
+}
+
+HDLFramePtr HDLManager::getRecentFrame() {
+  std::shared_ptr<HDLFrame> result;
+  {
+    std::lock_guard<std::mutex> lock(framesMutex);
+    result = frames.back();
+  }
+  return prepareFrame(result);
+}
+HDLFramePtr HDLManager::getFrameAt(ptime& t) { return prepareFrame(frames.getExactDataAt(t)); }
+HDLFramePtr HDLManager::getFrameNear(ptime& t) { return prepareFrame(frames.getNearestData(t)); }
+
+std::vector<std::shared_ptr<HDLFrame> > HDLManager::getAllFrameMeta() {
+  std::lock_guard<std::mutex> lock(framesMutex);
+  return frames.getAll();
+}
+
+std::vector<HDLFramePtr> HDLManager::getRangeBetween(ptime& a, ptime& b) {
+  // inclusive on both ends (HDLManager.h:148, TimeLine.h:316-382)
+  std::vector<std::shared_ptr<HDLFrame> > vec;
+  for (const auto& f : frames.items())
+    if (f->timestamp >= a && f->timestamp <= b) vec.push_back(f);
+  std::vector<HDLFramePtr> result;
+  for (auto& f : vec) result.push_back(prepareFrame(f));
+  return result;
+}
+
+void HDLManager::setBufferSize(size_t n) { bufferSize = n; }
+size_t HDLManager::getBufferSize() { return bufferSize; }
+
+bool HDLManager::setBufferDir(std::string dirname, bool shouldCreateSubDir) {
+  if (!isDirectory(dirname)) {
+    std::cerr << "Name of directory invalid" << std::endl;
+    return false;
+  }
+  if (dirname.back() != '/') dirname.append("/");
+  if (shouldCreateSubDir) {
+    dirname += to_iso_string(localTimeNow()) + "/";
+    if (mkdir(dirname.c_str(), 0777) != 0) {
+      std::cerr << "Failed to create sub directory inside: " << dirname << std::endl;
+      return false;
+    }
+  }
+  std::lock_guard<std::mutex> lock(writerMutex);
+  this->bufferDirName = dirname;
+  return true;
+}
+
+void HDLManager::resetBufferDir() {
+  std::lock_guard<std::mutex> lock(writerMutex);
+  this->bufferDirName = "/tmp/";
+}
+
+void HDLManager::setFileBufferMode(bool m) {
+  std::lock_guard<std::mutex> lock(framesMutex);
+  fileBufferMode = m;
+}
+
+void HDLManager::flushFileBuffer() { switchBuffer(); }
+
+bool HDLManager::writePackets() {
+  Buffer* buff;
+  std::string filename;
+  ptime filenameTime;
+  {
+    std::lock_guard<std::mutex> lock(writerMutex);
+    buff = isUsingBuffer1 ? &hardDriveBuffer2 : &hardDriveBuffer1;
+    if (buff->empty() || buff->front()->packets.empty()) {
+      writerIdle = true;
+      return false;
+    }
+    filenameTime = buff->front()->packets.front().first;
+    filename = bufferDirName + to_iso_string(filenameTime) + ".pcap";
+  }
+  if (packetWriter->isOpen()) packetWriter->close();
+  packetWriter->open(filename);
+  long long posOffset = PCAP_GLOBAL_HEADER_LEN;
+  for (size_t i = 0; i < buff->size(); ++i) {
+    int packetsNum = 0;
+    auto& f = buff->at(i)->packets;
+    for (size_t j = 0; j < f.size(); ++j) {
+      packetWriter->writePacket(reinterpret_cast<const unsigned char*>(f[j].second.c_str()),
+                                (unsigned int)f[j].second.length(), f[j].first);
+      ++packetsNum;
+    }
+    buff->at(i)->filenameTime = filenameTime;
+    buff->at(i)->fileStartPos = posOffset;
+    posOffset += (long long)packetsNum * PCAP_PACKET_LEN;
+    buff->at(i)->isOnHardDrive = true;
+    cache.push_back(buff->at(i).get());
+    ++cacheCounter;
+  }
+  packetWriter->close();
+  bufferFileNames.insert(filename);
+  buff->clear();
+  updateCacheSize();
+  writerIdle = true;
+  return true;
+}
+
+void HDLManager::startSwaping() {
+  fileBufferMode = true;
+  writerIdle = true;
+}
+void HDLManager::stopSwaping() {}
+
+void HDLManager::pushCache(std::shared_ptr<HDLFrame>& frame) {
+  cache.push_back(frame.get());
+  ++cacheCounter;
+  updateCacheSize();
+}
+
+void HDLManager::updateCacheSize() {
+  int putBackTimes = 10;
+  while (cacheCounter > (int)maxCacheSize && putBackTimes && !cache.empty()) {
+    HDLFrame* obj = cache.front();
+    cache.pop_front();
+    if (obj->count) {
+      cache.push_back(obj);
+      --putBackTimes;
+    } else {
+      obj->clear();
+      --cacheCounter;
+    }
+  }
+}
+
+void HDLManager::cleanCache() {
+  const size_t tmp = maxCacheSize;
+  maxCacheSize = 0;
+  updateCacheSize();
+  maxCacheSize = tmp;
+}
+
+bool HDLManager::saveHDLMeta() {
+  const std::string filename = this->bufferDirName + to_iso_string(localTimeNow()) + "-" +
+                               std::to_string(metaSerial++) + HDL_META_EXT_NAME;
+  std::ofstream ofs(filename, std::ios::binary);
+  if (!ofs) return false;
+  for (const auto& f : frames.getAll()) writeFrameRecord(ofs, *f);
+  return true;
+}
+
+bool HDLManager::saveINSMeta() {
+  const std::string filename = this->bufferDirName + to_iso_string(localTimeNow()) + "-" +
+                               std::to_string(metaSerial++) + INS_META_EXT_NAME;
+  return transMgr->writeToMetaFile(filename);
+}
+
+bool HDLManager::loadHDLMeta() {
+  scanBufferDir();
+  if (hdlMetaNames.empty()) return false;
+  for (const auto& name : hdlMetaNames) {
+    std::ifstream ifs(name, std::ios::binary);
+    while (true) {
+      std::shared_ptr<HDLFrame> item(new HDLFrame);
+      if (!readFrameRecord(ifs, *item)) break;
+      frames.addData(item);
+    }
+  }
+  return true;
+}
+
+bool HDLManager::loadINSMeta() {
+  scanBufferDir();
+  if (insMetaNames.empty()) return false;
+  for (const auto& f : insMetaNames) transMgr->loadFromMetaFile(f);
+  return true;
+}

@@ -34,6 +34,7 @@ class HDLParser::vsInternal {
     vs_carry_init(&carry);
   }
   ~vsInternal() {
+    unloadRecording();
     if (ctx) vs_destroy(ctx);
     vs_host_free(pinnedPkts);
     vs_host_free(pinnedTimes);
@@ -151,8 +152,22 @@ class HDLParser::vsInternal {
     if (!ensureContext() || !syncConfig()) return false;
     uint64_t ticket = 0;
     vs_result r;
-    int rc = vs_submit(ctx, pinnedPkts, VS_PACKET_BYTES, pinnedTimes, pending, 0, VS_MODE_STREAMING,
-                       0, pinnedTimes[0], &carry, &ticket);
+    int rc;
+    // raw packet bytes / times on the host, for HDLFrame::packets
+    const uint8_t* rawBase = pinnedPkts;
+    size_t rawStride = VS_PACKET_BYTES;
+    if (recCursor >= 0) {
+      // packets come from the recording resident in HBM: no host -> device copy at all
+      const uint8_t* dev = static_cast<const uint8_t*>(recDev) + VS_PCAP_PAYLOAD_OFFSET +
+                           (size_t)recCursor * VS_PCAP_RECORD_BYTES;
+      rc = vs_submit(ctx, dev, VS_PCAP_RECORD_BYTES, nullptr, pending, 0, VS_MODE_STREAMING,
+                     VS_FLAG_DEVICE_INPUT | VS_FLAG_PCAP_TIMES, 0, &carry, &ticket);
+      rawBase = recHost.data() + VS_PCAP_PAYLOAD_OFFSET + (size_t)recCursor * VS_PCAP_RECORD_BYTES;
+      rawStride = VS_PCAP_RECORD_BYTES;
+    } else {
+      rc = vs_submit(ctx, pinnedPkts, VS_PACKET_BYTES, pinnedTimes, pending, 0, VS_MODE_STREAMING, 0,
+                     pinnedTimes[0], &carry, &ticket);
+    }
     if (rc == VS_OK) rc = vs_wait(ctx, ticket, &r);
     if (rc != VS_OK) {
       error = vs_last_error(ctx);
@@ -161,6 +176,12 @@ class HDLParser::vsInternal {
       pendingWrap = false;
       return false;
     }
+    auto rawTime = [&](int p) -> ptime {
+      if (recCursor < 0) return ptime(pinnedTimes[p]);
+      uint32_t tv[2];
+      std::memcpy(tv, rawBase + (size_t)p * rawStride - 58, 8);
+      return timevalToPtime(tv[0], tv[1]);
+    };
     error.clear();
     const size_t n = (size_t)r.n_points;
     hx.resize(n);
@@ -189,10 +210,10 @@ class HDLParser::vsInternal {
         const int first = (i == 0) ? 0 : e.start_packet + 1;
         const int last = (i + 1 < r.n_frames) ? r.frames[i + 1].start_packet : (int)pending - 1;
         for (int p = first; p <= last; ++p) {
-          const std::string raw(reinterpret_cast<const char*>(pinnedPkts) + (size_t)p * VS_PACKET_BYTES,
+          const std::string raw(reinterpret_cast<const char*>(rawBase) + (size_t)p * rawStride,
                                 VS_PACKET_BYTES);
-          if (p == e.meta_packet) f.packets.push_back(std::make_pair(ptime(pinnedTimes[p]), raw));
-          f.packets.push_back(std::make_pair(ptime(pinnedTimes[p]), raw));
+          if (p == e.meta_packet) f.packets.push_back(std::make_pair(rawTime(p), raw));
+          f.packets.push_back(std::make_pair(rawTime(p), raw));
         }
       }
       const size_t nl = f.points.size();
@@ -225,6 +246,58 @@ class HDLParser::vsInternal {
     pendingWrap = false;
     return true;
   }
+
+  // ---- recording resident in HBM (loadRecording) ----------------------------------------------
+  bool loadRecording(const std::string& file) {
+    unloadRecording();
+    if (!ensureContext()) return false;
+    FILE* f = std::fopen(file.c_str(), "rb");
+    if (!f) return false;
+    std::fseek(f, 0, SEEK_END);
+    const long long bytes = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    const long long body = bytes - PCAP_GLOBAL_HEADER_LEN;
+    bool ok = bytes > PCAP_GLOBAL_HEADER_LEN && body % VS_PCAP_RECORD_BYTES == 0;
+    if (ok) {
+      recHost.resize((size_t)bytes);
+      ok = std::fread(recHost.data(), 1, (size_t)bytes, f) == (size_t)bytes;
+    }
+    std::fclose(f);
+    const int64_t n = ok ? body / VS_PCAP_RECORD_BYTES : 0;
+    // every record must be a 1206-byte payload behind the 42-byte header: fixed stride
+    for (int64_t i = 0; ok && i < n; ++i) {
+      uint32_t len[2];
+      std::memcpy(len, recHost.data() + PCAP_GLOBAL_HEADER_LEN + (size_t)i * VS_PCAP_RECORD_BYTES + 8, 8);
+      ok = len[0] == VS_PACKET_BYTES + 42 && len[1] == VS_PACKET_BYTES + 42;
+    }
+    ok = ok && recHost[0] == 0xd4 && recHost[1] == 0xc3 && recHost[2] == 0xb2 && recHost[3] == 0xa1;
+    if (ok) ok = vs_device_alloc(ctx, (uint64_t)bytes + 64, &recDev) == VS_OK;
+    if (ok) ok = vs_device_upload(ctx, recDev, recHost.data(), (uint64_t)bytes) == VS_OK;
+    if (!ok) {
+      unloadRecording();
+      return false;
+    }
+    recName = file;
+    recPackets = n;
+    return true;
+  }
+  void unloadRecording() {
+    if (recDev) vs_device_free(ctx, recDev);
+    recDev = nullptr;
+    recPackets = 0;
+    recCursor = -1;
+    recName.clear();
+    recAlias.clear();
+    std::vector<uint8_t>().swap(recHost);
+  }
+  bool hasRecording(const std::string& file) const {
+    return recDev && (file == recName || (!recAlias.empty() && file == recAlias));
+  }
+  void* recDev = nullptr;
+  std::vector<uint8_t> recHost;  // the same file image on the host (raw packets of HDLFrames)
+  int64_t recPackets = 0;
+  int64_t recCursor = -1;        // >= 0: decodePending takes `pending` packets from here
+  std::string recName, recAlias; // alias: the name readFrameInformation renamed the file to
 
   vs_ctx* ctx;
   int device;
@@ -410,8 +483,9 @@ bool HDLParser::getFrame(std::shared_ptr<HDLFrame>& dest, const std::string& fil
                          int64_t& startPos, const int& skip) {
   vsInternal* in = this->internal_;
   this->unloadData();
+  const bool resident = in->hasRecording(filename);
   vtkPacketFileReader reader;
-  if (!reader.open(filename)) {
+  if (!resident && !reader.open(filename)) {
     std::cerr << "failed to open packets file: " << filename << std::endl;
     return false;
   }
@@ -420,16 +494,30 @@ bool HDLParser::getFrame(std::shared_ptr<HDLFrame>& dest, const std::string& fil
     return false;
   }
   if (!in->ensureContext()) return false;
-  reader.setFilePosition(&startPos);
+  if (!resident) reader.setFilePosition(&startPos);
   in->carry.firing_skip = skip;
   const unsigned char* data = nullptr;
   unsigned int len = 0;
   ptime t;
   std::deque<std::shared_ptr<HDLFrame> > closed;
   bool eof = false;
+  int64_t cursor = resident ? (startPos - PCAP_GLOBAL_HEADER_LEN) / VS_PCAP_RECORD_BYTES : 0;
   while (closed.empty() && !eof) {
     // one chunk: enough for a rotation of either sensor, decoded in one launch
     const int chunk = std::min(in->batchPackets, 512);
+    if (resident) {
+      // the rotation is decoded straight out of the recording in HBM
+      const int64_t left = in->recPackets - cursor;
+      if (left <= 0) break;
+      in->pending = std::min<int64_t>(chunk, left);
+      in->recCursor = cursor;
+      const bool ok = in->decodePending(&closed);
+      in->recCursor = -1;
+      if (!ok) return false;
+      cursor += std::min<int64_t>(chunk, left);
+      eof = cursor >= in->recPackets;
+      continue;
+    }
     while (in->pending < chunk) {
       if (!reader.nextPacket(data, len, t)) {
         eof = true;
@@ -453,9 +541,13 @@ bool HDLParser::getFrame(std::shared_ptr<HDLFrame>& dest, const std::string& fil
     this->unloadData();
     return true;
   }
-  // end of file: force the split (HDLParser.cxx:540-543)
+  // end of file: force the split (HDLParser.cxx:540-543).  The reference swaps the two frame
+  // objects here, which leaves the caller's own frame (e.g. HDLManager's TimeLine entry)
+  // empty and hands back an object only the local shared_ptr owns; the contents are moved
+  // into the caller's frame instead, as in the branch above.
   in->closeFrame(in->currentFrame, in->carry.is_hdl64 != 0);
-  dest.swap(in->currentFrame);
+  dest->points = std::move(in->currentFrame->points);
+  dest->pointsMeta = std::move(in->currentFrame->pointsMeta);
   this->unloadData();
   return true;
 }
@@ -463,6 +555,58 @@ bool HDLParser::getFrame(std::shared_ptr<HDLFrame>& dest, const std::string& fil
 std::vector<std::shared_ptr<HDLFrame> > HDLParser::readFrameInformation(const std::string& name,
                                                                        bool touchOnly) {
   std::vector<std::shared_ptr<HDLFrame> > result;
+  vsInternal* in = this->internal_;
+  if (!touchOnly && in->hasRecording(name) && in->recPackets > 0) {
+    // the index of a resident recording is one pass of the segmentation kernel over HBM
+    const int64_t n = in->recPackets;
+    int32_t cap = (int32_t)std::min<int64_t>(12 * n + 1, std::max<int64_t>(4096, n / 16));
+    std::vector<int32_t> sp, sk;
+    std::vector<int64_t> ts;
+    int32_t nf = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      sp.assign((size_t)cap, 0);
+      sk.assign((size_t)cap, 0);
+      ts.assign((size_t)cap, 0);
+      const uint8_t* dev = static_cast<const uint8_t*>(in->recDev) + VS_PCAP_PAYLOAD_OFFSET;
+      const int rc = vs_read_frame_information(in->ctx, dev, VS_PCAP_RECORD_BYTES, nullptr, n,
+                                               VS_FLAG_DEVICE_INPUT | VS_FLAG_PCAP_TIMES, sp.data(),
+                                               sk.data(), ts.data(), cap, &nf);
+      if (rc != VS_OK) {
+        in->error = vs_last_error(in->ctx);
+        std::cerr << "HDLParser: GPU frame index failed: " << in->error << std::endl;
+        return result;
+      }
+      if (nf <= cap) break;
+      cap = nf;
+    }
+    const ptime filenameTime(ts[0]);
+    for (int32_t i = 0; i < nf; ++i) {
+      std::shared_ptr<HDLFrame> f(new HDLFrame);
+      f->fileStartPos = PCAP_GLOBAL_HEADER_LEN + (int64_t)sp[i] * VS_PCAP_RECORD_BYTES;
+      f->skips = (uint8_t)sk[i];
+      f->isOnHardDrive = true;
+      f->timestamp = ptime(ts[i]);
+      f->filenameTime = filenameTime;
+      result.push_back(f);
+    }
+    // files are named after their first packet's time (reference HDLParser.cxx:1080-1085, 1150-1158)
+    std::string stem = name;
+    const size_t slash = stem.find_last_of('/');
+    const std::string dir = slash == std::string::npos ? std::string(".") : stem.substr(0, slash);
+    if (slash != std::string::npos) stem = stem.substr(slash + 1);
+    const size_t dot = stem.find_last_of('.');
+    if (dot != std::string::npos) stem = stem.substr(0, dot);
+    ptime nameTime;
+    if (!from_iso_string(stem, &nameTime) && name == in->recName) {
+      const std::string newname = dir + "/" + to_iso_string(filenameTime) + ".pcap";
+      if (std::rename(name.c_str(), newname.c_str()) == 0) {
+        in->recAlias = newname;
+        std::cout << "The original filename: '" << name << "' was converted to: '" << newname << '\''
+                  << std::endl;
+      }
+    }
+    return result;
+  }
   vtkPacketFileReader reader;
   if (!reader.open(name)) {
     std::cerr << "Failed to open packet file: " << name << std::endl << reader.getLastError() << std::endl;
@@ -531,6 +675,10 @@ void HDLParser::setTransformMgr(std::shared_ptr<TransformManager> mgr) {
 }
 int HDLParser::getApplyTransform() { return this->internal_->applyTransform; }
 void HDLParser::setApplyTransform(int apply) { this->internal_->applyTransform = apply; }
+
+bool HDLParser::loadRecording(const std::string& pcapfile) { return this->internal_->loadRecording(pcapfile); }
+void HDLParser::unloadRecording() { this->internal_->unloadRecording(); }
+bool HDLParser::hasRecording(const std::string& pcapfile) const { return this->internal_->hasRecording(pcapfile); }
 
 void HDLParser::setDevice(int d) { this->internal_->device = d; }
 void HDLParser::setBatchPackets(int n) {

@@ -92,6 +92,13 @@ class HDLParser {
   void setBatchPackets(int maxPackets);    // capacity of the pinned ring; default 4096
   void setStorePackets(bool store);        // keep raw packets inside HDLFrame::packets; default on
   void flush();                            // decode whatever is buffered now
+  // Keep a whole packet file (vtkPacketFileWriter format, fixed 1264-byte records) resident in
+  // HBM: readFrameInformation() of that file becomes one segmentation pass on the GPU and
+  // getFrame() decodes rotations straight out of HBM instead of re-reading the file
+  // (HDLManager::loadOffline / prepareFrame).  false: not such a file, nothing changes.
+  bool loadRecording(const std::string& pcapfile);
+  void unloadRecording();
+  bool hasRecording(const std::string& pcapfile) const;
   const std::string& lastError() const;    // empty when the last GPU call succeeded
 
  protected:

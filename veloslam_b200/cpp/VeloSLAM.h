@@ -2,6 +2,7 @@
 #ifndef VELOSLAM_B200_VELOSLAM_H
 #define VELOSLAM_B200_VELOSLAM_H
 #include "HDLFrame.h"
+#include "HDLManager.h"
 #include "HDLParser.h"
 #include "TimeLine.h"
 #include "TransformManager.h"

@@ -1051,24 +1051,32 @@ int vs_read_frame_information(vs_ctx* ctx, const uint8_t* pkts, int64_t stride,
                               const int64_t* pkt_time_us, int64_t n, uint32_t flags,
                               int32_t* start_packet, int32_t* skips, int64_t* timestamp_us,
                               int32_t cap, int32_t* n_frames) {
-  if (!ctx || !n_frames || cap < 0)
+  if (!ctx || !n_frames || cap < 0 || n < 1)
     return fail(ctx, VS_ERR_INVALID_ARG, "vs_read_frame_information: bad arguments");
-  uint64_t tk = 0;
+  // arrays longer than one batch are indexed in chunks; the carry (lastAzimuth) links them
   vs_carry c;
   vs_carry_init(&c);
-  int rc = submit_common(ctx, pkts, stride, pkt_time_us, n, 0, VS_MODE_OFFLINE, flags, 0, &c, &tk,
-                         true);
-  if (rc != VS_OK) return rc;
-  vs_result r;
-  rc = vs_wait(ctx, tk, &r);
-  if (rc != VS_OK) return rc;
-  *n_frames = r.n_frames;
-  for (int i = 0; i < r.n_frames && i < cap; ++i) {
-    const vs_frame& f = r.frames[i];
-    start_packet[i] = (i == 0) ? 0 : f.start_packet;
-    skips[i] = (i == 0) ? 0 : f.start_block;
-    timestamp_us[i] = f.timestamp_us;
+  int64_t total = 0;
+  for (int64_t base = 0; base < n; base += ctx->max_packets) {
+    const int64_t m = std::min<int64_t>(ctx->max_packets, n - base);
+    uint64_t tk = 0;
+    int rc = submit_common(ctx, pkts + base * stride, stride, pkt_time_us ? pkt_time_us + base : nullptr,
+                           m, 0, VS_MODE_OFFLINE, flags, 0, &c, &tk, true);
+    if (rc != VS_OK) return rc;
+    vs_result r;
+    rc = vs_wait(ctx, tk, &r);
+    if (rc != VS_OK) return rc;
+    // entry 0 of a later chunk continues the previous chunk's open frame
+    for (int i = (base == 0 ? 0 : 1); i < r.n_frames; ++i, ++total) {
+      if (total >= cap) continue;
+      const vs_frame& f = r.frames[i];
+      start_packet[total] = (total == 0) ? 0 : (int32_t)(base + f.start_packet);
+      skips[total] = (total == 0) ? 0 : f.start_block;
+      timestamp_us[total] = f.timestamp_us;
+    }
+    c = r.carry_out;
   }
+  *n_frames = (int32_t)total;
   return VS_OK;
 }
 
@@ -1079,6 +1087,27 @@ int vs_host_alloc(uint64_t bytes, void** out) {
 }
 void vs_host_free(void* p) {
   if (p) cudaFreeHost(p);
+}
+
+int vs_device_alloc(vs_ctx* ctx, uint64_t bytes, void** out_dev) {
+  if (!ctx || !out_dev || bytes == 0) return fail(ctx, VS_ERR_INVALID_ARG, "vs_device_alloc: bad arguments");
+  *out_dev = nullptr;
+  cudaSetDevice(ctx->device);
+  VS_CUDA(cudaMalloc(out_dev, (size_t)bytes));
+  return VS_OK;
+}
+void vs_device_free(vs_ctx* ctx, void* dev) {
+  if (!ctx || !dev) return;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < ctx->n_slots; ++i)
+    if (ctx->slots[i].stream) cudaStreamSynchronize(ctx->slots[i].stream);  // batches may read it
+  cudaFree(dev);
+}
+int vs_device_upload(vs_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes) {
+  if (!ctx || !dst_dev || !src_host) return fail(ctx, VS_ERR_INVALID_ARG, "vs_device_upload: bad arguments");
+  cudaSetDevice(ctx->device);
+  VS_CUDA(cudaMemcpy(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice));
+  return VS_OK;
 }
 
 void* vs_stream(vs_ctx* ctx) { return ctx ? (void*)ctx->slots[0].stream : nullptr; }
