@@ -214,6 +214,49 @@ VS_API int vs_device_alloc(vs_ctx* ctx, uint64_t bytes, void** out_dev);
 VS_API void vs_device_free(vs_ctx* ctx, void* dev);
 VS_API int vs_device_upload(vs_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes);
 
+/* ---- online front end in batch form ------------------------------- */
+
+/* State of TimeSolver::calcTimestamp(uint32_t) (TimeSolver.cxx:34-49): hdlHourTime + hdlOffset
+ * folded into one number, lastHdlReport and hdlInited.  Zero-initialise before the first call. */
+typedef struct vs_time_solver {
+  int64_t  base_us;
+  uint32_t last_report;
+  int32_t  inited;
+} vs_time_solver;
+
+/* TimeSolver::calcTimestamp(uint32_t microsecToHour) for n packets (HDLSource.cxx:216-217):
+ * packet time = base + whole hours wrapped so far + the packet's gpsTimestamp field (payload
+ * bytes 1200-1203); the hour wraps are a 1-bit scan over the array, done on the GPU.
+ * now_us is the local clock the reference reads at the very first packet (ignored once
+ * state->inited).  With VS_FLAG_DEVICE_INPUT pkts and out_time_us are device pointers (the
+ * times can go straight into vs_submit), else host pointers.  state is updated in place. */
+VS_API int vs_solve_packet_times(vs_ctx* ctx, const uint8_t* pkts, int64_t stride, int64_t n,
+                          uint32_t flags, int64_t now_us, vs_time_solver* state,
+                          int64_t* out_time_us);
+
+/* NovAtel INSPVA record as the reference lays it out (type_defs.h:39-58). */
+typedef struct vs_ins_pva {
+  uint16_t message_id;
+  uint16_t week_number;
+  uint32_t milliseconds;
+  uint32_t week_number_pos;
+  uint32_t pad0;
+  double   seconds_pos;
+  double   llh[3];       /* latitude, longitude (degrees), height (m) */
+  double   v[3];
+  double   eulr[3];      /* roll, pitch, yaw (degrees) */
+  int32_t  ins_status;
+  int32_t  pad1;
+} vs_ins_pva;
+
+/* INSSource's PacketConsumer::calcTransform (INSSource.cxx:300-326) for n records: T = ENU of
+ * the position about the ECEF origin (llh2enu, CoordiTran.cpp:271-276), R = eulr, V = v, and
+ * TimeSolver::calcTimestamp(InsPVA const*) (TimeSolver.cxx:20-33) = arrival + (time of pose -
+ * time of packet send), arrival_us being the local clock at reception of each record.
+ * Host arrays in and out (out_trv = n x 9); the result is what vs_set_poses takes. */
+VS_API int vs_poses_from_ins(vs_ctx* ctx, const vs_ins_pva* recs, int64_t n, const double origin_xyz[3],
+                      const int64_t* arrival_us, int64_t* out_t_us, double* out_trv);
+
 /* The CUDA stream the context launches on (cudaStream_t), for callers that time or order
  * work against it. */
 VS_API void* vs_stream(vs_ctx* ctx);

@@ -14,7 +14,7 @@ OUT_DIR = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT_DIR, "libvelo_ref.so")
 SHIM = os.path.join(HERE, "ref_shim")
 REF_SOURCES = ["TransformManager.cxx", "type_defs.cxx", "HDLFrame.cxx", "vtkPacketFileWriter.cxx",
-               "CoordiTran.cpp"]   # HDLParser.cxx is included by ref_capi.cpp
+               "CoordiTran.cpp", "TimeSolver.cxx"]   # HDLParser.cxx is included by ref_capi.cpp
 CXXFLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-w", "-DLINUX"]
 
 

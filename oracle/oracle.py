@@ -25,6 +25,25 @@ class FrameInfo(C.Structure):
 _lib = None
 
 
+class TimeSolverState(C.Structure):
+    _fields_ = [("base_us", C.c_int64), ("last_report", C.c_uint32), ("inited", C.c_int32)]
+
+
+class InsPVA(C.Structure):
+    """NovAtel INSPVA record, the reference's layout (type_defs.h:39-58)."""
+    _fields_ = [("message_id", C.c_uint16), ("week_number", C.c_uint16),
+                ("milliseconds", C.c_uint32), ("week_number_pos", C.c_uint32), ("pad0", C.c_uint32),
+                ("seconds_pos", C.c_double), ("LLH", C.c_double * 3), ("V", C.c_double * 3),
+                ("Eulr", C.c_double * 3), ("ins_status", C.c_int32), ("pad1", C.c_int32)]
+
+
+INS_DTYPE = np.dtype([("message_id", "<u2"), ("week_number", "<u2"), ("milliseconds", "<u4"),
+                      ("week_number_pos", "<u4"), ("pad0", "<u4"), ("seconds_pos", "<f8"),
+                      ("LLH", "<f8", (3,)), ("V", "<f8", (3,)), ("Eulr", "<f8", (3,)),
+                      ("ins_status", "<i4"), ("pad1", "<i4")])
+assert INS_DTYPE.itemsize == C.sizeof(InsPVA) == 104
+
+
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
@@ -72,6 +91,13 @@ def lib():
         "vo_read_frame_information": (i32, [u8p, i64, i64, C.POINTER(i64), C.POINTER(i32),
                                             C.POINTER(i32), C.POINTER(i64), i32]),
         "vo_get_frame": (i32, [vp, u8p, i64, i64, C.POINTER(i64), i64, i32]),
+        "vo_llh2xyz": (None, [dp, dp]),
+        "vo_xyz2llh": (None, [dp, dp]),
+        "vo_llh2enu": (None, [dp, dp, dp]),
+        "vo_ts_init": (None, [C.POINTER(TimeSolverState)]),
+        "vo_ts_hdl": (i64, [C.POINTER(TimeSolverState), C.c_uint32, i64]),
+        "vo_ts_ins": (i64, [C.POINTER(InsPVA), i64]),
+        "vo_ins_pose": (None, [C.POINTER(InsPVA), dp, dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -264,3 +290,61 @@ class Oracle:
         if not ok:
             return None
         return self.frame(0 if first else self.num_frames() - 1)
+
+
+# ---- geodesy, TimeSolver, INS record -> pose (module-level: no parser state) ----
+def llh2enu(llh, orgxyz):
+    a = (C.c_double * 3)(*llh)
+    o = (C.c_double * 3)(*orgxyz)
+    e = (C.c_double * 3)()
+    lib().vo_llh2enu(a, o, e)
+    return np.array(e[:])
+
+
+def llh2xyz(llh):
+    a = (C.c_double * 3)(*llh)
+    x = (C.c_double * 3)()
+    lib().vo_llh2xyz(a, x)
+    return np.array(x[:])
+
+
+def xyz2llh(xyz):
+    a = (C.c_double * 3)(*xyz)
+    x = (C.c_double * 3)()
+    lib().vo_xyz2llh(a, x)
+    return np.array(x[:])
+
+
+class TimeSolver:
+    """TimeSolver::calcTimestamp(uint32_t) restated with the clock as an argument."""
+
+    def __init__(self):
+        self.state = TimeSolverState()
+        lib().vo_ts_init(C.byref(self.state))
+
+    def hdl(self, gps, now_us):
+        return int(lib().vo_ts_hdl(C.byref(self.state), int(gps), int(now_us)))
+
+    def hdl_many(self, gps, now_us):
+        return np.array([self.hdl(g, now_us) for g in gps], dtype=np.int64)
+
+
+def ins_times(recs, now_us):
+    """TimeSolver::calcTimestamp(InsPVA const*) per record; now_us: scalar or per record."""
+    recs = np.ascontiguousarray(recs, dtype=INS_DTYPE)
+    now = np.broadcast_to(np.asarray(now_us, np.int64), (len(recs),))
+    base = recs.ctypes.data
+    return np.array([lib().vo_ts_ins(C.cast(base + i * INS_DTYPE.itemsize, C.POINTER(InsPVA)),
+                                     int(now[i])) for i in range(len(recs))], dtype=np.int64)
+
+
+def ins_poses(recs, orgxyz):
+    """calcTransform (INSSource.cxx:300-326) per record -> n x 9 (T ENU, R, V)."""
+    recs = np.ascontiguousarray(recs, dtype=INS_DTYPE)
+    o = (C.c_double * 3)(*orgxyz)
+    out = np.zeros((len(recs), 9))
+    base = recs.ctypes.data
+    for i in range(len(recs)):
+        lib().vo_ins_pose(C.cast(base + i * INS_DTYPE.itemsize, C.POINTER(InsPVA)), o,
+                          out[i].ctypes.data_as(C.POINTER(C.c_double)))
+    return out

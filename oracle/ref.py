@@ -65,6 +65,14 @@ def lib():
         "vr_get_frame": (i32, [vp, C.c_char_p, i64, i32]),
         "vr_num_snapshot_frames": (i32, [vp]),
         "vr_write_pcap": (i32, [C.c_char_p, u8p, i64, i64, C.POINTER(i64)]),
+        "vr_set_fake_now": (None, [i64]),
+        "vr_ts_create": (vp, []),
+        "vr_ts_destroy": (None, [vp]),
+        "vr_ts_hdl": (i64, [vp, C.c_uint32]),
+        "vr_ts_ins": (i64, [vp, vp]),
+        "vr_llh2enu": (None, [dp, dp, dp]),
+        "vr_llh2xyz": (None, [dp, dp]),
+        "vr_sizeof_inspva": (i32, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -206,3 +214,48 @@ class RefParser:
         t = np.ascontiguousarray(t_us, dtype=np.int64)
         return bool(lib().vr_write_pcap(path.encode(), _p(d, C.c_uint8), d.shape[0], d.shape[1],
                                         _p(t, C.c_int64)))
+
+
+# ---- the reference's TimeSolver.cxx / CoordiTran.cpp behind a settable clock ----
+def set_fake_now(us):
+    """Every clock the reference reads (microsec_clock / day_clock in the shim) returns this."""
+    lib().vr_set_fake_now(int(us))
+
+
+class RefTimeSolver:
+    def __init__(self, now_us):
+        set_fake_now(now_us)          # the constructor reads the clock too
+        self._h = lib().vr_ts_create()
+
+    def __del__(self):
+        try:
+            lib().vr_ts_destroy(self._h)
+        except Exception:
+            pass
+
+    def hdl(self, gps, now_us):
+        set_fake_now(now_us)
+        return int(lib().vr_ts_hdl(self._h, int(gps)))
+
+    def ins(self, rec_addr, now_us):
+        set_fake_now(now_us)
+        return int(lib().vr_ts_ins(self._h, rec_addr))
+
+
+def llh2enu(llh, orgxyz):
+    a = (C.c_double * 3)(*llh)
+    o = (C.c_double * 3)(*orgxyz)
+    e = (C.c_double * 3)()
+    lib().vr_llh2enu(a, o, e)
+    return np.array(e[:])
+
+
+def llh2xyz(llh):
+    a = (C.c_double * 3)(*llh)
+    x = (C.c_double * 3)()
+    lib().vr_llh2xyz(a, x)
+    return np.array(x[:])
+
+
+def sizeof_inspva():
+    return int(lib().vr_sizeof_inspva())

@@ -1,6 +1,7 @@
 // ref_shim: the slice of Boost.DateTime the reference's hot-path sources use, with ptime as
 // int64 microseconds since 1970-01-01 plus a not_a_date_time state (test infrastructure).
 #pragma once
+#include <climits>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +35,21 @@ inline void civil_from_days(int64_t z, int64_t& y, unsigned& m, unsigned& d) {
 }
 }  // namespace date_detail
 
+// test hook: when set (!= INT64_MIN) every clock below reads this instead of the wall clock, so
+// that the reference's wall-clock dependent code (TimeSolver.cxx) is reproducible
+namespace shim_clock {
+inline int64_t& fake_now_us() {
+  static int64_t v = INT64_MIN;
+  return v;
+}
+inline int64_t now_us() {
+  if (fake_now_us() != INT64_MIN) return fake_now_us();
+  timeval tv;
+  gettimeofday(&tv, nullptr);
+  return static_cast<int64_t>(tv.tv_sec) * 1000000ll + tv.tv_usec;
+}
+}  // namespace shim_clock
+
 namespace gregorian {
 struct days {
   int64_t n;
@@ -45,6 +61,11 @@ class date {
   explicit date(int64_t days_since_epoch) : d_(days_since_epoch) {}
   date(int y, int m, int d) : d_(date_detail::days_from_civil(y, m, d)) {}
   int64_t day_count() const { return d_; }
+  int year() const {
+    int64_t y; unsigned m, d;
+    date_detail::civil_from_days(d_, y, m, d);
+    return static_cast<int>(y);
+  }
   date operator-(const days& o) const { return date(d_ - o.n); }
   date operator+(const days& o) const { return date(d_ + o.n); }
   int week_number() const {  // ISO 8601 week number
@@ -57,6 +78,14 @@ class date {
   }
  private:
   int64_t d_;
+};
+struct day_clock {
+  static date local_day() {
+    const int64_t us = shim_clock::now_us();
+    int64_t d = us / 86400000000ll;
+    if (us % 86400000000ll < 0) --d;
+    return date(d);
+  }
 };
 inline std::tm to_tm(const date& d) {
   std::tm t = std::tm();
@@ -181,11 +210,7 @@ inline std::ostream& operator<<(std::ostream& os, const time_duration& d) {
   return os << d.total_microseconds() << "us";
 }
 struct microsec_clock {
-  static ptime local_time() {
-    timeval tv;
-    gettimeofday(&tv, nullptr);
-    return ptime::from_us(static_cast<int64_t>(tv.tv_sec) * 1000000ll + tv.tv_usec);
-  }
+  static ptime local_time() { return ptime::from_us(shim_clock::now_us()); }
   static ptime universal_time() { return local_time(); }
 };
 }  // namespace posix_time

@@ -49,6 +49,9 @@ struct vr_frame_info {
   double carpose_seconds_pos;
 };
 
+#include "CoordiTran.h"
+#include "TimeSolver.h"
+
 extern "C" {
 
 vr_parser* vr_create(void) { return new vr_parser; }
@@ -224,5 +227,25 @@ int32_t vr_write_pcap(const char* filename, const uint8_t* data, int64_t n, int6
   w.close();
   return 1;
 }
+
+/* ---- N3: TimeSolver.cxx / CoordiTran.cpp / INSSource.cxx:300-326 ------------------------- */
+void vr_set_fake_now(int64_t us) { boost::shim_clock::fake_now_us() = us; }
+void* vr_ts_create(void) { return new TimeSolver; }
+void vr_ts_destroy(void* ts) { delete static_cast<TimeSolver*>(ts); }
+int64_t vr_ts_hdl(void* ts, uint32_t microsec_to_hour) {
+  return ptime_to_us(static_cast<TimeSolver*>(ts)->calcTimestamp(microsec_to_hour));
+}
+int64_t vr_ts_ins(void* ts, const InsPVA* rec) {
+  return ptime_to_us(static_cast<TimeSolver*>(ts)->calcTimestamp(rec));
+}
+void vr_llh2enu(const double llh[3], const double orgxyz[3], double enu[3]) {
+  double a[3] = {llh[0], llh[1], llh[2]}, o[3] = {orgxyz[0], orgxyz[1], orgxyz[2]};
+  llh2enu(a, o, enu);
+}
+void vr_llh2xyz(const double llh[3], double xyz[3]) {
+  double a[3] = {llh[0], llh[1], llh[2]};
+  llh2xyz(a, xyz);
+}
+int32_t vr_sizeof_inspva(void) { return (int32_t)sizeof(InsPVA); }
 
 } /* extern "C" */

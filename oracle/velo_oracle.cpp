@@ -1035,4 +1035,126 @@ int32_t vo_get_frame(vo_parser* h, const uint8_t* data, int64_t n, int64_t strid
   return h->p.getFrame(data, n, stride, t_us, start_packet, skip) ? 1 : 0;
 }
 
+/* ---- N3: geodesy, TimeSolver, INS record -> pose ------------------------------------------- */
+namespace vo {
+const double kWgsA = 6378137.0000;  /* semi-major axis, CoordiTran.cpp:58 */
+const double kWgsB = 6356752.3142;  /* semi-minor axis, CoordiTran.cpp:59 */
+}
+
+void vo_llh2xyz(const double llh[3], double xyz[3]) {
+  /* CoordiTran.cpp:51-80, operation order kept */
+  const double phi = llh[0], lambda = llh[1], h = llh[2];
+  const double a = vo::kWgsA, b = vo::kWgsB;
+  const double e = std::sqrt(1 - (b / a) * (b / a));
+  const double sinphi = std::sin(phi), cosphi = std::cos(phi);
+  const double coslam = std::cos(lambda), sinlam = std::sin(lambda);
+  const double tan2phi = (std::tan(phi)) * (std::tan(phi));
+  const double tmp = 1 - e * e;
+  const double tmpden = std::sqrt(1 + tmp * tan2phi);
+  xyz[0] = (a * coslam) / tmpden + h * coslam * cosphi;
+  xyz[1] = (a * sinlam) / tmpden + h * sinlam * cosphi;
+  const double tmp2 = std::sqrt(1 - e * e * sinphi * sinphi);
+  xyz[2] = (a * tmp * sinphi) / tmp2 + h * sinphi;
+}
+
+void vo_xyz2llh(const double xyz[3], double llh[3]) {
+  /* CoordiTran.cpp:82-150: closed-form (Heikkinen-style) inverse */
+  const double pi = 3.141592653589793;
+  const double x = xyz[0], y = xyz[1], z = xyz[2];
+  const double x2 = x * x, y2 = y * y, z2 = z * z;
+  const double a = vo::kWgsA, b = vo::kWgsB;
+  const double e = std::sqrt(1 - (b / a) * (b / a));
+  const double b2 = b * b;
+  const double e2 = e * e;
+  const double ep = e * (a / b);
+  const double r = std::sqrt(x2 + y2);
+  const double r2 = r * r;
+  const double E2 = a * a - b * b;
+  const double F = 54 * b2 * z2;
+  const double G = r2 + (1 - e2) * z2 - e2 * E2;
+  const double c = (e2 * e2 * F * r2) / (G * G * G);
+  const double s = std::pow(double(1 + c + std::sqrt(c * c + 2 * c)), double(1.0 / 3.0));
+  const double P = F / (3 * (s + 1 / s + 1) * (s + 1 / s + 1) * G * G);
+  const double Q = std::sqrt(1 + 2 * e2 * e2 * P);
+  const double ro = -(P * e2 * r) / (1 + Q) +
+                    std::sqrt((a * a / 2) * (1 + 1 / Q) - (P * (1 - e2) * z2) / (Q * (1 + Q)) - P * r2 / 2);
+  const double tmp = (r - e2 * ro) * (r - e2 * ro);
+  const double U = std::sqrt(tmp + z2);
+  const double V = std::sqrt(tmp + (1 - e2) * z2);
+  const double zo = (b2 * z) / (a * V);
+  const double height = U * (a * V - b2) / (a * V);
+  const double lat = std::atan((z + ep * ep * zo) / r);
+  const double temp = std::atan(y / x);
+  double lon;
+  if (x >= 0)
+    lon = temp;
+  else if ((x < 0) & (y >= 0))
+    lon = pi + temp;
+  else
+    lon = temp - pi;
+  llh[0] = lat;
+  llh[1] = lon;
+  llh[2] = height;
+}
+
+void vo_llh2enu(const double llh[3], const double orgxyz[3], double enu[3]) {
+  /* llh2enu (CoordiTran.cpp:271-276) = llh2xyz then xyz2enu (:152-187) */
+  double xyz[3] = {0, 0, 0};
+  vo_llh2xyz(llh, xyz);
+  double dif[3], orgllh[3];
+  for (int i = 0; i < 3; ++i) dif[i] = xyz[i] - orgxyz[i];
+  vo_xyz2llh(orgxyz, orgllh);
+  const double phi = orgllh[0], lam = orgllh[1];
+  const double sinphi = std::sin(phi), cosphi = std::cos(phi);
+  const double sinlam = std::sin(lam), coslam = std::cos(lam);
+  const double R[3][3] = {{-sinlam, coslam, 0},
+                          {-sinphi * coslam, -sinphi * sinlam, cosphi},
+                          {cosphi * coslam, cosphi * sinlam, sinphi}};
+  enu[0] = enu[1] = enu[2] = 0;
+  for (int i = 0; i < 3; ++i) {
+    enu[0] = enu[0] + R[0][i] * dif[i];
+    enu[1] = enu[1] + R[1][i] * dif[i];
+    enu[2] = enu[2] + R[2][i] * dif[i];
+  }
+}
+
+void vo_ts_init(vo_time_solver* s) {
+  s->base_us = 0;
+  s->last_report = 0;  /* TimeSolver.cxx:8 */
+  s->inited = 0;
+}
+
+int64_t vo_ts_hdl(vo_time_solver* s, uint32_t gps, int64_t now_us) {
+  /* TimeSolver.cxx:34-49 */
+  if (!s->inited) {
+    /* hdlHourTime = now truncated to the hour, hdlOffset = now - hdlHourTime - gps:
+     * their sum is all that is ever used */
+    s->base_us = now_us - (int64_t)gps;
+    s->inited = 1;
+  }
+  if (s->last_report > gps) s->base_us += 3600ll * 1000000ll;  /* one hour wrapped */
+  s->last_report = gps;
+  return s->base_us + (int64_t)gps;
+}
+
+int64_t vo_ts_ins(const vo_ins_pva* d, int64_t now_us) {
+  /* TimeSolver.cxx:20-33; time_duration(h, 0, 0, frac) truncates the double to ticks (us) */
+  const int64_t hour_us = 3600ll * 1000000ll;
+  const int64_t p = (int64_t)(d->week_number * 168) * hour_us + (int64_t)(double(d->milliseconds) * 1e3);
+  const int64_t ins = (int64_t)(d->week_number_pos * 168) * hour_us + (int64_t)(double(d->seconds_pos) * 1e6);
+  return now_us + (ins - p);
+}
+
+void vo_ins_pose(const vo_ins_pva* d, const double orgxyz[3], double trv[9]) {
+  /* INSSource.cxx:305-317: TO_RADIUS(x) = x * M_PI / 180 (type_defs.h) */
+  const double in[3] = {d->LLH[0] * M_PI / 180, d->LLH[1] * M_PI / 180, d->LLH[2]};
+  double out[3] = {0, 0, 0};
+  vo_llh2enu(in, orgxyz, out);
+  for (int k = 0; k < 3; ++k) {
+    trv[k] = out[k];
+    trv[3 + k] = d->Eulr[k];
+    trv[6 + k] = d->V[k];
+  }
+}
+
 } /* extern "C" */

@@ -106,6 +106,47 @@ int32_t vo_read_frame_information(const uint8_t* data, int64_t n, int64_t stride
 int32_t vo_get_frame(vo_parser*, const uint8_t* data, int64_t n, int64_t stride,
                      const int64_t* t_us, int64_t start_packet, int32_t skip);
 
+/* ---- online ingest front end --------------------------------------- */
+
+/* CoordiTran.cpp:51-80 (llh2xyz), :82-150 (xyz2llh), :152-187 + :271-276 (xyz2enu, llh2enu):
+ * WGS-84 geodetic (radians, metres) -> ECEF -> local ENU about an ECEF origin. */
+void vo_llh2xyz(const double llh[3], double xyz[3]);
+void vo_xyz2llh(const double xyz[3], double llh[3]);
+void vo_llh2enu(const double llh[3], const double orgxyz[3], double enu[3]);
+
+/* TimeSolver::calcTimestamp(uint32_t microsecToHour) (TimeSolver.cxx:34-49).  The state the
+ * reference keeps in hdlHourTime + hdlOffset is one number, base_us; now_us is the local clock
+ * it reads at the very first packet. */
+typedef struct vo_time_solver {
+  int64_t  base_us;
+  uint32_t last_report;
+  int32_t  inited;
+} vo_time_solver;
+void    vo_ts_init(vo_time_solver*);
+int64_t vo_ts_hdl(vo_time_solver*, uint32_t microsec_to_hour, int64_t now_us);
+
+/* NovAtel INSPVA record as the reference lays it out (type_defs.h:39-58, natural alignment). */
+typedef struct vo_ins_pva {
+  uint16_t message_id;
+  uint16_t week_number;
+  uint32_t milliseconds;
+  uint32_t week_number_pos;
+  uint32_t pad0;
+  double   seconds_pos;
+  double   LLH[3];
+  double   V[3];
+  double   Eulr[3];
+  int32_t  ins_status;
+  int32_t  pad1;
+} vo_ins_pva;
+/* TimeSolver::calcTimestamp(InsPVA const*) (TimeSolver.cxx:20-33).  insInited is never set, so
+ * the offset is re-taken from the clock on every call and the result is
+ * now + (time of pose - time of packet send); the epoch cancels. */
+int64_t vo_ts_ins(const vo_ins_pva* rec, int64_t now_us);
+/* PacketConsumer::calcTransform (INSSource.cxx:300-326) without the timestamp: T = ENU of the
+ * position, R = Eulr, V = V. */
+void    vo_ins_pose(const vo_ins_pva* rec, const double orgxyz[3], double trv[9]);
+
 #ifdef __cplusplus
 }
 #endif

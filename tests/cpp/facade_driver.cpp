@@ -153,6 +153,37 @@ static int hostModes(int argc, char** argv) {
     os.write((const char*)vert, sizeof(vert));
     return 0;
   }
+  if (mode == "frontend" && argc >= 5) {
+    // TimeSolver / CoordiTran of the facade on the host:
+    //   frontend <gps.bin (u32)> <ins.bin (104-byte records)> <out.bin>
+    // out: int64 per packet, then per INS record int64 t + 3 doubles ENU
+    std::vector<char> g = slurp(argv[2]);
+    std::vector<char> ins = slurp(argv[3]);
+    std::ofstream os(argv[4], std::ios::binary);
+    int64_t clock = 1467331234567890ll;
+    TimeSolver ts;
+    ts.setClock([&clock]() { return clock; });
+    for (size_t i = 0; i + 4 <= g.size(); i += 4) {
+      uint32_t v;
+      std::memcpy(&v, g.data() + i, 4);
+      const int64_t t = ts.calcTimestamp(v).us;
+      clock += 553;
+      os.write((const char*)&t, 8);
+    }
+    double org[3] = {-2781621.9891904, 4672106.75052387, 18.8910392};
+    static_assert(sizeof(InsPVA) == 104, "INSPVA layout");
+    for (size_t i = 0; i + sizeof(InsPVA) <= ins.size(); i += sizeof(InsPVA)) {
+      InsPVA rec;
+      std::memcpy(&rec, ins.data() + i, sizeof(rec));
+      clock = 1467331200000000ll + 10000ll * (int64_t)(i / sizeof(InsPVA));
+      const int64_t t = ts.calcTimestamp(&rec).us;
+      double llh[3] = {TO_RADIUS(rec.LLH[0]), TO_RADIUS(rec.LLH[1]), rec.LLH[2]}, enu[3];
+      llh2enu(llh, org, enu);
+      os.write((const char*)&t, 8);
+      os.write((const char*)enu, sizeof(enu));
+    }
+    return 0;
+  }
   if (mode == "manager_host" && argc >= 4) {
     // HDLManager host logic without a GPU: time queries, cache, hard-drive buffers written as
     // pcap files, .hdlmeta round trip.  argv[2]: scratch directory, argv[3]: report file.

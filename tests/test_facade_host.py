@@ -118,3 +118,30 @@ def test_hdlmanager_host_logic(tmp_path):
                                          for i in range(7)]
     assert [int(l[3]) for l in meta] == [int(l[3]) for l in disk]
     assert all(l[5] == "1" for l in meta)
+
+
+# --- facade TimeSolver / CoordiTran against the oracle, bit for bit -----------------
+def test_facade_time_solver_and_geodesy(tmp_path):
+    from oracle import oracle as O
+    rng = np.random.default_rng(8)
+    gps = ((3_599_500_000 + 288 * np.arange(4000, dtype=np.int64)) % 3_600_000_000).astype("<u4")
+    gps[1234] = gps[1233] - 5
+    gps.tofile(tmp_path / "gps.bin")
+    recs = np.zeros(64, dtype=O.INS_DTYPE)
+    recs["week_number"] = 1903
+    recs["week_number_pos"] = 1903
+    recs["milliseconds"] = 345_600_000 + 10 * np.arange(64)
+    recs["seconds_pos"] = 345_600.0 + 0.01 * np.arange(64) + rng.uniform(0, 0.004, 64)
+    recs["LLH"] = np.array([39.8569901, 116.1736406, 89.09]) + rng.normal(0, 1e-4, (64, 3))
+    recs.tofile(tmp_path / "ins.bin")
+    r = F.run(["frontend", tmp_path / "gps.bin", tmp_path / "ins.bin", tmp_path / "out.bin"])
+    assert r.returncode == 0, r.stderr
+    raw = open(tmp_path / "out.bin", "rb").read()
+    t_pk = np.frombuffer(raw, "<i8", len(gps))
+    # only the first packet reads the clock (TimeSolver.cxx:35-42)
+    assert np.array_equal(t_pk, O.TimeSolver().hdl_many(gps, 1467331234567890))
+    rec = np.frombuffer(raw, dtype=[("t", "<i8"), ("enu", "<f8", (3,))], offset=8 * len(gps))
+    arrival = 1467331200000000 + 10000 * np.arange(64)
+    assert np.array_equal(rec["t"], O.ins_times(recs, arrival))
+    want = O.ins_poses(recs, (-2781621.9891904, 4672106.75052387, 18.8910392))[:, :3]
+    assert np.array_equal(rec["enu"], want)

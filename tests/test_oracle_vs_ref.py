@@ -217,3 +217,74 @@ def test_pcap_writer_matches_the_reference_byte_for_byte(tmp_path):
     assert theirs.shape == ours.shape and np.array_equal(theirs, ours)
     back, tb = pcapio.read_pcap_image(theirs)
     assert np.array_equal(back, b) and np.array_equal(tb, t)
+
+
+# --- geodesy, TimeSolver, INS record -> pose ------------------------------------
+R = ref
+ORIG_XYZ = (-2781621.9891904, 4672106.75052387, 18.8910392)     # INSSource.cxx:334
+
+
+def _ins_records(n, seed=3):
+    from oracle.oracle import INS_DTYPE
+    rng = np.random.default_rng(seed)
+    r = np.zeros(n, dtype=INS_DTYPE)
+    r["message_id"] = 508
+    r["week_number"] = 1903
+    r["milliseconds"] = 345_600_000 + 10 * np.arange(n)
+    r["week_number_pos"] = 1903
+    r["seconds_pos"] = 345_600.0 + 0.01 * np.arange(n) + rng.uniform(0, 0.004, n)
+    r["LLH"][:, 0] = 39.8569901 + np.cumsum(rng.normal(0, 1e-6, n))
+    r["LLH"][:, 1] = 116.1736406 + np.cumsum(rng.normal(0, 1e-6, n))
+    r["LLH"][:, 2] = 89.09 + rng.normal(0, 0.05, n)
+    r["V"] = rng.normal(0, 5, (n, 3))
+    r["Eulr"] = rng.uniform(-180, 180, (n, 3))
+    return r
+
+
+def test_geodesy_matches_reference_bit_for_bit():
+    from oracle import oracle as O
+    assert R.sizeof_inspva() == O.INS_DTYPE.itemsize
+    rng = np.random.default_rng(11)
+    org = O.llh2xyz(np.radians([39.8569901, 116.1736406, 0]) + [0, 0, 89.09])
+    for _ in range(200):
+        llh = [np.radians(rng.uniform(-80, 80)), np.radians(rng.uniform(-179, 179)),
+               rng.uniform(-100, 9000)]
+        assert np.array_equal(O.llh2xyz(llh), R.llh2xyz(llh))
+        for o in (ORIG_XYZ, org, O.llh2xyz(llh)):
+            assert np.array_equal(O.llh2enu(llh, o), R.llh2enu(llh, o))
+    # round trip sanity: a point 100 m east of the origin
+    here = np.radians([39.8569901, 116.1736406, 0]) + [0, 0, 89.09]
+    enu = O.llh2enu(here + [0, 100 / 6378137.0 / np.cos(here[0]), 0], O.llh2xyz(here))
+    assert abs(enu[0] - 100) < 0.5 and abs(enu[1]) < 0.01 and abs(enu[2]) < 0.01
+
+
+def test_time_solver_hdl_matches_reference():
+    from oracle import oracle as O
+    now0 = 1_467_331_234_567_890
+    rng = np.random.default_rng(5)
+    # two hour wraps, a duplicate, and a backwards step that the reference counts as a wrap
+    gps = np.concatenate([np.arange(3_599_000_000, 3_600_000_000, 137_000),
+                          np.arange(500, 2_000_000, 211_000), [2_000_000, 1_999_999],
+                          np.arange(3_599_900_000, 3_600_000_000, 33_000), [7, 7, 8]]).astype(np.uint32)
+    ref = R.RefTimeSolver(now0)
+    mine = O.TimeSolver()
+    for i, g in enumerate(gps):
+        now = now0 + 553 * i + int(rng.integers(0, 50))     # the clock only matters at packet 0
+        assert mine.hdl(g, now) == ref.hdl(g, now), i
+
+
+def test_time_solver_ins_and_pose_match_reference():
+    from oracle import oracle as O
+    recs = _ins_records(300)
+    recs["week_number_pos"][100:] += 1          # week roll-over between send and pose time
+    now = 1_467_331_200_000_000 + 10_000 * np.arange(len(recs))
+    ref = R.RefTimeSolver(int(now[0]))
+    want = np.array([ref.ins(recs.ctypes.data + i * recs.dtype.itemsize, int(now[i]))
+                     for i in range(len(recs))])
+    assert np.array_equal(O.ins_times(recs, now), want)
+    trv = O.ins_poses(recs, ORIG_XYZ)
+    for i in (0, 1, 150, 299):
+        llh = [np.radians(1.0) * 0 + recs["LLH"][i, 0] * np.pi / 180, recs["LLH"][i, 1] * np.pi / 180,
+               recs["LLH"][i, 2]]
+        assert np.array_equal(trv[i, :3], R.llh2enu(llh, ORIG_XYZ))
+    assert np.array_equal(trv[:, 3:6], recs["Eulr"]) and np.array_equal(trv[:, 6:], recs["V"])

@@ -18,6 +18,9 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
+    # device code keeps the reference's separate multiplies and adds everywhere (the decode path
+    # uses explicit __dmul_rn/__dadd_rn already; this covers the N3 geodesy kernel)
+    "-fmad=false",
     # host side restates reference arithmetic: no FMA contraction there either
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
     "-shared", "-cudart", "static",
@@ -44,7 +47,7 @@ def build_library(force=False, verbose=False):
 
 FACADE_DIR = os.path.join(HERE, "cpp")
 FACADE_LIB = os.path.join(HERE, "libveloslam_facade.so")
-FACADE_SOURCES = ["type_defs.cpp", "TransformManager.cpp", "vtkPacketFile.cpp", "HDLManager.cpp",
+FACADE_SOURCES = ["type_defs.cpp", "TransformManager.cpp", "vtkPacketFile.cpp", "HDLManager.cpp", "CoordiTran.cpp", "TimeSolver.cpp",
                   "CalibrationFile.cpp", "HDLParser.cpp"]
 DRIVER_SRC = os.path.join(os.path.dirname(HERE), "tests", "cpp", "facade_driver.cpp")
 DRIVER_EXE = os.path.join(os.path.dirname(HERE), "tests", "cpp", "facade_driver")

@@ -24,13 +24,25 @@ EXPORTS = ["vs_version", "vs_create", "vs_destroy", "vs_last_error", "vs_set_cal
            "vs_set_filters", "vs_set_poses", "vs_interpolate", "vs_carry_init", "vs_submit",
            "vs_wait", "vs_fetch_points", "vs_read_frame_information", "vs_host_alloc",
            "vs_host_free", "vs_stream", "vs_slot_stream", "vs_device_alloc", "vs_device_free",
-           "vs_device_upload"]
+           "vs_device_upload", "vs_solve_packet_times", "vs_poses_from_ins"]
 
 
 class LaserCorr(C.Structure):
     _fields_ = [("rot_correction_deg", C.c_double), ("vert_correction_deg", C.c_double),
                 ("dist_correction_cm", C.c_double), ("vert_offset_correction_cm", C.c_double),
                 ("horiz_offset_correction_cm", C.c_double)]
+
+
+class TimeSolver(C.Structure):
+    """vs_time_solver: state of TimeSolver::calcTimestamp(uint32_t)."""
+    _fields_ = [("base_us", C.c_int64), ("last_report", C.c_uint32), ("inited", C.c_int32)]
+
+
+# vs_ins_pva (NovAtel INSPVA, reference type_defs.h:39-58) as a numpy record
+INS_PVA_DTYPE = np.dtype([("message_id", "<u2"), ("week_number", "<u2"), ("milliseconds", "<u4"),
+                          ("week_number_pos", "<u4"), ("pad0", "<u4"), ("seconds_pos", "<f8"),
+                          ("llh", "<f8", (3,)), ("v", "<f8", (3,)), ("eulr", "<f8", (3,)),
+                          ("ins_status", "<i4"), ("pad1", "<i4")])
 
 
 class Filters(C.Structure):
@@ -113,6 +125,16 @@ def load_library():
     L.vs_read_frame_information.restype = C.c_int
     L.vs_read_frame_information.argtypes = [vp, vp, i64, vp, i64, C.c_uint32, vp, vp, vp, i32,
                                             C.POINTER(i32)]
+    L.vs_device_alloc.restype = C.c_int
+    L.vs_device_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+    L.vs_device_free.restype = None
+    L.vs_device_free.argtypes = [vp, vp]
+    L.vs_device_upload.restype = C.c_int
+    L.vs_device_upload.argtypes = [vp, vp, vp, u64]
+    L.vs_solve_packet_times.restype = C.c_int
+    L.vs_solve_packet_times.argtypes = [vp, vp, i64, i64, C.c_uint32, i64, C.POINTER(TimeSolver), vp]
+    L.vs_poses_from_ins.restype = C.c_int
+    L.vs_poses_from_ins.argtypes = [vp, vp, i64, C.POINTER(C.c_double), vp, vp, vp]
     L.vs_stream.restype = vp
     L.vs_stream.argtypes = [vp]
     L.vs_slot_stream.restype = vp
@@ -266,6 +288,34 @@ class Context:
         self._check(self._L.vs_interpolate(self._h, int(t_us), out, C.byref(found),
                                            C.byref(valid)))
         return bool(found.value), np.array(list(out)), bool(valid.value)
+
+    # -- online front end in batch form ----------------------------------
+    def solve_packet_times(self, pkts, now_us, state=None, n=None, stride=None, flags=0, out=None):
+        """TimeSolver::calcTimestamp(uint32_t) for a packet array; returns (times, state).
+        Host arrays by default; with FLAG_DEVICE_INPUT pkts / out are device tensors."""
+        if state is None:
+            state = TimeSolver()
+        if n is None:
+            n = int(pkts.shape[0])
+        if stride is None:
+            stride = int(pkts.shape[1]) if pkts.ndim == 2 else 1206
+        if out is None:
+            out = np.empty(n, dtype=np.int64)
+        self._check(self._L.vs_solve_packet_times(self._h, _ptr(pkts), stride, n, flags, int(now_us),
+                                                  C.byref(state), _ptr(out)))
+        return out, state
+
+    def poses_from_ins(self, recs, origin_xyz, arrival_us):
+        """INSPVA records -> (t_us, trv n x 9): calcTransform + calcTimestamp(InsPVA) on the GPU."""
+        recs = np.ascontiguousarray(recs)
+        assert recs.dtype.itemsize == INS_PVA_DTYPE.itemsize
+        n = len(recs)
+        arr = np.ascontiguousarray(np.broadcast_to(np.asarray(arrival_us, np.int64), (n,)))
+        t = np.empty(n, dtype=np.int64)
+        trv = np.empty((n, 9), dtype=np.float64)
+        org = (C.c_double * 3)(*[float(v) for v in origin_xyz])
+        self._check(self._L.vs_poses_from_ins(self._h, _ptr(recs), n, org, _ptr(arr), _ptr(t), _ptr(trv)))
+        return t, trv
 
     # -- batches ----------------------------------------------------------------------
     def submit(self, pkts, pkt_time_us, n=None, stride=None, n_halo=0, mode=MODE_STREAMING,

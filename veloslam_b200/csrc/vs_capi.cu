@@ -1110,6 +1110,133 @@ int vs_device_upload(vs_ctx* ctx, void* dst_dev, const void* src_host, uint64_t 
   return VS_OK;
 }
 
+int vs_solve_packet_times(vs_ctx* ctx, const uint8_t* pkts, int64_t stride, int64_t n, uint32_t flags,
+                          int64_t now_us, vs_time_solver* state, int64_t* out_time_us) {
+  if (!ctx || !pkts || !state || !out_time_us || n < 1 || stride < kPacketBytes || (stride & 1))
+    return fail(ctx, VS_ERR_INVALID_ARG, "vs_solve_packet_times: bad arguments");
+  const bool dev = (flags & VS_FLAG_DEVICE_INPUT) != 0;
+  Slot& s = ctx->slots[0];
+  if (s.busy && !s.done) return fail(ctx, VS_ERR_STATE, "vs_solve_packet_times: slot 0 is busy");
+  cudaSetDevice(ctx->device);
+  // scratch of slot 0: gps fields in the segment records' array, times in d_time
+  uint32_t* d_gps = reinterpret_cast<uint32_t*>(s.d_seg);
+  std::vector<uint32_t> h_gps;
+  for (int64_t base = 0; base < n; base += ctx->max_packets) {
+    const int64_t m = std::min<int64_t>(ctx->max_packets, n - base);
+    const int tiles = (int)((m + kGpsThreads * kGpsItems - 1) / (kGpsThreads * kGpsItems));
+    VS_CUDA(cudaMemsetAsync(s.d_st_map, 0, (size_t)tiles * 8, s.stream));
+    VS_CUDA(cudaMemsetAsync(s.d_counters, 0, 64, s.stream));
+    if (dev) {
+      k_gps_gather<<<(unsigned)((m + 255) / 256), 256, 0, s.stream>>>(pkts + base * stride, stride, (int)m, d_gps);
+      VS_CUDA(cudaGetLastError());
+    } else {
+      h_gps.resize((size_t)m);
+      for (int64_t i = 0; i < m; ++i) std::memcpy(&h_gps[(size_t)i], pkts + (base + i) * stride + 1200, 4);
+      VS_CUDA(cudaMemcpyAsync(d_gps, h_gps.data(), (size_t)m * 4, cudaMemcpyHostToDevice, s.stream));
+    }
+    uint32_t first_gps = 0;
+    if (!state->inited) {
+      // hdlOffset = now - hdlHourTime - gps of the first packet (TimeSolver.cxx:36-42)
+      if (dev)
+        VS_CUDA(cudaMemcpyAsync(&first_gps, d_gps, 4, cudaMemcpyDeviceToHost, s.stream));
+      else
+        first_gps = h_gps[0];
+      VS_CUDA(cudaStreamSynchronize(s.stream));
+      state->base_us = now_us - (int64_t)first_gps;
+      state->last_report = 0;
+      state->inited = 1;
+    }
+    GpsParams gp;
+    gp.gps = d_gps;
+    gp.n = (int)m;
+    gp.last_report = state->last_report;
+    gp.base_us = state->base_us;
+    gp.t_out = dev ? reinterpret_cast<long long*>(out_time_us + base) : s.d_time;
+    gp.st = s.d_st_map;
+    gp.tile_counter = s.d_counters;
+    gp.total_wraps = reinterpret_cast<unsigned long long*>(s.d_counters + 8);
+    k_gps_times<<<tiles, kGpsThreads, 0, s.stream>>>(gp);
+    VS_CUDA(cudaGetLastError());
+    unsigned long long wraps = 0;
+    uint32_t last = 0;
+    VS_CUDA(cudaMemcpyAsync(&wraps, gp.total_wraps, 8, cudaMemcpyDeviceToHost, s.stream));
+    VS_CUDA(cudaMemcpyAsync(&last, d_gps + (m - 1), 4, cudaMemcpyDeviceToHost, s.stream));
+    if (!dev)
+      VS_CUDA(cudaMemcpyAsync(out_time_us + base, s.d_time, (size_t)m * 8, cudaMemcpyDeviceToHost, s.stream));
+    VS_CUDA(cudaStreamSynchronize(s.stream));
+    state->base_us += (int64_t)wraps * 3600000000ll;  // hdlHourTime += 1 h per wrap
+    state->last_report = last;
+  }
+  return VS_OK;
+}
+
+namespace {
+// xyz2llh of the ENU origin (CoordiTran.cpp:82-150), evaluated once per call on the host
+void origin_rotation(const double org[3], double R[9]) {
+  const double pi = 3.141592653589793;
+  const double x = org[0], y = org[1], z = org[2];
+  const double x2 = x * x, y2 = y * y, z2 = z * z;
+  const double a = 6378137.0000, b = 6356752.3142;
+  const double e = std::sqrt(1 - (b / a) * (b / a));
+  const double b2 = b * b, e2 = e * e, ep = e * (a / b);
+  const double r = std::sqrt(x2 + y2), r2 = r * r;
+  const double E2 = a * a - b * b;
+  const double F = 54 * b2 * z2;
+  const double G = r2 + (1 - e2) * z2 - e2 * E2;
+  const double c = (e2 * e2 * F * r2) / (G * G * G);
+  const double s = std::pow(double(1 + c + std::sqrt(c * c + 2 * c)), double(1.0 / 3.0));
+  const double P = F / (3 * (s + 1 / s + 1) * (s + 1 / s + 1) * G * G);
+  const double Q = std::sqrt(1 + 2 * e2 * e2 * P);
+  const double ro = -(P * e2 * r) / (1 + Q) +
+                    std::sqrt((a * a / 2) * (1 + 1 / Q) - (P * (1 - e2) * z2) / (Q * (1 + Q)) - P * r2 / 2);
+  const double tmp = (r - e2 * ro) * (r - e2 * ro);
+  const double V = std::sqrt(tmp + (1 - e2) * z2);
+  const double zo = (b2 * z) / (a * V);
+  const double lat = std::atan((z + ep * ep * zo) / r);
+  const double t = std::atan(y / x);
+  const double lon = (x >= 0) ? t : (((x < 0) & (y >= 0)) ? pi + t : t - pi);
+  const double sinphi = std::sin(lat), cosphi = std::cos(lat);
+  const double sinlam = std::sin(lon), coslam = std::cos(lon);
+  const double M[9] = {-sinlam, coslam, 0, -sinphi * coslam, -sinphi * sinlam, cosphi,
+                       cosphi * coslam, cosphi * sinlam, sinphi};  // CoordiTran.cpp:175
+  std::memcpy(R, M, sizeof(M));
+}
+}  // namespace
+
+int vs_poses_from_ins(vs_ctx* ctx, const vs_ins_pva* recs, int64_t n, const double origin_xyz[3],
+                      const int64_t* arrival_us, int64_t* out_t_us, double* out_trv) {
+  static_assert(sizeof(vs_ins_pva) == sizeof(InsPva) && sizeof(InsPva) == 104, "INSPVA layout");
+  if (!ctx || !recs || !origin_xyz || !arrival_us || !out_t_us || !out_trv || n < 1 || n > (1ll << 28))
+    return fail(ctx, VS_ERR_INVALID_ARG, "vs_poses_from_ins: bad arguments");
+  cudaSetDevice(ctx->device);
+  uint8_t* d = nullptr;
+  const size_t o_arr = (size_t)n * sizeof(InsPva);
+  const size_t o_t = o_arr + (size_t)n * 8;
+  const size_t o_trv = o_t + (size_t)n * 8;
+  VS_CUDA(cudaMalloc(&d, o_trv + (size_t)n * 72));
+  InsParams ip;
+  ip.recs = reinterpret_cast<const InsPva*>(d);
+  ip.n = (int)n;
+  for (int k = 0; k < 3; ++k) ip.org[k] = origin_xyz[k];
+  origin_rotation(origin_xyz, ip.R);
+  ip.arrival_us = reinterpret_cast<const long long*>(d + o_arr);
+  ip.t_out = reinterpret_cast<long long*>(d + o_t);
+  ip.trv_out = reinterpret_cast<double*>(d + o_trv);
+  cudaStream_t st = ctx->slots[0].stream;
+  cudaError_t e = cudaMemcpyAsync(d, recs, o_arr, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_arr, arrival_us, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    k_ins_pose<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ip);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_t_us, d + o_t, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_trv, d + o_trv, (size_t)n * 72, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, VS_ERR_CUDA, std::string("vs_poses_from_ins: ") + cudaGetErrorString(e));
+  return VS_OK;
+}
+
 void* vs_stream(vs_ctx* ctx) { return ctx ? (void*)ctx->slots[0].stream : nullptr; }
 void* vs_slot_stream(vs_ctx* ctx, int slot) {
   return (ctx && slot >= 0 && slot < ctx->n_slots) ? (void*)ctx->slots[slot].stream : nullptr;

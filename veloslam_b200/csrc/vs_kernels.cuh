@@ -1367,6 +1367,160 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
 }
 
 // =========================================================================================
+// SURVEY.md 8f row N3 -- the online front end's per-packet / per-record arithmetic in data-
+// parallel form.
+//
+// k_gps_gather / k_gps_times: TimeSolver::calcTimestamp(uint32_t microsecToHour)
+// (TimeSolver.cxx:34-49) for a packet array.  The reference adds one hour to hdlHourTime every
+// time the sensor's microseconds-past-the-hour field steps backwards; over an array that is an
+// inclusive scan of a 1-bit flag (decoupled look-back across 1024-packet tiles):
+//   t[i] = base + 3600 s * #{k <= i : gps[k-1] > gps[k]} + gps[i]
+// =========================================================================================
+__global__ void k_gps_gather(const uint8_t* __restrict__ pkts, long long stride, int n,
+                             uint32_t* __restrict__ gps) {
+  const int P = blockIdx.x * blockDim.x + threadIdx.x;
+  if (P >= n) return;
+  // gpsTimestamp sits at byte 1200 of the payload (HDLSource.cxx:216); packets are 2-byte aligned
+  const unsigned short* h = reinterpret_cast<const unsigned short*>(pkts + (long long)P * stride + 1200);
+  gps[P] = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
+}
+
+struct GpsParams {
+  const uint32_t* gps;
+  int n;
+  uint32_t last_report;  // lastHdlReport entering the array (0 before the first packet)
+  long long base_us;     // hdlHourTime + hdlOffset
+  long long* t_out;
+  unsigned long long* st;  // look-back words, one per tile, zeroed
+  int* tile_counter;       // zeroed
+  unsigned long long* total_wraps;
+};
+constexpr int kGpsThreads = 256;
+constexpr int kGpsItems = 4;
+
+__global__ void __launch_bounds__(kGpsThreads) k_gps_times(const GpsParams p) {
+  __shared__ unsigned s_warp[kGpsThreads / 32];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  const int i0 = (tile * kGpsThreads + tid) * kGpsItems;
+  uint32_t g[kGpsItems];
+  unsigned f[kGpsItems];
+  uint32_t prev = (i0 == 0) ? p.last_report : ((i0 - 1 < p.n) ? __ldg(&p.gps[i0 - 1]) : 0u);
+  unsigned mine = 0;
+#pragma unroll
+  for (int k = 0; k < kGpsItems; ++k) {
+    g[k] = (i0 + k < p.n) ? __ldg(&p.gps[i0 + k]) : prev;
+    f[k] = (i0 + k < p.n && prev > g[k]) ? 1u : 0u;  // TimeSolver.cxx:43
+    mine += f[k];
+    prev = g[k];
+  }
+  unsigned inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = (lane < kGpsThreads / 32) ? s_warp[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < kGpsThreads / 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    if (lane < kGpsThreads / 32) s_warp[lane] = w;
+    const unsigned long long ex =
+        lookback_exclusive<SumTraits>(p.st, tile, (unsigned long long)__shfl_sync(0xffffffffu, w, kGpsThreads / 32 - 1));
+    if (lane == 0) s_prefix = ex;
+  }
+  __syncthreads();
+  unsigned long long hours = s_prefix + (warp > 0 ? s_warp[warp - 1] : 0u) + (inc - mine);
+#pragma unroll
+  for (int k = 0; k < kGpsItems; ++k) {
+    hours += f[k];
+    if (i0 + k < p.n) {
+      p.t_out[i0 + k] = p.base_us + (long long)hours * 3600000000ll + (long long)g[k];
+      if (i0 + k == p.n - 1) *p.total_wraps = hours;
+    }
+  }
+}
+
+// =========================================================================================
+// k_ins_pose: INSSource PacketConsumer::calcTransform (INSSource.cxx:300-326) and
+// TimeSolver::calcTimestamp(InsPVA const*) (TimeSolver.cxx:20-33) for an array of NovAtel
+// INSPVA records: geodetic -> ECEF (llh2xyz, CoordiTran.cpp:51-80) -> local ENU about the
+// origin (xyz2enu, :152-187; the origin's rotation is evaluated once on the host).
+// =========================================================================================
+struct InsPva {  // type_defs.h:39-58, natural alignment (104 bytes)
+  uint16_t message_id;
+  uint16_t week_number;
+  uint32_t milliseconds;
+  uint32_t week_number_pos;
+  uint32_t pad0;
+  double seconds_pos;
+  double LLH[3];
+  double V[3];
+  double Eulr[3];
+  int32_t ins_status;
+  int32_t pad1;
+};
+struct InsParams {
+  const InsPva* recs;
+  int n;
+  double org[3];   // ECEF origin
+  double R[9];     // ENU rotation at the origin (row-major)
+  const long long* arrival_us;  // the local clock at reception of each record
+  long long* t_out;
+  double* trv_out;  // n x 9
+};
+
+__global__ void k_ins_pose(const InsParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const InsPva& d = p.recs[i];
+  // TO_RADIUS(x) = x * M_PI / 180 (type_defs.h:25)
+  const double phi = d.LLH[0] * 3.14159265358979323846 / 180;
+  const double lambda = d.LLH[1] * 3.14159265358979323846 / 180;
+  const double h = d.LLH[2];
+  const double a = 6378137.0000, b = 6356752.3142;
+  const double e = sqrt(1 - (b / a) * (b / a));
+  const double sinphi = sin(phi), cosphi = cos(phi);
+  const double coslam = cos(lambda), sinlam = sin(lambda);
+  const double tan2phi = (tan(phi)) * (tan(phi));
+  const double tmp = 1 - e * e;
+  const double tmpden = sqrt(1 + tmp * tan2phi);
+  const double x = (a * coslam) / tmpden + h * coslam * cosphi;
+  const double y = (a * sinlam) / tmpden + h * sinlam * cosphi;
+  const double tmp2 = sqrt(1 - e * e * sinphi * sinphi);
+  const double z = (a * tmp * sinphi) / tmp2 + h * sinphi;
+  const double dif[3] = {x - p.org[0], y - p.org[1], z - p.org[2]};
+  double enu[3] = {0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    enu[0] = enu[0] + p.R[0 + k] * dif[k];
+    enu[1] = enu[1] + p.R[3 + k] * dif[k];
+    enu[2] = enu[2] + p.R[6 + k] * dif[k];
+  }
+  double* o = p.trv_out + (long long)i * 9;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    o[k] = enu[k];
+    o[3 + k] = d.Eulr[k];
+    o[6 + k] = d.V[k];
+  }
+  // now + (time of pose - time of packet send); time_duration truncates the doubles to ticks
+  const long long hour_us = 3600000000ll;
+  const long long sent = (long long)((int)d.week_number * 168) * hour_us + (long long)((double)d.milliseconds * 1e3);
+  const long long pose = (long long)((int)d.week_number_pos * 168) * hour_us + (long long)(d.seconds_pos * 1e6);
+  p.t_out[i] = p.arrival_us[i] + (pose - sent);
+}
+
+// =========================================================================================
 // k_frames: per frame started inside the batch, find the packet that initialises its meta
 // (streaming: the packet after the one holding the frame's wrap, provided that wrap is the
 // packet's last one, HDLParser.cxx:993-1001; offline: the wrap packet itself).
