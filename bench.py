@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-online", action="store_true")
+    ap.add_argument("--no-deskew", action="store_true")
     return ap.parse_args()
 
 
@@ -429,6 +430,37 @@ def run_ours(args):
                 "note": "k_decode timed with CUDA events on its launch stream while the other "
                         "result slot's k_scan/k_pose may overlap it (two batches in flight)"}
 
+    # ---- per-point deskew extension, same batch, off the headline number -------
+    deskew = None
+    if not args.no_deskew:
+        off = np.zeros((12, 32), dtype=np.uint16)
+        for j in range(12):   # S2-like timing: block pairs 48 us apart, lasers 1.5 us apart
+            off[j] = np.round((j // 2) * 48.0 + np.arange(32) * 1.5).astype(np.uint16)
+        ctx.set_firing_offsets(off)
+
+        def step_dsk():
+            return ctx.wait(ctx.submit(d_pk, d_t, n=n_sub, stride=1206, n_halo=halo,
+                                       mode=capi.MODE_STREAMING,
+                                       flags=capi.FLAG_DEVICE_INPUT | capi.FLAG_DESKEW_PER_POINT,
+                                       t_base_us=t_base), frames=False)
+        for _ in range(3):
+            step_dsk()
+        barrier()
+        d0 = torch.cuda.Event(enable_timing=True)
+        d1 = torch.cuda.Event(enable_timing=True)
+        d0.record(ext)
+        dk = []
+        for _ in range(5):
+            dk.append(step_dsk().decode_ms)
+        d1.record(ext)
+        barrier()
+        ms = d0.elapsed_time(d1) / 5
+        deskew = {"points_per_s_per_gpu": n_emitted / (ms * 1e-3), "ms_per_step": ms,
+                  "k_decode_ms": float(np.mean(dk)),
+                  "note": "VS_FLAG_DESKEW_PER_POINT: slerp/lerp pose per point, re-based to the "
+                          "frame origin (not a reference behaviour; one batch in flight)"}
+        ctx.set_calibration(calib)   # resets the firing table
+
     # ---- frame index exchange (off the timed loop) ------------------------------------------
     rr = step()
     tab = sharding.local_table(rr.frame_table, rank, first, halo)
@@ -485,6 +517,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if online is not None:
             line["online"] = online
+        if deskew is not None:
+            line["deskew_per_point"] = deskew
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

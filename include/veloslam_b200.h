@@ -66,6 +66,14 @@ typedef enum vs_mode {
                                      (ts_sec + 8 h, ts_usec: type_defs.cxx:69-72); pkts must
                                      then point at the first record's payload, stride 1264 */
 
+/* Per-point deskew extension (NOT a reference behaviour -- the reference
+ * applies one Euler-interpolated pose per packet and re-bases only the translation).  Every
+ * point is transformed with the pose at its own time t_packet + firing offset: quaternion
+ * slerp of the rotation and lerp of the translation inside the packet's pose bracket, and the
+ * result is expressed in the frame origin's coordinates (rotation and translation re-based).
+ * Needs >= 2 poses (else ignored).  Exact semantics: oracle/deskew_port.py. */
+#define VS_FLAG_DESKEW_PER_POINT 4u
+
 /* One <px> item of the calibration db.xml in its raw units (HDLParser.cxx:818-832). */
 typedef struct vs_laser_corr {
   double rot_correction_deg;          /* rotCorrection_          */
@@ -163,6 +171,13 @@ VS_API const char* vs_last_error(vs_ctx* ctx);
  * n_rows calibration rows (id_ == index) and the count of enabled_ items equal to 1. */
 VS_API int vs_set_calibration(vs_ctx* ctx, const vs_laser_corr* corr, int n_rows, int n_lasers_enabled);
 VS_API int vs_set_filters(vs_ctx* ctx, const vs_filters* f);
+/* Firing time of each (block, return) slot inside a packet, microseconds after the packet
+ * time, for sensors whose table the reference does not have (HDL-64E: the reference gives all
+ * 384 returns the packet time): 12 x 32 values, row-major.  HDL-32E / VLP-16 use
+ * the reference's own table (HDLParser.cxx:133-137) and reject this call.  Used by
+ * VS_FLAG_DESKEW_PER_POINT (pose per point; the t_us column then includes the offset).  Call
+ * after vs_set_calibration, which resets the table. */
+VS_API int vs_set_firing_offsets(vs_ctx* ctx, const uint16_t* off_us);
 
 /* TransformManager::addTransform / clearTransforms as an immutable snapshot per batch
  * (TransformManager.cxx:61-79): n poses sorted by strictly increasing time, trv = n x 9

@@ -16,7 +16,7 @@ from .build import LIB
 INT64_MIN = -(2 ** 63)
 VS_TIME_NONE = INT64_MIN
 MODE_STREAMING, MODE_OFFLINE = 0, 1
-FLAG_DEVICE_INPUT, FLAG_PCAP_TIMES = 1, 2
+FLAG_DEVICE_INPUT, FLAG_PCAP_TIMES, FLAG_DESKEW_PER_POINT = 1, 2, 4
 STATUS = {0: "VS_OK", 1: "VS_ERR_INVALID_ARG", 2: "VS_ERR_NOT_CALIBRATED", 3: "VS_ERR_CUDA",
           4: "VS_ERR_CAPACITY", 5: "VS_ERR_NO_DEVICE", 6: "VS_ERR_HALO", 7: "VS_ERR_STATE"}
 
@@ -24,7 +24,7 @@ EXPORTS = ["vs_version", "vs_create", "vs_destroy", "vs_last_error", "vs_set_cal
            "vs_set_filters", "vs_set_poses", "vs_interpolate", "vs_carry_init", "vs_submit",
            "vs_wait", "vs_fetch_points", "vs_read_frame_information", "vs_host_alloc",
            "vs_host_free", "vs_stream", "vs_slot_stream", "vs_device_alloc", "vs_device_free",
-           "vs_device_upload", "vs_solve_packet_times", "vs_poses_from_ins"]
+           "vs_device_upload", "vs_solve_packet_times", "vs_poses_from_ins", "vs_set_firing_offsets"]
 
 
 class LaserCorr(C.Structure):
@@ -135,6 +135,8 @@ def load_library():
     L.vs_solve_packet_times.argtypes = [vp, vp, i64, i64, C.c_uint32, i64, C.POINTER(TimeSolver), vp]
     L.vs_poses_from_ins.restype = C.c_int
     L.vs_poses_from_ins.argtypes = [vp, vp, i64, C.POINTER(C.c_double), vp, vp, vp]
+    L.vs_set_firing_offsets.restype = C.c_int
+    L.vs_set_firing_offsets.argtypes = [vp, vp]
     L.vs_stream.restype = vp
     L.vs_stream.argtypes = [vp]
     L.vs_slot_stream.restype = vp
@@ -273,6 +275,11 @@ class Context:
         f = Filters(mask, points_skip, int(bool(crop_returns)), int(bool(crop_inside)), 0,
                     (C.c_double * 6)(*[float(v) for v in crop_region]))
         self._check(self._L.vs_set_filters(self._h, C.byref(f)))
+
+    def set_firing_offsets(self, off_us):
+        """12 x 32 firing offsets (us) for sensors without a built-in table (HDL-64E)."""
+        o = np.ascontiguousarray(off_us, dtype=np.uint16).reshape(12, 32)
+        self._check(self._L.vs_set_firing_offsets(self._h, _ptr(o)))
 
     def set_poses(self, t_us, trv):
         t = np.ascontiguousarray(t_us, dtype=np.int64)

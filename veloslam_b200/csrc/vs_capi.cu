@@ -221,7 +221,7 @@ int alloc_slot(vs_ctx* ctx, Slot& s) {
   VS_CUDA(cudaMalloc(&s.d_seg, np * sizeof(PktSeg)));
   VS_CUDA(cudaMalloc(&s.d_recs, np * kBlocks * sizeof(BlkRec)));
   VS_CUDA(cudaMalloc(&s.d_pkt_off, (np + 2) * sizeof(unsigned long long)));  // k_decode copies even-aligned pairs
-  VS_CUDA(cudaMalloc(&s.d_pose_mat, np * 12 * sizeof(double)));
+  VS_CUDA(cudaMalloc(&s.d_pose_mat, np * kDeskewRow * sizeof(double)));  // 12 used without deskew
   VS_CUDA(cudaMalloc(&s.d_x, pts * sizeof(float)));
   VS_CUDA(cudaMalloc(&s.d_y, pts * sizeof(float)));
   VS_CUDA(cudaMalloc(&s.d_z, pts * sizeof(float)));
@@ -309,21 +309,23 @@ int copy_frame_rows(vs_ctx* ctx, Slot& s, size_t n_rows) {
   return VS_OK;
 }
 
-template <int ADJ>
-int launch_decode(vs_ctx* ctx, Slot& s, const DecParams& dp) {
-  const size_t smem = (size_t)DecLayout<ADJ>::kStages + kDecStages * (size_t)dp.stage_bytes;
+template <int ADJ, int DSK>
+int launch_decode(vs_ctx* ctx, Slot& s, DecParams dp, int64_t stride) {
+  typedef DecLayout<ADJ, DSK> L;
+  dp.stage_bytes = (int)align_up((size_t)L::kDPkts + (size_t)kDecTile * stride + 48, 128);
+  const size_t smem = (size_t)L::kStages + L::kNumStages * (size_t)dp.stage_bytes;
   static size_t cached_smem = 0;  // one process drives one GPU: cache per instantiation
   static int per_sm = 0;
   if (cached_smem != smem) {
-    VS_CUDA(cudaFuncSetAttribute(k_decode<ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VS_CUDA(cudaFuncSetAttribute(k_decode<ADJ, DSK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode<ADJ>, kDecThreads, smem));
+    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode<ADJ, DSK>, kDecThreads, smem));
     cached_smem = smem;
   }
   if (per_sm < 1) return fail(ctx, VS_ERR_CUDA, "k_decode does not fit on an SM");
   int grid = ctx->sm_count * per_sm;
   if (grid > dp.n_tiles) grid = dp.n_tiles;
-  k_decode<ADJ><<<grid, kDecThreads, smem, s.stream>>>(dp);
+  k_decode<ADJ, DSK><<<grid, kDecThreads, smem, s.stream>>>(dp);
   VS_CUDA(cudaGetLastError());
   return VS_OK;
 }
@@ -422,6 +424,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
   const bool pose_valid = n_poses >= 2;
   const int adj = ctx->h_cfg.adj_mode;
   const bool crop = ctx->h_cfg.crop_returns != 0 && !index_only;
+  const bool deskew = (flags & VS_FLAG_DESKEW_PER_POINT) != 0 && pose_valid && !index_only;
   {
     ScanParams sp;
     sp.pkts = d_pkts;
@@ -478,6 +481,8 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     pp.pose_t = ctx->d_pose_t;
     pp.pose_trv = ctx->d_pose_trv;
     for (int k = 0; k < 3; ++k) pp.carry_origin_T[k] = cin.origin_T[k];
+    pp.deskew = deskew ? 1 : 0;
+    pp.carry_origin_time = cin.frame_timestamp_us;
     pp.pose_mat = s.d_pose_mat;
     pp.frame_first_point = s.d_frame_first;
     pp.frame_start_block = s.d_frame_start;
@@ -504,7 +509,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     dp.mode = mode;
     dp.pose_valid = pose_valid ? 1 : 0;
     dp.n_tiles = (int)dec_tiles;
-    dp.stage_bytes = (int)align_up((size_t)kDPkts + (size_t)kDecTile * stride + 48, 128);
+    dp.stage_bytes = 0;  // set per kernel variant by launch_decode
     dp.x = s.d_x;
     dp.y = s.d_y;
     dp.z = s.d_z;
@@ -518,12 +523,21 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     VS_CUDA(cudaEventRecord(s.ev_d0, s.stream));
     if (dec_tiles > 0) {
       int rc;
-      if (adj == 0)
-        rc = launch_decode<0>(ctx, s, dp);
-      else if (adj == 1)
-        rc = launch_decode<1>(ctx, s, dp);
-      else
-        rc = launch_decode<2>(ctx, s, dp);
+      if (deskew) {
+        if (adj == 0)
+          rc = launch_decode<0, 1>(ctx, s, dp, stride);
+        else if (adj == 1)
+          rc = launch_decode<1, 1>(ctx, s, dp, stride);
+        else
+          rc = launch_decode<2, 1>(ctx, s, dp, stride);
+      } else {
+        if (adj == 0)
+          rc = launch_decode<0, 0>(ctx, s, dp, stride);
+        else if (adj == 1)
+          rc = launch_decode<1, 0>(ctx, s, dp, stride);
+        else
+          rc = launch_decode<2, 0>(ctx, s, dp, stride);
+      }
       if (rc != VS_OK) return rc;
       ++s.n_launches;
     }
@@ -826,6 +840,19 @@ int vs_set_calibration(vs_ctx* ctx, const vs_laser_corr* corr, int n_rows, int n
   cudaSetDevice(ctx->device);
   VS_CUDA(cudaMemcpy(ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), cudaMemcpyHostToDevice));
   ctx->calibrated = true;
+  return VS_OK;
+}
+
+int vs_set_firing_offsets(vs_ctx* ctx, const uint16_t* off_us) {
+  if (!ctx || !off_us) return fail(ctx, VS_ERR_INVALID_ARG, "vs_set_firing_offsets: bad arguments");
+  if (!ctx->calibrated || ctx->h_cfg.adj_mode != 0)
+    return fail(ctx, VS_ERR_STATE,
+                "vs_set_firing_offsets: only for sensors without a built-in firing table "
+                "(set the calibration first)");
+  for (int j = 0; j < kBlocks; ++j)
+    for (int d = 0; d < kReturns; ++d) ctx->h_cfg.tadj[j][d] = off_us[j * kReturns + d];
+  cudaSetDevice(ctx->device);
+  VS_CUDA(cudaMemcpy(ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), cudaMemcpyHostToDevice));
   return VS_OK;
 }
 

@@ -578,7 +578,9 @@ struct PoseParams {
   const long long* pose_t;
   const double* pose_trv;  // n_poses x 9
   double carry_origin_T[3];
-  double* pose_mat;  // n x 12
+  int deskew;                   // per-point deskew rows (kDeskewRow doubles) instead of [L | t]
+  long long carry_origin_time;  // time of the carried frame's origin packet (deskew, origin < 0)
+  double* pose_mat;  // n x 12 (n x kDeskewRow with deskew)
   long long* frame_first_point;
   int* frame_start_block;
   int frame_cap;
@@ -682,6 +684,109 @@ __device__ __forceinline__ void rotate_by(double L[3][3], double angle, int axis
 #pragma unroll
     for (int j = 0; j < 3; ++j) L[i][j] = out[i][j];
 }
+
+// ---- per-point deskew extension (semantics: oracle/deskew_port.py) -------
+struct Quat {
+  double w, x, y, z;
+};
+__device__ __forceinline__ Quat quat_mul(const Quat& a, const Quat& b) {
+  Quat r;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x;
+  r.z = a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w;
+  return r;
+}
+__device__ __forceinline__ Quat quat_conj(const Quat& q) {
+  Quat r = {q.w, -q.x, -q.y, -q.z};
+  return r;
+}
+// p + w t + v x t with t = 2 v x p
+__device__ __forceinline__ void quat_rotate(const Quat& q, const double p[3], double o[3]) {
+  const double tx = 2.0 * (q.y * p[2] - q.z * p[1]);
+  const double ty = 2.0 * (q.z * p[0] - q.x * p[2]);
+  const double tz = 2.0 * (q.x * p[1] - q.y * p[0]);
+  o[0] = p[0] + q.w * tx + (q.y * tz - q.z * ty);
+  o[1] = p[1] + q.w * ty + (q.z * tx - q.x * tz);
+  o[2] = p[2] + q.w * tz + (q.x * ty - q.y * tx);
+}
+// Unit quaternion of PoseTransform::getMatrix's Ry(R0) Rx(R1) Rz(R2) (degrees), largest pivot.
+__device__ __forceinline__ Quat quat_from_rpy(const double* __restrict__ R) {
+  double m[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  rotate_by(m, to_radians(R[0]), 1);
+  rotate_by(m, to_radians(R[1]), 0);
+  rotate_by(m, to_radians(R[2]), 2);
+  const double tr = m[0][0] + m[1][1] + m[2][2];
+  Quat q;
+  if (tr > 0) {
+    const double s = sqrt(tr + 1.0) * 2;
+    q.w = 0.25 * s;
+    q.x = (m[2][1] - m[1][2]) / s;
+    q.y = (m[0][2] - m[2][0]) / s;
+    q.z = (m[1][0] - m[0][1]) / s;
+  } else if (m[0][0] > m[1][1] && m[0][0] > m[2][2]) {
+    const double s = sqrt(1.0 + m[0][0] - m[1][1] - m[2][2]) * 2;
+    q.w = (m[2][1] - m[1][2]) / s;
+    q.x = 0.25 * s;
+    q.y = (m[0][1] + m[1][0]) / s;
+    q.z = (m[0][2] + m[2][0]) / s;
+  } else if (m[1][1] > m[2][2]) {
+    const double s = sqrt(1.0 + m[1][1] - m[0][0] - m[2][2]) * 2;
+    q.w = (m[0][2] - m[2][0]) / s;
+    q.x = (m[0][1] + m[1][0]) / s;
+    q.y = 0.25 * s;
+    q.z = (m[1][2] + m[2][1]) / s;
+  } else {
+    const double s = sqrt(1.0 + m[2][2] - m[0][0] - m[1][1]) * 2;
+    q.w = (m[1][0] - m[0][1]) / s;
+    q.x = (m[0][2] + m[2][0]) / s;
+    q.y = (m[1][2] + m[2][1]) / s;
+    q.z = 0.25 * s;
+  }
+  return q;
+}
+// bracket of time t: i = clamp(lower_bound, 1, N-1)
+__device__ __forceinline__ int pose_bracket(const long long* __restrict__ pt, int np, long long t) {
+  const int lo = pose_lower_bound(pt, np, t);
+  const int i = lo < 1 ? 1 : lo;
+  return i > np - 1 ? np - 1 : i;
+}
+// slerp weights along the shorter arc; theta = angle between the (sign-aligned) quaternions
+__device__ __forceinline__ void slerp_weights(double theta, double r, double& w0, double& w1) {
+  if (theta < 1e-8) {
+    w0 = 1.0 - r;
+    w1 = r;
+  } else {
+    const double inv = 1.0 / sin(theta);
+    w0 = sin((1.0 - r) * theta) * inv;
+    w1 = sin(r * theta) * inv;
+  }
+}
+// the pose function of the extension at time t, evaluated in t's own bracket
+__device__ __forceinline__ void pose_at(const long long* __restrict__ pt, const double* __restrict__ trv,
+                                        int np, long long t, Quat& q, double T[3]) {
+  const int i = pose_bracket(pt, np, t);
+  const long long ta = __ldg(&pt[i - 1]), tb = __ldg(&pt[i]);
+  const double r = (double)(t - ta) / (double)(tb - ta);
+  const double* a = trv + (long long)(i - 1) * 9;
+  const double* b = trv + (long long)i * 9;
+  const Quat qa = quat_from_rpy(a + 3);
+  Quat qb = quat_from_rpy(b + 3);
+  double d = qa.w * qb.w + qa.x * qb.x + qa.y * qb.y + qa.z * qb.z;
+  if (d < 0) {
+    qb.w = -qb.w; qb.x = -qb.x; qb.y = -qb.y; qb.z = -qb.z;
+    d = -d;
+  }
+  double w0, w1;
+  slerp_weights(acos(fmin(1.0, d)), r, w0, w1);
+  q.w = w0 * qa.w + w1 * qb.w;
+  q.x = w0 * qa.x + w1 * qb.x;
+  q.y = w0 * qa.y + w1 * qb.y;
+  q.z = w0 * qa.z + w1 * qb.z;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) T[k] = __ldg(&a[k]) + (__ldg(&b[k]) - __ldg(&a[k])) * r;
+}
+constexpr int kDeskewRow = 18;  // doubles per packet: qa[4] qb[4] Ta[3] dT[3] r0 dr theta 1/sin(theta)
 
 __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
   __shared__ unsigned long long s_w[kPoseThreads / 32];
@@ -826,6 +931,45 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
   }
 
   if (p.n_poses < 2) return;
+  if (p.deskew) {
+    // per-point deskew: the packet's bracket endpoints, re-based to the frame origin's pose
+    Quat qo;
+    double To[3];
+    pose_at(p.pose_t, p.pose_trv, p.n_poses,
+            origin < 0 ? p.carry_origin_time : __ldg(&p.pkt_time[origin]), qo, To);
+    const Quat qoc = quat_conj(qo);
+    const int i = pose_bracket(p.pose_t, p.n_poses, t);
+    const long long ta = __ldg(&p.pose_t[i - 1]), tb = __ldg(&p.pose_t[i]);
+    const double* a = p.pose_trv + (long long)(i - 1) * 9;
+    const double* b = p.pose_trv + (long long)i * 9;
+    const Quat qa = quat_mul(qoc, quat_from_rpy(a + 3));
+    Quat qb = quat_mul(qoc, quat_from_rpy(b + 3));
+    double d = qa.w * qb.w + qa.x * qb.x + qa.y * qb.y + qa.z * qb.z;
+    if (d < 0) {
+      qb.w = -qb.w; qb.x = -qb.x; qb.y = -qb.y; qb.z = -qb.z;
+      d = -d;
+    }
+    const double theta = acos(fmin(1.0, d));
+    const double da[3] = {__ldg(&a[0]) - To[0], __ldg(&a[1]) - To[1], __ldg(&a[2]) - To[2]};
+    const double db[3] = {__ldg(&b[0]) - __ldg(&a[0]), __ldg(&b[1]) - __ldg(&a[1]), __ldg(&b[2]) - __ldg(&a[2])};
+    double Ta[3], dT[3];
+    quat_rotate(qoc, da, Ta);
+    quat_rotate(qoc, db, dT);
+    double* o = p.pose_mat + (long long)P * kDeskewRow;
+    o[0] = qa.w; o[1] = qa.x; o[2] = qa.y; o[3] = qa.z;
+    o[4] = qb.w; o[5] = qb.x; o[6] = qb.y; o[7] = qb.z;
+    o[8] = Ta[0]; o[9] = Ta[1]; o[10] = Ta[2];
+    o[11] = dT[0]; o[12] = dT[1]; o[13] = dT[2];
+    o[14] = (double)(t - ta) / (double)(tb - ta);
+    o[15] = 1.0 / (double)(tb - ta);
+    o[16] = theta;
+    o[17] = theta < 1e-8 ? 0.0 : 1.0 / sin(theta);
+    if (P == p.n - 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) p.hdr->carry_origin_T[k] = To[k];
+    }
+    return;
+  }
   double T[3], R[3];
   interp_pose(p.pose_t, p.pose_trv, p.n_poses, t, T, R, true);
   double To[3];
@@ -921,7 +1065,7 @@ struct DecParams {
 };
 
 constexpr int kDecTile = 8;  // packets per tile
-constexpr int kDecStages = 3;
+constexpr int kDecStagesMax = 3;
 constexpr int kDecThreads = 256;
 constexpr int kDecWarps = kDecThreads / 32;
 constexpr int kDecPairs = kDecWarps / 2;
@@ -932,9 +1076,8 @@ constexpr int kDecIlp = 2;  // firing blocks per straight-line body (divides 6)
 constexpr int kDRec = 0;                            // 12 BlkRec per packet
 constexpr int kDSeg = kDRec + kDecTile * 96;        // PktSeg per packet
 constexpr int kDOff = kDSeg + kDecTile * 16;        // u64 point offset per packet (+2 pad)
-constexpr int kDPose = kDOff + (kDecTile + 2) * 8;  // 12 doubles per packet
-constexpr int kDPkts = kDPose + kDecTile * 96;      // packet bytes (16-byte granular span)
-static_assert(kDPose % 16 == 0 && kDPkts % 16 == 0, "stage sections must be 16-byte aligned");
+constexpr int kDPose = kDOff + (kDecTile + 2) * 8;  // pose rows: 12 (18: per-point deskew) doubles per packet
+static_assert(kDPose % 16 == 0, "stage sections must be 16-byte aligned");
 static_assert(kDecRecs <= 32, "one lane per block record");
 // output staging of one pair: its packets' points + 16 elements of phase, column after column
 constexpr int kOutCap = kDecPktsPerWarp * 384 + 16;
@@ -945,17 +1088,23 @@ constexpr int kOutBytes = (22 * kOutCap + 127) & ~127;
 static_assert(kOutCap % 16 == 0, "column bases must stay 16-byte aligned");
 
 struct DecCtl {
-  uint64_t full[kDecStages];
-  int released[kDecStages];  // warps that are done with the stage
+  uint64_t full[kDecStagesMax];
+  int released[kDecStagesMax];  // warps that are done with the stage
 };
 
 // dynamic shared memory: [DecCtl | block records | DevConfig (ADJ != 0) | staging | stages]
-template <int ADJ>
+// DSK: per-point deskew extension (18-double pose rows; one input stage fewer when the DevConfig
+// is in shared memory too, to stay at 2 CTAs per SM)
+template <int ADJ, int DSK>
 struct DecLayout {
+  static constexpr int kNumStages = (ADJ != 0 && DSK != 0) ? 2 : 3;
+  static constexpr int kRowBytes = DSK ? kDeskewRow * 8 : 96;
+  static constexpr int kDPkts = kDPose + kDecTile * kRowBytes;  // packet bytes (16-byte granular span)
   static constexpr int kRec = 128;
   static constexpr int kCfg = kRec + kDecWarps * kDecRecs * 32;
   static constexpr int kOut = kCfg + ((ADJ == 0) ? 0 : (((int)sizeof(DevConfig) + 127) & ~127));
   static constexpr int kStages = kOut + kDecPairs * kOutBytes;
+  static_assert(kDPkts % 16 == 0, "stage sections must be 16-byte aligned");
 };
 static_assert(sizeof(DecCtl) <= 128, "DecCtl must fit its slot");
 
@@ -1022,9 +1171,18 @@ __device__ __forceinline__ void rigid(const double* M, double& px, double& py, d
   pz = qz;
 }
 
-template <int ADJ>
+// sin(x) for |x| < 0.2: odd Taylor polynomial through x^9 (error < 2e-17 relative)
+__device__ __forceinline__ double sin_small(double x) {
+  const double x2 = x * x;
+  return x * (1.0 + x2 * (-1.0 / 6 + x2 * (1.0 / 120 + x2 * (-1.0 / 5040 + x2 * (1.0 / 362880)))));
+}
+
+template <int ADJ, int DSK>
 __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
-  typedef DecLayout<ADJ> L;
+  typedef DecLayout<ADJ, DSK> L;
+  constexpr int kDecStages = L::kNumStages;
+  constexpr int kDPkts = L::kDPkts;
+  constexpr int kRowD = L::kRowBytes / 8;  // doubles per pose row
   extern __shared__ __align__(128) uint8_t smem_raw[];
   DecCtl& sh = *reinterpret_cast<DecCtl*>(smem_raw);
   const DevConfig& cfg =
@@ -1052,13 +1210,13 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
     const uint32_t sbytes = (uint32_t)sp.npk * 16u;
     const int odd = (int)(first & 1);  // the offsets are copied from an even index
     const uint32_t obytes = (uint32_t)((sp.npk + odd + 1) & ~1) * 8u;
-    const uint32_t pbytes = p.pose_valid ? (uint32_t)sp.npk * 96u : 0u;
+    const uint32_t pbytes = p.pose_valid ? (uint32_t)sp.npk * (uint32_t)L::kRowBytes : 0u;
     fence_proxy_async();
     mbar_expect_tx(&sh.full[s], bytes + rbytes + sbytes + obytes + pbytes);
     bulk_g2s(st + kDRec, p.recs + first * kBlocks, rbytes, &sh.full[s]);
     bulk_g2s(st + kDSeg, p.pkt_seg + first, sbytes, &sh.full[s]);
     bulk_g2s(st + kDOff, p.pkt_off + (first - odd), obytes, &sh.full[s]);
-    if (pbytes) bulk_g2s(st + kDPose, p.pose_mat + first * 12, pbytes, &sh.full[s]);
+    if (pbytes) bulk_g2s(st + kDPose, p.pose_mat + first * kRowD, pbytes, &sh.full[s]);
     if (bytes) bulk_g2s(st + kDPkts, reinterpret_cast<const void*>(sp.s0), bytes, &sh.full[s]);
   };
 
@@ -1118,12 +1276,47 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
     }
     double px, py, pz;
     sensor_point(cal, sA, cA, dist, px, py, pz);
-    if (pose_valid) rigid(M, px, py, pz);
+    // firing offset of this return (us): defines the t_us column and the per-point pose
+    unsigned fire = 0;
+    if (ADJ != 0)
+      fire = cfg.tadj[j][lane];
+    else if (DSK)
+      fire = __ldg(&p.cfg->tadj[j][lane]);
+    if (pose_valid) {
+      if (DSK) {
+        // pose at t_packet + fire inside the packet's bracket: slerp + lerp, already re-based to
+        // the frame origin by k_pose (semantics: oracle/deskew_port.py)
+        const double rr = M[14] + (double)fire * M[15];
+        double w0, w1;
+        if (M[17] == 0.0) {
+          w0 = 1.0 - rr;
+          w1 = rr;
+        } else if (M[16] < 0.1 && fabs(rr) < 2.0) {
+          w0 = sin_small((1.0 - rr) * M[16]) * M[17];
+          w1 = sin_small(rr * M[16]) * M[17];
+        } else {
+          w0 = sin((1.0 - rr) * M[16]) * M[17];
+          w1 = sin(rr * M[16]) * M[17];
+        }
+        Quat q;
+        q.w = w0 * M[0] + w1 * M[4];
+        q.x = w0 * M[1] + w1 * M[5];
+        q.y = w0 * M[2] + w1 * M[6];
+        q.z = w0 * M[3] + w1 * M[7];
+        const double pin[3] = {px, py, pz};
+        double po[3];
+        quat_rotate(q, pin, po);
+        px = po[0] + (M[8] + M[11] * rr);
+        py = po[1] + (M[9] + M[12] * rr);
+        pz = po[2] + (M[10] + M[13] * rr);
+      } else {
+        rigid(M, px, py, pz);
+      }
+    }
     const unsigned pred = (m >> lane) & 1u;
     const unsigned o = (unsigned)r.y + __popc(m & lt_mask);  // position in the pair's staging
     stage_point(pred, out_a + kOX + 4u * o, out_a + kOAz + 2u * o, out_a + kOInt + o, (float)px,
-                (float)py, (float)pz, tpk + (ADJ != 0 ? (uint32_t)cfg.tadj[j][lane] : 0u), az, dist,
-                inten, (unsigned)laser_id);
+                (float)py, (float)pz, tpk + fire, az, dist, inten, (unsigned)laser_id);
     cnt += pred;
   };
 
@@ -1224,10 +1417,11 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
       // lane's first return of block `par`: 3 bytes per return after the 4-byte block header
       const uint32_t blk_a = pkt_a + (unsigned)lp * stride + 100u * (unsigned)par + 4u + 3u * (unsigned)lane;
       const uint32_t rk_a = rec_a + 32u * 6u * (unsigned)k;
-      double M[12];  // [L | t] of this packet, warp-uniform
+      double M[kRowD];  // pose row of this packet ([L | t], or the deskew row), warp-uniform
       if (pose_valid) {
 #pragma unroll
-        for (int q = 0; q < 6; ++q) lds_v2f64(pose_a + 96u * (unsigned)lp + 16u * (unsigned)q, M[2 * q], M[2 * q + 1]);
+        for (int q = 0; q < kRowD / 2; ++q)
+          lds_v2f64(pose_a + (unsigned)L::kRowBytes * (unsigned)lp + 16u * (unsigned)q, M[2 * q], M[2 * q + 1]);
       }
       const unsigned pm = par ? 0xaaau : 0x555u;  // the blocks of this warp
       const unsigned ub = um & pm;
@@ -1282,9 +1476,11 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
           if (((unsigned)r.z >> 17) & 1u) {
             // offline: blocks at/after the packet's first wrap start a frame whose origin is
             // this very packet -> zero translation
-            M[3] = 0.0;
-            M[7] = 0.0;
-            M[11] = 0.0;
+            if (!DSK) {
+              M[3] = 0.0;
+              M[7] = 0.0;
+              M[11] = 0.0;
+            }
           }
           if (r.w != cnt_frame || bank != cnt_bank) {
             flush_counts();
