@@ -1124,6 +1124,18 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint
                "r"(src_smem), "r"(bytes)
                : "memory");
 }
+// The same from a converged warp: one elected lane issues it (operands are warp-uniform), which
+// lets ptxas feed UBLKCP from uniform registers without a per-value loop.
+__device__ __forceinline__ void bulk_s2g_elect(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "@p cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+      "}\n" ::"l"(dst_gmem),
+      "r"(src_smem), "r"(bytes)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -1521,20 +1533,21 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
         const unsigned s1 = phu + totu;                   // staging range [phu, s1)
         const unsigned b0 = (phu + 15u) & ~15u, b1 = s1 & ~15u;  // whole granules [b0, b1)
         const unsigned long long g0 = Pu - phu;           // global index of staging element 0
-        if (b1 > b0 && lane == 0) {
-          // warp `par` stores two 4-byte columns, one 2-byte and one 1-byte column
+        if (b1 > b0) {
+          // warp `par` stores two 4-byte columns, one 2-byte and one 1-byte column (the whole
+          // warp is converged here; one elected lane issues each copy)
           const unsigned nb = b1 - b0;
           const unsigned long long gb = g0 + b0;
           if (par == 0) {
-            bulk_s2g(p.x + gb, out_a + kOX + 4u * b0, 4u * nb);
-            bulk_s2g(p.y + gb, out_a + kOY + 4u * b0, 4u * nb);
-            bulk_s2g(p.azimuth + gb, out_a + kOAz + 2u * b0, 2u * nb);
-            bulk_s2g(p.intensity + gb, out_a + kOInt + b0, nb);
+            bulk_s2g_elect(p.x + gb, out_a + kOX + 4u * b0, 4u * nb);
+            bulk_s2g_elect(p.y + gb, out_a + kOY + 4u * b0, 4u * nb);
+            bulk_s2g_elect(p.azimuth + gb, out_a + kOAz + 2u * b0, 2u * nb);
+            bulk_s2g_elect(p.intensity + gb, out_a + kOInt + b0, nb);
           } else {
-            bulk_s2g(p.z + gb, out_a + kOZ + 4u * b0, 4u * nb);
-            bulk_s2g(p.t_us + gb, out_a + kOT + 4u * b0, 4u * nb);
-            bulk_s2g(p.distance + gb, out_a + kODist + 2u * b0, 2u * nb);
-            bulk_s2g(p.laser + gb, out_a + kOLas + b0, nb);
+            bulk_s2g_elect(p.z + gb, out_a + kOZ + 4u * b0, 4u * nb);
+            bulk_s2g_elect(p.t_us + gb, out_a + kOT + 4u * b0, 4u * nb);
+            bulk_s2g_elect(p.distance + gb, out_a + kODist + 2u * b0, 2u * nb);
+            bulk_s2g_elect(p.laser + gb, out_a + kOLas + b0, nb);
           }
           bulk_commit();
         }
