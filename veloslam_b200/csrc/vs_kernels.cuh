@@ -1341,15 +1341,16 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
     if (tile >= p.n_tiles) break;
     const int s = it % kDecStages;
     mbar_wait(&sh.full[s], (uint32_t)(it / kDecStages) & 1u);
-    const long long first = (long long)p.halo + (long long)tile * kDecTile;
-    const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, 0, kDecTile);
-    const int npk = sp.npk;
+    // consumer view of the tile: packet count and where its first byte sits in the 16-byte
+    // granular span the producer copied (32-bit arithmetic; the producer did the full span)
+    const int first = p.halo + tile * kDecTile;
+    const int npk = min(kDecTile, p.n - first);
     const uint32_t st_a = stage_a0 + (uint32_t)s * (uint32_t)p.stage_bytes;
     const uint32_t brec_a = st_a + kDRec;
     const uint32_t seg_a = st_a + kDSeg;
     const uint32_t off_a = st_a + kDOff + 8u * (unsigned)(first & 1);
     const uint32_t pose_a = st_a + kDPose;
-    const uint32_t pkt_a = st_a + kDPkts + (uint32_t)(sp.a0 - sp.s0);
+    const uint32_t pkt_a = st_a + kDPkts + (((unsigned)in_base + (unsigned)first * stride) & 15u);
     // global index of the pair's first point and the number of points of its packets
     unsigned long long P0 = 0;
     unsigned tot = 0;
@@ -1402,7 +1403,7 @@ __global__ void __launch_bounds__(kDecThreads, 2) k_decode(const DecParams p) {
       if (pf_ok && lane < kDecRecs) {
         const int k = lane / 6, i = lane - 6 * k;
         const int lp = lp0 + k, j = par + 2 * i;
-        const long long first_n = first + (long long)gridDim.x * kDecTile;
+        const int first_n = first + (int)gridDim.x * kDecTile;
         if (first_n + lp < p.n) {
           const unsigned info = lds_u32(stage_a0 + (uint32_t)sn_ * (uint32_t)p.stage_bytes + kDRec +
                                         8u * (unsigned)(lp * kBlocks + j) + 4u);
