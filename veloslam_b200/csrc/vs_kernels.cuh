@@ -399,29 +399,34 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
     }
 
     // ---- phase B1: which return slots of each block could be emitted ------------------------
+    // (distance != 0 / crop, laser selection).  Independent of phase A: warps 1..7 run it while
+    // warp 0 resolves the firingSkip chain.
     if (!CROP) {
       // lane per block: scan the 32 distance fields of a block with 16-bit loads (the 100-byte
       // block stride spreads the lanes of a warp over the banks)
-      for (int b = tid; b < kTileBlocks; b += kScanThreads) {
-        const int lp = b / kBlocks, j = b - lp * kBlocks;
-        unsigned bits = 0;
-        if (lp < npk) {
-          const uint8_t* blk = tile_smem + (size_t)lp * p.stride + 100 * j;
-          unsigned h[50];
+      if (warp > 0) {
+        for (int b = tid - 32; b < kTileBlocks; b += kScanThreads - 32) {
+          const int lp = b / kBlocks, j = b - lp * kBlocks;
+          unsigned bits = 0;
+          if (lp < npk) {
+            const uint8_t* blk = tile_smem + (size_t)lp * p.stride + 100 * j;
+            unsigned h[50];
 #pragma unroll
-          for (int k = 2; k < 50; ++k) h[k] = ld_smem_u16(blk + 2 * k);
+            for (int k = 2; k < 50; ++k) h[k] = ld_smem_u16(blk + 2 * k);
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const int o = 4 + 3 * r;  // byte offset of the distance field
-            unsigned d;
-            if ((o & 1) == 0)
-              d = h[o >> 1];
-            else
-              d = (h[o >> 1] & 0xff00u) | (h[(o >> 1) + 1] & 0x00ffu);
-            bits |= (d != 0u ? 1u : 0u) << r;
+            for (int r = 0; r < 32; ++r) {
+              const int o = 4 + 3 * r;  // byte offset of the distance field
+              unsigned d;
+              if ((o & 1) == 0)
+                d = h[o >> 1];
+              else
+                d = (h[o >> 1] & 0xff00u) | (h[(o >> 1) + 1] & 0x00ffu);
+              bits |= (d != 0u ? 1u : 0u) << r;
+            }
+            bits &= (ld_smem_u16(blk) != 0xeeffu) ? sel_hi : sel_lo;
           }
+          sh.nz[b] = bits;
         }
-        sh.nz[b] = bits;
       }
     } else {
       // crop test needs the sensor-frame position (HDLParser.cxx:629-639): warp per block
@@ -462,38 +467,30 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
           const bool in_box = px >= cfg.crop[0] && px <= cfg.crop[1] && py >= cfg.crop[2] &&
                               py <= cfg.crop[3] && pz >= cfg.crop[4] && pz <= cfg.crop[5];
           bits = __ballot_sync(0xffffffffu, dist != 0 && (in_box == (cfg.crop_inside != 0)));
+          bits &= off ? sel_hi : sel_lo;
         }
         if (lane == 0) sh.nz[b] = bits;
       }
     }
-    __syncthreads();
+    __syncthreads();  // skip / wrap (phase A) and nz (phase B1) are complete
 
-    // ---- phase B2: final masks (iterated, gated, selected lasers) ---------------------------
-    for (int b = tid; b < kTileBlocks; b += kScanThreads) {
-      const int lp = b / kBlocks, j = b - lp * kBlocks;
-      if (lp < npk) {
-        unsigned mk = 0;
-        if (j >= sh.skip[lp] && (pskip == 0 || (j % (pskip + 1)) == 0)) {
-          const bool upper = ld_smem_u16(tile_smem + (size_t)lp * p.stride + 100 * j) != 0xeeffu;
-          mk = sh.nz[b] & (upper ? sel_hi : sel_lo);
-        }
-        sh.nz[b] = mk;
-      }
-    }
-    __syncthreads();
-    // ---- phase B3: block records -------------------------------------------------------------
+    // ---- phase B2: block records: the final mask applies the gates of HDLParser.cxx:1042-1051
+    // (block iterated: j >= firingSkip; pointsSkip) to the slot bits -----------------------------
     for (int b = tid; b < kTileBlocks; b += kScanThreads) {
       const int lp = b / kBlocks, j = b - lp * kBlocks;
       if (lp < npk) {
         const uint8_t* blk = tile_smem + (size_t)lp * p.stride + 100 * j;
+        const int skip = sh.skip[lp];
         unsigned pre = 0;
-        for (int q = 0; q < j; ++q) pre += __popc(sh.nz[lp * kBlocks + q]);
+        for (int q = skip; q < j; ++q)
+          if (pskip == 0 || (q % (pskip + 1)) == 0) pre += __popc(sh.nz[lp * kBlocks + q]);
+        const bool open = j >= skip && (pskip == 0 || (j % (pskip + 1)) == 0);
         const unsigned upper = ld_smem_u16(blk) != 0xeeffu ? 1u : 0u;
         const unsigned wb = __popc(sh.wrap[lp] & ((2u << j) - 1u));
         unsigned az = ld_smem_u16(blk + 2);
         if (ADJ == 0) az %= 36000u;  // HDLParser.cxx:597 (ADJ != 0: adjusted per return later)
         BlkRec r;
-        r.x = sh.nz[b];
+        r.x = open ? sh.nz[b] : 0u;
         r.y = az | (pre << 16) | (upper << 25) | (wb << 26);
         p.recs[(first + lp) * kBlocks + j] = r;
       }
@@ -501,8 +498,8 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
     if (warp == 0) {
       unsigned cnt = 0;
       if (lane < npk) {
-#pragma unroll
-        for (int j = 0; j < kBlocks; ++j) cnt += __popc(sh.nz[lane * kBlocks + j]);
+        for (int j = s_in; j < kBlocks; ++j)
+          if (pskip == 0 || (j % (pskip + 1)) == 0) cnt += __popc(sh.nz[lane * kBlocks + j]);
         const long long P = first + lane;
         PktSeg r;
         r.x = s_in | (int)(wrapmask << 4) | (azdiff << 16);
