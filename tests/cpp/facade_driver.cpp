@@ -18,6 +18,7 @@
 #include <iostream>
 #include <string>
 #include <vector>
+#include <unistd.h>
 
 #include "VeloSLAM.h"
 
@@ -184,6 +185,41 @@ static int hostModes(int argc, char** argv) {
     }
     return 0;
   }
+  if (mode == "udp_host" && argc >= 5) {
+    // HDLSource receive path without a GPU: udp_host <port> <n_expected> <out.bin>
+    // out: per packet int64 time + the first 8 payload bytes + uint32 length
+    const int port = std::atoi(argv[2]);
+    const size_t want = (size_t)std::atoll(argv[3]);
+    std::vector<char> rec;
+    HDLSource src(port);
+    std::shared_ptr<TimeSolver> ts(new TimeSolver);
+    ts->setClock([]() { return (int64_t)1467331234567890ll; });
+    src.setTimeSolver(ts);
+    size_t got = 0;
+    src.setPacketCallback([&](const unsigned char* d, unsigned int len, ptime t) {
+      const int64_t us = t.us;
+      rec.insert(rec.end(), (const char*)&us, (const char*)&us + 8);
+      rec.insert(rec.end(), (const char*)d, (const char*)d + 8);
+      rec.insert(rec.end(), (const char*)&len, (const char*)&len + 4);
+      ++got;
+    });
+    src.start();
+    if (!src.isRunning()) return 1;
+    std::cout << "ready" << std::endl;
+    for (int i = 0; i < 1000; ++i) {  // up to 10 s
+      uint64_t r, d, c;
+      src.getCounters(&r, &d, &c);
+      if (c >= want) break;
+      usleep(10000);
+    }
+    src.stop();
+    uint64_t r, d, c;
+    src.getCounters(&r, &d, &c);
+    std::cerr << "received " << r << " dropped " << d << " consumed " << c << std::endl;
+    std::ofstream os(argv[4], std::ios::binary);
+    os.write(rec.data(), (std::streamsize)rec.size());
+    return 0;
+  }
   if (mode == "manager_host" && argc >= 4) {
     // HDLManager host logic without a GPU: time queries, cache, hard-drive buffers written as
     // pcap files, .hdlmeta round trip.  argv[2]: scratch directory, argv[3]: report file.
@@ -313,6 +349,43 @@ int main(int argc, char** argv) {
       return 1;
     }
     std::ofstream os(argv[6], std::ios::binary);
+    const int32_t nf = (int32_t)all.size();
+    os.write((const char*)&nf, 4);
+    for (auto& f : all) dumpFrame(os, *f);
+    return 0;
+  }
+  if (mode == "udp") {
+    // the whole online path: UDP -> HDLSource -> TimeSolver -> HDLParser (GPU) -> HDLManager
+    //   facade_driver udp <calib.xml> <port> <poses.bin|-> <out.bin> <n_expected>
+    if (argc < 7) return 2;
+    const size_t want = (size_t)std::atoll(argv[6]);
+    HDLManager mgr(1000);
+    HDLSource src(std::atoi(argv[3]));
+    src.setCorrectionsFile(argv[2]);
+    src.setTransformManager(loadPoses(argv[4]));
+    std::shared_ptr<TimeSolver> ts(new TimeSolver);
+    ts->setClock([]() { return (int64_t)1467331200000000ll; });  // == synth.T0_US
+    src.setTimeSolver(ts);
+    src.setHDLManager(&mgr);
+    src.start();
+    if (!src.isRunning()) return 1;
+    std::cout << "ready" << std::endl;
+    for (int i = 0; i < 3000; ++i) {  // up to 30 s
+      uint64_t r, d, c;
+      src.getCounters(&r, &d, &c);
+      if (c >= want) break;
+      usleep(10000);
+    }
+    src.stop();
+    uint64_t r, d, c;
+    src.getCounters(&r, &d, &c);
+    std::cerr << "received " << r << " dropped " << d << " consumed " << c << std::endl;
+    if (!src.getHDLParser()->lastError().empty()) {
+      std::cerr << "facade error: " << src.getHDLParser()->lastError() << std::endl;
+      return 1;
+    }
+    std::vector<std::shared_ptr<HDLFrame> > all = mgr.getAllFrameMeta();
+    std::ofstream os(argv[5], std::ios::binary);
     const int32_t nf = (int32_t)all.size();
     os.write((const char*)&nf, 4);
     for (auto& f : all) dumpFrame(os, *f);

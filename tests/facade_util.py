@@ -56,3 +56,38 @@ def read_frames(path):
         frames.append(f)
     assert off == len(raw)
     return frames
+
+
+def free_udp_port():
+    import socket
+    s = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def run_with_udp_feed(args, port, packets_u8, pace_s=40e-6, timeout=60):
+    """Start the driver (it prints "ready" once its socket is bound), send every row of
+    packets_u8 as one UDP datagram to 127.0.0.1:port, return (returncode, stderr)."""
+    import socket
+    import time
+    p = subprocess.Popen([DRIVER] + [str(a) for a in args], stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, text=True)
+    line = p.stdout.readline()
+    if line.strip() != "ready":
+        p.kill()
+        return 1, "driver did not come up: " + line + p.stderr.read()
+    tx = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    for row in packets_u8:
+        tx.sendto(row.tobytes(), ("127.0.0.1", port))
+        t_end = time.perf_counter() + pace_s
+        while time.perf_counter() < t_end:
+            pass
+    tx.close()
+    try:
+        _, err = p.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        p.kill()
+        return 1, "timeout"
+    return p.returncode, err

@@ -145,3 +145,23 @@ def test_facade_time_solver_and_geodesy(tmp_path):
     assert np.array_equal(rec["t"], O.ins_times(recs, arrival))
     want = O.ins_poses(recs, (-2781621.9891904, 4672106.75052387, 18.8910392))[:, :3]
     assert np.array_equal(rec["enu"], want)
+
+
+# --- HDLSource receive path: UDP -> ring -> TimeSolver stamp -> consumer -------------
+def test_hdlsource_udp_receive_ring(tmp_path):
+    from oracle import oracle as O
+    n = 600
+    pk, _ = synth.hdl64_packets(n, seed=21)
+    gps = ((3_599_950_000 + 288 * np.arange(n, dtype=np.int64)) % 3_600_000_000).astype(np.uint32)
+    pk["gps"] = gps                               # the sensor clock wraps the hour mid-stream
+    b = synth.as_bytes(pk)
+    feed = [row for row in b]
+    feed.insert(100, np.zeros(512, dtype=np.uint8))   # a position packet: ignored (length != 1206)
+    port = F.free_udp_port()
+    rc, err = F.run_with_udp_feed(["udp_host", port, n, tmp_path / "out.bin"], port, feed)
+    assert rc == 0, err
+    assert f"received {n + 1} dropped 0" in err, err
+    rec = np.fromfile(tmp_path / "out.bin", dtype=[("t", "<i8"), ("head", "u1", (8,)), ("len", "<u4")])
+    assert len(rec) == n and np.all(rec["len"] == 1206)
+    assert np.array_equal(rec["head"], b[:, :8])                      # in order, intact
+    assert np.array_equal(rec["t"], O.TimeSolver().hdl_many(gps, 1467331234567890))

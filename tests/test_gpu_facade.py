@@ -132,3 +132,25 @@ def test_hdlmanager_renames_recording_and_index_spans_batches(tmp_path):
         assert f.timestamp_us == ts[i] and f.skips == sk[i] and f.n_points == want.n_points
         assert np.array_equal(f.azimuth, want.azimuth)
         assert np.array_equal(f.xyzi.view(np.uint32), want.xyzi.view(np.uint32))
+
+
+# --- the whole online path over loopback UDP -------------------------------------------
+def test_online_udp_to_hdlmanager(tmp_path):
+    n = 1500
+    pk, t = synth.hdl64_packets(n, seed=33)
+    # the sensor clock: microseconds past the hour, consistent with the packet times
+    pk["gps"] = ((t - synth.T0_US) % 3_600_000_000).astype(np.uint32)
+    calib = synth.calib_hdl64()
+    poses = synth.ins_trajectory(80)
+    b = synth.as_bytes(pk)
+    F.write_poses(tmp_path / "poses.bin", *poses)
+    calibxml.write_db_xml(str(tmp_path / "db.xml"), calib)
+    port = F.free_udp_port()
+    rc, err = F.run_with_udp_feed(["udp", tmp_path / "db.xml", port, tmp_path / "poses.bin",
+                                   tmp_path / "out.bin", n], port, [row for row in b], pace_s=60e-6)
+    assert rc == 0, err
+    assert f"received {n} dropped 0 consumed {n}" in err, err
+    # TimeSolver: first packet = the (injected) clock, later ones by the sensor clock: == t
+    o = P.make_oracle(calib, poses)
+    o.process_packets(b, t)
+    compare(F.read_frames(tmp_path / "out.bin"), o.frames(), P.TOL_DESKEW)

@@ -47,7 +47,7 @@ def build_library(force=False, verbose=False):
 
 FACADE_DIR = os.path.join(HERE, "cpp")
 FACADE_LIB = os.path.join(HERE, "libveloslam_facade.so")
-FACADE_SOURCES = ["type_defs.cpp", "TransformManager.cpp", "vtkPacketFile.cpp", "HDLManager.cpp", "CoordiTran.cpp", "TimeSolver.cpp",
+FACADE_SOURCES = ["type_defs.cpp", "TransformManager.cpp", "vtkPacketFile.cpp", "HDLManager.cpp", "CoordiTran.cpp", "TimeSolver.cpp", "HDLSource.cpp",
                   "CalibrationFile.cpp", "HDLParser.cpp"]
 DRIVER_SRC = os.path.join(os.path.dirname(HERE), "tests", "cpp", "facade_driver.cpp")
 DRIVER_EXE = os.path.join(os.path.dirname(HERE), "tests", "cpp", "facade_driver")
@@ -63,12 +63,12 @@ def build_facade(force=False):
     if (force or not os.path.exists(FACADE_LIB)
             or os.path.getmtime(FACADE_LIB) < max(os.path.getmtime(d) for d in deps)):
         subprocess.check_call(["g++"] + CXXFLAGS + ["-shared", "-o", FACADE_LIB] + srcs +
-                              ["-L", HERE, "-lveloslam_b200", "-Wl,-rpath,$ORIGIN"])
+                              ["-L", HERE, "-lveloslam_b200", "-lpthread", "-Wl,-rpath,$ORIGIN"])
     if (force or not os.path.exists(DRIVER_EXE)
             or os.path.getmtime(DRIVER_EXE) < max(os.path.getmtime(DRIVER_SRC),
                                                   os.path.getmtime(FACADE_LIB))):
         subprocess.check_call(["g++"] + CXXFLAGS + ["-o", DRIVER_EXE, DRIVER_SRC, "-I", FACADE_DIR,
-                               "-L", HERE, "-lveloslam_facade", "-lveloslam_b200",
+                               "-L", HERE, "-lveloslam_facade", "-lveloslam_b200", "-lpthread",
                                "-Wl,-rpath,$ORIGIN/../../veloslam_b200"])
     return FACADE_LIB
 

@@ -5,6 +5,7 @@
 #include "HDLFrame.h"
 #include "HDLManager.h"
 #include "HDLParser.h"
+#include "HDLSource.h"
 #include "TimeLine.h"
 #include "TimeSolver.h"
 #include "TransformManager.h"
