@@ -143,51 +143,49 @@ void HDLManager::addFrame(std::shared_ptr<HDLFrame> frame) {
     std::lock_guard<std::mutex> lock(framesMutex);
     frames.addData(frame);
     hasNewData = true;
-    cond_.notify_one();
   }
-  if (fileBufferMode && (!frame->isOnHardDrive)) {
-    hardDriveBuffer->push_back(frame);
-    if (hardDriveBuffer->size() == bufferSize && writerIdle) switchBuffer();
-  } else {
+  cond_.notify_one();
+  const bool toDisk = fileBufferMode && !frame->isOnHardDrive;
+  if (!toDisk) {
     pushCache(frame);
+    return;
   }
+  hardDriveBuffer->push_back(frame);
+  if (writerIdle && hardDriveBuffer->size() == bufferSize) switchBuffer();
 }
 
+// A frame in memory is handed out as it is; one that only exists on disk is decoded again --
+// out of HBM when its recording is resident, else from the pcap file (HDLManager.cxx:195-211).
 HDLFramePtr HDLManager::prepareFrame(std::shared_ptr<HDLFrame> frame) {
   if (!frame) return HDLFramePtr();
-  if (frame->isInMemory) {
-    return HDLFramePtr(frame.get());
-  } else if (frame->isOnHardDrive) {
-    const std::string filename = bufferDirName + to_iso_string(frame->filenameTime) + ".pcap";
-    if (hdlParser->getFrame(frame, filename, frame->fileStartPos, frame->skips)) {
-      frame->isInMemory = true;
-      this->pushCache(frame);
-      return HDLFramePtr(frame.get());
-    }
-    return HDLFramePtr();
-  }
-  return HDLFramePtr();
+  if (frame->isInMemory) return HDLFramePtr(frame.get());
+  if (!frame->isOnHardDrive) return HDLFramePtr();
+  const std::string pcap = bufferDirName + to_iso_string(frame->filenameTime) + ".pcap";
+  if (!hdlParser->getFrame(frame, pcap, frame->fileStartPos, frame->skips)) return HDLFramePtr();
+  frame->isInMemory = true;
+  pushCache(frame);
+  return HDLFramePtr(frame.get());
 }
 
 HDLFramePtr HDLManager::waitForFrame(int64_t micro) {
-  std::unique_lock<std::mutex> lock(framesMutex);
-  cond_.wait_for(lock, std::chrono::microseconds(micro), [this] { return hasNewData; });
-  if (hasNewData) {
+  std::shared_ptr<HDLFrame> newest;
+  {
+    std::unique_lock<std::mutex> lock(framesMutex);
+    cond_.wait_for(lock, std::chrono::microseconds(micro), [this] { return hasNewData; });
+    if (!hasNewData) return HDLFramePtr();
     hasNewData = false;
-    std::shared_ptr<HDLFrame> f = frames.back();
-    lock.unlock();
-    return prepareFrame(f);
+    newest = frames.back();
   }
-  return HDLFramePtr();
+  return prepareFrame(newest);
 }
 
 HDLFramePtr HDLManager::getRecentFrame() {
-  std::shared_ptr<HDLFrame> result;
+  std::shared_ptr<HDLFrame> newest;
   {
     std::lock_guard<std::mutex> lock(framesMutex);
-    result = frames.back();
+    newest = frames.back();
   }
-  return prepareFrame(result);
+  return prepareFrame(newest);
 }
 HDLFramePtr HDLManager::getFrameAt(ptime& t) { return prepareFrame(frames.getExactDataAt(t)); }
 HDLFramePtr HDLManager::getFrameNear(ptime& t) { return prepareFrame(frames.getNearestData(t)); }
@@ -240,41 +238,40 @@ void HDLManager::setFileBufferMode(bool m) {
 
 void HDLManager::flushFileBuffer() { switchBuffer(); }
 
+// One pcap file per filled buffer, named after its first packet; every frame of the buffer gets
+// the file's name time and the byte offset of its first record (HDLManager.cxx:318-371).
 bool HDLManager::writePackets() {
-  Buffer* buff;
-  std::string filename;
-  ptime filenameTime;
+  Buffer* full = nullptr;
+  std::string path;
+  ptime stamp;
   {
     std::lock_guard<std::mutex> lock(writerMutex);
-    buff = isUsingBuffer1 ? &hardDriveBuffer2 : &hardDriveBuffer1;
-    if (buff->empty() || buff->front()->packets.empty()) {
+    full = isUsingBuffer1 ? &hardDriveBuffer2 : &hardDriveBuffer1;  // the one NOT being filled
+    const bool nothing = full->empty() || full->front()->packets.empty();
+    if (nothing) {
       writerIdle = true;
       return false;
     }
-    filenameTime = buff->front()->packets.front().first;
-    filename = bufferDirName + to_iso_string(filenameTime) + ".pcap";
+    stamp = full->front()->packets.front().first;
+    path = bufferDirName + to_iso_string(stamp) + ".pcap";
   }
   if (packetWriter->isOpen()) packetWriter->close();
-  packetWriter->open(filename);
-  long long posOffset = PCAP_GLOBAL_HEADER_LEN;
-  for (size_t i = 0; i < buff->size(); ++i) {
-    int packetsNum = 0;
-    auto& f = buff->at(i)->packets;
-    for (size_t j = 0; j < f.size(); ++j) {
-      packetWriter->writePacket(reinterpret_cast<const unsigned char*>(f[j].second.c_str()),
-                                (unsigned int)f[j].second.length(), f[j].first);
-      ++packetsNum;
-    }
-    buff->at(i)->filenameTime = filenameTime;
-    buff->at(i)->fileStartPos = posOffset;
-    posOffset += (long long)packetsNum * PCAP_PACKET_LEN;
-    buff->at(i)->isOnHardDrive = true;
-    cache.push_back(buff->at(i).get());
+  packetWriter->open(path);
+  int64_t recordPos = PCAP_GLOBAL_HEADER_LEN;  // fpos of the next record, kept by hand
+  for (const std::shared_ptr<HDLFrame>& frame : *full) {
+    for (const auto& pkt : frame->packets)
+      packetWriter->writePacket(reinterpret_cast<const unsigned char*>(pkt.second.data()),
+                                (unsigned int)pkt.second.size(), pkt.first);
+    frame->filenameTime = stamp;
+    frame->fileStartPos = recordPos;
+    frame->isOnHardDrive = true;
+    recordPos += (int64_t)frame->packets.size() * PCAP_PACKET_LEN;
+    cache.push_back(frame.get());
     ++cacheCounter;
   }
   packetWriter->close();
-  bufferFileNames.insert(filename);
-  buff->clear();
+  bufferFileNames.insert(path);
+  full->clear();
   updateCacheSize();
   writerIdle = true;
   return true;
@@ -292,18 +289,19 @@ void HDLManager::pushCache(std::shared_ptr<HDLFrame>& frame) {
   updateCacheSize();
 }
 
+// Evict from the front until the cache fits; a frame an end user still holds (count != 0) goes
+// back to the end, at most ten times per call (HDLManager.cxx:400-421).
 void HDLManager::updateCacheSize() {
-  int putBackTimes = 10;
-  while (cacheCounter > (int)maxCacheSize && putBackTimes && !cache.empty()) {
-    HDLFrame* obj = cache.front();
+  for (int putBacks = 0; cacheCounter > (int)maxCacheSize && putBacks < 10 && !cache.empty();) {
+    HDLFrame* oldest = cache.front();
     cache.pop_front();
-    if (obj->count) {
-      cache.push_back(obj);
-      --putBackTimes;
-    } else {
-      obj->clear();
-      --cacheCounter;
+    if (oldest->count != 0) {
+      cache.push_back(oldest);
+      ++putBacks;
+      continue;
     }
+    oldest->clear();
+    --cacheCounter;
   }
 }
 
