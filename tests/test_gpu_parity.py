@@ -397,3 +397,36 @@ def test_full_minute_hdl64_properties():
     for k in ("x", "y", "z"):
         assert np.max(np.abs(c[k].astype(np.float64) - tr[k])) <= P.TOL_DESKEW
     ctx.close()
+
+
+def test_config1_hdl32_minute_pcap_file_no_poses():
+    """BASELINE.json configs[0] at full size: 60 s of HDL-32E (108 480 packets, 41.66 M slots) in
+    vtkPacketFileWriter format, decoded in place out of the file image (1264-byte records, record
+    timestamps on the GPU), no poses.  Bit-exact against the oracle end to end."""
+    from veloslam_b200 import pcapio
+    n = 108_480
+    pk, t = synth.hdl32_packets(n)
+    b = synth.as_bytes(pk)
+    calib = synth.calib_hdl32()
+    img = pcapio.write_pcap_image(b, t)
+    assert img.size == 137_118_744                       # SURVEY 8d config 1
+    recs, nrec = pcapio.payload_view(img)
+    assert nrec == n
+    ctx = P.make_ctx(calib, max_batch_packets=n)
+    r = ctx.decode(recs, None, n=n, stride=pcapio.RECORD_BYTES, flags=capi.FLAG_PCAP_TIMES)
+    assert 599 <= r.n_closed <= 601
+    o = P.make_oracle(calib)
+    o.trace_enable()
+    o.process_packets(b, t)
+    tr = o.trace()
+    c = r.fetch()
+    assert r.n_points == len(tr["x"])
+    for k in ("laser", "intensity", "azimuth", "distance"):
+        assert np.array_equal(c[k], tr[k]), k
+    for k in ("x", "y", "z"):                            # rotCorrection == 0: LUT branch, bit-exact
+        assert np.array_equal(c[k].view(np.uint32), tr[k].astype(np.float32).view(np.uint32)), k
+    of = o.frames()
+    assert len(of) == r.n_closed
+    assert [f.n_points for f in of] == [fr.n_points for fr in r.frames[:r.n_closed]]
+    assert [f.timestamp_us for f in of[1:]] == [fr.timestamp_us for fr in r.frames[1:r.n_closed]]
+    ctx.close()

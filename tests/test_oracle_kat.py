@@ -346,3 +346,22 @@ def test_offline_index_and_get_frame_have_no_drops():
     assert f1.timestamp_us == t[sp[1]] and f1.skips == sk[1]
     last = o.get_frame(b, t, sp[-1], sk[-1])            # forced split at end of data
     assert last.n_points == int(np.count_nonzero(d[wraps[-1]:]))
+
+
+def test_config1_hdl32_minute_on_the_oracle():
+    """BASELINE.json configs[0], the reference's own CPU-runnable case, at full size: 60 s of
+    HDL-32E at 10 Hz: 108 480 packets, 41.66 M return slots, 600 +- 1 frames."""
+    from veloslam_b200 import synth
+    n = 108_480
+    pk, t = synth.hdl32_packets(n)
+    o = Oracle()
+    o.set_calibration(synth.calib_hdl32())
+    o.process_packets(synth.as_bytes(pk), t)
+    assert n * 384 == 41_656_320
+    assert 599 <= o.num_frames() <= 601
+    d = pk["blocks"]["returns"]["distance"]
+    frames = o.frames()
+    total = sum(f.n_points for f in frames) + o.open_frame_points()
+    # streaming drops the blocks of the packet after a wrap that precede the wrap block (F4a)
+    assert 0 <= int(np.count_nonzero(d)) - total < 600 * 11 * 32
+    assert all(f.n_lasers == 32 for f in frames)
