@@ -185,6 +185,38 @@ static int hostModes(int argc, char** argv) {
     }
     return 0;
   }
+  if (mode == "ins_host" && argc >= 6) {
+    // INSSource over loopback: ins_host <port> <n_expected> <out.bin> <out.insmeta>
+    // out: per pose int64 t + 9 doubles, in timeline order; then the count re-read from the meta file
+    const int port = std::atoi(argv[2]);
+    const uint64_t want = (uint64_t)std::atoll(argv[3]);
+    INSSource src(port);
+    std::shared_ptr<TransformManager> tm(new TransformManager);
+    std::shared_ptr<TimeSolver> ts(new TimeSolver);
+    int64_t clock = 1467331200000000ll;
+    ts->setClock([&clock]() { return clock; });   // frozen clock: t = clock + (pose - sent)
+    src.setTimeSolver(ts);
+    src.setTransformManager(tm);
+    src.setOutputFile(argv[5]);
+    src.start();
+    if (!src.isRunning()) return 1;
+    std::cout << "ready" << std::endl;
+    for (int i = 0; i < 1000 && src.posesReceived() < want; ++i) usleep(10000);
+    src.stop();
+    std::vector<int64_t> t;
+    std::vector<double> trv;
+    tm->snapshot(&t, &trv);
+    std::ofstream os(argv[4], std::ios::binary);
+    for (size_t i = 0; i < t.size(); ++i) {
+      os.write((const char*)&t[i], 8);
+      os.write((const char*)&trv[9 * i], 72);
+    }
+    TransformManager again;
+    again.loadFromMetaFile(argv[5]);
+    std::cerr << "poses " << src.posesReceived() << " timeline " << t.size() << " meta "
+              << again.getNumberOfTransforms() << std::endl;
+    return 0;
+  }
   if (mode == "udp_host" && argc >= 5) {
     // HDLSource receive path without a GPU: udp_host <port> <n_expected> <out.bin>
     // out: per packet int64 time + the first 8 payload bytes + uint32 length

@@ -165,3 +165,35 @@ def test_hdlsource_udp_receive_ring(tmp_path):
     assert len(rec) == n and np.all(rec["len"] == 1206)
     assert np.array_equal(rec["head"], b[:, :8])                      # in order, intact
     assert np.array_equal(rec["t"], O.TimeSolver().hdl_many(gps, 1467331234567890))
+
+
+def test_inssource_udp_to_transform_manager(tmp_path):
+    from oracle import oracle as O
+    rng = np.random.default_rng(12)
+    n = 150
+    recs = np.zeros(n, dtype=O.INS_DTYPE)
+    recs["message_id"] = 508
+    recs["week_number"] = 1903
+    recs["week_number_pos"] = 1903
+    recs["milliseconds"] = 345_600_000 + 10 * np.arange(n)
+    # pose time - send time: distinct per record (equal timestamps overwrite each other in the
+    # TimeLine, as in the reference), not monotonic
+    recs["seconds_pos"] = 345_600.0 + 0.01 * np.arange(n) + (np.arange(n) % 7) * 1e-3 + np.arange(n) * 2e-6
+    recs["LLH"] = np.array([39.8569901, 116.1736406, 89.09]) + np.cumsum(rng.normal(0, 1e-6, (n, 3)), axis=0)
+    recs["V"] = rng.normal(0, 5, (n, 3))
+    recs["Eulr"] = rng.uniform(-180, 180, (n, 3))
+    feed = [np.frombuffer(recs[i].tobytes(), dtype=np.uint8) for i in range(n)]
+    other = np.zeros(24, dtype=np.uint8)
+    other[:2] = np.frombuffer(np.uint16(325).tobytes(), dtype=np.uint8)    # RAWINS: ignored
+    feed.insert(40, other)
+    port = F.free_udp_port()
+    rc, err = F.run_with_udp_feed(["ins_host", port, n, tmp_path / "out.bin", tmp_path / "a.insmeta"],
+                                  port, feed, pace_s=100e-6)
+    assert rc == 0, err
+    assert f"poses {n} timeline {n} meta {n}" in err, err
+    got = np.fromfile(tmp_path / "out.bin", dtype=[("t", "<i8"), ("trv", "<f8", (9,))])
+    want_t = O.ins_times(recs, 1467331200000000)
+    order = np.argsort(want_t, kind="stable")
+    assert np.array_equal(got["t"], want_t[order])
+    want = O.ins_poses(recs, (-2781621.9891904, 4672106.75052387, 18.8910392))
+    assert np.array_equal(got["trv"], want[order])                   # host libm on both sides

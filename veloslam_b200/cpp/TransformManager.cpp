@@ -25,7 +25,7 @@ void TransformManager::addTransform(std::shared_ptr<PoseTransform> trans) {
 namespace {
 // .insmeta record: T/R/V interleaved per axis, timestamp, week, ms, week_pos, seconds_pos
 // (reference type_defs.cxx:4-33 with ptime stored as int64 microseconds)
-void writePose(std::ofstream& os, const PoseTransform& p) {
+void writePose(std::ostream& os, const PoseTransform& p) {
   for (int i = 0; i < 3; ++i) {
     os.write(reinterpret_cast<const char*>(p.T + i), sizeof(double));
     os.write(reinterpret_cast<const char*>(p.R + i), sizeof(double));
@@ -51,6 +51,8 @@ bool readPose(std::ifstream& is, PoseTransform& p) {
   return (bool)is;
 }
 }  // namespace
+
+void TransformManager::writePoseRecord(std::ostream& os, const PoseTransform& p) { writePose(os, p); }
 
 bool TransformManager::loadFromMetaFile(std::string filename, bool clearOldData) {
   std::ifstream ifs(filename, std::ios::binary);

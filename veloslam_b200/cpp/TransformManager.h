@@ -6,6 +6,7 @@
 
 #include <cstdint>
 #include <memory>
+#include <ostream>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -29,6 +30,8 @@ class TransformManager {
   // reference TransformManager.cxx:95-125)
   bool loadFromTxtFile(std::string filename, bool clearOldData = false);
   bool writeToMetaFile(const std::string& filename);
+  // one .insmeta record (also what INSSource appends to its output file while receiving)
+  static void writePoseRecord(std::ostream& os, const PoseTransform& p);
 
   // Linear interpolation of T, R (Euler degrees) and V between the bracketing samples; with
   // one sample: velocity extrapolation that leaves the pose flagged invalid; empty: false

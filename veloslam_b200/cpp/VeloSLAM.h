@@ -6,6 +6,7 @@
 #include "HDLManager.h"
 #include "HDLParser.h"
 #include "HDLSource.h"
+#include "INSSource.h"
 #include "TimeLine.h"
 #include "TimeSolver.h"
 #include "TransformManager.h"
