@@ -18,6 +18,7 @@
 #include <iostream>
 #include <string>
 #include <vector>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include "VeloSLAM.h"
@@ -391,15 +392,33 @@ int main(int argc, char** argv) {
     //   facade_driver udp <calib.xml> <port> <poses.bin|-> <out.bin> <n_expected>
     if (argc < 7) return 2;
     const size_t want = (size_t)std::atoll(argv[6]);
+    // HDLManager::startOnline wires HDLSource / INSSource / TimeSolver / TransformManager
     HDLManager mgr(1000);
-    HDLSource src(std::atoi(argv[3]));
-    src.setCorrectionsFile(argv[2]);
-    src.setTransformManager(loadPoses(argv[4]));
-    std::shared_ptr<TimeSolver> ts(new TimeSolver);
-    ts->setClock([]() { return (int64_t)1467331200000000ll; });  // == synth.T0_US
-    src.setTimeSolver(ts);
-    src.setHDLManager(&mgr);
-    src.start();
+    const std::string scratch = std::string(argv[5]) + ".dir";
+    mkdir(scratch.c_str(), 0777);
+    mgr.setBufferDir(scratch, false);   // stopOnline writes the .hdlmeta here
+    mgr.setCalibFile(argv[2]);
+    mgr.setPorts(std::atoi(argv[3]), std::atoi(argv[3]) + 1);
+    {
+      std::shared_ptr<TransformManager> poses = loadPoses(argv[4]);
+      std::vector<int64_t> pt;
+      std::vector<double> trv;
+      poses->snapshot(&pt, &trv);
+      for (size_t i = 0; i < pt.size(); ++i) {
+        std::shared_ptr<PoseTransform> p(new PoseTransform);
+        for (int k = 0; k < 3; ++k) {
+          p->T[k] = trv[9 * i + k];
+          p->R[k] = trv[9 * i + 3 + k];
+          p->V[k] = trv[9 * i + 6 + k];
+        }
+        p->timestamp = ptime(pt[i]);
+        p->seconds_pos = 0;
+        mgr.getTransformMgr()->addTransform(p);
+      }
+    }
+    mgr.getTimeSolver()->setClock([]() { return (int64_t)1467331200000000ll; });  // == synth.T0_US
+    mgr.startOnline();
+    HDLSource& src = *mgr.getHDLSource();
     if (!src.isRunning()) return 1;
     std::cout << "ready" << std::endl;
     for (int i = 0; i < 3000; ++i) {  // up to 30 s
@@ -408,7 +427,7 @@ int main(int argc, char** argv) {
       if (c >= want) break;
       usleep(10000);
     }
-    src.stop();
+    mgr.stopOnline();
     uint64_t r, d, c;
     src.getCounters(&r, &d, &c);
     std::cerr << "received " << r << " dropped " << d << " consumed " << c << std::endl;

@@ -75,8 +75,44 @@ HDLManager::HDLManager(int capacity)
     : hardDriveBuffer(&hardDriveBuffer1), cacheCounter(0), hasNewData(false), bufferSize(100),
       maxCacheSize((size_t)capacity), bufferDirName("/tmp/"), isUsingBuffer1(true),
       writerIdle(true), fileBufferMode(false), packetWriter(new vtkPacketFileWriter),
-      transMgr(new TransformManager), hdlParser(new HDLParser), metaSerial(0) {
+      transMgr(new TransformManager), hdlParser(new HDLParser), timeSolver(new TimeSolver),
+      hdlPort_(2368), insPort_(6777), metaSerial(0) {
   hdlParser->setTransformMgr(transMgr);
+}
+
+void HDLManager::setPorts(int hdlPort, int insPort) {
+  hdlPort_ = hdlPort;
+  insPort_ = insPort;
+}
+
+void HDLManager::startOnline(bool shouldSwap) {
+  this->loadHDLMeta();
+  this->loadINSMeta();
+  if (!insSrc) {
+    insSrc.reset(new INSSource(insPort_));
+    insSrc->setTimeSolver(timeSolver);
+    insSrc->setTransformManager(transMgr);
+  }
+  if (!hdlSrc) {
+    hdlSrc.reset(new HDLSource(hdlPort_));
+    hdlSrc->setHDLManager(this);
+    hdlSrc->setTimeSolver(timeSolver);
+    hdlSrc->setTransformManager(transMgr);
+    if (!calibFile_.empty()) hdlSrc->setCorrectionsFile(calibFile_);
+  }
+  insSrc->start();
+  hdlSrc->start();
+  if (shouldSwap) startSwaping();
+}
+
+void HDLManager::stopOnline() {
+  if (hdlSrc) hdlSrc->stop();
+  if (insSrc) insSrc->stop();
+  if (fileBufferMode) {
+    this->flushFileBuffer();
+    this->stopSwaping();
+  }
+  this->saveHDLMeta();
 }
 
 HDLManager::~HDLManager() { delete packetWriter; }
@@ -136,7 +172,11 @@ void HDLManager::switchBuffer() {
   writePackets();
 }
 
-void HDLManager::setCalibFile(std::string filename) { hdlParser->setCorrectionsFile(filename); }
+void HDLManager::setCalibFile(std::string filename) {
+  calibFile_ = filename;
+  if (hdlSrc) hdlSrc->setCorrectionsFile(filename);
+  hdlParser->setCorrectionsFile(filename);
+}
 
 void HDLManager::addFrame(std::shared_ptr<HDLFrame> frame) {
   {

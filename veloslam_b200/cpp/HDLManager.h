@@ -14,9 +14,9 @@
 //    index is one segmentation pass on the GPU and every later prepareFrame() decodes its
 //    rotation out of HBM -- the reference re-opens and re-reads the pcap file per frame.
 //  * writePackets() runs synchronously when a buffer fills (the reference runs it on a
-//    boost::thread); startOnline()/stopOnline() -- UDP sockets, HDLSource / INSSource -- are
-//    out of scope: feed packets with HDLParser::processHDLPacket and
-//    frames with addFrame().
+//    boost::thread).
+//  * the sources are created by startOnline() (ports: setPorts) instead of in the constructor,
+//    so that offline users open no sockets.
 //  * ptime is int64 microseconds and fpos_t an int64 byte offset (type_defs.h), so meta
 //    files are not byte-compatible with ones the reference wrote.
 #ifndef VELOSLAM_B200_HDLMANAGER_H
@@ -32,6 +32,8 @@
 
 #include "HDLFrame.h"
 #include "HDLParser.h"
+#include "HDLSource.h"
+#include "INSSource.h"
 #include "TimeLine.h"
 #include "TransformManager.h"
 #include "vtkPacketFile.h"
@@ -65,6 +67,15 @@ class HDLManager {
 
   HDLManager(int capacity = 200);  // 600 hdl frames ~= 1 minute
   virtual ~HDLManager();
+
+  // online: HDLSource (sensor UDP port) -> this manager, INSSource (INS UDP port) -> the pose
+  // timeline, one TimeSolver for both (reference HDLManager.cxx:43-100)
+  void startOnline(bool shouldSwap = false);
+  void stopOnline();
+  void setPorts(int hdlPort, int insPort);   // before startOnline; defaults 2368 / 6777
+  std::shared_ptr<HDLSource> getHDLSource() const { return hdlSrc; }
+  std::shared_ptr<INSSource> getINSSource() const { return insSrc; }
+  std::shared_ptr<TimeSolver> getTimeSolver() const { return timeSolver; }
 
   void loadOffline(const std::string& insTxt, const std::string& pcapfile);
   /* the purpose of 'touch' is rename the file if necessary */
@@ -137,6 +148,11 @@ class HDLManager {
   std::mutex writerMutex;
   std::shared_ptr<TransformManager> transMgr;
   std::shared_ptr<HDLParser> hdlParser;
+  std::shared_ptr<HDLSource> hdlSrc;
+  std::shared_ptr<INSSource> insSrc;
+  std::shared_ptr<TimeSolver> timeSolver;
+  int hdlPort_, insPort_;
+  std::string calibFile_;
   int metaSerial;  // keeps meta file names of one process distinct within a microsecond
 };
 
