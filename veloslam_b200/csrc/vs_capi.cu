@@ -12,6 +12,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -106,6 +107,7 @@ struct vs_ctx {
   std::vector<int64_t> pose_t;
   std::vector<double> pose_trv;
   int dec_blocks_per_sm = 2;
+  bool two_pass = true;  // false (VELOSLAM_SINGLE_PASS=1): k_pose_pre + k_decode<.., FUSED> where it applies
   std::string err;
 };
 
@@ -250,6 +252,9 @@ int alloc_slot(vs_ctx* ctx, Slot& s) {
   off += align_up(groups * 4, 256);
   const size_t o_fc = off;
   off += (size_t)fc * kMaxLasers * sizeof(unsigned);
+  // single-pass pipeline: [tile counter | 32-byte look-back records per 8-packet tile], carved
+  // per batch right behind the frame counts the batch can touch (one memset covers both)
+  off += 256 + (size_t)((np + kDecTile - 1) / kDecTile) * 32;
   s.zero_bytes = off;
   VS_CUDA(cudaMalloc(&s.d_zero, off));
   s.d_st_map = reinterpret_cast<unsigned long long*>(s.d_zero + o_map);
@@ -309,23 +314,24 @@ int copy_frame_rows(vs_ctx* ctx, Slot& s, size_t n_rows) {
   return VS_OK;
 }
 
-template <int ADJ, int DSK>
+template <int ADJ, int DSK, int FUSED = 0>
 int launch_decode(vs_ctx* ctx, Slot& s, DecParams dp, int64_t stride) {
-  typedef DecLayout<ADJ, DSK> L;
+  typedef DecLayout<ADJ, DSK, FUSED> L;
+  constexpr int kThreads = FUSED ? kFusedThreads : kDecThreads;
   dp.stage_bytes = (int)align_up((size_t)L::kDPkts + (size_t)kDecTile * stride + 48, 128);
   const size_t smem = (size_t)L::kStages + L::kNumStages * (size_t)dp.stage_bytes;
   static size_t cached_smem = 0;  // one process drives one GPU: cache per instantiation
   static int per_sm = 0;
   if (cached_smem != smem) {
-    VS_CUDA(cudaFuncSetAttribute(k_decode<ADJ, DSK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VS_CUDA(cudaFuncSetAttribute(k_decode<ADJ, DSK, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode<ADJ, DSK>, kDecThreads, smem));
+    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode<ADJ, DSK, FUSED>, kThreads, smem));
     cached_smem = smem;
   }
   if (per_sm < 1) return fail(ctx, VS_ERR_CUDA, "k_decode does not fit on an SM");
   int grid = ctx->sm_count * per_sm;
   if (grid > dp.n_tiles) grid = dp.n_tiles;
-  k_decode<ADJ, DSK><<<grid, kDecThreads, smem, s.stream>>>(dp);
+  k_decode<ADJ, DSK, FUSED><<<grid, kThreads, smem, s.stream>>>(dp);
   VS_CUDA(cudaGetLastError());
   return VS_OK;
 }
@@ -390,12 +396,26 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
   const int64_t n_dec = n - halo;
   const int64_t dec_tiles = (n_dec + kDecTile - 1) / kDecTile;
   const int64_t frames_possible = std::min<int64_t>(ctx->frame_cap, 12 * n + 1);
+  const int n_poses = (int)ctx->pose_t.size();
+  const bool pose_valid = n_poses >= 2;
+  const int adj = ctx->h_cfg.adj_mode;
+  const bool crop = ctx->h_cfg.crop_returns != 0 && !index_only;
+  const bool deskew = (flags & VS_FLAG_DESKEW_PER_POINT) != 0 && pose_valid && !index_only;
+  // single-pass pipeline (k_decode<.., FUSED>): everything but the crop filter, the per-point
+  // deskew extension and index-only passes
+  const bool fused = !ctx->two_pass && !crop && !deskew && !index_only;
+  const int64_t fused_tiles = (n + kDecTile - 1) / kDecTile;
+  const size_t fc_bytes = (size_t)frames_possible * kMaxLasers * sizeof(unsigned);
+  int* d_ctr2 = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(s.d_frame_counts) + fc_bytes);
+  ulonglong2* d_st = reinterpret_cast<ulonglong2*>(reinterpret_cast<uint8_t*>(d_ctr2) + 256);
   {
     // zero only what this batch can touch
-    const size_t head = (size_t)((uint8_t*)s.d_frame_counts - s.d_zero);
-    VS_CUDA(cudaMemsetAsync(s.d_zero, 0,
-                            head + (size_t)frames_possible * kMaxLasers * sizeof(unsigned),
-                            s.stream));
+    if (fused) {
+      VS_CUDA(cudaMemsetAsync(s.d_frame_counts, 0, fc_bytes + 256 + (size_t)fused_tiles * 32, s.stream));
+    } else {
+      const size_t head = (size_t)((uint8_t*)s.d_frame_counts - s.d_zero);
+      VS_CUDA(cudaMemsetAsync(s.d_zero, 0, head + fc_bytes, s.stream));
+    }
     VS_CUDA(cudaMemsetAsync(s.d_frame_first, 0xff, (size_t)frames_possible * 8, s.stream));
     VS_CUDA(cudaMemsetAsync(s.d_frame_start, 0xff, (size_t)frames_possible * 4, s.stream));
     BatchHeader& hi = *s.h_hdr_init;
@@ -420,11 +440,61 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
   else
     cin = *carry_in;
 
-  const int n_poses = (int)ctx->pose_t.size();
-  const bool pose_valid = n_poses >= 2;
-  const int adj = ctx->h_cfg.adj_mode;
-  const bool crop = ctx->h_cfg.crop_returns != 0 && !index_only;
-  const bool deskew = (flags & VS_FLAG_DESKEW_PER_POINT) != 0 && pose_valid && !index_only;
+  if (fused) {
+    if (pose_valid) {
+      k_pose_pre<<<(unsigned)((n + 255) / 256), 256, 0, s.stream>>>(d_time, (int)n, n_poses, ctx->d_pose_t,
+                                                                    ctx->d_pose_trv, s.d_pose_mat);
+      VS_CUDA(cudaGetLastError());
+      ++s.n_launches;
+    }
+    DecParams dp;
+    std::memset(&dp, 0, sizeof(dp));
+    dp.pkts = d_pkts;
+    dp.stride = stride;
+    dp.total_bytes = payload_bytes;
+    dp.pose_mat = s.d_pose_mat;
+    dp.lut_sin = ctx->d_lut_sin;
+    dp.lut_cos = ctx->d_lut_cos;
+    dp.cfg = ctx->d_cfg;
+    dp.n = (int)n;
+    dp.halo = (int)halo;
+    dp.mode = mode;
+    dp.pose_valid = pose_valid ? 1 : 0;
+    dp.n_tiles = (int)fused_tiles;
+    dp.x = s.d_x;
+    dp.y = s.d_y;
+    dp.z = s.d_z;
+    dp.intensity = s.d_inten;
+    dp.laser = s.d_laser;
+    dp.azimuth = s.d_az;
+    dp.distance = s.d_dist;
+    dp.t_us = s.d_t;
+    dp.frame_laser_counts = s.d_frame_counts;
+    dp.frame_cap = (int)ctx->frame_cap;
+    dp.pkt_time = d_time;
+    dp.t_base = t_base;
+    dp.seg_out = s.d_seg;
+    dp.st = d_st;
+    dp.tile_counter = d_ctr2;
+    dp.frame_first_point = s.d_frame_first;
+    dp.frame_start_block = s.d_frame_start;
+    dp.hdr = s.d_hdr;
+    dp.carry_last_az = cin.last_azimuth;
+    dp.carry_skip = cin.firing_skip;
+    dp.carry_meta_inited = cin.frame_meta_inited;
+    for (int k = 0; k < 3; ++k) dp.carry_origin_T[k] = cin.origin_T[k];
+    VS_CUDA(cudaEventRecord(s.ev_d0, s.stream));
+    int rc;
+    if (adj == 0)
+      rc = launch_decode<0, 0, 1>(ctx, s, dp, stride);
+    else if (adj == 1)
+      rc = launch_decode<1, 0, 1>(ctx, s, dp, stride);
+    else
+      rc = launch_decode<2, 0, 1>(ctx, s, dp, stride);
+    if (rc != VS_OK) return rc;
+    ++s.n_launches;
+    VS_CUDA(cudaEventRecord(s.ev_d1, s.stream));
+  } else {
   {
     ScanParams sp;
     sp.pkts = d_pkts;
@@ -543,6 +613,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     }
     VS_CUDA(cudaEventRecord(s.ev_d1, s.stream));
   }
+  }  // two-pass pipeline
 
   {
     // frame meta gather over every frame the batch can hold; rows beyond total_wraps are
@@ -740,6 +811,12 @@ int vs_create(int device, int64_t max_batch_packets, int64_t max_poses, int n_sl
     return bail(VS_ERR_NO_DEVICE);
   }
   ctx->sm_count = prop.multiProcessorCount;
+  {
+    // the single-pass pipeline (k_decode<.., FUSED>) is opt-in: measured slower than the two-pass
+    // one on B200
+    const char* e = std::getenv("VELOSLAM_SINGLE_PASS");
+    ctx->two_pass = !(e && e[0] == '1');
+  }
   auto init = [&]() -> int {
     VS_CUDA(cudaMalloc(&ctx->d_cfg, sizeof(DevConfig)));
     VS_CUDA(cudaMalloc(&ctx->d_lut_sin, kLutSize * sizeof(double)));
@@ -1263,6 +1340,18 @@ int vs_poses_from_ins(vs_ctx* ctx, const vs_ins_pva* recs, int64_t n, const doub
   if (e != cudaSuccess) return fail(ctx, VS_ERR_CUDA, std::string("vs_poses_from_ins: ") + cudaGetErrorString(e));
   return VS_OK;
 }
+
+#ifdef VS_PROFILE_FUSED
+__attribute__((visibility("default"))) int vs_debug_fused_prof(unsigned long long* out16, int reset) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(out16, g_fused_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_fused_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 void* vs_stream(vs_ctx* ctx) { return ctx ? (void*)ctx->slots[0].stream : nullptr; }
 void* vs_slot_stream(vs_ctx* ctx, int slot) {

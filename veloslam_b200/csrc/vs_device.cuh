@@ -150,6 +150,32 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// 16-byte look-back words (single-copy atomic: SASS LDG/STG.E.128.STRONG.GPU), so that two
+// scanned quantities travel under one flag.
+__device__ __forceinline__ void ld_relaxed_b128(const void* p, unsigned long long& lo,
+                                                unsigned long long& hi) {
+  asm volatile(
+      "{\n"
+      ".reg .b128 v;\n"
+      "ld.relaxed.gpu.global.b128 v, [%2];\n"
+      "mov.b128 {%0, %1}, v;\n"
+      "}\n"
+      : "=l"(lo), "=l"(hi)
+      : "l"(p)
+      : "memory");
+}
+__device__ __forceinline__ void st_relaxed_b128(void* p, unsigned long long lo,
+                                                unsigned long long hi) {
+  asm volatile(
+      "{\n"
+      ".reg .b128 v;\n"
+      "mov.b128 v, {%0, %1};\n"
+      "st.relaxed.gpu.global.b128 [%2], v;\n"
+      "}\n" ::"l"(lo),
+      "l"(hi), "l"(p)
+      : "memory");
+}
+
 // ---------------------------------------------------------------------------------------
 // Decoupled look-back (single-pass chained scan across tiles).  One 64-bit word per tile:
 // bits 63-62 flag (0 empty, 1 tile aggregate, 2 inclusive prefix), bits 61-0 payload.
