@@ -207,7 +207,12 @@ struct ScanShared {
   unsigned nz[kTileBlocks];  // raw "distance != 0" (or crop-tested) bits per block
   int skip[kTilePkts];
   unsigned wrap[kTilePkts];  // wrap mask over the iterated blocks of each packet
-  int tile_id;
+  // block headers kept from the header pass, so that nothing reads the stage after the mid-tile
+  // barrier and the next tile's copy can start there
+  unsigned short hdr_az[kTilePkts][kBlocks];
+  unsigned hdr_um[kTilePkts];  // bit j: block j is a 0xddff ("upper") block
+  int tile_id;                 // first tile of the CTA
+  int tile_next;               // tile whose copy was started at the mid-tile barrier
 };
 
 // 12-entry skip map of one packet from its block azimuths and the azimuth that precedes it.
@@ -231,7 +236,9 @@ __device__ __forceinline__ unsigned long long packet_skip_map(const int az[12], 
   return m;
 }
 
-// One stage per CTA, 4-5 CTAs per SM: the TMA latency of one CTA is hidden by the others.
+// One stage per CTA, 4-5 CTAs per SM: the TMA latency of one CTA is hidden by the others, and
+// inside a CTA the copy of the next tile starts at the mid-tile barrier (the block-record pass
+// works from shared-memory copies of the headers), its tile id dealt one tile earlier still.
 // The tile's lead bytes hold the whole previous packet, so the firingSkip entering the tile is
 // known locally whenever that packet's skip map is constant (always, on sensor data); only
 // otherwise does the tile fall back to the look-back over the published tile maps.
@@ -252,27 +259,37 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
   const int lead = (int)p.stride + kLead;
   const unsigned sel_lo = cfg.sel_lo, sel_hi = cfg.sel_hi;
   const int pskip = cfg.points_skip;
+  unsigned gate_mask = 0;  // bit j: block j passes the pointsSkip gate (HDLParser.cxx:1042)
+#pragma unroll
+  for (int j = 0; j < kBlocks; ++j)
+    if (pskip == 0 || (j % (pskip + 1)) == 0) gate_mask |= 1u << j;
 
-  uint32_t phase = 0u;
-  while (true) {
-    if (tid == 0) {
-      const int t = atomicAdd(p.tile_counter, 1);
-      sh.tile_id = t;
-      if (t < p.n_tiles) {
-        const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, (long long)t * kTilePkts, lead);
-        const uint32_t bytes = (uint32_t)(sp.s1 - sp.s0);
-        fence_proxy_async();
-        if (bytes) {
-          mbar_expect_tx(&sh.full, bytes);
-          bulk_g2s(stage, reinterpret_cast<const void*>(sp.s0), bytes, &sh.full);
-        } else {
-          mbar_arrive(&sh.full);
-        }
+  // start the copy of tile t into the stage (thread 0)
+  auto start_copy = [&](int t) {
+    if (t < p.n_tiles) {
+      const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, (long long)t * kTilePkts, lead);
+      const uint32_t bytes = (uint32_t)(sp.s1 - sp.s0);
+      fence_proxy_async();
+      if (bytes) {
+        mbar_expect_tx(&sh.full, bytes);
+        bulk_g2s(stage, reinterpret_cast<const void*>(sp.s0), bytes, &sh.full);
+      } else {
+        mbar_arrive(&sh.full);
       }
     }
-    __syncthreads();
-    const int tile = sh.tile_id;
-    if (tile >= p.n_tiles) break;
+  };
+  long long fub_seen = 0x7fffffffffffffffll;  // smallest first-upper-block candidate of this thread
+  int next_t = 0;  // thread 0: id of the tile after the one being copied
+  if (tid == 0) {
+    const int t = atomicAdd(p.tile_counter, 1);
+    sh.tile_id = t;
+    start_copy(t);
+    next_t = atomicAdd(p.tile_counter, 1);
+  }
+  __syncthreads();
+  int tile = sh.tile_id;
+  uint32_t phase = 0u;
+  while (tile < p.n_tiles) {
     const long long first = (long long)tile * kTilePkts;
     const TileSpan sp = tile_span(in_base, p.stride, p.total_bytes, p.n, first, lead);
     const int npk = sp.npk;
@@ -302,6 +319,10 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
           az[j] = (int)ld_smem_u16(pk + 100 * j + 2);
         }
         az11 = az[11];
+#pragma unroll
+        for (int j = 0; j < 12; j += 2)
+          *reinterpret_cast<unsigned*>(&sh.hdr_az[lane][j]) = (unsigned)az[j] | ((unsigned)az[j + 1] << 16);
+        sh.hdr_um[lane] = um;
       }
       // lastAzimuth entering the packet: block 11 of the previous packet (always iterated)
       int prev11 = __shfl_up_sync(0xffffffffu, az11, 1);
@@ -472,22 +493,31 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
         if (lane == 0) sh.nz[b] = bits;
       }
     }
-    __syncthreads();  // skip / wrap (phase A) and nz (phase B1) are complete
+    __syncthreads();  // skip / wrap / headers (phase A) and nz (phase B1) are complete
+    // nothing reads the stage from here on: the next tile's copy overlaps the record pass
+    if (tid == 0) {
+      sh.tile_next = next_t;
+      start_copy(next_t);
+      next_t = atomicAdd(p.tile_counter, 1);
+    }
 
     // ---- phase B2: block records: the final mask applies the gates of HDLParser.cxx:1042-1051
     // (block iterated: j >= firingSkip; pointsSkip) to the slot bits -----------------------------
     for (int b = tid; b < kTileBlocks; b += kScanThreads) {
       const int lp = b / kBlocks, j = b - lp * kBlocks;
       if (lp < npk) {
-        const uint8_t* blk = tile_smem + (size_t)lp * p.stride + 100 * j;
         const int skip = sh.skip[lp];
+        // blocks the parser iterates and emits: j >= firingSkip and the pointsSkip gate
+        const unsigned open_mask = gate_mask & ~((1u << skip) - 1u);
+        const unsigned before = open_mask & ((1u << j) - 1u);
         unsigned pre = 0;
-        for (int q = skip; q < j; ++q)
-          if (pskip == 0 || (q % (pskip + 1)) == 0) pre += __popc(sh.nz[lp * kBlocks + q]);
-        const bool open = j >= skip && (pskip == 0 || (j % (pskip + 1)) == 0);
-        const unsigned upper = ld_smem_u16(blk) != 0xeeffu ? 1u : 0u;
+#pragma unroll
+        for (int q = 0; q < kBlocks - 1; ++q)
+          pre += ((before >> q) & 1u) ? __popc(sh.nz[lp * kBlocks + q]) : 0u;
+        const bool open = ((open_mask >> j) & 1u) != 0u;
+        const unsigned upper = (sh.hdr_um[lp] >> j) & 1u;
         const unsigned wb = __popc(sh.wrap[lp] & ((2u << j) - 1u));
-        unsigned az = ld_smem_u16(blk + 2);
+        unsigned az = sh.hdr_az[lp][j];
         if (ADJ == 0) az %= 36000u;  // HDLParser.cxx:597 (ADJ != 0: adjusted per return later)
         BlkRec r;
         r.x = open ? sh.nz[b] : 0u;
@@ -498,8 +528,10 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
     if (warp == 0) {
       unsigned cnt = 0;
       if (lane < npk) {
-        for (int j = s_in; j < kBlocks; ++j)
-          if (pskip == 0 || (j % (pskip + 1)) == 0) cnt += __popc(sh.nz[lane * kBlocks + j]);
+        const unsigned open_mask = gate_mask & ~((1u << s_in) - 1u);
+#pragma unroll
+        for (int j = 0; j < kBlocks; ++j)
+          cnt += ((open_mask >> j) & 1u) ? __popc(sh.nz[lane * kBlocks + j]) : 0u;
         const long long P = first + lane;
         PktSeg r;
         r.x = s_in | (int)(wrapmask << 4) | (azdiff << 16);
@@ -510,10 +542,13 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
         const unsigned ium = um & ~((1u << s_in) - 1u);
         if (ium) {
           const long long fu = P * 12 + (__ffs(ium) - 1);
-          // tiles run in order: after the first one almost every packet fails this test
-          if (fu < *reinterpret_cast<volatile long long*>(&p.hdr->first_upper_block))
-            atomicMin(reinterpret_cast<unsigned long long*>(&p.hdr->first_upper_block),
-                      (unsigned long long)fu);
+          // a CTA's tile ids only grow: after a lane's first candidate every later one is larger,
+          // so the header is touched once per lane and kernel
+          if (fu < fub_seen) {
+            const unsigned long long old = atomicMin(
+                reinterpret_cast<unsigned long long*>(&p.hdr->first_upper_block), (unsigned long long)fu);
+            fub_seen = min((long long)old, fu);
+          }
         }
         if (P == p.n - 1) {
           p.hdr->last_azimuth = az11;
@@ -544,7 +579,8 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
         }
       }
     }
-    __syncthreads();  // stage, nz, skip and tile_id are free again
+    __syncthreads();  // nz, skip, wrap and the headers are free again
+    tile = sh.tile_next;
   }
 }
 
