@@ -226,6 +226,9 @@ __device__ __forceinline__ unsigned long long packet_skip_map(const int az[12], 
 #pragma unroll
   for (int j = 0; j < 12; ++j)
     if (az[j] < prev11) em |= 1u << j;
+  // no wrap inside the packet and none against the azimuth in front of it (all but one packet
+  // per rotation): every firingSkip leaves as 0
+  if ((wm | em) == 0u) return 0ull;
   unsigned long long m = 0;
 #pragma unroll
   for (int s = 0; s < 12; ++s) {
@@ -2046,9 +2049,10 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kDecThreads, VS_DEC_CT
     }
     __syncwarp();
     // LUT gather of the NEXT tile's blocks, issued now so that its L2 round trip hides behind
-    // this tile's math (only when that tile has already landed; else it is gathered later)
-    pf_ok = false;
-    if (ADJ == 0 && (FUSED || tile + (int)gridDim.x < p.n_tiles)) {
+    // this tile's math; when that tile has not landed yet (a warp running ahead of its CTA), a
+    // second attempt follows the block loops
+    auto prefetch_lut = [&]() {
+      if (!(ADJ == 0 && (FUSED || tile + (int)gridDim.x < p.n_tiles))) return;
       const int sn_ = (it + 1) % kDecStages;
       int first_n = first + (int)gridDim.x * kDecTile;
       if (FUSED) {
@@ -2073,7 +2077,9 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kDecThreads, VS_DEC_CT
           pf_cs = __ldg(&p.lut_cos[info & 0xffffu]);
         }
       }
-    }
+    };
+    pf_ok = false;
+    prefetch_lut();
     // staging is free once both warps' bulk stores of the previous tile have read it
     if (it > 0) {
       if (lane == 0) bulk_wait_read0();
@@ -2174,6 +2180,7 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kDecThreads, VS_DEC_CT
         }
       }
     }
+    if (!pf_ok) prefetch_lut();
     __syncwarp();  // every lane is done with the stage and with the records
     if (lane == 0) {
       if (FUSED) {
