@@ -296,7 +296,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-NCU_FULL_CSV = os.path.join(ROOT, "profiles", "r1y_k_decode_ncu_full.csv")
+NCU_FULL_CSV = os.path.join(ROOT, "profiles", "r1z_k_decode_ncu_full.csv")
 NCU_FULL_PACKETS = 1 << 20  # packets per launch of the captured k_decode
 
 
