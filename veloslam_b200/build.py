@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libveloslam_b200.so")
 SOURCES = [os.path.join(CSRC, "vs_capi.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("vs_kernels.cuh", "vs_device.cuh")] + \
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("vs_kernels.cuh", "vs_single_pass.cuh", "vs_device.cuh")] + \
     [os.path.join(os.path.dirname(HERE), "include", "veloslam_b200.h")]
 
 NVCC_FLAGS = [
