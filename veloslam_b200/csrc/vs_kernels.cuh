@@ -506,26 +506,38 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
 
     // ---- phase B2: block records: the final mask applies the gates of HDLParser.cxx:1042-1051
     // (block iterated: j >= firingSkip; pointsSkip) to the slot bits -----------------------------
-    for (int b = tid; b < kTileBlocks; b += kScanThreads) {
-      const int lp = b / kBlocks, j = b - lp * kBlocks;
-      if (lp < npk) {
-        const int skip = sh.skip[lp];
-        // blocks the parser iterates and emits: j >= firingSkip and the pointsSkip gate
-        const unsigned open_mask = gate_mask & ~((1u << skip) - 1u);
-        const unsigned before = open_mask & ((1u << j) - 1u);
-        unsigned pre = 0;
+    // Half a warp per packet (lanes 0-11 of each half == its blocks): the points in front of a
+    // block are a 16-lane prefix sum of the open blocks' popcounts.
+    {
+      static_assert(kTilePkts % (2 * (kScanThreads / 32)) == 0, "whole passes of two packets per warp");
+      const int j = lane & 15;
+#pragma unroll 1
+      for (int lp = 2 * warp + (lane >> 4); lp < kTilePkts; lp += 2 * (kScanThreads / 32)) {
+        const bool act = lp < npk && j < kBlocks;
+        unsigned bits = 0, open = 0;
+        if (act) {
+          // blocks the parser iterates and emits: j >= firingSkip and the pointsSkip gate
+          open = ((gate_mask & ~((1u << sh.skip[lp]) - 1u)) >> j) & 1u;
+          bits = sh.nz[lp * kBlocks + j];
+        }
+        const unsigned v = open ? __popc(bits) : 0u;
+        unsigned inc = v;
 #pragma unroll
-        for (int q = 0; q < kBlocks - 1; ++q)
-          pre += ((before >> q) & 1u) ? __popc(sh.nz[lp * kBlocks + q]) : 0u;
-        const bool open = ((open_mask >> j) & 1u) != 0u;
-        const unsigned upper = (sh.hdr_um[lp] >> j) & 1u;
-        const unsigned wb = __popc(sh.wrap[lp] & ((2u << j) - 1u));
-        unsigned az = sh.hdr_az[lp][j];
-        if (ADJ == 0) az %= 36000u;  // HDLParser.cxx:597 (ADJ != 0: adjusted per return later)
-        BlkRec r;
-        r.x = open ? sh.nz[b] : 0u;
-        r.y = az | (pre << 16) | (upper << 25) | (wb << 26);
-        p.recs[(first + lp) * kBlocks + j] = r;
+        for (int o = 1; o < 16; o <<= 1) {
+          const unsigned t = __shfl_up_sync(0xffffffffu, inc, o, 16);
+          if (j >= o) inc += t;
+        }
+        if (act) {
+          const unsigned pre = inc - v;
+          const unsigned upper = (sh.hdr_um[lp] >> j) & 1u;
+          const unsigned wb = __popc(sh.wrap[lp] & ((2u << j) - 1u));
+          unsigned az = sh.hdr_az[lp][j];
+          if (ADJ == 0) az %= 36000u;  // HDLParser.cxx:597 (ADJ != 0: adjusted per return later)
+          BlkRec r;
+          r.x = open ? bits : 0u;
+          r.y = az | (pre << 16) | (upper << 25) | (wb << 26);
+          p.recs[(first + lp) * kBlocks + j] = r;
+        }
       }
     }
     if (warp == 0) {
@@ -563,14 +575,12 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams p) {
       // (F4b); offline -> the wrap packet itself.  marker - 1 == origin packet index.
       const long long P = first + lane;
       const unsigned nw = __popc(wrapmask);
-      unsigned long long aw =
-          ((unsigned long long)nw << 32) | (nw ? (unsigned)(P + (p.mode == 0 ? 2 : 1)) : 0u);
-      unsigned long long ac = (lane < npk && P >= p.halo) ? (unsigned long long)cnt : 0ull;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        aw = WrapTraits::combine(aw, __shfl_xor_sync(0xffffffffu, aw, o));
-        ac += __shfl_xor_sync(0xffffffffu, ac, o);
-      }
+      // per-tile sums fit 32 bits: one REDUX each (wraps, latest origin marker, points)
+      const unsigned tw = __reduce_add_sync(0xffffffffu, nw);
+      const unsigned tm = __reduce_max_sync(0xffffffffu, nw ? (unsigned)(P + (p.mode == 0 ? 2 : 1)) : 0u);
+      const unsigned long long aw = ((unsigned long long)tw << 32) | tm;
+      const unsigned long long ac =
+          __reduce_add_sync(0xffffffffu, (lane < npk && P >= p.halo) ? cnt : 0u);
       if (lane == 0) {
         p.agg_wrap[tile] = aw;
         p.agg_cnt[tile] = ac;
