@@ -10,13 +10,16 @@ namespace vsd {
 // =========================================================================================
 // Single-pass variant (FUSED): k_decode with the segmentation scans inside.
 //
-// A ninth warp per CTA (the scan warp) does, for each 8-packet tile and one to two tiles ahead of
-// the decode warps, what k_scan and the scan half of k_pose do in the two-pass pipeline:
-//   * deals itself the next tile id (global atomic: forward progress never depends on CTAs that
-//     are not resident), starts the TMA copies of the packets and of the pose rows [L | T];
+// Two extra warps per CTA (the scan warps, alternating over the CTA's tile sequence) do, for each
+// 8-packet tile and up to two tiles ahead of the decode warps, what k_scan and the scan half of
+// k_pose do in the two-pass pipeline:
+//   * deal the CTA the next tile id (global atomic, in sequence order inside the CTA: forward
+//     progress never depends on CTAs that are not resident), start the TMA copies of the packets
+//     and of the pose rows [L | T];
 //   * from the staged bytes: wrap masks, firingSkip chain (the previous packet's own map decides
-//     it on sensor data; look-back over per-tile maps otherwise), azimuthDiff, the slot bits
-//     "distance != 0 and laser selected" of the 96 firing blocks;
+//     it on sensor data; look-back over per-tile maps otherwise), azimuthDiff; the slot bits
+//     "distance != 0 and laser selected" of the 96 firing blocks come from the decode warps (one
+//     ballot per block, written two tiles ahead of their decode pass, `masks` mbarrier);
 //   * one decoupled look-back over 16-byte words {flag | emitted points, wraps << 32 | origin
 //     marker} gives the tile's first point, frame id and frame-origin packet;
 //   * writes the block records, segment records and point offsets of the tile straight into the
@@ -243,8 +246,8 @@ __device__ __forceinline__ void fused_scan_role(const DecParams& p, DecCtl& sh, 
     }
     const unsigned long long agg = __shfl_sync(kFull, inc, 31);
     // the map of the packet in front of the tile decides the firingSkip entering the tile whenever
-    // it is constant (always, on sensor data); lane 1 evaluates it (lane == packet: az[] = its
-    // azimuths, prev11 = the azimuth in front of it)
+    // it is constant (always, on sensor data); lane 0 evaluates it from the 13 azimuths the lanes
+    // requested before the wait
     int paz[12];
 #pragma unroll
     for (int j = 0; j < 12; ++j) paz[j] = __shfl_sync(kFull, hv, j);
