@@ -317,6 +317,36 @@ def ncu_traffic(n_per):
     return (tot if tot > 0 else None), os.path.relpath(NCU_FULL_CSV, ROOT)
 
 
+def pin_to_gpu_numa_node(cuda_index):
+    """Run this rank's host threads on the CPUs NVML reports as local to its GPU, so that the
+    pinned packet ring and result columns are allocated on the memory node next to the GPU's PCIe
+    root (host<->device copies then do not cross the socket interconnect).  Best effort."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+        handle = None
+        for cand in (uuid, "GPU-" + uuid):
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(cand.encode())
+                break
+            except Exception:
+                handle = None
+        if handle is None:
+            return None
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     from veloslam_b200 import capi, sharding, synth
@@ -328,6 +358,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_cpus_all = len(os.sched_getaffinity(0))
+    numa_cpus = pin_to_gpu_numa_node(local)
 
     n_per = args.packets
     halo = sharding.HALO_HDL64 if rank > 0 else 0
@@ -507,6 +539,8 @@ def run_ours(args):
                 "l2": "inputs (1.26 GB) and outputs (8.4 GB) per step exceed the 126 MB L2",
                 "slots_per_s": world * n_per * 384 / (ms_per_step * 1e-3),
                 "global_frames": n_global_frames, "stitch_timestamp_mismatches": mism,
+                "host_affinity": (f"{numa_cpus} of {host_cpus_all} CPUs (NVML: local to the GPU)"
+                                  if numa_cpus else "unchanged"),
                 "wall_ms_per_step": wall / args.steps * 1e3,
             },
             "roofline": roofline, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
