@@ -427,8 +427,12 @@ def run_ours(args):
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     elapsed_ms = e0.elapsed_time(e1)
+    per_rank_ms = [elapsed_ms / args.steps]
     if world > 1:
         tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(tt) for _ in range(world)]
+        torch.distributed.all_gather(allt, tt)
+        per_rank_ms = [float(x.item()) / args.steps for x in allt]
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
         elapsed_ms = float(tt.item())
         pts = torch.tensor([n_emitted], dtype=torch.int64, device=dev)
@@ -542,6 +546,7 @@ def run_ours(args):
                 "host_affinity": (f"{numa_cpus} of {host_cpus_all} CPUs (NVML: local to the GPU)"
                                   if numa_cpus else "unchanged"),
                 "wall_ms_per_step": wall / args.steps * 1e3,
+                "per_rank_ms_per_step": [round(x, 4) for x in per_rank_ms],
             },
             "roofline": roofline, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
