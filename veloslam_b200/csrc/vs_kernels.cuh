@@ -1265,7 +1265,11 @@ __device__ __forceinline__ void rigid(const double* M, double& px, double& py, d
 // sin(x) for |x| < 0.2: odd Taylor polynomial through x^9 (error < 2e-17 relative)
 __device__ __forceinline__ double sin_small(double x) {
   const double x2 = x * x;
-  return x * (1.0 + x2 * (-1.0 / 6 + x2 * (1.0 / 120 + x2 * (-1.0 / 5040 + x2 * (1.0 / 362880)))));
+  double p = __fma_rn(x2, 1.0 / 362880, -1.0 / 5040);
+  p = __fma_rn(x2, p, 1.0 / 120);
+  p = __fma_rn(x2, p, -1.0 / 6);
+  p = __fma_rn(x2, p, 1.0);
+  return x * p;
 }
 
 }  // namespace vsd
@@ -1397,7 +1401,8 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kDecThreads, VS_DEC_CT
       if (DSK) {
         // pose at t_packet + fire inside the packet's bracket: slerp + lerp, already re-based to
         // the frame origin by k_pose (semantics: oracle/deskew_port.py)
-        const double rr = M[14] + (double)fire * M[15];
+        // (an extension with no reference arithmetic to reproduce: fused multiply-adds throughout)
+        const double rr = __fma_rn((double)fire, M[15], M[14]);
         double w0, w1;
         if (M[17] == 0.0) {
           w0 = 1.0 - rr;
@@ -1409,17 +1414,23 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kDecThreads, VS_DEC_CT
           w0 = sin((1.0 - rr) * M[16]) * M[17];
           w1 = sin(rr * M[16]) * M[17];
         }
-        Quat q;
-        q.w = w0 * M[0] + w1 * M[4];
-        q.x = w0 * M[1] + w1 * M[5];
-        q.y = w0 * M[2] + w1 * M[6];
-        q.z = w0 * M[3] + w1 * M[7];
-        const double pin[3] = {px, py, pz};
-        double po[3];
-        quat_rotate(q, pin, po);
-        px = po[0] + (M[8] + M[11] * rr);
-        py = po[1] + (M[9] + M[12] * rr);
-        pz = po[2] + (M[10] + M[13] * rr);
+        const double qw = __fma_rn(w1, M[4], w0 * M[0]);
+        const double qx = __fma_rn(w1, M[5], w0 * M[1]);
+        const double qy = __fma_rn(w1, M[6], w0 * M[2]);
+        const double qz = __fma_rn(w1, M[7], w0 * M[3]);
+        // p + w t + v x t with t = 2 v x p
+        double tx = __fma_rn(qy, pz, -(qz * py));
+        double ty = __fma_rn(qz, px, -(qx * pz));
+        double tz = __fma_rn(qx, py, -(qy * px));
+        tx += tx;
+        ty += ty;
+        tz += tz;
+        const double ox = __fma_rn(qy, tz, __fma_rn(-qz, ty, __fma_rn(qw, tx, px)));
+        const double oy = __fma_rn(qz, tx, __fma_rn(-qx, tz, __fma_rn(qw, ty, py)));
+        const double oz = __fma_rn(qx, ty, __fma_rn(-qy, tx, __fma_rn(qw, tz, pz)));
+        px = ox + __fma_rn(M[11], rr, M[8]);
+        py = oy + __fma_rn(M[12], rr, M[9]);
+        pz = oz + __fma_rn(M[13], rr, M[10]);
       } else {
         rigid(M, px, py, pz);
       }
