@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-online", action="store_true")
     ap.add_argument("--no-deskew", action="store_true")
+    ap.add_argument("--no-single-pass", action="store_true")
     return ap.parse_args()
 
 
@@ -497,6 +498,44 @@ def run_ours(args):
                           "frame origin (not a reference behaviour; one batch in flight)"}
         ctx.set_calibration(calib)   # resets the firing table
 
+    # ---- the opt-in single-pass decode kernel on the same batch, off the headline number -------
+    single = None
+    if world == 1 and not args.no_single_pass:
+        try:
+            os.environ["VELOSLAM_SINGLE_PASS"] = "1"   # read by vs_create
+            ctx2 = capi.Context(local, max_batch_packets=n_sub, max_poses=len(poses[0]) + 8, n_slots=2)
+            ctx2.set_calibration(calib)
+            ctx2.set_poses(poses[0], poses[1])
+
+            def submit2():
+                return ctx2.submit(d_pk, d_t, n=n_sub, stride=1206, n_halo=halo,
+                                   mode=capi.MODE_STREAMING, flags=capi.FLAG_DEVICE_INPUT,
+                                   t_base_us=t_base)
+            for _ in range(3):
+                r2 = ctx2.wait(submit2(), frames=False)
+            torch.cuda.synchronize()
+            k2, dk2 = 8, []
+            w0 = time.perf_counter()
+            pend = submit2()
+            for i in range(k2):
+                nxt = submit2() if i + 1 < k2 else None
+                dk2.append(ctx2.wait(pend, frames=False).decode_ms)
+                pend = nxt
+            torch.cuda.synchronize()
+            ms2 = (time.perf_counter() - w0) / k2 * 1e3
+            single = {"points_per_s_per_gpu": r2.n_points / (ms2 * 1e-3), "ms_per_step": ms2,
+                      "k_decode_ms": float(np.mean(dk2)), "points": r2.n_points,
+                      "same_point_count_as_two_pass": bool(r2.n_points == n_emitted),
+                      "note": "VELOSLAM_SINGLE_PASS=1: k_pose_pre + k_decode<.,0,FUSED> (segmentation "
+                              "scans inside the decode kernel, packets read once); host wall clock, "
+                              "two batches in flight; slower than the default two-pass pipeline "
+                              "(DESIGN.md 4)"}
+            ctx2.close()
+        except Exception as e:  # informational only: never breaks the headline line
+            single = {"error": str(e)}
+        finally:
+            os.environ.pop("VELOSLAM_SINGLE_PASS", None)
+
     # ---- frame index exchange (off the timed loop) ------------------------------------------
     rr = step()
     tab = sharding.local_table(rr.frame_table, rank, first, halo)
@@ -558,6 +597,8 @@ def run_ours(args):
             line["online"] = online
         if deskew is not None:
             line["deskew_per_point"] = deskew
+        if single is not None:
+            line["single_pass_variant"] = single
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

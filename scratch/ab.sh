@@ -7,7 +7,7 @@ for r in $(seq 1 $R); do
   for v in A B; do
     eval f=\$$v
     cp $f veloslam_b200/libveloslam_b200.so
-    timeout 120 python bench.py --no-cpu --no-e2e --no-online --no-deskew --steps 20 > /tmp/ab.json 2>/dev/null
+    timeout 120 python bench.py --no-cpu --no-e2e --no-online --no-deskew --no-single-pass --steps 20 > /tmp/ab.json 2>/dev/null
     python - <<PY
 import json
 for l in open("/tmp/ab.json"):
