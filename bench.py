@@ -498,6 +498,37 @@ def run_ours(args):
                           "frame origin (not a reference behaviour; one batch in flight)"}
         ctx.set_calibration(calib)   # resets the firing table
 
+    # ---- frame index exchange (off the timed loop) ------------------------------------------
+    rr = step()
+    tab = sharding.local_table(rr.frame_table, rank, first, halo)
+    if world > 1:
+        tables = sharding.all_gather_tables(tab)
+    else:
+        tables = [tab]
+    frames = sharding.stitch(tables)
+    n_global_frames = len(frames)
+    mism = sum(1 for f in frames if "timestamp_mismatch" in f)
+
+    # ---- e2e through the C ABI with host buffers ---------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, ctx_args=(local, calib, poses), b=b[halo:], t=t[halo:], t_base=t_base,
+                      world=world, dev=dev)
+    online = None
+    if not args.no_online:
+        online = run_online(local, calib, poses, b[halo:], t[halo:], t_base)
+        if world > 1:
+            allo = [None] * world
+            torch.distributed.all_gather_object(allo, online)
+            online = {"per_rank_p99_ms": [o["index_only"]["p99_ms"] for o in allo],
+                      "per_rank_p50_ms": [o["index_only"]["p50_ms"] for o in allo],
+                      "aggregate_points_per_s": sum(o["index_only"]["points_per_s"] for o in allo),
+                      "with_points_p99_ms": [o["with_points"]["p99_ms"] for o in allo],
+                      "streams": world, "note": allo[0]["note"]}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = run_cpu_baseline(calib, poses, args.cpu_seconds)
+
     # ---- the opt-in single-pass decode kernel on the same batch, off the headline number -------
     single = None
     if world == 1 and not args.no_single_pass:
@@ -536,36 +567,6 @@ def run_ours(args):
         finally:
             os.environ.pop("VELOSLAM_SINGLE_PASS", None)
 
-    # ---- frame index exchange (off the timed loop) ------------------------------------------
-    rr = step()
-    tab = sharding.local_table(rr.frame_table, rank, first, halo)
-    if world > 1:
-        tables = sharding.all_gather_tables(tab)
-    else:
-        tables = [tab]
-    frames = sharding.stitch(tables)
-    n_global_frames = len(frames)
-    mism = sum(1 for f in frames if "timestamp_mismatch" in f)
-
-    # ---- e2e through the C ABI with host buffers ---------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        e2e = run_e2e(args, ctx_args=(local, calib, poses), b=b[halo:], t=t[halo:], t_base=t_base,
-                      world=world, dev=dev)
-    online = None
-    if not args.no_online:
-        online = run_online(local, calib, poses, b[halo:], t[halo:], t_base)
-        if world > 1:
-            allo = [None] * world
-            torch.distributed.all_gather_object(allo, online)
-            online = {"per_rank_p99_ms": [o["index_only"]["p99_ms"] for o in allo],
-                      "per_rank_p50_ms": [o["index_only"]["p50_ms"] for o in allo],
-                      "aggregate_points_per_s": sum(o["index_only"]["points_per_s"] for o in allo),
-                      "with_points_p99_ms": [o["with_points"]["p99_ms"] for o in allo],
-                      "streams": world, "note": allo[0]["note"]}
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = run_cpu_baseline(calib, poses, args.cpu_seconds)
 
     if rank == 0:
         line = {
