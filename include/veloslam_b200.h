@@ -208,6 +208,53 @@ VS_API int vs_fetch_points(vs_ctx* ctx, uint64_t ticket, int64_t first, int64_t 
                     float* y, float* z, uint8_t* intensity, uint8_t* laser, uint16_t* azimuth,
                     uint16_t* distance, uint32_t* t_us);
 
+/* ---- HDLFrame layout built on the device ------------------------------------------------------
+ * The reference appends every emitted point to currentFrame->points[laserId] and
+ * currentFrame->pointsMeta[laserId] (HDLParser.cxx:733-751) and, when a frame is closed on
+ * HDL-64 data, permutes the rows by HDL64BeamLUT (splitFrame, :880-893).  vs_layout_frames()
+ * produces exactly those lists for a finished batch as two device arrays of ready-made records
+ * -- pcl::PointXYZI {x, y, z, intensity} and PointMeta {azimuth, distance (metres), 3 flag bytes}
+ * (type_defs.h:168-176) -- in which every frame is one contiguous run of slots and every row of a
+ * frame one contiguous run inside it, rows in the order the closed frame holds them.  A caller
+ * builds points[row] from one copy per frame instead of scattering point by point. */
+typedef struct vs_frame_rows {
+  int64_t  first_slot;                  /* the frame's first slot in the layout arrays          */
+  int64_t  n_slots;                     /* its points, carried ones included                    */
+  uint32_t row_start[VS_MAX_LASERS];    /* slot of row r, relative to first_slot                */
+  uint32_t row_count[VS_MAX_LASERS];    /* elements of row r (the carried ones come first)      */
+  uint32_t row_carried[VS_MAX_LASERS];  /* leading elements of row r that earlier batches hold: */
+                                        /* left unwritten, the caller copies them in            */
+  int32_t  row_laser[VS_MAX_LASERS];    /* laser id pushed into row r (HDL64BeamLUT[r] when the */
+                                        /* frame was closed on HDL-64 data, else r)             */
+} vs_frame_rows;
+
+typedef struct vs_layout {
+  const void* xyzi;           /* device: n_slots records of xyzi_stride bytes                    */
+  const void* meta;           /* device: n_slots PointMeta records of 12 bytes; NULL if not asked */
+  int64_t n_slots;            /* n_points of the batch + carried points                          */
+  const vs_frame_rows* rows;  /* host, one entry per vs_result.frames entry; owned by the context */
+  int32_t n_frames;
+  int32_t xyzi_stride;
+  int32_t n_kernel_launches;
+  int32_t reserved;
+} vs_layout;
+
+/* Lay a finished batch (after vs_wait) out as HDLFrames.  carried_counts (64 entries by laser
+ * id, or NULL): sizes of the open frame's rows as earlier batches left them
+ * (currentFrame->points[laser]->size()); the batch's first frame continues that frame, so its
+ * rows leave that many leading slots free.  xyzi_stride: 16 (x, y, z, intensity) or 32
+ * (pcl::PointXYZI with its padding, data[3] = 1).  The kernels run asynchronously on the
+ * ticket's stream; the arrays stay valid until the slot's next submit. */
+VS_API int vs_layout_frames(vs_ctx* ctx, uint64_t ticket, const uint32_t* carried_counts,
+                            int xyzi_stride, int with_meta, vs_layout* out);
+/* Enqueue the copy of slots [first_slot, first_slot + n_slots) to host memory (page-locked for
+ * a truly asynchronous copy; either pointer may be NULL).  Returns at once. */
+VS_API int vs_fetch_layout(vs_ctx* ctx, uint64_t ticket, int64_t first_slot, int64_t n_slots,
+                           void* xyzi_host, void* meta_host);
+/* Wait for everything enqueued for the ticket (layout kernels, vs_fetch_layout copies);
+ * *layout_ms (may be NULL) = device time of the layout kernels. */
+VS_API int vs_sync(vs_ctx* ctx, uint64_t ticket, float* layout_ms);
+
 /* HDLParser::readFrameInformation (HDLParser.cxx:1065-1160) over a packet array: fills up
  * to cap entries (start packet, start block == skips, timestamp) and returns the count in
  * *n_frames.  Equivalent to a VS_MODE_OFFLINE submit that skips the decode. */

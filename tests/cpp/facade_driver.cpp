@@ -1,8 +1,12 @@
 // facade_driver.cpp -- drives the C++ facade the way the reference's consumers do and dumps the
 // frames it produces, so that pytest can compare them with the oracle.
 //
-//   facade_driver stream  <calib.xml> <packets.bin> <times.bin> <poses.bin|-> <out.bin> [batch]
+//   facade_driver stream  <calib.xml> <packets.bin> <times.bin> <poses.bin|-> <out.bin> [batch] [pipelined 0|1]
 //       per packet: processHDLPacket(); getAllFrames(); clearAllFrames()   (HDLSource.cxx:209-225)
+//   facade_driver bench   <calib.xml> <packets.bin> <times.bin> <poses.bin|-> <batch> <passes>
+//                         <store_packets 0|1> <fetch_meta 0|1> <pipelined 0|1>
+//       the same consumer loop over the packet array `passes` times (+1 untimed warm-up pass),
+//       prints one JSON line with points, frames and seconds
 //   facade_driver offline <calib.xml> <file.pcap> <poses.bin|-> <out.bin>
 //       readFrameInformation() then getFrame() for every index entry     (HDLManager.cxx:103-117,195-211)
 //
@@ -10,6 +14,7 @@
 // out.bin: per frame { int64 timestamp_us, int32 skips, int32 n_lasers, int32 n_packets,
 // int32 carpose_valid, double carpose[9], int32 counts[n_lasers], then per point
 // float x,y,z,intensity, uint16 azimuth, float distance } preceded by int32 n_frames.
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -91,8 +96,55 @@ static std::shared_ptr<TransformManager> loadPoses(const std::string& path) {
 //   index    <file.pcap> <out.bin>                        int32 n, then n x (int64 pos, int32 skips, int64 ts)
 //   writepcap <packets.bin> <times.bin> <out.pcap>
 //   calib    <db.xml> <out.bin>                           int32 n_enabled, int32 n_rows, 64 x 5 doubles
+//   arena    <out.txt>                                    zero-copy adoption checks (FrameArena.h)
 static int hostModes(int argc, char** argv) {
   const std::string mode = argv[1];
+  if (mode == "arena" && argc >= 3) {
+    std::ofstream rep(argv[2]);
+    std::weak_ptr<vs::Arena> watch;
+    {
+      std::shared_ptr<vs::Arena> a = vs::Arena::heap(1 << 16);
+      watch = a;
+      pcl::PointXYZI* rec = reinterpret_cast<pcl::PointXYZI*>(a->data());
+      for (int i = 0; i < 100; ++i) {
+        rec[i].x = (float)i;
+        rec[i].y = 2.f * i;
+        rec[i].z = -1.f * i;
+        rec[i].intensity = (float)(i % 7);
+      }
+      pcl::PointCloud<pcl::PointXYZI> cloud;
+      vs::adopt(cloud.points, a, rec + 10, 50);
+      a.reset();  // the vector keeps the arena alive
+      rep << "alive_while_adopted " << (watch.expired() ? 0 : 1) << "\n";
+      rep << "zero_copy " << ((void*)cloud.points.data() == (void*)(rec + 10) ? 1 : 0) << "\n";
+      rep << "size " << cloud.points.size() << "\n";
+      rep << "first " << cloud.points.front().x << " last " << cloud.points.back().x << "\n";
+      // an ordinary vector in every other respect
+      std::vector<pcl::PointXYZI, vs::ArenaAllocator<pcl::PointXYZI> > copy = cloud.points;
+      rep << "copy_is_heap " << ((void*)copy.data() != (void*)cloud.points.data() ? 1 : 0) << "\n";
+      pcl::PointXYZI extra = {1000.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < 200; ++i) cloud.points.push_back(extra);
+      rep << "grown_size " << cloud.points.size() << " kept " << cloud.points[49].x << " new "
+          << cloud.points[249].x << "\n";
+      cloud.points.resize(300);
+      rep << "resized_zero " << cloud.points[299].x + cloud.points[299].intensity << "\n";
+      // moving the vector moves the adoption
+      std::vector<PointMeta, vs::ArenaAllocator<PointMeta> > m1, m2;
+      std::shared_ptr<vs::Arena> b = vs::Arena::heap(4096);
+      PointMeta* pm = reinterpret_cast<PointMeta*>(b->data());
+      for (int i = 0; i < 20; ++i) {
+        pm[i].azimuth = (unsigned short)(100 * i);
+        pm[i].distance = 0.5f * i;
+      }
+      vs::adopt(m1, b, pm, 20);
+      m2 = std::move(m1);
+      rep << "moved " << ((void*)m2.data() == (void*)pm ? 1 : 0) << " " << m2[19].azimuth << "\n";
+      vs::adopt(m2, b, pm, 0);
+      rep << "empty " << m2.size() << "\n";
+    }
+    rep << "released " << (watch.expired() ? 1 : 0) << "\n";
+    return 0;
+  }
   if (mode == "interp" && argc >= 5) {
     std::shared_ptr<TransformManager> tm = loadPoses(argv[2]);
     std::vector<char> q = slurp(argv[3]);
@@ -349,7 +401,7 @@ static int hostModes(int argc, char** argv) {
 }
 
 int main(int argc, char** argv) {
-  if (argc < 4) {
+  if (argc < 3) {
     std::cerr << "usage: see the header comment" << std::endl;
     return 2;
   }
@@ -361,6 +413,7 @@ int main(int argc, char** argv) {
   if (mode == "stream") {
     if (argc < 7) return 2;
     if (argc > 7) parser.setBatchPackets(std::atoi(argv[7]));
+    if (argc > 8) parser.setPipelined(std::atoi(argv[8]) != 0);
     parser.setCorrectionsFile(argv[2]);
     parser.setTransformMgr(loadPoses(argv[5]));
     std::vector<char> pk = slurp(argv[3]);
@@ -377,6 +430,13 @@ int main(int argc, char** argv) {
         parser.clearAllFrames();
       }
     }
+    if (argc > 8 && std::atoi(argv[8]) != 0) {
+      // pipelined: whole batches still sit in the rings / on the GPU; everything that closed
+      // comes out now (the open frame stays open, as with the per-rotation flush)
+      parser.flush();
+      for (auto& f : parser.getAllFrames()) all.push_back(f);
+      parser.clearAllFrames();
+    }
     if (!parser.lastError().empty()) {
       std::cerr << "facade error: " << parser.lastError() << std::endl;
       return 1;
@@ -385,6 +445,65 @@ int main(int argc, char** argv) {
     const int32_t nf = (int32_t)all.size();
     os.write((const char*)&nf, 4);
     for (auto& f : all) dumpFrame(os, *f);
+    return 0;
+  }
+  if (mode == "bench") {
+    if (argc < 11) return 2;
+    const int batch = std::atoi(argv[6]), passes = std::atoi(argv[7]);
+    parser.setBatchPackets(batch);
+    parser.setStorePackets(std::atoi(argv[8]) != 0);
+    parser.setFetchMeta(std::atoi(argv[9]) != 0);
+    parser.setPipelined(std::atoi(argv[10]) != 0);
+    parser.setCorrectionsFile(argv[2]);
+    parser.setTransformMgr(loadPoses(argv[5]));
+    std::vector<char> pk = slurp(argv[3]);
+    std::vector<char> tm = slurp(argv[4]);
+    const size_t n = pk.size() / 1206;
+    if (n < 2) return 2;
+    std::vector<int64_t> t(n);
+    std::memcpy(t.data(), tm.data(), 8 * n);
+    const int64_t span = t[n - 1] - t[0] + (t[n - 1] - t[0]) / (int64_t)(n - 1);
+    uint64_t points = 0, frames = 0;
+    double touch = 0.0;
+    auto consume = [&](bool count) {
+      // what HDLSource's consumer does with a finished rotation (HDLSource.cxx:220-224): take the
+      // frames, hand them on, clear the parser's list
+      std::deque<std::shared_ptr<HDLFrame> > fr = parser.getAllFrames();
+      if (fr.empty()) return;
+      for (auto& f : fr) {
+        if (count) {
+          points += f->numberOfPoints();
+          ++frames;
+        }
+        for (auto& c : f->points)
+          if (c && !c->points.empty()) touch += c->points.front().x + c->points.back().z;
+      }
+      parser.clearAllFrames();
+    };
+    auto onePass = [&](int pass, bool count) {
+      const int64_t shift = span * pass;
+      for (size_t i = 0; i < n; ++i) {
+        parser.processHDLPacket((unsigned char*)pk.data() + 1206 * i, 1206, ptime(t[i] + shift));
+        if (parser.getAllFrames().size()) consume(count);
+      }
+    };
+    onePass(0, false);
+    parser.flush();
+    consume(false);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int p = 1; p <= passes; ++p) onePass(p, true);
+    parser.flush();
+    consume(true);
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!parser.lastError().empty()) {
+      std::cerr << "facade error: " << parser.lastError() << std::endl;
+      return 1;
+    }
+    std::printf("{\"points\": %llu, \"frames\": %llu, \"seconds\": %.6f, \"packets\": %llu, \"passes\": %d, "
+                "\"batch\": %d, \"pinned_pool_bytes\": %llu, \"touch\": %.3f}\n",
+                (unsigned long long)points, (unsigned long long)frames, sec,
+                (unsigned long long)(n * (size_t)passes), passes, batch,
+                (unsigned long long)vs::Arena::pooledBytes(), touch);
     return 0;
   }
   if (mode == "udp") {

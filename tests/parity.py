@@ -171,3 +171,81 @@ def assert_frames_parity(o, batches, tol, calib=None):
             corr[:calib.n_rows] = calib.dist_cm
             assert np.array_equal(point_meta_distance(a.distance_raw, rows, corr), f.distance), k
         del seg0
+
+
+# ------------------------------------------------------------------------------------------
+# HDLFrame layout built on the device (vs_layout_frames)
+# ------------------------------------------------------------------------------------------
+def gpu_layout_stream(ctx, pk_bytes, t_us, splits=(), mode=capi.MODE_STREAMING, with_meta=True):
+    """Decode in batches cut at `splits` and take every frame in the device-built HDLFrame
+    layout, the way the C++ facade does: the batch's first frame continues the open frame, its
+    rows leave room for the carried points, which are copied into the gaps.  Returns the closed
+    frames as dicts {xyzi (n, 4), meta, row_count (64,), order} -- NO host-side sort or scatter."""
+    n = pk_bytes.shape[0]
+    cuts = [0] + sorted({int(s) for s in splits if 0 < s < n}) + [n]
+    carry = capi.carry_init()
+    carried = np.zeros(64, np.uint32)
+    partial = None
+    out = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if b <= a:
+            continue
+        r = ctx.decode(np.ascontiguousarray(pk_bytes[a:b]), np.ascontiguousarray(t_us[a:b]),
+                       mode=mode, carry=carry, t_base_us=int(t_us[0]))
+        xyzi, meta, rows = ctx.fetch_frames_layout(r.ticket, carried if carried.any() else None,
+                                                   with_meta)
+        assert len(rows) == r.n_frames
+        for i, fr in enumerate(r.frames):
+            rw = rows[i]
+            s0, ns = int(rw["first_slot"]), int(rw["n_slots"])
+            fx = xyzi[s0:s0 + ns].copy()
+            fm = meta[s0:s0 + ns].copy() if with_meta else None
+            if i == 0 and partial is not None:
+                px, pm, pstart, pcount = partial
+                for rr in range(64):
+                    c = int(rw["row_carried"][rr])
+                    if c == 0:
+                        continue
+                    laser = int(rw["row_laser"][rr])
+                    assert c == pcount[laser]
+                    d0 = int(rw["row_start"][rr])
+                    fx[d0:d0 + c] = px[pstart[laser]:pstart[laser] + c]
+                    if with_meta:
+                        fm[d0:d0 + c] = pm[pstart[laser]:pstart[laser] + c]
+            else:
+                assert not rw["row_carried"].any()
+            if fr.closed:
+                out.append({"xyzi": fx, "meta": fm, "row_count": rw["row_count"].astype(np.int64),
+                            "order": bool(fr.hdl64_order), "row_laser": rw["row_laser"].copy()})
+                partial = None
+            else:
+                assert np.array_equal(rw["row_laser"], np.arange(64))   # open frames: by laser id
+                partial = (fx, fm, rw["row_start"].astype(np.int64), rw["row_count"].astype(np.int64))
+                carried = rw["row_count"].astype(np.uint32)
+        carry = r.carry_out
+    return out
+
+
+def assert_layout_parity(o, frames, tol, with_meta=True):
+    """Device-built frames == the oracle's HDLFrames, element for element in the reference's own
+    order (rows of points[]/pointsMeta[], HDL64BeamLUT applied)."""
+    of = o.frames()
+    assert len(frames) == len(of), (len(frames), len(of))
+    worst = 0.0
+    for k, (g, f) in enumerate(zip(frames, of)):
+        n_rows = len(f.laser_counts)
+        assert g["order"] == f.is_hdl64_order, k
+        assert np.array_equal(g["row_count"][:n_rows], f.laser_counts), k
+        assert int(g["row_count"][n_rows:].sum()) == 0, k
+        assert g["xyzi"].shape[0] == f.n_points, (k, g["xyzi"].shape, f.n_points)
+        if f.n_points == 0:
+            continue
+        assert np.array_equal(g["xyzi"][:, 3], f.xyzi[:f.n_points, 3]), k
+        d = np.abs(g["xyzi"][:, :3].astype(np.float64) - f.xyzi[:f.n_points, :3].astype(np.float64))
+        worst = max(worst, float(d.max()))
+        assert d.max() <= tol, (k, d.max())
+        if with_meta:
+            assert np.array_equal(g["meta"]["azimuth"], f.azimuth[:f.n_points]), k
+            assert np.array_equal(g["meta"]["distance"], f.distance[:f.n_points]), k
+            assert not g["meta"]["flags"].any() and not g["meta"]["intensityFlag"].any()
+    return worst

@@ -42,16 +42,19 @@ def test_ctypes_struct_layouts_match_the_header(lib, tmp_path):
     prog = tmp_path / "sizes.c"
     prog.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "veloslam_b200.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vs_laser_corr),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vs_laser_corr),'
         ' sizeof(vs_filters), sizeof(vs_carry), sizeof(vs_frame), sizeof(vs_result),'
         ' offsetof(vs_result, carry_out), offsetof(vs_frame, laser_counts),'
-        ' offsetof(vs_carry, frames_closed)); return 0;}\n')
+        ' offsetof(vs_carry, frames_closed), sizeof(vs_frame_rows), sizeof(vs_layout),'
+        ' offsetof(vs_frame_rows, row_laser), offsetof(vs_layout, rows)); return 0;}\n')
     exe = tmp_path / "sizes"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(capi.LaserCorr), C.sizeof(capi.Filters), C.sizeof(capi.Carry),
             C.sizeof(capi.Frame), C.sizeof(capi.Result), capi.Result.carry_out.offset,
-            capi.Frame.laser_counts.offset, capi.Carry.frames_closed.offset]
+            capi.Frame.laser_counts.offset, capi.Carry.frames_closed.offset,
+            C.sizeof(capi.FrameRows), C.sizeof(capi.Layout), capi.FrameRows.row_laser.offset,
+            capi.Layout.rows.offset]
     assert got == want
 
 

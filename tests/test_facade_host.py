@@ -197,3 +197,17 @@ def test_inssource_udp_to_transform_manager(tmp_path):
     assert np.array_equal(got["t"], want_t[order])
     want = O.ins_poses(recs, (-2781621.9891904, 4672106.75052387, 18.8910392))
     assert np.array_equal(got["trv"], want[order])                   # host libm on both sides
+
+
+def test_frame_arena_adoption_is_zero_copy(tmp_path):
+    """HDLFrame::points[row]->points adopts a slice of the frame's arena (FrameArena.h): same
+    address, ordinary std::vector afterwards, arena released with its last vector."""
+    r = F.run(["arena", tmp_path / "rep.txt"])
+    assert r.returncode == 0, r.stderr
+    rep = dict(line.split(" ", 1) for line in open(tmp_path / "rep.txt").read().splitlines())
+    assert rep["alive_while_adopted"] == "1" and rep["zero_copy"] == "1"
+    assert rep["size"] == "50" and rep["first"] == "10 last 59"
+    assert rep["copy_is_heap"] == "1"
+    assert rep["grown_size"] == "250 kept 59 new 1000"
+    assert rep["resized_zero"] == "0"
+    assert rep["moved"] == "1 1900" and rep["empty"] == "0" and rep["released"] == "1"

@@ -33,8 +33,9 @@ def compare(frames, oracle_frames, tol):
         assert d.size == 0 or d.max() <= tol
 
 
-@pytest.mark.parametrize("sensor,batch", [("hdl64", 4096), ("hdl64", 100), ("hdl32", 4096)])
-def test_streaming_like_hdlsource(tmp_path, sensor, batch):
+@pytest.mark.parametrize("sensor,batch,pipelined", [("hdl64", 4096, 0), ("hdl64", 100, 0), ("hdl32", 4096, 0),
+                                                   ("hdl64", 400, 1), ("hdl64", 64, 1), ("hdl32", 500, 1)])
+def test_streaming_like_hdlsource(tmp_path, sensor, batch, pipelined):
     if sensor == "hdl64":
         pk, t = synth.hdl64_packets(1500)
         calib = synth.calib_hdl64()
@@ -48,7 +49,7 @@ def test_streaming_like_hdlsource(tmp_path, sensor, batch):
     F.write_poses(tmp_path / "poses.bin", *poses)
     calibxml.write_db_xml(str(tmp_path / "db.xml"), calib)
     r = F.run(["stream", tmp_path / "db.xml", tmp_path / "pk.bin", tmp_path / "t.bin",
-               tmp_path / "poses.bin", tmp_path / "out.bin", batch])
+               tmp_path / "poses.bin", tmp_path / "out.bin", batch, pipelined])
     assert r.returncode == 0, r.stderr
     o = P.make_oracle(calib, poses)
     o.process_packets(b, t)

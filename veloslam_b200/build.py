@@ -47,7 +47,7 @@ def build_library(force=False, verbose=False):
 
 FACADE_DIR = os.path.join(HERE, "cpp")
 FACADE_LIB = os.path.join(HERE, "libveloslam_facade.so")
-FACADE_SOURCES = ["type_defs.cpp", "TransformManager.cpp", "vtkPacketFile.cpp", "HDLManager.cpp", "CoordiTran.cpp", "TimeSolver.cpp", "HDLSource.cpp", "INSSource.cpp",
+FACADE_SOURCES = ["FrameArena.cpp", "type_defs.cpp", "TransformManager.cpp", "vtkPacketFile.cpp", "HDLManager.cpp", "CoordiTran.cpp", "TimeSolver.cpp", "HDLSource.cpp", "INSSource.cpp",
                   "CalibrationFile.cpp", "HDLParser.cpp"]
 DRIVER_SRC = os.path.join(os.path.dirname(HERE), "tests", "cpp", "facade_driver.cpp")
 DRIVER_EXE = os.path.join(os.path.dirname(HERE), "tests", "cpp", "facade_driver")

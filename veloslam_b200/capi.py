@@ -24,7 +24,8 @@ EXPORTS = ["vs_version", "vs_create", "vs_destroy", "vs_last_error", "vs_set_cal
            "vs_set_filters", "vs_set_poses", "vs_interpolate", "vs_carry_init", "vs_submit",
            "vs_wait", "vs_fetch_points", "vs_read_frame_information", "vs_host_alloc",
            "vs_host_free", "vs_stream", "vs_slot_stream", "vs_device_alloc", "vs_device_free",
-           "vs_device_upload", "vs_solve_packet_times", "vs_poses_from_ins", "vs_set_firing_offsets"]
+           "vs_device_upload", "vs_solve_packet_times", "vs_poses_from_ins", "vs_set_firing_offsets",
+           "vs_layout_frames", "vs_fetch_layout", "vs_sync"]
 
 
 class LaserCorr(C.Structure):
@@ -76,6 +77,26 @@ class Result(C.Structure):
                 ("carry_out", Carry), ("t_base_us", C.c_int64), ("first_upper_block", C.c_int64),
                 ("gpu_ms", C.c_float), ("decode_ms", C.c_float), ("n_kernel_launches", C.c_int32),
                 ("reserved", C.c_int32)]
+
+
+class FrameRows(C.Structure):
+    """vs_frame_rows: where the rows of one frame sit in the HDLFrame layout arrays."""
+    _fields_ = [("first_slot", C.c_int64), ("n_slots", C.c_int64),
+                ("row_start", C.c_uint32 * 64), ("row_count", C.c_uint32 * 64),
+                ("row_carried", C.c_uint32 * 64), ("row_laser", C.c_int32 * 64)]
+
+
+class Layout(C.Structure):
+    _fields_ = [("xyzi", C.c_void_p), ("meta", C.c_void_p), ("n_slots", C.c_int64),
+                ("rows", C.POINTER(FrameRows)), ("n_frames", C.c_int32),
+                ("xyzi_stride", C.c_int32), ("n_kernel_launches", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+# PointMeta as the reference lays it out (type_defs.h:168-176), 12 bytes
+POINT_META_DTYPE = np.dtype({"names": ["azimuth", "distance", "intensityFlag", "distanceFlag", "flags"],
+                             "formats": ["<u2", "<f4", "u1", "u1", "u1"],
+                             "offsets": [0, 4, 8, 9, 10], "itemsize": 12})
 
 
 class VeloError(RuntimeError):
@@ -141,6 +162,12 @@ def load_library():
     L.vs_stream.argtypes = [vp]
     L.vs_slot_stream.restype = vp
     L.vs_slot_stream.argtypes = [vp, C.c_int]
+    L.vs_layout_frames.restype = C.c_int
+    L.vs_layout_frames.argtypes = [vp, u64, vp, C.c_int, C.c_int, C.POINTER(Layout)]
+    L.vs_fetch_layout.restype = C.c_int
+    L.vs_fetch_layout.argtypes = [vp, u64, i64, i64, vp, vp]
+    L.vs_sync.restype = C.c_int
+    L.vs_sync.argtypes = [vp, u64, C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -363,6 +390,42 @@ class Context:
     def fetch_into(self, ticket, first, count, host_ptrs):
         """vs_fetch_points into caller-owned (e.g. pinned) buffers: host_ptrs = 8 addresses."""
         self._check(self._L.vs_fetch_points(self._h, ticket, first, count, *host_ptrs))
+
+    # -- HDLFrame layout on the device ------------------------------------------------------
+    def layout_frames(self, ticket, carried_counts=None, xyzi_stride=16, with_meta=True):
+        """vs_layout_frames: returns (Layout struct, rows as a structured numpy array copy)."""
+        lay = Layout()
+        car = None
+        if carried_counts is not None:
+            car = np.ascontiguousarray(carried_counts, dtype=np.uint32)
+            assert car.shape == (64,)
+        self._check(self._L.vs_layout_frames(self._h, ticket, _ptr(car), xyzi_stride,
+                                             1 if with_meta else 0, C.byref(lay)))
+        rows = np.ctypeslib.as_array(lay.rows, shape=(lay.n_frames,)).copy() if lay.n_frames else \
+            np.zeros(0, dtype=np.dtype(FrameRows))
+        return lay, rows
+
+    def fetch_layout(self, ticket, first_slot, n_slots, xyzi_host=None, meta_host=None):
+        """Enqueue the D2H copy of layout slots into host buffers (addresses / arrays)."""
+        self._check(self._L.vs_fetch_layout(self._h, ticket, first_slot, n_slots, _ptr(xyzi_host),
+                                            _ptr(meta_host)))
+
+    def sync(self, ticket):
+        ms = C.c_float()
+        self._check(self._L.vs_sync(self._h, ticket, C.byref(ms)))
+        return float(ms.value)
+
+    def fetch_frames_layout(self, ticket, carried_counts=None, with_meta=True):
+        """Convenience for tests: whole layout of a finished batch as numpy arrays
+        (xyzi (n_slots, 4) float32, meta POINT_META_DTYPE or None, rows)."""
+        lay, rows = self.layout_frames(ticket, carried_counts, 16, with_meta)
+        n = int(lay.n_slots)
+        xyzi = np.zeros((n, 4), dtype=np.float32)
+        meta = np.zeros(n, dtype=POINT_META_DTYPE) if with_meta else None
+        if n:
+            self.fetch_layout(ticket, 0, n, xyzi, meta)
+        self.sync(ticket)
+        return xyzi, meta, rows
 
     def read_frame_information(self, pkts, pkt_time_us, flags=0):
         n, stride = int(pkts.shape[0]), int(pkts.shape[1])

@@ -4,6 +4,7 @@
 #ifndef VELOSLAM_B200_HDLFRAME_H
 #define VELOSLAM_B200_HDLFRAME_H
 
+#include <atomic>
 #include <memory>
 #include <string>
 #include <utility>
@@ -17,12 +18,12 @@ struct HDLFrame {
   }
   ptime timestamp;
   std::vector<pcl::PointCloud<pcl::PointXYZI>::Ptr> points;
-  std::vector<std::shared_ptr<std::vector<PointMeta> > > pointsMeta;
+  std::vector<std::shared_ptr<PointMetaVector> > pointsMeta;
   std::vector<std::pair<ptime, std::string> > packets;
   std::shared_ptr<PoseTransform> carpose;
   bool isInMemory;
   bool isOnHardDrive;
-  unsigned char count;   // intrusive reference count of end users (reference HDLFrame.cxx:211-219)
+  std::atomic<unsigned char> count;   // intrusive reference count of end users (reference HDLFrame.cxx:211-219)
   ptime filenameTime;
   int64_t fileStartPos;  // byte offset of the frame's first packet record (fpos_t in the reference)
   uint8_t skips;
@@ -36,13 +37,17 @@ struct HDLFrame {
   // release points, meta and packets, keep the file locator (reference HDLFrame.cxx:142-158)
   void clear() {
     std::vector<pcl::PointCloud<pcl::PointXYZI>::Ptr>().swap(points);
-    std::vector<std::shared_ptr<std::vector<PointMeta> > >().swap(pointsMeta);
+    std::vector<std::shared_ptr<PointMetaVector> >().swap(pointsMeta);
     std::vector<std::pair<ptime, std::string> >().swap(packets);
     isInMemory = false;
   }
 };
 
 inline void intrusive_ptr_add_ref(HDLFrame* p) { ++p->count; }
-inline void intrusive_ptr_release(HDLFrame* p) { if (p->count != 0) --p->count; }
+inline void intrusive_ptr_release(HDLFrame* p) {
+  unsigned char c = p->count.load();
+  while (c != 0 && !p->count.compare_exchange_weak(c, (unsigned char)(c - 1))) {
+  }
+}
 
 #endif

@@ -118,7 +118,10 @@ void HDLManager::stopOnline() {
 HDLManager::~HDLManager() { delete packetWriter; }
 
 void HDLManager::loadOffline(const std::string& insTxt, const std::string& pcapfile) {
-  frames.clear();
+  {
+    std::lock_guard<std::mutex> lock(framesMutex);
+    frames.clear();
+  }
   transMgr->loadFromTxtFile(insTxt, true);
   std::cout << "Read " << transMgr->getNumberOfTransforms() << " transforms.\n";
   // the whole recording goes to HBM once; when the file is not a fixed-stride packet file the
@@ -190,8 +193,13 @@ void HDLManager::addFrame(std::shared_ptr<HDLFrame> frame) {
     pushCache(frame);
     return;
   }
-  hardDriveBuffer->push_back(frame);
-  if (writerIdle && hardDriveBuffer->size() == bufferSize) switchBuffer();
+  bool full;
+  {
+    std::lock_guard<std::mutex> lock(writerMutex);
+    hardDriveBuffer->push_back(frame);
+    full = writerIdle && hardDriveBuffer->size() == bufferSize;
+  }
+  if (full) switchBuffer();
 }
 
 // A frame in memory is handed out as it is; one that only exists on disk is decoded again --
@@ -227,8 +235,24 @@ HDLFramePtr HDLManager::getRecentFrame() {
   }
   return prepareFrame(newest);
 }
-HDLFramePtr HDLManager::getFrameAt(ptime& t) { return prepareFrame(frames.getExactDataAt(t)); }
-HDLFramePtr HDLManager::getFrameNear(ptime& t) { return prepareFrame(frames.getNearestData(t)); }
+// the timeline is read under framesMutex (addFrame inserts into it from the consumer thread);
+// the shared_ptr is copied out before the decode
+HDLFramePtr HDLManager::getFrameAt(ptime& t) {
+  std::shared_ptr<HDLFrame> f;
+  {
+    std::lock_guard<std::mutex> lock(framesMutex);
+    f = frames.getExactDataAt(t);
+  }
+  return prepareFrame(f);
+}
+HDLFramePtr HDLManager::getFrameNear(ptime& t) {
+  std::shared_ptr<HDLFrame> f;
+  {
+    std::lock_guard<std::mutex> lock(framesMutex);
+    f = frames.getNearestData(t);
+  }
+  return prepareFrame(f);
+}
 
 std::vector<std::shared_ptr<HDLFrame> > HDLManager::getAllFrameMeta() {
   std::lock_guard<std::mutex> lock(framesMutex);
@@ -238,8 +262,11 @@ std::vector<std::shared_ptr<HDLFrame> > HDLManager::getAllFrameMeta() {
 std::vector<HDLFramePtr> HDLManager::getRangeBetween(ptime& a, ptime& b) {
   // inclusive on both ends (HDLManager.h:148, TimeLine.h:316-382)
   std::vector<std::shared_ptr<HDLFrame> > vec;
-  for (const auto& f : frames.items())
-    if (f->timestamp >= a && f->timestamp <= b) vec.push_back(f);
+  {
+    std::lock_guard<std::mutex> lock(framesMutex);
+    for (const auto& f : frames.items())
+      if (f->timestamp >= a && f->timestamp <= b) vec.push_back(f);
+  }
   std::vector<HDLFramePtr> result;
   for (auto& f : vec) result.push_back(prepareFrame(f));
   return result;
@@ -306,6 +333,7 @@ bool HDLManager::writePackets() {
     frame->fileStartPos = recordPos;
     frame->isOnHardDrive = true;
     recordPos += (int64_t)frame->packets.size() * PCAP_PACKET_LEN;
+    std::lock_guard<std::mutex> lock(cacheMutex);
     cache.push_back(frame.get());
     ++cacheCounter;
   }
@@ -313,7 +341,10 @@ bool HDLManager::writePackets() {
   bufferFileNames.insert(path);
   full->clear();
   updateCacheSize();
-  writerIdle = true;
+  {
+    std::lock_guard<std::mutex> lock(writerMutex);
+    writerIdle = true;
+  }
   return true;
 }
 
@@ -323,15 +354,22 @@ void HDLManager::startSwaping() {
 }
 void HDLManager::stopSwaping() {}
 
+// the cache is touched by the HDLSource consumer thread (addFrame) and by user threads
+// (prepareFrame, cleanCache): one mutex guards the deque and its counter
 void HDLManager::pushCache(std::shared_ptr<HDLFrame>& frame) {
+  std::lock_guard<std::mutex> lock(cacheMutex);
   cache.push_back(frame.get());
   ++cacheCounter;
-  updateCacheSize();
+  updateCacheSizeLocked();
 }
 
 // Evict from the front until the cache fits; a frame an end user still holds (count != 0) goes
 // back to the end, at most ten times per call (HDLManager.cxx:400-421).
 void HDLManager::updateCacheSize() {
+  std::lock_guard<std::mutex> lock(cacheMutex);
+  updateCacheSizeLocked();
+}
+void HDLManager::updateCacheSizeLocked() {
   for (int putBacks = 0; cacheCounter > (int)maxCacheSize && putBacks < 10 && !cache.empty();) {
     HDLFrame* oldest = cache.front();
     cache.pop_front();
@@ -346,9 +384,10 @@ void HDLManager::updateCacheSize() {
 }
 
 void HDLManager::cleanCache() {
+  std::lock_guard<std::mutex> lock(cacheMutex);
   const size_t tmp = maxCacheSize;
   maxCacheSize = 0;
-  updateCacheSize();
+  updateCacheSizeLocked();
   maxCacheSize = tmp;
 }
 
@@ -357,7 +396,12 @@ bool HDLManager::saveHDLMeta() {
                                std::to_string(metaSerial++) + HDL_META_EXT_NAME;
   std::ofstream ofs(filename, std::ios::binary);
   if (!ofs) return false;
-  for (const auto& f : frames.getAll()) writeFrameRecord(ofs, *f);
+  std::vector<std::shared_ptr<HDLFrame> > all;
+  {
+    std::lock_guard<std::mutex> lock(framesMutex);
+    all = frames.getAll();
+  }
+  for (const auto& f : all) writeFrameRecord(ofs, *f);
   return true;
 }
 
@@ -375,6 +419,7 @@ bool HDLManager::loadHDLMeta() {
     while (true) {
       std::shared_ptr<HDLFrame> item(new HDLFrame);
       if (!readFrameRecord(ifs, *item)) break;
+      std::lock_guard<std::mutex> lock(framesMutex);
       frames.addData(item);
     }
   }

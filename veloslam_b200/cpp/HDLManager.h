@@ -134,7 +134,9 @@ class HDLManager {
   void operator=(const HDLManager&);
   void scanBufferDir();
 
+  void updateCacheSizeLocked();  // caller holds cacheMutex
   std::mutex framesMutex;
+  std::mutex cacheMutex;         // cache + cacheCounter (consumer thread and user threads)
   std::condition_variable cond_;
   bool hasNewData;
   size_t bufferSize;

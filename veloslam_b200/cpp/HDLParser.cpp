@@ -22,27 +22,73 @@ const int kHDL64BeamLUT[64] = {38, 39, 42, 43, 32, 33, 36, 37, 40, 41, 46, 47, 5
 
 class HDLParser::vsInternal {
  public:
+  // points of the open frame that earlier batches decoded, as they sit on the host: rows by
+  // laser id (an open frame is not permuted yet), in an arena of its own
+  struct Partial {
+    std::shared_ptr<vs::Arena> arena;
+    size_t metaOffset = 0;
+    uint32_t rowStart[HDL_MAX_NUM_LASERS];
+    uint32_t rowCount[HDL_MAX_NUM_LASERS];
+    uint64_t total = 0;
+    Partial() {
+      std::memset(rowStart, 0, sizeof(rowStart));
+      std::memset(rowCount, 0, sizeof(rowCount));
+    }
+  };
+  // one batch on its way through the GPU
+  struct Batch {
+    int stage = 0;  // 1: submitted (kernels running), 2: laid out, device -> host copies running
+    uint64_t ticket = 0;
+    int ring = 0;
+    int64_t n = 0;
+    int64_t recCursor = -1;
+    int64_t packetBase = 0;
+    int nLasers = 0;
+    std::vector<vs_frame> frames;
+    std::vector<vs_frame_rows> rows;
+    std::vector<std::shared_ptr<vs::Arena> > arenas;
+    std::vector<size_t> metaOffset;
+    std::vector<std::vector<std::pair<ptime, std::string> > > packets;
+  };
+
   vsInternal()
-      : ctx(nullptr), device(0), batchPackets(4096), storePackets(true), pinnedPkts(nullptr),
-        pinnedTimes(nullptr), pending(0), pendingWrap(false), hostLastAz(-1),
+      : ctx(nullptr), device(0), batchPackets(4096), storePackets(true), fetchMeta(true),
+        pipelined(false), fill(0), pending(0), pendingWrap(false), hostLastAz(-1),
         correctionsInitialized(false), calibFileReportedNumLasers(64), numberOfTrailingFrames(0),
         applyTransform(0), pointsSkip(0), shouldCropReturns(false), shouldCropInside(false),
-        dualReturnFilter(0), configDirty(true), poseVersion(0), warnedNoCalib(false) {
+        dualReturnFilter(0), configDirty(true), warnedNoCalib(false) {
     for (int i = 0; i < 6; ++i) cropRegion[i] = 0.0;
     for (int i = 0; i < HDL_MAX_NUM_LASERS; ++i) laserSelections[i] = 1;
+    for (int i = 0; i < 2; ++i) {
+      ringPkts[i] = nullptr;
+      ringTimes[i] = nullptr;
+    }
     std::memset(&calib, 0, sizeof(calib));
+    std::memset(openCounts, 0, sizeof(openCounts));
     vs_carry_init(&carry);
   }
   ~vsInternal() {
+    drain();
     unloadRecording();
-    if (ctx) vs_destroy(ctx);
-    vs_host_free(pinnedPkts);
-    vs_host_free(pinnedTimes);
+    destroyContext();
   }
 
+  void destroyContext() {
+    if (ctx) vs_destroy(ctx);
+    ctx = nullptr;
+    for (int i = 0; i < 2; ++i) {
+      vs_host_free(ringPkts[i]);
+      vs_host_free(ringTimes[i]);
+      ringPkts[i] = nullptr;
+      ringTimes[i] = nullptr;
+    }
+  }
+
+  // all or nothing: a context without its packet rings is torn down again
   bool ensureContext() {
     if (ctx) return true;
-    const int rc = vs_create(device, batchPackets, 1 << 20, 1, &ctx);
+    const int64_t maxPoses = std::max<int64_t>(1 << 16, batchPackets / 4);
+    const int rc = vs_create(device, batchPackets, maxPoses, pipelined ? 2 : 1, &ctx);
     if (rc != VS_OK) {
       error = std::string("vs_create failed: ") + vs_last_error(nullptr) +
               " (status " + std::to_string(rc) + "; there is no CPU fallback)";
@@ -50,16 +96,24 @@ class HDLParser::vsInternal {
       ctx = nullptr;
       return false;
     }
-    if (vs_host_alloc((uint64_t)batchPackets * VS_PACKET_BYTES, (void**)&pinnedPkts) != VS_OK ||
-        vs_host_alloc((uint64_t)batchPackets * sizeof(int64_t), (void**)&pinnedTimes) != VS_OK) {
+    bool ok = true;
+    for (int i = 0; i < (pipelined ? 2 : 1) && ok; ++i)
+      ok = vs_host_alloc((uint64_t)batchPackets * VS_PACKET_BYTES, (void**)&ringPkts[i]) == VS_OK &&
+           vs_host_alloc((uint64_t)batchPackets * sizeof(int64_t), (void**)&ringTimes[i]) == VS_OK;
+    if (!ok) {
       error = "pinned host allocation failed for the packet ring";
+      std::cerr << error << std::endl;
+      destroyContext();
       return false;
     }
+    maxPosesCtx = maxPoses;
     configDirty = true;
     return true;
   }
 
-  bool syncConfig() {
+  // calibration / filters when they changed; the slice of the pose timeline the batch's packet
+  // times [tmin, tmax] can touch (not the whole, ever-growing history)
+  bool syncConfig(int64_t tmin, int64_t tmax) {
     if (configDirty) {
       if (correctionsInitialized) {
         if (vs_set_calibration(ctx, calib.rows, calib.n_rows, calibFileReportedNumLasers) != VS_OK) {
@@ -81,20 +135,27 @@ class HDLParser::vsInternal {
       }
       configDirty = false;
     }
-    const uint64_t v = transMgr ? transMgr->version() : 0;
-    if (v != poseVersion) {
-      std::vector<int64_t> t;
-      std::vector<double> trv;
-      if (transMgr) transMgr->snapshot(&t, &trv);
-      if (vs_set_poses(ctx, t.data(), trv.data(), (int64_t)t.size()) != VS_OK) {
-        error = vs_last_error(ctx);
-        return false;
-      }
-      poseVersion = v;
+    poseT.clear();
+    poseTrv.clear();
+    if (transMgr) transMgr->snapshotWindow(tmin, tmax, &poseT, &poseTrv);
+    if ((int64_t)poseT.size() > maxPosesCtx) {
+      error = "the batch spans more poses than the context holds (lower setBatchPackets)";
+      return false;
+    }
+    if (vs_set_poses(ctx, poseT.data(), poseTrv.data(), (int64_t)poseT.size()) != VS_OK) {
+      error = vs_last_error(ctx);
+      return false;
     }
     return true;
   }
 
+  // frame object without the reference's 128 reserve(2200) calls: its lists are built by
+  // adoption when the frame closes
+  std::shared_ptr<HDLFrame> newFrameShell() {
+    std::shared_ptr<HDLFrame> f(new HDLFrame);
+    f->isInMemory = true;
+    return f;
+  }
   std::shared_ptr<HDLFrame> createHDLFrame() {
     std::shared_ptr<HDLFrame> f(new HDLFrame);
     f->points.resize(calibFileReportedNumLasers);
@@ -102,34 +163,61 @@ class HDLParser::vsInternal {
     for (int i = 0; i < calibFileReportedNumLasers; ++i) {
       f->points[i] = pcl::PointCloud<pcl::PointXYZI>::Ptr(new pcl::PointCloud<pcl::PointXYZI>);
       f->points[i]->points.reserve(HDL_MAX_PTS_PER_LASER);
-      f->pointsMeta[i] = std::shared_ptr<std::vector<PointMeta> >(new std::vector<PointMeta>);
+      f->pointsMeta[i] = std::shared_ptr<PointMetaVector>(new PointMetaVector);
       f->pointsMeta[i]->reserve(HDL_MAX_PTS_PER_LASER);
     }
     f->isInMemory = true;
     return f;
   }
 
-  // close a frame the way splitFrame does (reference HDLParser.cxx:867-897)
-  void closeFrame(std::shared_ptr<HDLFrame>& f, bool hdl64Order) {
-    for (auto& cloud : f->points) {
+  // HDLFrame::points / pointsMeta of a frame on top of its arena: the rows the GPU laid out
+  // (already in the order splitFrame leaves them, reference HDLParser.cxx:867-897) are adopted,
+  // not copied.  nRows: 64 for a frame closed on HDL-64 data, else the calibrated laser count;
+  // rows of lasers the calibration does not have stay empty.
+  void adoptRows(HDLFrame& f, const std::shared_ptr<vs::Arena>& arena, size_t metaOff,
+                 const uint32_t* rowStart, const uint32_t* rowCount, const int32_t* rowLaser,
+                 bool hdl64Order, int nLasers) {
+    const int nRows = hdl64Order ? 64 : nLasers;
+    f.points.resize((size_t)nRows);
+    f.pointsMeta.resize((size_t)nRows);
+    pcl::PointXYZI* xyzi = arena ? reinterpret_cast<pcl::PointXYZI*>(arena->data()) : nullptr;
+    PointMeta* meta = arena ? reinterpret_cast<PointMeta*>(arena->data() + metaOff) : nullptr;
+    for (int r = 0; r < nRows; ++r) {
+      pcl::PointCloud<pcl::PointXYZI>::Ptr cloud(new pcl::PointCloud<pcl::PointXYZI>);
+      std::shared_ptr<PointMetaVector> pm(new PointMetaVector);
+      const int laser = rowLaser ? rowLaser[r] : r;
+      if (arena && laser < nLasers && rowCount[r] > 0) {
+        vs::adopt(cloud->points, arena, xyzi + rowStart[r], (size_t)rowCount[r]);
+        if (fetchMeta) vs::adopt(*pm, arena, meta + rowStart[r], (size_t)rowCount[r]);
+      }
       cloud->width = (uint32_t)cloud->points.size();
       cloud->height = 1;
+      f.points[(size_t)r] = cloud;
+      f.pointsMeta[(size_t)r] = pm;
     }
+  }
+
+  // the open frame as the reference's forced split leaves it (getFrame at end of file,
+  // HDLParser.cxx:540-543): rows by laser id, then the pointer shuffle of splitFrame
+  void materializeOpenFrame(bool hdl64Order) {
+    HDLFrame& f = *currentFrame;
+    adoptRows(f, partial.arena, partial.metaOffset, partial.rowStart, partial.rowCount, nullptr, false,
+              calibFileReportedNumLasers);
     if (hdl64Order) {
       std::vector<pcl::PointCloud<pcl::PointXYZI>::Ptr> pts(64);
-      std::vector<std::shared_ptr<std::vector<PointMeta> > > ptm(64);
+      std::vector<std::shared_ptr<PointMetaVector> > ptm(64);
       for (int i = 0; i < 64; ++i) {
         const size_t src = (size_t)kHDL64BeamLUT[i];
-        if (src < f->points.size()) {
-          pts[i] = f->points[src];
-          ptm[i] = f->pointsMeta[src];
+        if (src < f.points.size()) {
+          pts[i] = f.points[src];
+          ptm[i] = f.pointsMeta[src];
         } else {
           pts[i] = pcl::PointCloud<pcl::PointXYZI>::Ptr(new pcl::PointCloud<pcl::PointXYZI>);
-          ptm[i] = std::shared_ptr<std::vector<PointMeta> >(new std::vector<PointMeta>);
+          ptm[i] = std::shared_ptr<PointMetaVector>(new PointMetaVector);
         }
       }
-      f->points = std::move(pts);
-      f->pointsMeta = std::move(ptm);
+      f.points = std::move(pts);
+      f.pointsMeta = std::move(ptm);
     }
   }
 
@@ -145,106 +233,233 @@ class HDLParser::vsInternal {
     f.carpose->timestamp = f.timestamp;
   }
 
-  // Decode the buffered packets and distribute the points over currentFrame / new frames.
-  // mode / carryIn are those of the streaming parser; returns false on a GPU error.
-  bool decodePending(std::deque<std::shared_ptr<HDLFrame> >* closedOut) {
+  void failBatches(const std::string& what) {
+    error = what;
+    std::cerr << "HDLParser: GPU decode failed: " << error << std::endl;
+    // the packets of the failed batch (and of any batch behind it) are lost; the parser carries
+    // on from the state before them
+    inflight.clear();
+    pending = 0;
+    pendingWrap = false;
+  }
+
+  // ---- stage 0 -> 1: hand the filled ring (or a slice of the resident recording) to the GPU ----
+  bool submitBatch(int64_t recCursorArg) {
     if (pending == 0) return true;
-    if (!ensureContext() || !syncConfig()) return false;
-    uint64_t ticket = 0;
-    vs_result r;
-    int rc;
-    // raw packet bytes / times on the host, for HDLFrame::packets
-    const uint8_t* rawBase = pinnedPkts;
-    size_t rawStride = VS_PACKET_BYTES;
-    if (recCursor >= 0) {
-      // packets come from the recording resident in HBM: no host -> device copy at all
-      const uint8_t* dev = static_cast<const uint8_t*>(recDev) + VS_PCAP_PAYLOAD_OFFSET +
-                           (size_t)recCursor * VS_PCAP_RECORD_BYTES;
-      rc = vs_submit(ctx, dev, VS_PCAP_RECORD_BYTES, nullptr, pending, 0, VS_MODE_STREAMING,
-                     VS_FLAG_DEVICE_INPUT | VS_FLAG_PCAP_TIMES, 0, &carry, &ticket);
-      rawBase = recHost.data() + VS_PCAP_PAYLOAD_OFFSET + (size_t)recCursor * VS_PCAP_RECORD_BYTES;
-      rawStride = VS_PCAP_RECORD_BYTES;
-    } else {
-      rc = vs_submit(ctx, pinnedPkts, VS_PACKET_BYTES, pinnedTimes, pending, 0, VS_MODE_STREAMING, 0,
-                     pinnedTimes[0], &carry, &ticket);
-    }
-    if (rc == VS_OK) rc = vs_wait(ctx, ticket, &r);
-    if (rc != VS_OK) {
-      error = vs_last_error(ctx);
-      std::cerr << "HDLParser: GPU decode failed: " << error << std::endl;
+    if (!ensureContext()) {
       pending = 0;
       pendingWrap = false;
       return false;
     }
-    auto rawTime = [&](int p) -> ptime {
-      if (recCursor < 0) return ptime(pinnedTimes[p]);
-      uint32_t tv[2];
-      std::memcpy(tv, rawBase + (size_t)p * rawStride - 58, 8);
-      return timevalToPtime(tv[0], tv[1]);
-    };
-    error.clear();
-    const size_t n = (size_t)r.n_points;
-    hx.resize(n);
-    hy.resize(n);
-    hz.resize(n);
-    hi.resize(n);
-    hl.resize(n);
-    ha.resize(n);
-    hd.resize(n);
-    if (n) {
-      rc = vs_fetch_points(ctx, ticket, 0, r.n_points, hx.data(), hy.data(), hz.data(), hi.data(),
-                           hl.data(), ha.data(), hd.data(), nullptr);
-      if (rc != VS_OK) {
-        error = vs_last_error(ctx);
-        return false;
+    Batch b;
+    b.n = pending;
+    b.ring = fill;
+    b.recCursor = recCursorArg;
+    b.packetBase = packetBase;
+    b.nLasers = calibFileReportedNumLasers;
+    int64_t tmin, tmax;
+    if (recCursorArg >= 0) {
+      const uint8_t* h = recHost.data() + VS_PCAP_PAYLOAD_OFFSET + (size_t)recCursorArg * VS_PCAP_RECORD_BYTES;
+      tmin = INT64_MAX;
+      tmax = INT64_MIN;
+      for (int64_t i = 0; i < pending; ++i) {
+        uint32_t tv[2];
+        std::memcpy(tv, h + (size_t)i * VS_PCAP_RECORD_BYTES - 58, 8);
+        const int64_t t = timevalToPtime(tv[0], tv[1]).us;
+        tmin = std::min(tmin, t);
+        tmax = std::max(tmax, t);
       }
+    } else {
+      const int64_t* tt = ringTimes[fill];
+      tmin = *std::min_element(tt, tt + pending);
+      tmax = *std::max_element(tt, tt + pending);
     }
-    for (int i = 0; i < r.n_frames; ++i) {
-      const vs_frame& e = r.frames[i];
-      if (i > 0) currentFrame = createHDLFrame();
-      HDLFrame& f = *currentFrame;
-      if (e.meta_packet >= 0) applyMeta(f, e);  // -1: carried (already applied), -2: never
-      // raw packets: a packet is stored in the frame that is current when it arrives; the
-      // frame's first packet is stored twice (reference HDLParser.cxx:999 + 1009)
-      if (storePackets) {
-        const int first = (i == 0) ? 0 : e.start_packet + 1;
-        const int last = (i + 1 < r.n_frames) ? r.frames[i + 1].start_packet : (int)pending - 1;
-        for (int p = first; p <= last; ++p) {
-          const std::string raw(reinterpret_cast<const char*>(rawBase) + (size_t)p * rawStride,
-                                VS_PACKET_BYTES);
-          if (p == e.meta_packet) f.packets.push_back(std::make_pair(rawTime(p), raw));
-          f.packets.push_back(std::make_pair(rawTime(p), raw));
-        }
-      }
-      const size_t nl = f.points.size();
-      for (int64_t k = e.first_point; k < e.first_point + e.n_points; ++k) {
-        const unsigned laser = hl[k];
-        if (laser >= nl) continue;
-        pcl::PointXYZI p;
-        p.x = hx[k];
-        p.y = hy[k];
-        p.z = hz[k];
-        p.intensity = hi[k];
-        f.points[laser]->points.push_back(p);
-        PointMeta m;
-        m.azimuth = ha[k];
-        // PointMeta::distance = float(dist * 0.002 + distanceCorrection) (HDLParser.cxx:614,747)
-        m.distance = (float)(hd[k] * 0.002 + calib.rows[laser].dist_correction_cm / 100.0);
-        m.intensityFlag = m.distanceFlag = m.flags = 0;
-        f.pointsMeta[laser]->push_back(m);
-      }
-      if (e.closed) {
-        closeFrame(currentFrame, e.hdl64_order != 0);
-        closedOut->push_back(currentFrame);
-        closedBy.push_back(packetBase + r.frames[i + 1].start_packet);  // packet holding the wrap
-      }
+    if (!syncConfig(tmin, tmax)) {
+      failBatches(error);
+      return false;
     }
-    if (r.n_frames > 0 && r.frames[r.n_frames - 1].closed) currentFrame = createHDLFrame();
-    carry = r.carry_out;
+    int rc;
+    if (recCursorArg >= 0) {
+      // packets come from the recording resident in HBM: no host -> device copy at all
+      const uint8_t* dev = static_cast<const uint8_t*>(recDev) + VS_PCAP_PAYLOAD_OFFSET +
+                           (size_t)recCursorArg * VS_PCAP_RECORD_BYTES;
+      rc = vs_submit(ctx, dev, VS_PCAP_RECORD_BYTES, nullptr, pending, 0, VS_MODE_STREAMING,
+                     VS_FLAG_DEVICE_INPUT | VS_FLAG_PCAP_TIMES, tmin, &carry, &b.ticket);
+    } else {
+      // the t_us column counts from the earliest packet of the batch
+      rc = vs_submit(ctx, ringPkts[fill], VS_PACKET_BYTES, ringTimes[fill], pending, 0,
+                     VS_MODE_STREAMING, 0, tmin, &carry, &b.ticket);
+    }
+    if (rc != VS_OK) {
+      failBatches(vs_last_error(ctx));
+      return false;
+    }
+    b.stage = 1;
+    inflight.push_back(std::move(b));
     packetBase += pending;
     pending = 0;
     pendingWrap = false;
+    if (pipelined) fill ^= 1;
     return true;
+  }
+
+  // ---- stage 1 -> 2: frame table, HDLFrame layout on the device, device -> host copies ----------
+  bool advance(Batch& b) {
+    vs_result r;
+    int rc = vs_wait(ctx, b.ticket, &r);
+    if (rc != VS_OK) {
+      failBatches(vs_last_error(ctx));
+      return false;
+    }
+    b.frames.assign(r.frames, r.frames + r.n_frames);
+    bool anyCarried = false;
+    for (int l = 0; l < HDL_MAX_NUM_LASERS; ++l) anyCarried = anyCarried || openCounts[l] != 0;
+    vs_layout lay;
+    rc = vs_layout_frames(ctx, b.ticket, anyCarried ? openCounts : nullptr, 16, fetchMeta ? 1 : 0, &lay);
+    if (rc != VS_OK) {
+      failBatches(vs_last_error(ctx));
+      return false;
+    }
+    b.rows.assign(lay.rows, lay.rows + lay.n_frames);
+    b.arenas.resize(b.rows.size());
+    b.metaOffset.assign(b.rows.size(), 0);
+    for (size_t i = 0; i < b.rows.size(); ++i) {
+      const size_t n = (size_t)b.rows[i].n_slots;
+      if (n == 0) continue;
+      const size_t metaOff = (n * sizeof(pcl::PointXYZI) + 255) & ~(size_t)255;
+      b.arenas[i] = vs::Arena::acquire(metaOff + (fetchMeta ? n * sizeof(PointMeta) : 0));
+      if (!b.arenas[i]) {
+        failBatches("page-locked host memory for a frame could not be allocated");
+        return false;
+      }
+      b.metaOffset[i] = metaOff;
+      rc = vs_fetch_layout(ctx, b.ticket, b.rows[i].first_slot, (int64_t)n, b.arenas[i]->data(),
+                           fetchMeta ? b.arenas[i]->data() + metaOff : nullptr);
+      if (rc != VS_OK) {
+        failBatches(vs_last_error(ctx));
+        return false;
+      }
+    }
+    // raw packets: a packet is stored in the frame that is current when it arrives; the frame's
+    // first packet is stored twice (reference HDLParser.cxx:999 + 1009).  Copied now: the ring
+    // is handed back to the receiver as soon as this returns.
+    if (storePackets) {
+      const uint8_t* rawBase = ringPkts[b.ring];
+      size_t rawStride = VS_PACKET_BYTES;
+      if (b.recCursor >= 0) {
+        rawBase = recHost.data() + VS_PCAP_PAYLOAD_OFFSET + (size_t)b.recCursor * VS_PCAP_RECORD_BYTES;
+        rawStride = VS_PCAP_RECORD_BYTES;
+      }
+      auto rawTime = [&](int p) -> ptime {
+        if (b.recCursor < 0) return ptime(ringTimes[b.ring][p]);
+        uint32_t tv[2];
+        std::memcpy(tv, rawBase + (size_t)p * rawStride - 58, 8);
+        return timevalToPtime(tv[0], tv[1]);
+      };
+      b.packets.resize(b.frames.size());
+      for (size_t i = 0; i < b.frames.size(); ++i) {
+        const vs_frame& e = b.frames[i];
+        const int first = (i == 0) ? 0 : e.start_packet + 1;
+        const int last = (i + 1 < b.frames.size()) ? b.frames[i + 1].start_packet : (int)b.n - 1;
+        for (int p = first; p <= last; ++p) {
+          const std::string raw(reinterpret_cast<const char*>(rawBase) + (size_t)p * rawStride, VS_PACKET_BYTES);
+          if (p == e.meta_packet) b.packets[i].push_back(std::make_pair(rawTime(p), raw));
+          b.packets[i].push_back(std::make_pair(rawTime(p), raw));
+        }
+      }
+    }
+    // parser state after the batch: what the next submit starts from
+    carry = r.carry_out;
+    const vs_frame_rows& open = b.rows.back();
+    for (int l = 0; l < HDL_MAX_NUM_LASERS; ++l) openCounts[l] = open.row_count[l];  // rows == laser ids
+    b.stage = 2;
+    return true;
+  }
+
+  // ---- stage 2 -> frames: wait for the copies, adopt the rows ------------------------------------
+  bool collect(Batch& b, std::deque<std::shared_ptr<HDLFrame> >* closedOut) {
+    const int rc = vs_sync(ctx, b.ticket, nullptr);
+    if (rc != VS_OK) {
+      failBatches(vs_last_error(ctx));
+      return false;
+    }
+    error.clear();
+    for (size_t i = 0; i < b.frames.size(); ++i) {
+      const vs_frame& e = b.frames[i];
+      const vs_frame_rows& rw = b.rows[i];
+      if (i > 0) currentFrame = newFrameShell();
+      HDLFrame& f = *currentFrame;
+      if (e.meta_packet >= 0) applyMeta(f, e);  // -1: carried (already applied), -2: never
+      if (storePackets)
+        for (auto& pk : b.packets[i]) f.packets.push_back(std::move(pk));
+      const std::shared_ptr<vs::Arena>& arena = b.arenas[i];
+      if (i == 0 && partial.total > 0 && arena) {
+        // what earlier batches decoded of this frame goes into the gaps the GPU left at the head
+        // of each row
+        pcl::PointXYZI* dx = reinterpret_cast<pcl::PointXYZI*>(arena->data());
+        PointMeta* dm = reinterpret_cast<PointMeta*>(arena->data() + b.metaOffset[0]);
+        const pcl::PointXYZI* sx = reinterpret_cast<const pcl::PointXYZI*>(partial.arena->data());
+        const PointMeta* sm = reinterpret_cast<const PointMeta*>(partial.arena->data() + partial.metaOffset);
+        for (int r = 0; r < HDL_MAX_NUM_LASERS; ++r) {
+          const uint32_t c = rw.row_carried[r];
+          if (!c) continue;
+          const int laser = rw.row_laser[r];
+          std::memcpy(dx + rw.row_start[r], sx + partial.rowStart[laser], (size_t)c * sizeof(pcl::PointXYZI));
+          if (fetchMeta) std::memcpy(dm + rw.row_start[r], sm + partial.rowStart[laser], (size_t)c * sizeof(PointMeta));
+        }
+      }
+      if (e.closed) {
+        adoptRows(f, arena, b.metaOffset[i], rw.row_start, rw.row_count, rw.row_laser, e.hdl64_order != 0,
+                  b.nLasers);
+        closedOut->push_back(currentFrame);
+        closedBy.push_back(b.packetBase + b.frames[i + 1].start_packet);  // packet holding the wrap
+        partial = Partial();
+      } else {
+        // still open: its points wait in their arena for the batch that closes the frame
+        partial = Partial();
+        partial.arena = arena;
+        partial.metaOffset = b.metaOffset[i];
+        for (int r = 0; r < HDL_MAX_NUM_LASERS; ++r) {
+          partial.rowStart[r] = rw.row_start[r];
+          partial.rowCount[r] = rw.row_count[r];
+        }
+        partial.total = (uint64_t)rw.n_slots;
+      }
+    }
+    return true;
+  }
+
+  // Non-pipelined decode of whatever is buffered: submit, lay out, fetch, adopt.
+  bool decodePending(std::deque<std::shared_ptr<HDLFrame> >* closedOut, int64_t recCursorArg = -1) {
+    if (pending == 0) return true;
+    if (!drainTo(closedOut)) return false;
+    if (!submitBatch(recCursorArg)) return false;
+    return drainTo(closedOut);
+  }
+
+  // finish every batch in flight
+  bool drainTo(std::deque<std::shared_ptr<HDLFrame> >* closedOut) {
+    while (!inflight.empty()) {
+      Batch& b = inflight.front();
+      if (b.stage == 1 && !advance(b)) return false;
+      if (!collect(inflight.front(), closedOut)) return false;
+      inflight.pop_front();
+    }
+    return true;
+  }
+  bool drain() { return ctx ? drainTo(&frames) : true; }
+
+  // Pipelined mode, ring full: the batch submitted one ring ago has long finished on the GPU --
+  // lay it out and start its device -> host copies; finish the one before it (its copies had a
+  // whole ring-fill to complete); hand the ring just filled to the GPU.  Host fill, host ->
+  // device copy + kernels and device -> host copy of three consecutive batches overlap.
+  bool pump() {
+    if (!inflight.empty() && inflight.back().stage == 1 && !advance(inflight.back())) return false;
+    while (inflight.size() > 1) {
+      if (!collect(inflight.front(), &frames)) return false;
+      inflight.pop_front();
+    }
+    return submitBatch(-1);
   }
 
   // ---- recording resident in HBM (loadRecording) ----------------------------------------------
@@ -285,7 +500,6 @@ class HDLParser::vsInternal {
     if (recDev) vs_device_free(ctx, recDev);
     recDev = nullptr;
     recPackets = 0;
-    recCursor = -1;
     recName.clear();
     recAlias.clear();
     std::vector<uint8_t>().swap(recHost);
@@ -296,20 +510,26 @@ class HDLParser::vsInternal {
   void* recDev = nullptr;
   std::vector<uint8_t> recHost;  // the same file image on the host (raw packets of HDLFrames)
   int64_t recPackets = 0;
-  int64_t recCursor = -1;        // >= 0: decodePending takes `pending` packets from here
   std::string recName, recAlias; // alias: the name readFrameInformation renamed the file to
 
   vs_ctx* ctx;
   int device;
   int batchPackets;
   bool storePackets;
-  uint8_t* pinnedPkts;
-  int64_t* pinnedTimes;
+  bool fetchMeta;
+  bool pipelined;
+  uint8_t* ringPkts[2];
+  int64_t* ringTimes[2];
+  int fill;                          // ring being filled
   int64_t pending;
   bool pendingWrap;
   int hostLastAz;
-  vs_carry carry;
-  int64_t packetBase = 0;            // packets decoded since unloadData
+  int64_t maxPosesCtx = 0;
+  vs_carry carry;                    // parser state after the last batch handed to advance()
+  uint32_t openCounts[HDL_MAX_NUM_LASERS];  // currentFrame->points[laser]->size() at that point
+  Partial partial;                   // the open frame's points (host), after the last collect()
+  std::deque<Batch> inflight;
+  int64_t packetBase = 0;            // packets handed to the GPU since unloadData
   std::vector<int64_t> closedBy;     // for each frame closed since unloadData: the closing packet
 
   std::deque<std::shared_ptr<HDLFrame> > frames;
@@ -329,13 +549,10 @@ class HDLParser::vsInternal {
   int laserSelections[HDL_MAX_NUM_LASERS];
   unsigned int dualReturnFilter;
   bool configDirty;
-  uint64_t poseVersion;
   bool warnedNoCalib;
   std::string error;
-
-  std::vector<float> hx, hy, hz;
-  std::vector<uint8_t> hi, hl;
-  std::vector<uint16_t> ha, hd;
+  std::vector<int64_t> poseT;
+  std::vector<double> poseTrv;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -429,16 +646,23 @@ int HDLParser::getNumberOfChannels() { return this->internal_->calibFileReported
 
 void HDLParser::unloadData() {
   vsInternal* in = this->internal_;
+  if (!in->inflight.empty()) {
+    // batches still on the GPU belong to the data being dropped: let them finish, discard them
+    std::deque<std::shared_ptr<HDLFrame> > dropped;
+    in->drainTo(&dropped);
+  }
   in->pending = 0;
   in->pendingWrap = false;
   in->hostLastAz = -1;
   const int skip = in->carry.firing_skip;  // unloadData does not reset firingSkip (HDLParser.cxx:478-486)
   vs_carry_init(&in->carry);
   in->carry.firing_skip = skip;
+  std::memset(in->openCounts, 0, sizeof(in->openCounts));
+  in->partial = vsInternal::Partial();
   in->frames.clear();
   in->closedBy.clear();
   in->packetBase = 0;
-  in->currentFrame = in->createHDLFrame();
+  in->currentFrame = in->newFrameShell();
 }
 
 void HDLParser::processHDLPacket(unsigned char* data, unsigned int bytesReceived, ptime t) {
@@ -454,8 +678,13 @@ void HDLParser::processHDLPacket(unsigned char* data, unsigned int bytesReceived
     return;
   }
   if (!in->ensureContext()) return;
-  std::memcpy(in->pinnedPkts + (size_t)in->pending * VS_PACKET_BYTES, data, VS_PACKET_BYTES);
-  in->pinnedTimes[in->pending] = t.us;
+  if (in->pending >= in->batchPackets) {
+    // cannot happen while every flush path resets `pending`; never write past the ring
+    in->error = "packet ring overrun: packet dropped";
+    return;
+  }
+  std::memcpy(in->ringPkts[in->fill] + (size_t)in->pending * VS_PACKET_BYTES, data, VS_PACKET_BYTES);
+  in->ringTimes[in->fill][in->pending] = t.us;
   ++in->pending;
   // an azimuth decrease anywhere in the packet is the only thing that can close a frame
   for (int j = 0; j < HDL_FIRING_PER_PKT; ++j) {
@@ -463,17 +692,28 @@ void HDLParser::processHDLPacket(unsigned char* data, unsigned int bytesReceived
     if (az < in->hostLastAz) in->pendingWrap = true;
     in->hostLastAz = az;
   }
-  if (in->pending >= in->batchPackets) this->flush();
+  if (in->pending >= in->batchPackets) {
+    if (in->pipelined)
+      in->pump();
+    else
+      in->decodePending(&in->frames);
+  }
 }
 
 void HDLParser::flush() {
   vsInternal* in = this->internal_;
-  if (in->pending == 0) return;
-  in->decodePending(&in->frames);
+  if (in->pending != 0) {
+    if (in->pipelined)
+      in->pump();
+    else
+      in->decodePending(&in->frames);
+  }
+  in->drain();
 }
 
 std::deque<std::shared_ptr<HDLFrame> > HDLParser::getAllFrames() {
-  if (this->internal_->pendingWrap) this->flush();
+  // pipelined: frames appear when their batch has come back; nothing is forced
+  if (this->internal_->pendingWrap && !this->internal_->pipelined) this->flush();
   return this->internal_->frames;
 }
 void HDLParser::clearAllFrames() { this->internal_->frames.clear(); }
@@ -510,10 +750,7 @@ bool HDLParser::getFrame(std::shared_ptr<HDLFrame>& dest, const std::string& fil
       const int64_t left = in->recPackets - cursor;
       if (left <= 0) break;
       in->pending = std::min<int64_t>(chunk, left);
-      in->recCursor = cursor;
-      const bool ok = in->decodePending(&closed);
-      in->recCursor = -1;
-      if (!ok) return false;
+      if (!in->decodePending(&closed, cursor)) return false;
       cursor += std::min<int64_t>(chunk, left);
       eof = cursor >= in->recPackets;
       continue;
@@ -524,8 +761,8 @@ bool HDLParser::getFrame(std::shared_ptr<HDLFrame>& dest, const std::string& fil
         break;
       }
       if (len != 1206) continue;
-      std::memcpy(in->pinnedPkts + (size_t)in->pending * VS_PACKET_BYTES, data, VS_PACKET_BYTES);
-      in->pinnedTimes[in->pending] = t.us;
+      std::memcpy(in->ringPkts[in->fill] + (size_t)in->pending * VS_PACKET_BYTES, data, VS_PACKET_BYTES);
+      in->ringTimes[in->fill][in->pending] = t.us;
       ++in->pending;
     }
     if (in->pending == 0) break;
@@ -545,7 +782,7 @@ bool HDLParser::getFrame(std::shared_ptr<HDLFrame>& dest, const std::string& fil
   // objects here, which leaves the caller's own frame (e.g. HDLManager's TimeLine entry)
   // empty and hands back an object only the local shared_ptr owns; the contents are moved
   // into the caller's frame instead, as in the branch above.
-  in->closeFrame(in->currentFrame, in->carry.is_hdl64 != 0);
+  in->materializeOpenFrame(in->carry.is_hdl64 != 0);
   dest->points = std::move(in->currentFrame->points);
   dest->pointsMeta = std::move(in->currentFrame->pointsMeta);
   this->unloadData();
@@ -671,7 +908,6 @@ std::shared_ptr<TransformManager> HDLParser::getTransformMgr() const { return th
 void HDLParser::setTransformMgr(std::shared_ptr<TransformManager> mgr) {
   this->flush();
   this->internal_->transMgr = mgr;
-  this->internal_->poseVersion = ~0ull;
 }
 int HDLParser::getApplyTransform() { return this->internal_->applyTransform; }
 void HDLParser::setApplyTransform(int apply) { this->internal_->applyTransform = apply; }
@@ -683,6 +919,13 @@ bool HDLParser::hasRecording(const std::string& pcapfile) const { return this->i
 void HDLParser::setDevice(int d) { this->internal_->device = d; }
 void HDLParser::setBatchPackets(int n) {
   if (!this->internal_->ctx && n > 0) this->internal_->batchPackets = n;
+}
+void HDLParser::setPipelined(bool on) {
+  if (!this->internal_->ctx) this->internal_->pipelined = on;
+}
+void HDLParser::setFetchMeta(bool on) {
+  this->flush();
+  this->internal_->fetchMeta = on;
 }
 void HDLParser::setStorePackets(bool s) { this->internal_->storePackets = s; }
 const std::string& HDLParser::lastError() const { return this->internal_->error; }

@@ -91,7 +91,16 @@ class HDLParser {
   void setDevice(int cudaDevice);          // before the first packet; default 0
   void setBatchPackets(int maxPackets);    // capacity of the pinned ring; default 4096
   void setStorePackets(bool store);        // keep raw packets inside HDLFrame::packets; default on
-  void flush();                            // decode whatever is buffered now
+  void setFetchMeta(bool fetch);           // fill HDLFrame::pointsMeta (12 of the 28 bytes per point
+                                           // that cross PCIe); default on
+  // Throughput mode for replay through the per-packet API (before the first packet; default off):
+  // two packet rings and two GPU result slots, so that filling the next ring, the host -> device
+  // copy + kernels of the current batch and the device -> host copy of the previous one overlap.
+  // getAllFrames() then returns frames when their batch has come back -- up to two rings
+  // (2 x setBatchPackets packets) after the packet that closed them -- instead of forcing the
+  // GPU round trip at every rotation; flush() drains everything.
+  void setPipelined(bool on);
+  void flush();                            // decode whatever is buffered now, wait for all of it
   // Keep a whole packet file (vtkPacketFileWriter format, fixed 1264-byte records) resident in
   // HBM: readFrameInformation() of that file becomes one segmentation pass on the GPU and
   // getFrame() decodes rotations straight out of HBM instead of re-reading the file

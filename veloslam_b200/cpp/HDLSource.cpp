@@ -43,7 +43,11 @@ class HDLSource::vsInternal {
     parser->processHDLPacket(const_cast<unsigned char*>(data), length, timestamp);
     std::deque<std::shared_ptr<HDLFrame> > fr = parser->getAllFrames();
     if (fr.size()) {
-      if (hdlMgr) hdlMgr->addFrame(fr.back());
+      // the reference adds getAllFrames().back(): with its per-packet parser at most one frame is
+      // ever waiting.  A packet that closes several frames (or a pipelined parser handing back a
+      // whole batch) leaves more than one here; none of them is dropped.
+      if (hdlMgr)
+        for (auto& f : fr) hdlMgr->addFrame(f);
       parser->clearAllFrames();
     }
   }
@@ -51,12 +55,16 @@ class HDLSource::vsInternal {
   void receiveLoop() {
     while (running.load()) {
       const uint64_t h = head.load(std::memory_order_relaxed);
-      unsigned char* slot = ring.data() + (size_t)(h % kRingSlots) * kSlotBytes;
+      // Ring full (consumer kRingSlots packets behind): slot h % kRingSlots is the oldest
+      // unconsumed packet, possibly being read right now -- receive into the scratch buffer and
+      // drop the newest packet instead, as a full socket buffer would.
+      const bool full = h - tail.load(std::memory_order_acquire) >= (uint64_t)kRingSlots;
+      unsigned char* slot = full ? scratch : ring.data() + (size_t)(h % kRingSlots) * kSlotBytes;
       const ssize_t n = recv(sock, slot, kSlotBytes, 0);  // SO_RCVTIMEO wakes it up to re-check
       if (n <= 0) continue;
       ++received;
-      if (h - tail.load(std::memory_order_acquire) >= (uint64_t)kRingSlots) {
-        ++dropped;  // consumer too slow: the newest packet is lost, as with a full socket buffer
+      if (full) {
+        ++dropped;
         continue;
       }
       lengths[h % kRingSlots] = (unsigned int)n;
@@ -93,6 +101,7 @@ class HDLSource::vsInternal {
   std::atomic<uint64_t> head, tail;
   std::atomic<uint64_t> received, dropped, consumed;
   std::vector<unsigned char> ring;
+  unsigned char scratch[1500];  // where a packet lands when the ring is full (then dropped)
   std::vector<unsigned int> lengths;
   std::thread receiver, consumer;
   std::mutex wakeMutex;

@@ -1,5 +1,7 @@
 #include "TransformManager.h"
 
+#include <algorithm>
+
 #include <fstream>
 
 TransformManager::TransformManager() : version_(1) { originLLH[0] = originLLH[1] = originLLH[2] = 0; }
@@ -133,6 +135,36 @@ void TransformManager::setOriginLLH(const double LLH[3]) {
 uint64_t TransformManager::version() {
   std::unique_lock<std::mutex> lock(mutex_);
   return version_;
+}
+
+void TransformManager::snapshotWindow(int64_t tmin_us, int64_t tmax_us, std::vector<int64_t>* t_us,
+                                      std::vector<double>* trv) {
+  std::unique_lock<std::mutex> lock(mutex_);
+  const auto& items = transforms.items();
+  const size_t n = items.size();
+  size_t a = 0, b = n;  // [a, b)
+  if (n >= 2) {
+    auto lower = [&](int64_t t) {
+      return (size_t)(std::lower_bound(items.begin(), items.end(), t,
+                                       [](const std::shared_ptr<PoseTransform>& p, int64_t v) {
+                                         return p->timestamp.us < v;
+                                       }) - items.begin());
+    };
+    const size_t lo = std::min(std::max<size_t>(lower(tmin_us), 1), n - 1);
+    const size_t hi = std::min(std::max<size_t>(lower(tmax_us), 1), n - 1);
+    a = lo - 1;
+    b = hi + 1;
+  }
+  t_us->resize(b - a);
+  trv->resize((b - a) * 9);
+  for (size_t i = a; i < b; ++i) {
+    (*t_us)[i - a] = items[i]->timestamp.us;
+    for (int k = 0; k < 3; ++k) {
+      (*trv)[9 * (i - a) + k] = items[i]->T[k];
+      (*trv)[9 * (i - a) + 3 + k] = items[i]->R[k];
+      (*trv)[9 * (i - a) + 6 + k] = items[i]->V[k];
+    }
+  }
 }
 
 void TransformManager::snapshot(std::vector<int64_t>* t_us, std::vector<double>* trv) {

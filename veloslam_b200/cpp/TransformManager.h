@@ -45,6 +45,12 @@ class TransformManager {
   uint64_t version();
   // sorted times (microseconds) and n x 9 doubles (T, R, V)
   void snapshot(std::vector<int64_t>* t_us, std::vector<double>* trv);
+  // The part of the timeline interpolateTransform() can touch for any time in [tmin, tmax]: the
+  // brackets clamp(lower_bound(t), 1, N-1) - 1 .. clamp(lower_bound(t), 1, N-1) of both ends and
+  // everything between them (so extrapolation past either end of the timeline still sees its
+  // two end samples).  What a batch of packets uploads instead of the whole history.
+  void snapshotWindow(int64_t tmin_us, int64_t tmax_us, std::vector<int64_t>* t_us,
+                      std::vector<double>* trv);
 
  protected:
   TimeLine<PoseTransform> transforms;

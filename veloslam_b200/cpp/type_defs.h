@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 
+#include "FrameArena.h"
+
 #define HDL_NUM_ROT_ANGLES 36001
 #define HDL_LASER_PER_FIRING 32
 #define HDL_MAX_NUM_LASERS 64
@@ -94,15 +96,21 @@ struct PointMeta {
   unsigned char distanceFlag;
   unsigned char flags;
 };
+static_assert(sizeof(PointMeta) == 12, "PointMeta is what the GPU writes (vs_layout_frames)");
+// HDLFrame::pointsMeta[row]: a std::vector whose storage may be a slice of the frame's arena
+typedef std::vector<PointMeta, vs::ArenaAllocator<PointMeta> > PointMetaVector;
 
 namespace pcl {
 struct PointXYZI {
   float x, y, z;
   float intensity;
 };
+static_assert(sizeof(PointXYZI) == 16, "PointXYZI is what the GPU writes (vs_layout_frames)");
 template <class PointT> struct PointCloud {
   typedef std::shared_ptr<PointCloud<PointT> > Ptr;
-  std::vector<PointT> points;
+  // PCL's own type here is std::vector<PointT, Eigen::aligned_allocator<PointT>>: also a vector
+  // with a non-default allocator.  This one can adopt a slice of the frame's page-locked arena.
+  std::vector<PointT, vs::ArenaAllocator<PointT> > points;
   uint32_t width = 0, height = 0;
   size_t size() const { return points.size(); }
 };

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "vs_kernels.cuh"
+#include "vs_layout.cuh"
 
 using namespace vsd;
 
@@ -61,6 +62,18 @@ struct Slot {
   long long* d_frame_meta_time = nullptr;
   int* d_frame_skips = nullptr;
   BatchHeader* d_hdr = nullptr;
+  // HDLFrame layout of the batch (vs_layout_frames), allocated on first use
+  uint8_t* d_lay_xyzi = nullptr;
+  uint8_t* d_lay_meta = nullptr;
+  size_t lay_xyzi_bytes = 0, lay_meta_bytes = 0;
+  unsigned long long* d_lay_rows = nullptr;  // [frame_cap][64]
+  uint8_t* d_lay_st = nullptr;               // [chunk counter | look-back words]
+  size_t lay_st_bytes = 0;
+  cudaEvent_t ev_l0 = nullptr, ev_l1 = nullptr;
+  bool lay_valid = false;     // layout kernels of the current ticket were launched
+  bool lay_inflight = false;  // ... and nobody has synchronised with them yet
+  std::vector<vs_frame_rows> lay_rows;
+  vs_layout layout;
   // pinned host
   BatchHeader* h_hdr = nullptr;
   BatchHeader* h_hdr_init = nullptr;
@@ -87,6 +100,13 @@ struct Slot {
   vs_result result;
 };
 
+// Opt-in and occupancy of one kernel variant, cached per context (see launch_decode).
+struct KernelCache {
+  bool attr_set = false;
+  size_t smem = 0;
+  int per_sm = 0;
+};
+
 }  // namespace
 
 struct vs_ctx {
@@ -106,7 +126,8 @@ struct vs_ctx {
   double* d_pose_trv = nullptr;
   std::vector<int64_t> pose_t;
   std::vector<double> pose_trv;
-  int dec_blocks_per_sm = 2;
+  KernelCache dec_cache[3][2][2];  // [ADJ][DSK][FUSED]
+  KernelCache scan_cache[3][2];    // [ADJ][CROP]
   bool two_pass = true;  // false (VELOSLAM_SINGLE_PASS=1): k_pose_pre + k_decode<.., FUSED> where it applies
   std::string err;
 };
@@ -190,6 +211,12 @@ void free_slot(Slot& s) {
   cudaFree(s.d_frame_meta_time);
   cudaFree(s.d_frame_skips);
   cudaFree(s.d_hdr);
+  cudaFree(s.d_lay_xyzi);
+  cudaFree(s.d_lay_meta);
+  cudaFree(s.d_lay_rows);
+  cudaFree(s.d_lay_st);
+  if (s.ev_l0) cudaEventDestroy(s.ev_l0);
+  if (s.ev_l1) cudaEventDestroy(s.ev_l1);
   cudaFreeHost(s.h_hdr);
   cudaFreeHost(s.h_hdr_init);
   cudaFreeHost(s.h_frame_first);
@@ -205,6 +232,24 @@ void free_slot(Slot& s) {
   if (s.ev_done) cudaEventDestroy(s.ev_done);
   if (s.stream) cudaStreamDestroy(s.stream);
   s = Slot();
+}
+
+// Copy a small host table (pageable memory) to the device so that it is complete and visible to
+// every slot stream when the call returns.  cudaMemcpy from pageable memory may return once the
+// data is staged, and the slot streams are non-blocking (not ordered against the legacy stream),
+// so the copy goes through slot 0's stream and is waited for.  Refused while a batch that may
+// read the table is still running.
+int upload_table(vs_ctx* ctx, void* dst, const void* src, size_t bytes, bool layout_reads_it,
+                 const char* who) {
+  for (int i = 0; i < ctx->n_slots; ++i) {
+    const Slot& s = ctx->slots[i];
+    if ((s.busy && !s.done) || (layout_reads_it && s.lay_inflight))
+      return fail(ctx, VS_ERR_STATE, std::string(who) + ": a batch is still in flight (vs_wait / vs_sync it first)");
+  }
+  cudaStream_t st = ctx->slots[0].stream;
+  VS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+  VS_CUDA(cudaStreamSynchronize(st));
+  return VS_OK;
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -314,41 +359,60 @@ int copy_frame_rows(vs_ctx* ctx, Slot& s, size_t n_rows) {
   return VS_OK;
 }
 
+// Opt-in and occupancy of one kernel variant, cached per context.  The dynamic shared memory
+// opt-in (cudaFuncAttributeMaxDynamicSharedMemorySize) is a per-device attribute of the function:
+// every context raises it to the size the largest legal stride (1280) needs, never to its own
+// batch's size, so contexts on other threads / other GPUs cannot lower it under a launch.
+constexpr int64_t kMaxStride = 1280;
+
 template <int ADJ, int DSK, int FUSED = 0>
 int launch_decode(vs_ctx* ctx, Slot& s, DecParams dp, int64_t stride) {
   typedef DecLayout<ADJ, DSK, FUSED> L;
   constexpr int kThreads = FUSED ? kFusedThreads : kDecThreads;
-  dp.stage_bytes = (int)align_up((size_t)L::kDPkts + (size_t)kDecTile * stride + 48, 128);
+  auto stage_bytes = [](int64_t st) {
+    return align_up((size_t)L::kDPkts + (size_t)kDecTile * (size_t)st + 48, 128);
+  };
+  dp.stage_bytes = (int)stage_bytes(stride);
   const size_t smem = (size_t)L::kStages + L::kNumStages * (size_t)dp.stage_bytes;
-  static size_t cached_smem = 0;  // one process drives one GPU: cache per instantiation
-  static int per_sm = 0;
-  if (cached_smem != smem) {
+  KernelCache& kc = ctx->dec_cache[ADJ][DSK][FUSED];
+  if (!kc.attr_set) {
+    const size_t smem_max = (size_t)L::kStages + L::kNumStages * stage_bytes(kMaxStride);
     VS_CUDA(cudaFuncSetAttribute(k_decode<ADJ, DSK, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode<ADJ, DSK, FUSED>, kThreads, smem));
-    cached_smem = smem;
+                                 (int)smem_max));
+    kc.attr_set = true;
   }
-  if (per_sm < 1) return fail(ctx, VS_ERR_CUDA, "k_decode does not fit on an SM");
-  int grid = ctx->sm_count * per_sm;
+  if (kc.smem != smem) {
+    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&kc.per_sm, k_decode<ADJ, DSK, FUSED>, kThreads, smem));
+    kc.smem = smem;
+  }
+  if (kc.per_sm < 1) return fail(ctx, VS_ERR_CUDA, "k_decode does not fit on an SM");
+  int grid = ctx->sm_count * kc.per_sm;
   if (grid > dp.n_tiles) grid = dp.n_tiles;
   k_decode<ADJ, DSK, FUSED><<<grid, kThreads, smem, s.stream>>>(dp);
   VS_CUDA(cudaGetLastError());
   return VS_OK;
 }
 
+inline size_t scan_stage_bytes(int64_t stride) {
+  return align_up((size_t)(kTilePkts + 1) * (size_t)stride + kLead + 48, 128);
+}
+
 template <int ADJ, bool CROP>
 int launch_scan(vs_ctx* ctx, Slot& s, const ScanParams& sp, size_t smem) {
-  static size_t cached_smem = 0;
-  static int per_sm = 0;
-  if (cached_smem != smem) {
+  KernelCache& kc = ctx->scan_cache[ADJ][CROP ? 1 : 0];
+  if (!kc.attr_set) {
+    const size_t smem_max = align_up(sizeof(ScanShared), 128) + scan_stage_bytes(kMaxStride);
     VS_CUDA(cudaFuncSetAttribute(k_scan<ADJ, CROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan<ADJ, CROP>, kScanThreads,
-                                                          smem));
-    cached_smem = smem;
+                                 (int)smem_max));
+    kc.attr_set = true;
   }
-  if (per_sm < 1) return fail(ctx, VS_ERR_CUDA, "k_scan does not fit on an SM");
-  int grid = ctx->sm_count * per_sm;
+  if (kc.smem != smem) {
+    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&kc.per_sm, k_scan<ADJ, CROP>, kScanThreads,
+                                                          smem));
+    kc.smem = smem;
+  }
+  if (kc.per_sm < 1) return fail(ctx, VS_ERR_CUDA, "k_scan does not fit on an SM");
+  int grid = ctx->sm_count * kc.per_sm;
   if (grid > sp.n_tiles) grid = sp.n_tiles;
   k_scan<ADJ, CROP><<<grid, kScanThreads, smem, s.stream>>>(sp);
   VS_CUDA(cudaGetLastError());
@@ -509,7 +573,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     sp.carry_last_az = cin.last_azimuth;
     sp.carry_skip = cin.firing_skip;
     sp.n_tiles = (int)scan_tiles;
-    sp.stage_bytes = (int)align_up((size_t)(kTilePkts + 1) * stride + kLead + 48, 128);
+    sp.stage_bytes = (int)scan_stage_bytes(stride);
     sp.pkt_seg = s.d_seg;
     sp.recs = s.d_recs;
     sp.st_map = s.d_st_map;
@@ -547,6 +611,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     pp.mode = mode;
     pp.n_poses = index_only ? 0 : n_poses;
     pp.carry_meta_inited = cin.frame_meta_inited;
+    pp.check_time = index_only ? 0 : 1;
     pp.t_base = t_base;
     pp.pose_t = ctx->d_pose_t;
     pp.pose_trv = ctx->d_pose_trv;
@@ -647,6 +712,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
 
   s.busy = true;
   s.done = false;
+  s.lay_valid = false;
   s.d_time_used = d_time;
   s.n = n;
   s.halo = halo;
@@ -664,6 +730,12 @@ int finish_batch(vs_ctx* ctx, Slot& s) {
   if (h.frame_overflow || (int64_t)h.total_wraps + 1 > ctx->frame_cap) {
     s.busy = false;
     return fail(ctx, VS_ERR_CAPACITY, "frame table capacity exceeded (too many azimuth wraps)");
+  }
+  if (h.time_range_error && !s.index_only) {
+    s.busy = false;
+    return fail(ctx, VS_ERR_INVALID_ARG,
+                "vs_submit: a packet time lies outside [t_base_us, t_base_us + 2^32 - 65536) us: "
+                "the t_us column cannot hold it (split the recording or move t_base_us)");
   }
   const int W = h.total_wraps;
   const int64_t frames_possible = std::min<int64_t>(ctx->frame_cap, 12 * s.n + 1);
@@ -847,6 +919,8 @@ int vs_create(int device, int64_t max_batch_packets, int64_t max_poses, int n_sl
   if (rc != VS_OK) return bail(rc);
   if (cudaMemcpy(ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), cudaMemcpyHostToDevice) != cudaSuccess)
     return bail(VS_ERR_CUDA);
+  // the tables above came from pageable memory: make sure they have landed, not just been staged
+  if (cudaDeviceSynchronize() != cudaSuccess) return bail(VS_ERR_CUDA);
   *out = ctx;
   return VS_OK;
 }
@@ -915,7 +989,8 @@ int vs_set_calibration(vs_ctx* ctx, const vs_laser_corr* corr, int n_rows, int n
   }
   update_selection(c);
   cudaSetDevice(ctx->device);
-  VS_CUDA(cudaMemcpy(ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), cudaMemcpyHostToDevice));
+  const int rc = upload_table(ctx, ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), true, "vs_set_calibration");
+  if (rc != VS_OK) return rc;
   ctx->calibrated = true;
   return VS_OK;
 }
@@ -929,8 +1004,7 @@ int vs_set_firing_offsets(vs_ctx* ctx, const uint16_t* off_us) {
   for (int j = 0; j < kBlocks; ++j)
     for (int d = 0; d < kReturns; ++d) ctx->h_cfg.tadj[j][d] = off_us[j * kReturns + d];
   cudaSetDevice(ctx->device);
-  VS_CUDA(cudaMemcpy(ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), cudaMemcpyHostToDevice));
-  return VS_OK;
+  return upload_table(ctx, ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), true, "vs_set_firing_offsets");
 }
 
 int vs_set_filters(vs_ctx* ctx, const vs_filters* f) {
@@ -944,8 +1018,7 @@ int vs_set_filters(vs_ctx* ctx, const vs_filters* f) {
   for (int i = 0; i < 6; ++i) c.crop[i] = f->crop_region[i];
   update_selection(c);
   cudaSetDevice(ctx->device);
-  VS_CUDA(cudaMemcpy(ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), cudaMemcpyHostToDevice));
-  return VS_OK;
+  return upload_table(ctx, ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), true, "vs_set_filters");
 }
 
 int vs_set_poses(vs_ctx* ctx, const int64_t* t_us, const double* trv, int64_t n) {
@@ -955,14 +1028,19 @@ int vs_set_poses(vs_ctx* ctx, const int64_t* t_us, const double* trv, int64_t n)
   for (int64_t i = 1; i < n; ++i)
     if (t_us[i] <= t_us[i - 1])
       return fail(ctx, VS_ERR_INVALID_ARG, "vs_set_poses: times must be strictly increasing");
-  ctx->pose_t.assign(t_us, t_us + n);
-  ctx->pose_trv.assign(trv, trv + n * 9);
   cudaSetDevice(ctx->device);
   if (n > 0) {
-    // pageable source: returns after the data is staged; ordered before later batch work
-    VS_CUDA(cudaMemcpy(ctx->d_pose_t, t_us, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice));
-    VS_CUDA(cudaMemcpy(ctx->d_pose_trv, trv, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice));
+    int rc = upload_table(ctx, ctx->d_pose_t, t_us, (size_t)n * sizeof(long long), false, "vs_set_poses");
+    if (rc == VS_OK)
+      rc = upload_table(ctx, ctx->d_pose_trv, trv, (size_t)n * 9 * sizeof(double), false, "vs_set_poses");
+    if (rc != VS_OK) return rc;
+  } else {
+    for (int i = 0; i < ctx->n_slots; ++i)
+      if (ctx->slots[i].busy && !ctx->slots[i].done)
+        return fail(ctx, VS_ERR_STATE, "vs_set_poses: a batch is still in flight (vs_wait it first)");
   }
+  ctx->pose_t.assign(t_us, t_us + n);
+  ctx->pose_trv.assign(trv, trv + n * 9);
   return VS_OK;
 }
 
@@ -1002,6 +1080,14 @@ static int submit_common(vs_ctx* ctx, const uint8_t* pkts, int64_t stride,
     } else {
       t_base_us = pkt_time_us[n_halo];
     }
+  }
+  if (!dev_in && !pcap_t && !index_only) {
+    // the t_us column is u32 microseconds after t_base (+ a u16 firing offset), HDLParser.cxx:969-970
+    for (int64_t i = n_halo; i < n; ++i)
+      if ((uint64_t)(pkt_time_us[i] - t_base_us) >= kTimeSpanMax)
+        return fail(ctx, VS_ERR_INVALID_ARG,
+                    "vs_submit: a packet time lies outside [t_base_us, t_base_us + 2^32 - 65536) us: "
+                    "the t_us column cannot hold it (split the recording or move t_base_us)");
   }
   const uint64_t tk = ctx->next_ticket;
   Slot& s = ctx->slots[tk % (uint64_t)ctx->n_slots];
@@ -1151,6 +1237,174 @@ int vs_fetch_points(vs_ctx* ctx, uint64_t ticket, int64_t first, int64_t count, 
   return VS_OK;
 }
 
+namespace {
+const int kBeamLutHost[64] = {38, 39, 42, 43, 32, 33, 36, 37, 40, 41, 46, 47, 50, 51, 54, 55,
+                              44, 45, 48, 49, 52, 53, 58, 59, 62, 63, 34, 35, 56, 57, 60, 61,
+                              6,  7,  10, 11, 0,  1,  4,  5,  8,  9,  14, 15, 18, 19, 22, 23,
+                              12, 13, 16, 17, 20, 21, 26, 27, 30, 31, 2,  3,  24, 25, 28, 29};
+
+int ensure_device_bytes(vs_ctx* ctx, uint8_t** buf, size_t* have, size_t need) {
+  if (need <= *have) return VS_OK;
+  cudaFree(*buf);
+  *buf = nullptr;
+  *have = 0;
+  VS_CUDA(cudaMalloc(buf, need));
+  *have = need;
+  return VS_OK;
+}
+}  // namespace
+
+int vs_layout_frames(vs_ctx* ctx, uint64_t ticket, const uint32_t* carried_counts, int xyzi_stride,
+                     int with_meta, vs_layout* out) {
+  if (!ctx || !out || (xyzi_stride != 16 && xyzi_stride != 32))
+    return fail(ctx, VS_ERR_INVALID_ARG, "vs_layout_frames: bad arguments");
+  Slot& s = ctx->slots[ticket % (uint64_t)ctx->n_slots];
+  if (!s.busy || !s.done || s.ticket != ticket)
+    return fail(ctx, VS_ERR_STATE, "vs_layout_frames: ticket not finished (vs_wait first)");
+  if (s.index_only) return fail(ctx, VS_ERR_STATE, "vs_layout_frames: the batch decoded no points");
+  cudaSetDevice(ctx->device);
+  const BatchHeader& h = *s.h_hdr;
+  const int n_frames = (int)s.frames.size();
+  const int f_lo = (s.halo > 0) ? h.frame_at_halo : 0;
+  uint64_t carried_total = 0;
+  if (carried_counts)
+    for (int l = 0; l < kMaxLasers; ++l) carried_total += carried_counts[l];
+  const int64_t n_slots = s.result.n_points + (int64_t)carried_total;
+
+  // host view of the rows (the same arithmetic as k_layout_rows)
+  s.lay_rows.assign((size_t)n_frames, vs_frame_rows());
+  for (int i = 0; i < n_frames; ++i) {
+    const vs_frame& fr = s.frames[(size_t)i];
+    vs_frame_rows& rw = s.lay_rows[(size_t)i];
+    rw.first_slot = (i == 0) ? 0 : fr.first_point + (int64_t)carried_total;
+    uint64_t acc = 0;
+    for (int r = 0; r < kMaxLasers; ++r) {
+      const int laser = fr.hdl64_order ? kBeamLutHost[r] : r;
+      const uint32_t car = (i == 0 && carried_counts) ? carried_counts[laser] : 0u;
+      rw.row_laser[r] = laser;
+      rw.row_carried[r] = car;
+      rw.row_start[r] = (uint32_t)acc;
+      rw.row_count[r] = car + fr.laser_counts[laser];
+      acc += (uint64_t)car + fr.laser_counts[laser];
+    }
+    if (acc >= (1ull << 32))
+      return fail(ctx, VS_ERR_CAPACITY, "vs_layout_frames: a frame holds 2^32 points or more");
+    rw.n_slots = (int64_t)acc;
+  }
+
+  int rc = ensure_device_bytes(ctx, &s.d_lay_xyzi, &s.lay_xyzi_bytes,
+                               (size_t)std::max<int64_t>(n_slots, 1) * (size_t)xyzi_stride);
+  if (rc != VS_OK) return rc;
+  if (with_meta) {
+    rc = ensure_device_bytes(ctx, &s.d_lay_meta, &s.lay_meta_bytes, (size_t)std::max<int64_t>(n_slots, 1) * 12);
+    if (rc != VS_OK) return rc;
+  }
+  const int64_t n_dec = s.n - s.halo;
+  const int n_chunks = (int)((n_dec + kLayChunk - 1) / kLayChunk);
+  rc = ensure_device_bytes(ctx, &s.d_lay_st, &s.lay_st_bytes, 256 + (size_t)n_chunks * 32 * 8);
+  if (rc != VS_OK) return rc;
+  if (!s.d_lay_rows) VS_CUDA(cudaMalloc(&s.d_lay_rows, (size_t)ctx->frame_cap * kMaxLasers * 8));
+  if (!s.ev_l0) {
+    VS_CUDA(cudaEventCreate(&s.ev_l0));
+    VS_CUDA(cudaEventCreate(&s.ev_l1));
+  }
+
+  VS_CUDA(cudaEventRecord(s.ev_l0, s.stream));
+  int launches = 0;
+  if (s.result.n_points > 0) {
+    VS_CUDA(cudaMemsetAsync(s.d_lay_st, 0, 256 + (size_t)n_chunks * 32 * 8, s.stream));
+    RowsParams rp;
+    rp.frame_first = s.d_frame_first;
+    rp.frame_start = s.d_frame_start;
+    rp.frame_counts = s.d_frame_counts;
+    rp.hdr = s.d_hdr;
+    rp.f_lo = f_lo;
+    rp.n_frames = n_frames;
+    rp.carry_is_hdl64 = s.carry_in.is_hdl64 ? 1 : 0;
+    for (int l = 0; l < kMaxLasers; ++l) rp.carried[l] = carried_counts ? carried_counts[l] : 0u;
+    rp.carried_total = carried_total;
+    rp.row_abs = s.d_lay_rows;
+    k_layout_rows<<<(unsigned)((n_frames + 127) / 128), 128, 0, s.stream>>>(rp);
+    VS_CUDA(cudaGetLastError());
+    LayoutParams lp;
+    lp.pkt_seg = s.d_seg;
+    lp.recs = s.d_recs;
+    lp.pkt_off = s.d_pkt_off;
+    lp.x = s.d_x;
+    lp.y = s.d_y;
+    lp.z = s.d_z;
+    lp.inten = s.d_inten;
+    lp.az = s.d_az;
+    lp.dist = s.d_dist;
+    lp.cfg = ctx->d_cfg;
+    lp.row_abs = s.d_lay_rows;
+    lp.st = reinterpret_cast<unsigned long long*>(s.d_lay_st + 256);
+    lp.chunk_counter = reinterpret_cast<int*>(s.d_lay_st);
+    lp.n = (int)s.n;
+    lp.halo = (int)s.halo;
+    lp.n_chunks = n_chunks;
+    lp.f_lo = f_lo;
+    lp.adj = ctx->h_cfg.adj_mode;
+    lp.xyzi = s.d_lay_xyzi;
+    lp.xyzi_stride = xyzi_stride;
+    lp.meta = with_meta ? s.d_lay_meta : nullptr;
+    k_layout<<<(unsigned)((n_chunks + kLayWarps - 1) / kLayWarps), kLayThreads, 0, s.stream>>>(lp);
+    VS_CUDA(cudaGetLastError());
+    launches = 2;
+  }
+  VS_CUDA(cudaEventRecord(s.ev_l1, s.stream));
+  s.lay_valid = true;
+  s.lay_inflight = true;
+  vs_layout& L = s.layout;
+  std::memset(&L, 0, sizeof(L));
+  L.xyzi = s.d_lay_xyzi;
+  L.meta = with_meta ? s.d_lay_meta : nullptr;
+  L.n_slots = n_slots;
+  L.rows = s.lay_rows.data();
+  L.n_frames = n_frames;
+  L.xyzi_stride = xyzi_stride;
+  L.n_kernel_launches = launches;
+  *out = L;
+  return VS_OK;
+}
+
+int vs_fetch_layout(vs_ctx* ctx, uint64_t ticket, int64_t first_slot, int64_t n_slots, void* xyzi_host,
+                    void* meta_host) {
+  if (!ctx) return VS_ERR_INVALID_ARG;
+  Slot& s = ctx->slots[ticket % (uint64_t)ctx->n_slots];
+  if (!s.busy || !s.done || s.ticket != ticket || !s.lay_valid)
+    return fail(ctx, VS_ERR_STATE, "vs_fetch_layout: no layout for this ticket (vs_layout_frames first)");
+  if (first_slot < 0 || n_slots < 0 || first_slot + n_slots > s.layout.n_slots)
+    return fail(ctx, VS_ERR_INVALID_ARG, "vs_fetch_layout: range outside the layout");
+  if (meta_host && !s.layout.meta)
+    return fail(ctx, VS_ERR_INVALID_ARG, "vs_fetch_layout: the layout was built without PointMeta");
+  if (n_slots == 0) return VS_OK;
+  cudaSetDevice(ctx->device);
+  const size_t st = (size_t)s.layout.xyzi_stride;
+  if (xyzi_host)
+    VS_CUDA(cudaMemcpyAsync(xyzi_host, s.d_lay_xyzi + (size_t)first_slot * st, (size_t)n_slots * st,
+                            cudaMemcpyDeviceToHost, s.stream));
+  if (meta_host)
+    VS_CUDA(cudaMemcpyAsync(meta_host, s.d_lay_meta + (size_t)first_slot * 12, (size_t)n_slots * 12,
+                            cudaMemcpyDeviceToHost, s.stream));
+  s.lay_inflight = true;
+  return VS_OK;
+}
+
+int vs_sync(vs_ctx* ctx, uint64_t ticket, float* layout_ms) {
+  if (!ctx) return VS_ERR_INVALID_ARG;
+  Slot& s = ctx->slots[ticket % (uint64_t)ctx->n_slots];
+  if (!s.busy || s.ticket != ticket) return fail(ctx, VS_ERR_STATE, "vs_sync: unknown ticket");
+  cudaSetDevice(ctx->device);
+  VS_CUDA(cudaStreamSynchronize(s.stream));
+  s.lay_inflight = false;
+  if (layout_ms) {
+    *layout_ms = 0.f;
+    if (s.lay_valid) cudaEventElapsedTime(layout_ms, s.ev_l0, s.ev_l1);
+  }
+  return VS_OK;
+}
+
 int vs_read_frame_information(vs_ctx* ctx, const uint8_t* pkts, int64_t stride,
                               const int64_t* pkt_time_us, int64_t n, uint32_t flags,
                               int32_t* start_packet, int32_t* skips, int64_t* timestamp_us,
@@ -1210,7 +1464,10 @@ void vs_device_free(vs_ctx* ctx, void* dev) {
 int vs_device_upload(vs_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes) {
   if (!ctx || !dst_dev || !src_host) return fail(ctx, VS_ERR_INVALID_ARG, "vs_device_upload: bad arguments");
   cudaSetDevice(ctx->device);
-  VS_CUDA(cudaMemcpy(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice));
+  // complete (not merely staged) before any slot stream reads it
+  cudaStream_t st = ctx->slots[0].stream;
+  VS_CUDA(cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, st));
+  VS_CUDA(cudaStreamSynchronize(st));
   return VS_OK;
 }
 

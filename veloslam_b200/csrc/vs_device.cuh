@@ -74,8 +74,13 @@ struct BatchHeader {
   int frame_at_halo;            // frame id at the first decoded packet
   int last_origin_packet;       // origin packet the next batch's first packet inherits
   int frame_overflow;           // a frame id exceeded the table capacity
-  int pad;
+  int time_range_error;         // a decoded packet's time - t_base does not fit the t_us column
 };
+
+// The t_us column is u32 microseconds after t_base plus the return's firing offset (a u16), the
+// same arithmetic as the reference's rawtime + round(timestampadjustment) (HDLParser.cxx:970):
+// packet times must lie in [t_base, t_base + kTimeSpanMax).
+constexpr unsigned long long kTimeSpanMax = 0xffff0000ull;
 
 // ---------------------------------------------------------------------------------------
 // PTX helpers

@@ -620,6 +620,7 @@ struct PoseParams {
   int mode;
   int n_poses;
   int carry_meta_inited;
+  int check_time;  // flag packet times outside [t_base, t_base + kTimeSpanMax)
   long long t_base;
   const long long* pose_t;
   const double* pose_trv;  // n_poses x 9
@@ -939,6 +940,8 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
   const long long t = __ldg(&p.pkt_time[P]);
   seg.y = frame_base;
   seg.z = (int)(unsigned)(t - p.t_base);
+  if (p.check_time && P >= p.halo && (unsigned long long)(t - p.t_base) >= kTimeSpanMax)
+    p.hdr->time_range_error = 1;
   p.pkt_seg[P] = seg;
   p.pkt_off[P] = exc;
 

@@ -399,6 +399,7 @@ __device__ __forceinline__ void fused_scan_role(const DecParams& p, DecCtl& sh, 
       seg.x = s_in | (int)(wrapmask << 4) | (azdiff << 16);
       seg.y = frame_base;
       seg.z = (int)(unsigned)(tp - p.t_base);
+      if ((unsigned long long)(tp - p.t_base) >= kTimeSpanMax && P >= p.halo) p.hdr->time_range_error = 1;
       seg.w = (int)(um | (cnt << 12));
       sts_v4(st_a + kDSeg + 16u * (unsigned)lane, (unsigned)seg.x, (unsigned)seg.y, (unsigned)seg.z,
              (unsigned)seg.w);
