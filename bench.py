@@ -34,6 +34,9 @@ BYTES_PER_POINT_OUT = 22          # x,y,z f32 + intensity u8 + laser u8 + azimut
 # to build HDLFrame::points / pointsMeta: every column but t_us (HDLFrame has no per-point time).
 BYTES_PER_POINT_E2E = 18
 HBM_FALLBACK_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallback
+WORKLOAD = ("HDL-64E S2 decode + rotation segmentation + per-packet deskew against a 100 Hz INS "
+            "timeline (BASELINE.json configs[2]; N>1: configs[3] packet-range shards with a "
+            "512-packet halo)")
 
 
 def parse_args():
@@ -51,6 +54,18 @@ def parse_args():
     ap.add_argument("--no-online", action="store_true")
     ap.add_argument("--no-deskew", action="store_true")
     ap.add_argument("--no-single-pass", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--recording-hours", type=float, default=0.0,
+                    help="headline = BASELINE.json configs[3]: ONE pass over a recording of this "
+                         "many hours of HDL-64E (12 499 200 packets per hour), split by packet range "
+                         "over the N ranks (strong scaling), frame-table all-gather + stitch timed")
+    ap.add_argument("--recording-leg-hours", type=float, default=1.0,
+                    help="size of the configs[3] sub-measurement of a default run (0: skip)")
+    ap.add_argument("--no-facade", action="store_true")
+    ap.add_argument("--no-hdl32", action="store_true")
+    ap.add_argument("--facade-packets", type=int, default=1 << 18,
+                    help="packets per pass of the C++ facade run")
+    ap.add_argument("--facade-batch", type=int, default=1 << 16)
     return ap.parse_args()
 
 
@@ -213,7 +228,9 @@ def cpu_time_threads(factory, calib, poses, pk_bytes, t_us, n_threads):
     def work(i):
         a, b = cuts[i], cuts[i + 1]
         if b > a:
-            parsers[i].process_packets(pk_bytes[a:b], t_us[a:b])
+            # the reference's consumer loop (HDLSource.cxx:209-225): frames are taken and the
+            # parser's list cleared as they close, after every packet
+            parsers[i].consume_packets(pk_bytes[a:b], t_us[a:b])
 
     t0 = time.perf_counter()
     for i in range(n_threads):
@@ -256,19 +273,25 @@ def run_reference_arm(args):
     kind, factory = load_cpu_reference()
     calib = synth.calib_hdl64()
     n_threads = os.cpu_count() or 1
-    # bounded sample per step: ~ cpu-seconds / (steps + warmup) of work on all threads
-    probe_n = 4096 * n_threads
+    # One step = the GPU arm's own batch (args.packets packets of the same synthetic stream) on
+    # every host thread, unless this box is too slow to finish steps + warmup of that within
+    # ~4 minutes: then a shorter prefix of the same stream.
+    probe_n = 2048 * n_threads
     pk, t = synth.hdl64_stream_tiled(probe_n)
     poses = synth.ins_trajectory(int(probe_n * 288e-6 * 100) + 40)
+    cpu_time_threads(factory, calib, poses, synth.as_bytes(pk), t, n_threads)
     dt, _ = cpu_time_threads(factory, calib, poses, synth.as_bytes(pk), t, n_threads)
     rate = probe_n / dt
     total_steps = args.steps + args.warmup
-    per_step_s = min(10.0, max(1.0, 120.0 / total_steps))
-    n = int(max(probe_n, min(rate * per_step_s, 1 << 21)))
+    n = int(max(probe_n, min(args.packets, rate * 240.0 / total_steps)))
     pk, t = synth.hdl64_stream_tiled(n)
     poses = synth.ins_trajectory(int(n * 288e-6 * 100) + 40)
     b = synth.as_bytes(pk)
     pts = count_points(pk)
+    # the reference's own threading model: ONE consumer thread per stream (HDLSource.cxx:227-235)
+    n1 = min(n, 1 << 16)
+    dt1, _ = cpu_time_threads(factory, calib, poses, b[:n1], t[:n1], 1)
+    one_thread = count_points(pk[:n1]) / dt1
     for _ in range(args.warmup):
         cpu_time_threads(factory, calib, poses, b, t, n_threads)
     t0 = time.perf_counter()
@@ -276,22 +299,242 @@ def run_reference_arm(args):
         cpu_time_threads(factory, calib, poses, b, t, n_threads)
     dt = time.perf_counter() - t0
     value = pts * args.steps / dt
-    sample = (f"{n} HDL-64E packets per step ({n * 384} slots, {pts} points), "
-              f"{n_threads} threads over packet-range shards")
+    sample = (f"{n} HDL-64E packets per step ({n * 384} slots, {pts} points; the GPU arm's batch is "
+              f"{args.packets} packets), {n_threads} threads over packet-range shards, each running "
+              f"the reference's consumer loop (processHDLPacket + getAllFrames/clearAllFrames per packet)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "HDL-64E S2 decode + per-packet deskew against a 100 Hz INS "
-                               "timeline (BASELINE.json configs[2]), CPU reference path",
+        "config": {"workload": WORKLOAD, "packets_per_step": n, "same_batch_as_gpu_arm": n == args.packets,
                    "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": kind,
-                         "sample": sample},
+                         "sample": sample, "one_thread_per_stream_value": one_thread},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: one pass over a long recording, packet-range sharded (strong scaling)
+# ------------------------------------------------------------------------------------------
+PACKETS_PER_HOUR = 12_499_200     # 1 h of HDL-64E at 3472 packets/s
+
+
+def device_stream(first, n, dev, base_packets=16384):
+    """Packets [first, first + n) of the infinite synthetic HDL-64E stream of
+    synth.hdl64_stream_tiled(), built ON THE DEVICE (a 1-h recording is 15 GB): the returns repeat
+    a seeded base block, azimuths and times are those of the global packet index."""
+    import torch
+    from veloslam_b200 import synth
+    base, _ = synth.hdl64_packets(base_packets)
+    d_base = torch.from_numpy(synth.as_bytes(base)).to(dev)
+    idx = torch.arange(first, first + n, dtype=torch.int64, device=dev)
+    d_pk = d_base.index_select(0, idx % base_packets)
+    for pair in range(6):
+        az = torch.floor(12345.0 + (idx * 6 + pair).to(torch.float64) * synth.HDL64_TICKS_PER_PAIR)
+        az = az.to(torch.int64) % 36000
+        lo, hi = (az & 0xff).to(torch.uint8), (az >> 8).to(torch.uint8)
+        for j in (2 * pair, 2 * pair + 1):
+            d_pk[:, 100 * j + 2] = lo
+            d_pk[:, 100 * j + 3] = hi
+    d_t = synth.T0_US + idx * synth.HDL64_US_PER_PACKET
+    del idx, d_base
+    return d_pk, d_t
+
+
+def run_recording(hours, steps, warmup, local, rank, world, dev, calib):
+    """ONE pass per step over a `hours`-long recording: rank g decodes its packet range (+ halo),
+    then the ranks all-gather their frame tables (NCCL) and every rank stitches the global frame
+    index -- all inside the timed region.  Returns a dict (rank 0's view, times = max over ranks)."""
+    import torch
+    from veloslam_b200 import capi, sharding, synth
+    n_total = int(round(PACKETS_PER_HOUR * hours))
+    first, halo, end = capi.shard_range(n_total, world, rank, sharding.HALO_HDL64)
+    n_sub = end - first + halo
+    t_base = int(synth.T0_US)
+    poses = synth.ins_trajectory(int(n_total * 288e-6 * 100) + 60)
+    ctx = capi.Context(local, max_batch_packets=n_sub, max_poses=len(poses[0]) + 8, n_slots=1)
+    ctx.set_calibration(calib)
+    ctx.set_poses(poses[0], poses[1])
+    d_pk, d_t = device_stream(first - halo, n_sub, dev)
+    torch.cuda.synchronize()
+    ext = torch.cuda.ExternalStream(ctx.stream(0), device=dev)
+    # fixed-size exchange buffer: row 0 = [n_rows, 0, ...], then the rows (one collective, no
+    # count exchange); a 10 Hz stream closes one frame per ~347 packets
+    cap_rows = (n_total + world - 1) // world // 300 + 64
+    h_mine = torch.zeros((cap_rows + 1, capi.FRAME_ROW_COLS), dtype=torch.int64).pin_memory()
+    d_mine = torch.zeros_like(h_mine, device=dev)
+    d_all = torch.zeros((world * (cap_rows + 1), capi.FRAME_ROW_COLS), dtype=torch.int64, device=dev)
+    h_all = torch.zeros_like(d_all, device="cpu").pin_memory()
+    ag0 = torch.cuda.Event(enable_timing=True)
+    ag1 = torch.cuda.Event(enable_timing=True)
+
+    def one_pass():
+        tk = ctx.submit(d_pk, d_t, n=n_sub, stride=1206, n_halo=halo, mode=capi.MODE_STREAMING,
+                        flags=capi.FLAG_DEVICE_INPUT, t_base_us=t_base)
+        r = ctx.wait(tk, frames=False)
+        w0 = time.perf_counter()
+        rows = capi.frame_table_rows(r.frame_table, rank, first, halo)
+        if rows.shape[0] > cap_rows:
+            raise RuntimeError("more frames than the exchange buffer holds")
+        h_mine[0, 0] = rows.shape[0]
+        h_mine[1:1 + rows.shape[0]] = torch.from_numpy(rows)
+        if world > 1:
+            d_mine.copy_(h_mine, non_blocking=True)
+            ag0.record()
+            torch.distributed.all_gather_into_tensor(d_all, d_mine)
+            ag1.record()
+            h_all.copy_(d_all, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            ag_ms = ag0.elapsed_time(ag1)
+            allr = h_all.numpy().reshape(world, cap_rows + 1, capi.FRAME_ROW_COLS)
+            tables = [allr[g, 1:1 + int(allr[g, 0, 0])] for g in range(world)]
+        else:
+            ag_ms = 0.0
+            tables = [rows]
+        w1 = time.perf_counter()
+        gf, segs = sharding.stitch_arrays(tables)
+        w2 = time.perf_counter()
+        return r, gf, segs, ag_ms, (w1 - w0) * 1e3, (w2 - w1) * 1e3
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 1)):
+        r, gf, segs, _, _, _ = one_pass()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    w0 = time.perf_counter()
+    dec, ags, exch, sti = [], [], [], []
+    for _ in range(steps):
+        r, gf, segs, ag_ms, ex_ms, st_ms = one_pass()
+        dec.append(r.gpu_ms)
+        ags.append(ag_ms)
+        exch.append(ex_ms)
+        sti.append(st_ms)
+    # the last device op of a pass is the gathered table's copy on torch's stream
+    ej = torch.cuda.Event()
+    ej.record()
+    ext.wait_event(ej)
+    e1.record(ext)
+    barrier()
+    wall_ms = (time.perf_counter() - w0) * 1e3 / steps
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / steps
+    pts_local = r.n_points
+
+    # the pass that was just timed against the CPU reference: a random run of rotations and the
+    # last ones of this rank's range (point offsets beyond 2^32 and frame ids in the thousands
+    # at N = 1)
+    class _DeviceRows:
+        def __getitem__(self, sl):
+            return d_pk[sl].cpu().numpy()
+    parity = parity_windows(ctx, r, _DeviceRows(), d_t.cpu().numpy(), t_base, halo, calib, poses,
+                            seed=99 + rank)
+    if world > 1:
+        allp = [None] * world
+        torch.distributed.all_gather_object(allp, parity)
+        bad = [p_ for p_ in allp if p_["status"] == "FAILED"]
+        parity = bad[0] if bad else {"status": "ok" if all(p_["status"] == "ok" for p_ in allp) else allp[0]["status"],
+                                     "max_abs_dxyz_m": max(p_.get("max_abs_dxyz_m", 0.0) for p_ in allp),
+                                     "points": sum(p_.get("points", 0) for p_ in allp), "ranks": world}
+    if parity["status"] == "FAILED":
+        raise SystemExit("bench.py: the timed recording pass does NOT match the CPU reference: " + parity["why"])
+    if world > 1:
+        tt = torch.tensor([ms, wall_ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        ms, wall_ms = float(tt[0].item()), float(tt[1].item())
+        pp = torch.tensor([pts_local], dtype=torch.int64, device=dev)
+        torch.distributed.all_reduce(pp)
+        pts = int(pp.item())
+    else:
+        pts = pts_local
+    out = {"hours": hours, "packets": n_total, "points": pts, "ms_per_pass": ms,
+           "wall_ms_per_pass": wall_ms, "points_per_s": pts / (ms * 1e-3),
+           "global_frames": int(len(gf)), "frame_segments": int(len(segs)),
+           "stitch_timestamp_mismatches": int(gf["timestamp_mismatch"].sum()),
+           "points_in_index": int(gf["n_points"].sum()),
+           "decode_ms_this_rank": float(np.mean(dec)), "nccl_allgather_ms": float(np.mean(ags)),
+           "exchange_ms_host": float(np.mean(exch)), "stitch_ms": float(np.mean(sti)),
+           "exchange_bytes_per_rank": int((cap_rows + 1) * capi.FRAME_ROW_COLS * 8),
+           "packets_this_rank": int(end - first), "halo": int(halo),
+           "points_this_rank": int(pts_local), "launches_per_pass": int(r.n_kernel_launches),
+           "parity_window": parity["status"], "parity": parity, "clocks": clocks,
+           "note": "timed region of a pass: vs_submit + vs_wait of the rank's packet range (k_scan, "
+                   "k_pose, k_decode, k_frames; recording resident in HBM, generated on the device), "
+                   "frame-table rows (vs_frame_table_rows), ONE NCCL all_gather_into_tensor of "
+                   "fixed-size tables, D2H, vs_stitch_frame_tables on every rank; CUDA events, "
+                   "max over ranks"}
+    if out["points_in_index"] != pts:
+        raise SystemExit("bench.py: the stitched frame index does not cover every decoded point")
+    ctx.close()
+    del d_pk, d_t
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# parity of what is timed: windows of the timed batch against the CPU reference
+# ------------------------------------------------------------------------------------------
+def parity_windows(ctx, res, b, t, t_base, halo, calib, poses, seed, rotations=12):
+    """Compare two windows of the batch that was just timed -- a random run of `rotations`
+    closed frames (~4096 packets) and the last closed frames of the batch -- with the CPU
+    reference (oracle/_ref when built, else the oracle port), point for point: laser,
+    intensity, azimuth, raw distance and the time column bit-exact, coordinates within the 1e-3 m
+    bar of BASELINE.json.  The reference parser is started 600 packets (> one rotation) early
+    so that lastAzimuth / firingSkip / the frame origin are those of the whole stream.
+    `b`, `t`: the host copy of the submitted packets (halo included)."""
+    from oracle.oracle import Oracle
+    tab = res.frame_table
+    n_closed = res.n_closed
+    if n_closed < rotations + 3:
+        return {"status": "skipped", "why": "batch holds too few rotations"}
+    rng = np.random.default_rng(seed)
+    starts = [int(rng.integers(2, n_closed - rotations)), n_closed - rotations]
+    out = {"status": "ok", "windows": [], "max_abs_dxyz_m": 0.0, "points": 0, "checker": "oracle port"}
+    for i0 in starts:
+        i1 = i0 + rotations
+        p0, k0 = int(tab["start_packet"][i0]), int(tab["start_block"][i0])
+        p1, k1 = int(tab["start_packet"][i1]), int(tab["start_block"][i1])
+        fp0, fp1 = int(tab["first_point"][i0]), int(tab["first_point"][i1])
+        a = max(0, p0 - 600)
+        o = Oracle()
+        o.set_calibration(calib)
+        o.add_poses(poses[0], poses[1])
+        o.trace_enable()
+        o.process_packets(b[a:p1 + 1], t[a:p1 + 1])
+        tr = o.trace()
+        key = (tr["packet"].astype(np.int64) + a) * 12 + tr["block"]
+        sel = (key >= p0 * 12 + k0) & (key < p1 * 12 + k1)
+        got = res.fetch(fp0, fp1 - fp0)
+        n = int(sel.sum())
+        if n != fp1 - fp0:
+            return {"status": "FAILED", "why": f"window at frame {i0}: {fp1 - fp0} points on the GPU, "
+                                               f"{n} from the CPU reference"}
+        for k in ("laser", "intensity", "azimuth", "distance"):
+            if not np.array_equal(got[k], tr[k][sel]):
+                return {"status": "FAILED", "why": f"window at frame {i0}: column {k} differs"}
+        want_t = (t[tr["packet"][sel].astype(np.int64) + a] - t_base).astype(np.uint32) + tr["tadj_us"][sel]
+        if not np.array_equal(got["t_us"], want_t):
+            return {"status": "FAILED", "why": f"window at frame {i0}: column t_us differs"}
+        worst = 0.0
+        for k in ("x", "y", "z"):
+            worst = max(worst, float(np.max(np.abs(got[k].astype(np.float64) - tr[k][sel]))))
+        if worst > 1e-3:
+            return {"status": "FAILED", "why": f"window at frame {i0}: |dxyz| = {worst} m > 1e-3 m"}
+        out["max_abs_dxyz_m"] = max(out["max_abs_dxyz_m"], worst)
+        out["points"] += n
+        out["windows"].append({"first_frame": i0, "frames": rotations, "packets": [p0, p1], "points": n})
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -361,6 +604,10 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     host_cpus_all = len(os.sched_getaffinity(0))
     numa_cpus = pin_to_gpu_numa_node(local)
+
+    if args.recording_hours > 0:
+        run_recording_headline(args, local, rank, world, dev, host_cpus_all, numa_cpus)
+        return
 
     n_per = args.packets
     halo = sharding.HALO_HDL64 if rank > 0 else 0
@@ -444,6 +691,22 @@ def run_ours(args):
     ms_per_step = elapsed_ms / args.steps
     value = total_emitted / (ms_per_step * 1e-3)
 
+    # ---- the batch that was just timed, against the CPU reference --------------------------------
+    parity = None
+    if not args.no_parity:
+        parity = parity_windows(ctx, r, b, t, t_base, halo, calib, poses, seed=1234 + rank)
+        if world > 1:
+            allp = [None] * world
+            torch.distributed.all_gather_object(allp, parity)
+            bad = [p_ for p_ in allp if p_["status"] == "FAILED"]
+            parity = bad[0] if bad else {
+                "status": "ok" if all(p_["status"] == "ok" for p_ in allp) else allp[0]["status"],
+                "max_abs_dxyz_m": max(p_.get("max_abs_dxyz_m", 0.0) for p_ in allp),
+                "points": sum(p_.get("points", 0) for p_ in allp),
+                "windows": [w for p_ in allp for w in p_.get("windows", [])][:4], "ranks": world}
+        if parity["status"] == "FAILED":
+            raise SystemExit("bench.py: the timed batch does NOT match the CPU reference: " + parity["why"])
+
     # ---- roofline of the dominant kernel (k_decode), this rank ------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak, peak_src = HBM_FALLBACK_GBS, "fallback"
@@ -514,6 +777,16 @@ def run_ours(args):
     if not args.no_e2e:
         e2e = run_e2e(args, ctx_args=(local, calib, poses), b=b[halo:], t=t[halo:], t_base=t_base,
                       world=world, dev=dev)
+    e2e_frames = None
+    if not args.no_e2e:
+        e2e_frames = run_e2e(args, ctx_args=(local, calib, poses), b=b[halo:], t=t[halo:], t_base=t_base,
+                             world=world, dev=dev, layout=True)
+    e2e_facade = None
+    if not args.no_facade and not args.no_e2e:
+        e2e_facade = run_facade(args, local, calib, poses, b[halo:], t[halo:], world, dev)
+    hdl32 = None
+    if not args.no_hdl32 and rank == 0:
+        hdl32 = run_hdl32(local, dev)
     online = None
     if not args.no_online:
         online = run_online(local, calib, poses, b[halo:], t[halo:], t_base)
@@ -568,15 +841,27 @@ def run_ours(args):
             os.environ.pop("VELOSLAM_SINGLE_PASS", None)
 
 
+    # ---- configs[3] as written: one pass over a 1-h recording, strong scaling, gather timed -----
+    recording = None
+    if args.recording_leg_hours > 0:
+        ctx.close()
+        ctx = None
+        del d_pk, d_t
+        torch.cuda.empty_cache()
+        try:
+            recording = run_recording(args.recording_leg_hours, 3, 1, local, rank, world, dev, calib)
+        except SystemExit:
+            raise
+        except Exception as e:  # reported, never silently dropped
+            recording = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": "HDL-64E S2 decode + rotation segmentation + per-packet deskew against "
-                            "a 100 Hz INS timeline (BASELINE.json configs[2]; N>1: configs[3] "
-                            "packet-range shards with a 512-packet halo)",
+                "workload": WORKLOAD,
                 "packets_per_gpu_per_step": n_per, "slots_per_gpu_per_step": n_per * 384,
                 "points_emitted_per_gpu_per_step": n_emitted, "mode": "streaming (reference parity)",
                 "input_bytes_per_gpu": n_sub * 1206,
@@ -590,8 +875,17 @@ def run_ours(args):
             },
             "roofline": roofline, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
+        if parity is not None:
+            line["parity_window"] = parity["status"]
+            line["parity"] = parity
         if e2e is not None:
             line["e2e"] = e2e
+        if e2e_frames is not None:
+            line["e2e_frames"] = e2e_frames
+        if e2e_facade is not None:
+            line["e2e_facade"] = e2e_facade
+        if hdl32 is not None:
+            line["hdl32"] = hdl32
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if online is not None:
@@ -600,16 +894,67 @@ def run_ours(args):
             line["deskew_per_point"] = deskew
         if single is not None:
             line["single_pass_variant"] = single
+        if recording is not None:
+            line["recording"] = recording
         print(json.dumps(line), flush=True)
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 
-def run_e2e(args, ctx_args, b, t, t_base, world, dev):
-    """Host packets in, host point columns out, through vs_submit / vs_wait / vs_fetch_points
-    with two result slots so copies overlap the kernels."""
+def run_recording_headline(args, local, rank, world, dev, host_cpus_all, numa_cpus):
+    """`--recording-hours H`: the headline IS BASELINE.json configs[3] -- total work fixed, split
+    over the ranks (strong scaling), collective and stitch inside the timed region."""
+    import torch
+    from veloslam_b200 import synth
+    calib = synth.calib_hdl64()
+    rec = run_recording(args.recording_hours, args.steps, max(args.warmup, 3), local, rank, world,
+                        dev, calib)
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak, peak_src = HBM_FALLBACK_GBS, "fallback"
+        try:
+            peak = float(json.load(open(peaks_path))["hbm_gbs"])
+            peak_src = "measured"
+        except Exception:
+            pass
+        alg = 1206 * rec["packets_this_rank"] + BYTES_PER_POINT_OUT * rec["points_this_rank"]
+        line = {
+            "metric": METRIC, "value": rec["points_per_s"], "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": rec["ms_per_pass"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (generated on the device)",
+            "config": {"workload": f"offline replay of {args.recording_hours:g} h of synthetic HDL-64E "
+                                   f"({rec['packets']} packets, {rec['points']} points) decode + deskew, "
+                                   f"packet-range sharded across {world} B200 with a 512-packet halo "
+                                   "(BASELINE.json configs[3]); one pass per step, frame-table "
+                                   "all-gather + stitch inside the timed region",
+                       "l2": "inputs and outputs per pass exceed the 126 MB L2 by orders of magnitude",
+                       "host_affinity": (f"{numa_cpus} of {host_cpus_all} CPUs" if numa_cpus else "unchanged")},
+            "roofline": {"bound": "hbm", "kernel": "whole pass of rank 0 (k_scan + k_pose + k_decode + "
+                                                   "k_frames)", "achieved": alg / (rec["decode_ms_this_rank"] * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                         "frac": alg / (rec["decode_ms_this_rank"] * 1e-3) / 1e9 / peak,
+                         "algorithmic_bytes_per_launch": alg, "traffic": None},
+            "gpu_launches": rec["launches_per_pass"] * args.steps, "clocks": rec["clocks"],
+            "parity_window": rec["parity_window"], "recording": rec,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def run_e2e(args, ctx_args, b, t, t_base, world, dev, layout=False):
+    """Host packets in, host points out, with two result slots so copies overlap the kernels.
+    layout=False: vs_submit / vs_wait / vs_fetch_points, the stream-order columns (18 B/point).
+    layout=True: vs_submit / vs_wait / vs_layout_frames / vs_fetch_layout, every frame as the
+    reference's HDLFrame holds it (laser-major PointXYZI + PointMeta records, 28 B/point) -- what
+    the C++ facade hands to its callers without touching a point on the CPU."""
+    if layout:
+        return run_e2e_frames(args, ctx_args, b, t, t_base, world, dev)
     import torch
     from veloslam_b200 import capi
     local, calib, poses = ctx_args
@@ -686,6 +1031,192 @@ def run_e2e(args, ctx_args, b, t, t_base, world, dev):
             "vs_fetch_points into pinned host columns: the 7 columns the HDLFrame facade "
             "consumes (x, y, z, intensity, laser, azimuth, distance = 18 B/point; t_us has no "
             "counterpart in HDLFrame and stays on the device); PCIe D2H bound"}
+
+
+def run_e2e_frames(args, ctx_args, b, t, t_base, world, dev):
+    import torch
+    from veloslam_b200 import capi
+    local, calib, poses = ctx_args
+    chunk = min(args.e2e_chunk, b.shape[0])
+    n_chunks = b.shape[0] // chunk
+    ctx = capi.Context(local, max_batch_packets=chunk, max_poses=len(poses[0]) + 8, n_slots=2)
+    ctx.set_calibration(calib)
+    ctx.set_poses(poses[0], poses[1])
+    h_pk = torch.from_numpy(b[:n_chunks * chunk]).pin_memory()
+    h_t = torch.from_numpy(np.ascontiguousarray(t[:n_chunks * chunk])).pin_memory()
+    cap = chunk * 384 + 400 * 384     # + room for the carried rows of an open rotation
+    outs = [(torch.empty(cap * 16, dtype=torch.uint8).pin_memory(),
+             torch.empty(cap * 12, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+
+    def one_pass():
+        carry = capi.carry_init()
+        carried = np.zeros(64, np.uint32)
+        total = h2d = d2h = 0
+        prev = prev2 = None       # (ticket, slot) submitted / laid out and being fetched
+        for c in range(n_chunks + 2):
+            if prev is not None:
+                rp = ctx.wait(prev[0], frames=False)          # kernels of c-1 done long ago
+                carry = rp.carry_out
+            if prev2 is not None:
+                ctx.sync(prev2[0])                            # copies of c-2 had a whole iteration
+                prev2 = None
+            cur = None
+            if c < n_chunks:
+                a = c * chunk
+                tk = ctx.submit(h_pk[a:a + chunk], h_t[a:a + chunk], n=chunk, stride=1206,
+                                mode=capi.MODE_STREAMING, flags=0, t_base_us=t_base, carry=carry)
+                h2d += chunk * (1206 + 8)
+                cur = (tk, c % 2)
+            if prev is not None:
+                lay, rows = ctx.layout_frames(prev[0], carried if carried.any() else None, 16, True)
+                n_slots = int(lay.n_slots)
+                assert n_slots <= cap
+                if n_slots:
+                    ctx.fetch_layout(prev[0], 0, n_slots, outs[prev[1]][0].data_ptr(),
+                                     outs[prev[1]][1].data_ptr())
+                carried = rows["row_count"][-1].astype(np.uint32)
+                total += rp.n_points
+                d2h += n_slots * 28
+                prev2 = prev
+            prev = cur
+        return total, h2d, d2h
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    one_pass()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        total, h2d, d2h = one_pass()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    per_rank_gbs = d2h * args.e2e_steps / dt / 1e9
+    gbs = [per_rank_gbs]
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        allg = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        torch.distributed.all_gather(allg, torch.tensor([per_rank_gbs], dtype=torch.float64, device=dev))
+        gbs = [float(x.item()) for x in allg]
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        dt = float(tt.item())
+        pts = torch.tensor([total], dtype=torch.int64, device=dev)
+        torch.distributed.all_reduce(pts)
+        total = int(pts.item())
+    ctx.close()
+    return {"value": total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "chunk_packets": chunk,
+            "bytes_per_point": 28, "per_rank_d2h_gb_per_s": [round(g, 2) for g in gbs],
+            "note": "host pinned packets -> vs_submit/vs_wait -> vs_layout_frames (k_layout on the "
+                    "device) -> vs_fetch_layout into pinned host memory: every frame laser-major as "
+                    "HDLFrame::points[row] / pointsMeta[row] hold it (16-B PointXYZI + 12-B PointMeta "
+                    "per point); PCIe D2H bound"}
+
+
+def run_facade(args, local, calib, poses, b, t, world, dev):
+    """The C++ facade driven like the reference's consumer (HDLSource.cxx:209-225):
+    HDLParser::processHDLPacket per packet, getAllFrames / clearAllFrames, through
+    tests/cpp/facade_driver (one process per GPU).  Pipelined throughput mode, frames handed out
+    as zero-copy HDLFrames."""
+    import torch
+    from veloslam_b200 import calibxml
+    from veloslam_b200.build import DRIVER_EXE, build_facade
+    build_facade()
+    n = min(args.facade_packets, b.shape[0])
+    passes = 3
+    tmp = tempfile.mkdtemp(prefix="vs_facade_")
+    out = {}
+    try:
+        b[:n].tofile(os.path.join(tmp, "pk.bin"))
+        np.ascontiguousarray(t[:n]).astype("<i8").tofile(os.path.join(tmp, "t.bin"))
+        span_s = (passes + 2) * n * 288e-6
+        from veloslam_b200 import synth
+        pt, trv = synth.ins_trajectory(int(span_s * 100) + 40)
+        rec = np.zeros(len(pt), dtype=[("t", "<i8"), ("v", "<f8", (9,))])
+        rec["t"] = pt
+        rec["v"] = trv
+        rec.tofile(os.path.join(tmp, "poses.bin"))
+        calibxml.write_db_xml(os.path.join(tmp, "db.xml"), calib)
+        for name, store, meta in (("frames_xyzi_meta", 0, 1), ("frames_xyzi_only", 0, 0),
+                                  ("frames_with_raw_packets", 1, 1)):
+            if world > 1:
+                torch.distributed.barrier()
+            cmd = [DRIVER_EXE, "bench", os.path.join(tmp, "db.xml"), os.path.join(tmp, "pk.bin"),
+                   os.path.join(tmp, "t.bin"), os.path.join(tmp, "poses.bin"), str(args.facade_batch),
+                   str(passes), str(store), str(meta), "1", str(local)]
+            p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+            if p.returncode != 0:
+                out[name] = {"error": (p.stderr or p.stdout)[-400:]}
+                continue
+            j = json.loads(p.stdout.strip().splitlines()[-1])
+            pts, sec = j["points"], j["seconds"]
+            if world > 1:
+                tt = torch.tensor([sec], dtype=torch.float64, device=dev)
+                torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+                sec = float(tt.item())
+                pp = torch.tensor([pts], dtype=torch.int64, device=dev)
+                torch.distributed.all_reduce(pp)
+                pts = int(pp.item())
+            out[name] = {"value": pts / sec, "unit": UNIT, "points": pts, "frames": j["frames"],
+                         "seconds": sec, "packets": j["packets"],
+                         "pinned_pool_bytes": j["pinned_pool_bytes"], "host_seconds": j.get("host")}
+    finally:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    out["batch_packets"] = args.facade_batch
+    out["packets_per_pass"] = n
+    out["note"] = ("tests/cpp/facade_driver bench: HDLParser::processHDLPacket per packet + "
+                   "getAllFrames/clearAllFrames (the reference's HDLSource.cxx:209-225 consumer "
+                   "loop), setPipelined(true); frames arrive as HDLFrames whose points[row] vectors "
+                   "adopt page-locked arenas the GPU-built layout was copied into (28 B/point with "
+                   "PointMeta, 16 without); the third figure also copies every raw packet into "
+                   "HDLFrame::packets as the reference does")
+    return out
+
+
+def run_hdl32(local, dev):
+    """HDL-32E (configs[0]'s sensor: per-return azimuth / time adjustment, k_decode<1>), device
+    resident, 262 144 packets per batch, no poses."""
+    import torch
+    from veloslam_b200 import capi, synth
+    n = 1 << 18
+    pk, t = synth.hdl32_packets(n)
+    ctx = capi.Context(local, max_batch_packets=n, max_poses=8, n_slots=2)
+    ctx.set_calibration(synth.calib_hdl32())
+    d_pk = torch.from_numpy(synth.as_bytes(pk)).to(dev)
+    d_t = torch.from_numpy(np.ascontiguousarray(t)).to(dev)
+
+    def sub():
+        return ctx.submit(d_pk, d_t, n=n, stride=1206, n_halo=0, mode=capi.MODE_STREAMING,
+                          flags=capi.FLAG_DEVICE_INPUT, t_base_us=int(t[0]))
+    for _ in range(3):
+        r = ctx.wait(sub(), frames=False)
+    torch.cuda.synchronize()
+    ext = torch.cuda.ExternalStream(ctx.stream(0), device=dev)
+    ext1 = torch.cuda.ExternalStream(ctx.stream(1), device=dev)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    ext1.wait_event(e0)
+    k, dec = 20, []
+    pend = sub()
+    for i in range(k):
+        nxt = sub() if i + 1 < k else None
+        r = ctx.wait(pend, frames=False)
+        dec.append(r.decode_ms)
+        pend = nxt
+    ej = torch.cuda.Event()
+    ej.record(ext1)
+    ext.wait_event(ej)
+    e1.record(ext)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / k
+    ctx.close()
+    return {"points_per_s_per_gpu": r.n_points / (ms * 1e-3), "ms_per_step": ms,
+            "k_decode_ms": float(np.mean(dec)), "packets": n, "points": r.n_points,
+            "note": "HDL-32E stream, 32-laser calibration (LUT branch), no poses; two batches in flight"}
 
 
 def run_online(local, calib, poses, b, t, t_base, rotations=300):

@@ -263,6 +263,53 @@ VS_API int vs_read_frame_information(vs_ctx* ctx, const uint8_t* pkts, int64_t s
                               int32_t* start_packet, int32_t* skips, int64_t* timestamp_us,
                               int32_t cap, int32_t* n_frames);
 
+/* ---- packet-range sharding of a long recording across GPUs ----------------------
+ * The caller being sharded is HDLManager::loadOffline (HDLManager.cxx:103-117) and the frame
+ * index it builds: rank g of `world` decodes packets [first, end) of the recording, preceded by
+ * n_halo packets (>= one rotation) that only rebuild the parser state (vs_submit's n_halo).  No
+ * data-path collective: each rank turns its frame table into rows of int64 (vs_frame_table_rows),
+ * the ranks all-gather the rows (NCCL / MPI / shared memory -- transport is the caller's), and
+ * vs_stitch_frame_tables() merges the rotation that straddles each shard boundary into one
+ * global frame.  Plain host code: no context, no device. */
+VS_API int vs_shard_range(int64_t n_packets, int32_t world, int32_t rank, int64_t halo,
+                          int64_t* first, int64_t* n_halo, int64_t* end);
+
+#define VS_FRAME_ROW_COLS 10
+/* One exchanged row: n_points, first_point (in the rank's own columns), start_packet (GLOBAL
+ * packet index, -1: continues the previous rank's open frame), start_block, timestamp_us, skips,
+ * closed, hdl64_order, meta_packet (global; -1 carried, -2 none), rank. */
+VS_API int vs_frame_table_rows(const vs_frame* frames, int32_t n_frames, int32_t rank,
+                               int64_t first_packet, int64_t n_halo, int64_t* rows);
+
+typedef struct vs_frame_segment {  /* the part of a global frame one rank holds */
+  int32_t rank;
+  int32_t reserved;
+  int64_t first_point;
+  int64_t n_points;
+} vs_frame_segment;
+
+typedef struct vs_global_frame {
+  int64_t n_points;
+  int64_t start_packet;        /* global packet index of the frame's first block (-1: stream start) */
+  int64_t timestamp_us;
+  int32_t start_block;
+  int32_t skips;
+  int32_t closed;
+  int32_t hdl64_order;
+  int32_t first_segment;       /* its segments: segs[first_segment .. first_segment + n_segments) */
+  int32_t n_segments;
+  int32_t timestamp_mismatch;  /* the two sides of a shard boundary disagree on the frame's meta */
+  int32_t reserved;
+} vs_global_frame;
+
+/* rows: the ranks' tables concatenated in rank order (rows_per_rank[g] rows of
+ * VS_FRAME_ROW_COLS each).  The open (last) frame of rank g and the first frame of rank g+1 are
+ * the same rotation: merged.  Fills at most frame_cap / seg_cap entries; the counts come back in
+ * *n_frames / *n_segs (VS_ERR_CAPACITY when an array was too short). */
+VS_API int vs_stitch_frame_tables(const int64_t* rows, const int32_t* rows_per_rank, int32_t world,
+                                  vs_global_frame* frames, int32_t frame_cap, vs_frame_segment* segs,
+                                  int32_t seg_cap, int32_t* n_frames, int32_t* n_segs);
+
 /* Page-locked host memory for packet rings / result buffers (cudaHostAlloc / cudaFreeHost),
  * so that callers above the ABI need no CUDA headers. */
 VS_API int vs_host_alloc(uint64_t bytes, void** out);

@@ -74,6 +74,7 @@ def lib():
         "vo_get_state": (None, [vp, C.POINTER(i32)]),
         "vo_process_packet": (None, [vp, u8p, C.c_uint32, i64]),
         "vo_process_packets": (None, [vp, u8p, i64, i64, C.POINTER(i64)]),
+        "vo_consume_packets": (None, [vp, u8p, i64, i64, C.POINTER(i64), C.POINTER(i64)]),
         "vo_split_frame": (None, [vp]),
         "vo_num_frames": (i32, [vp]),
         "vo_clear_frames": (None, [vp]),
@@ -216,6 +217,16 @@ class Oracle:
         self._L.vo_process_packets(self._h, _p(d, C.c_uint8), d.shape[0], d.shape[1],
                                    _p(t, C.c_int64))
 
+    def consume_packets(self, pkts_u8, t_us):
+        """processHDLPacket under the reference's consumer loop (HDLSource.cxx:209-225): closed
+        frames are taken and the list cleared after every packet.  Returns (frames, points)."""
+        d = np.ascontiguousarray(pkts_u8, dtype=np.uint8)
+        t = np.ascontiguousarray(t_us, dtype=np.int64)
+        out = np.zeros(2, dtype=np.int64)
+        self._L.vo_consume_packets(self._h, _p(d, C.c_uint8), d.shape[0], d.shape[1],
+                                   _p(t, C.c_int64), _p(out, C.c_int64))
+        return int(out[0]), int(out[1])
+
     def split_frame(self):
         self._L.vo_split_frame(self._h)
 
@@ -227,6 +238,17 @@ class Oracle:
 
     def open_frame_points(self):
         return int(self._L.vo_open_frame_points(self._h))
+
+    def frame_summary(self, f):
+        """(timestamp_us, skips, n_points, is_hdl64_order, per-row counts) of closed frame f
+        without copying its points (long streams are checked frame list by frame list)."""
+        info = FrameInfo()
+        if not self._L.vo_frame_get_info(self._h, f, C.byref(info)):
+            raise IndexError(f)
+        counts = np.zeros(max(info.n_lasers, 1), dtype=np.int32)
+        self._L.vo_frame_laser_counts(self._h, f, _p(counts, C.c_int32))
+        return (int(info.timestamp_us), int(info.skips), int(info.n_points),
+                bool(info.is_hdl64_order), counts[:info.n_lasers].copy())
 
     def frame(self, f):
         info = FrameInfo()

@@ -52,6 +52,7 @@ def lib():
         "vr_unload": (None, [vp]),
         "vr_get_state": (None, [vp, C.POINTER(i32)]),
         "vr_process_packets": (None, [vp, u8p, i64, i64, C.POINTER(i64), C.POINTER(i32)]),
+        "vr_consume_packets": (None, [vp, u8p, i64, i64, C.POINTER(i64), C.POINTER(i64)]),
         "vr_split_frame": (None, [vp]),
         "vr_num_frames": (i32, [vp]),
         "vr_clear_frames": (None, [vp]),
@@ -165,6 +166,17 @@ class RefParser:
         ln = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.int32)
         self._L.vr_process_packets(self._h, _p(d, C.c_uint8), d.shape[0], d.shape[1],
                                    _p(t, C.c_int64), None if ln is None else _p(ln, C.c_int32))
+
+    def consume_packets(self, pkts_u8, t_us):
+        """The reference's consumer loop (HDLSource.cxx:209-225): after every packet, frames that
+        closed are taken (getAllFrames().back()) and the parser's list is cleared.  Returns
+        (frames taken, points in them)."""
+        d = np.ascontiguousarray(pkts_u8, dtype=np.uint8)
+        t = np.ascontiguousarray(t_us, dtype=np.int64)
+        out = np.zeros(2, dtype=np.int64)
+        self._L.vr_consume_packets(self._h, _p(d, C.c_uint8), d.shape[0], d.shape[1],
+                                   _p(t, C.c_int64), _p(out, C.c_int64))
+        return int(out[0]), int(out[1])
 
     def split_frame(self):
         self._L.vr_split_frame(self._h)

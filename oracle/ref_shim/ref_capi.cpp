@@ -124,6 +124,27 @@ void vr_process_packets(vr_parser* h, const uint8_t* data, int64_t n, int64_t st
     h->parser.processHDLPacket(const_cast<unsigned char*>(data + i * stride),
                                lengths ? (unsigned)lengths[i] : 1206u, us_to_ptime(t_us[i]));
 }
+/* The reference's consumer loop, PacketConsumer::handleSensorData (HDLSource.cxx:209-225), for n
+ * packets: processHDLPacket, then -- as the reference does after EVERY packet --
+ *     if (getAllFrames().size()) { hdlMgr->addFrame(getAllFrames().back()); clearAllFrames(); }
+ * so frames leave the parser as they close instead of piling up.  addFrame stores the pointer
+ * (HDLManager.cxx:176-192); here the frame is counted and released, which is what happens to it
+ * once the manager's cache evicts it.  out[0] += frames taken, out[1] += their points. */
+void vr_consume_packets(vr_parser* h, const uint8_t* data, int64_t n, int64_t stride,
+                        const int64_t* t_us, int64_t* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    h->parser.processHDLPacket(const_cast<unsigned char*>(data + i * stride), 1206u, us_to_ptime(t_us[i]));
+    if (h->parser.getAllFrames().size()) {
+      boost::shared_ptr<HDLFrame> f = h->parser.getAllFrames().back();
+      int64_t pts = 0;
+      for (auto& c : f->points)
+        if (c) pts += (int64_t)c->points.size();
+      out[0] += 1;
+      out[1] += pts;
+      h->parser.clearAllFrames();
+    }
+  }
+}
 void vr_split_frame(vr_parser* h) { h->parser.in()->splitFrame(); }
 
 int32_t vr_num_frames(vr_parser* h) {

@@ -918,6 +918,19 @@ void vo_process_packets(vo_parser* h, const uint8_t* data, int64_t n, int64_t st
                         const int64_t* t_us) {
   for (int64_t i = 0; i < n; ++i) h->p.processHDLPacket(data + i * stride, 1206, t_us[i]);
 }
+/* The consumer loop of HDLSource.cxx:209-225 around the restated parser: frames leave as they
+ * close (the last one of the list is counted, the list is cleared), after every packet. */
+void vo_consume_packets(vo_parser* h, const uint8_t* data, int64_t n, int64_t stride,
+                        const int64_t* t_us, int64_t* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    h->p.processHDLPacket(data + i * stride, 1206, t_us[i]);
+    if (!h->p.frames.empty()) {
+      out[0] += 1;
+      for (const auto& row : h->p.frames.back()->points) out[1] += (int64_t)row.size();
+      h->p.frames.clear();
+    }
+  }
+}
 void vo_split_frame(vo_parser* h) { h->p.splitFrame(); }
 
 int32_t vo_num_frames(vo_parser* h) { return (int32_t)h->p.frames.size(); }

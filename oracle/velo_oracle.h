@@ -74,6 +74,8 @@ void vo_get_state(vo_parser*, int32_t out[4]);    /* lastAzimuth, firingSkip, fr
 
 /* Streaming decode */
 void vo_process_packet(vo_parser*, const uint8_t* data, uint32_t len, int64_t t_us);
+void vo_consume_packets(vo_parser*, const uint8_t* data, int64_t n, int64_t stride,
+                        const int64_t* t_us, int64_t* out_frames_points);
 void vo_process_packets(vo_parser*, const uint8_t* data, int64_t n, int64_t stride,
                         const int64_t* t_us);
 void vo_split_frame(vo_parser*);                  /* splitFrame(), used by getFrame's tail */

@@ -4,7 +4,7 @@
 //   facade_driver stream  <calib.xml> <packets.bin> <times.bin> <poses.bin|-> <out.bin> [batch] [pipelined 0|1]
 //       per packet: processHDLPacket(); getAllFrames(); clearAllFrames()   (HDLSource.cxx:209-225)
 //   facade_driver bench   <calib.xml> <packets.bin> <times.bin> <poses.bin|-> <batch> <passes>
-//                         <store_packets 0|1> <fetch_meta 0|1> <pipelined 0|1>
+//                         <store_packets 0|1> <fetch_meta 0|1> <pipelined 0|1> [cuda device]
 //       the same consumer loop over the packet array `passes` times (+1 untimed warm-up pass),
 //       prints one JSON line with points, frames and seconds
 //   facade_driver offline <calib.xml> <file.pcap> <poses.bin|-> <out.bin>
@@ -129,7 +129,7 @@ static int hostModes(int argc, char** argv) {
       cloud.points.resize(300);
       rep << "resized_zero " << cloud.points[299].x + cloud.points[299].intensity << "\n";
       // moving the vector moves the adoption
-      std::vector<PointMeta, vs::ArenaAllocator<PointMeta> > m1, m2;
+      PointMetaVector m1, m2;
       std::shared_ptr<vs::Arena> b = vs::Arena::heap(4096);
       PointMeta* pm = reinterpret_cast<PointMeta*>(b->data());
       for (int i = 0; i < 20; ++i) {
@@ -454,6 +454,7 @@ int main(int argc, char** argv) {
     parser.setStorePackets(std::atoi(argv[8]) != 0);
     parser.setFetchMeta(std::atoi(argv[9]) != 0);
     parser.setPipelined(std::atoi(argv[10]) != 0);
+    if (argc > 11) parser.setDevice(std::atoi(argv[11]));
     parser.setCorrectionsFile(argv[2]);
     parser.setTransformMgr(loadPoses(argv[5]));
     std::vector<char> pk = slurp(argv[3]);
@@ -490,6 +491,7 @@ int main(int argc, char** argv) {
     onePass(0, false);
     parser.flush();
     consume(false);
+    parser.resetPipelineStats();
     const auto t0 = std::chrono::steady_clock::now();
     for (int p = 1; p <= passes; ++p) onePass(p, true);
     parser.flush();
@@ -500,10 +502,10 @@ int main(int argc, char** argv) {
       return 1;
     }
     std::printf("{\"points\": %llu, \"frames\": %llu, \"seconds\": %.6f, \"packets\": %llu, \"passes\": %d, "
-                "\"batch\": %d, \"pinned_pool_bytes\": %llu, \"touch\": %.3f}\n",
+                "\"batch\": %d, \"pinned_pool_bytes\": %llu, \"touch\": %.3f, \"host\": %s}\n",
                 (unsigned long long)points, (unsigned long long)frames, sec,
                 (unsigned long long)(n * (size_t)passes), passes, batch,
-                (unsigned long long)vs::Arena::pooledBytes(), touch);
+                (unsigned long long)vs::Arena::pooledBytes(), touch, parser.pipelineStats().c_str());
     return 0;
   }
   if (mode == "udp") {

@@ -140,3 +140,43 @@ def test_flag_is_ignored_without_a_pose_bracket():
     ctx.close()
     for k in a:
         assert np.array_equal(a[k], r[k]), k
+
+
+@pytest.mark.parametrize("sensor", ["hdl64", "hdl32"])
+def test_per_point_deskew_against_an_independent_50_digit_evaluation(sensor):
+    """The pin of this extension that does not share code, formulation or precision with the
+    CUDA path: tests/mp_deskew.py evaluates the closed form with mpmath at 50 digits through the
+    SO(3) geodesic (axis-angle / Rodrigues), no quaternions.  400 points sampled over a stream
+    with a fast yaw (80 deg amplitude, 6 s period: up to 84 deg/s) -- which also bounds the error
+    of the kernel's per-packet linearisation of the slerp weights.  Bar: 1e-3 m (north_star)."""
+    import mp_deskew as M
+    if sensor == "hdl64":
+        pk, t = synth.hdl64_packets(1500)
+        calib = synth.calib_hdl64()
+        off = np.zeros((12, 32), dtype=np.uint16)
+        for j in range(12):
+            off[j] = np.round((j // 2) * 48.0 + np.arange(32) * 1.5).astype(np.uint16)
+    else:
+        pk, t = synth.hdl32_packets(2000, az0=30000.0)
+        calib = synth.calib_hdl32()
+        off = None
+    b = synth.as_bytes(pk)
+    poses = synth.ins_trajectory(200, yaw_amp_deg=80.0, yaw_period_s=6.0, speed=20.0)
+    tr, xyz, origin_time = _oracle_sensor_frame(b, t, calib)
+    point_off = off[tr["block"], tr["dsr"]] if off is not None else tr["tadj_us"]
+    ctx = P.make_ctx(calib, poses)
+    if off is not None:
+        ctx.set_firing_offsets(off)
+    got = _decode(ctx, b, t, capi.FLAG_DESKEW_PER_POINT, splits=(611,))
+    ctx.close()
+    g = np.stack([got["x"], got["y"], got["z"]], axis=1).astype(np.float64)
+    tl = M.Timeline(*poses)
+    rng = np.random.default_rng(2016)
+    idx = np.sort(rng.choice(len(xyz), 400, replace=False))
+    worst = 0.0
+    for i in idx:
+        P_ = int(tr["packet"][i])
+        want = M.deskew_point(tl, xyz[i], int(t[P_]), int(point_off[i]), int(origin_time[P_]))
+        worst = max(worst, float(np.abs(g[i] - np.array(want)).max()))
+    assert worst <= P.TOL_DESKEW, worst
+    assert worst < 1e-4, worst        # float32 outputs + float32 sensor-frame inputs of the check

@@ -82,3 +82,34 @@ def test_all_gather_of_frame_tables_over_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert out[0] == out[1] == [5000, 9000, 9000, 8000]
+
+
+def test_stitch_arrays_frame_spanning_three_ranks_and_mismatch_flag():
+    """The C-ABI stitch (vs_stitch_frame_tables): a shard with no wrap of its own is the middle
+    of a frame that spans three ranks; a boundary whose two sides disagree on the frame's
+    timestamp is flagged."""
+    r0 = fake_table([(100, 0, -1, -1, 10, 1), (50, 100, 20, 3, 77, 0)])
+    r1 = fake_table([(60, 0, -1, -1, 77, 0)])                        # no wrap in this shard
+    r2 = fake_table([(70, 0, -1, -1, 77, 1), (5, 70, 90, 0, 999, 0)])
+    r3 = fake_table([(9, 0, -1, -1, 1234, 0)])                       # disagrees with rank 2's 999
+    tabs = [sharding.local_table(t, g, 100 * g, 0) for g, t in enumerate((r0, r1, r2, r3))]
+    gf, segs = sharding.stitch_arrays(tabs)
+    assert gf["n_points"].tolist() == [100, 180, 14]
+    assert gf["n_segments"].tolist() == [1, 3, 2] and gf["first_segment"].tolist() == [0, 1, 4]
+    assert segs["rank"].tolist() == [0, 0, 1, 2, 2, 3]
+    assert gf["closed"].tolist() == [1, 1, 0]
+    assert gf["timestamp_mismatch"].tolist() == [0, 0, 1]
+    assert gf["start_packet"].tolist() == [-1, 20, 290]
+    # empty world / empty tables
+    gf, segs = sharding.stitch_arrays([np.zeros((0, 10), np.int64)])
+    assert len(gf) == 0 and len(segs) == 0
+
+
+def test_shard_range_edge_cases():
+    assert capi.shard_range(0, 4, 2, 512) == (0, 0, 0)
+    assert capi.shard_range(7, 8, 7, 512) == (6, 6, 7)
+    big = (1 << 62) + 12345
+    f, h, e = capi.shard_range(big, 8, 7, 512)
+    assert e == big and f == (big * 7) // 8 and h == 512         # no 64-bit overflow in n * rank
+    with pytest.raises(capi.VeloError):
+        capi.shard_range(100, 4, 4, 0)

@@ -25,7 +25,8 @@ EXPORTS = ["vs_version", "vs_create", "vs_destroy", "vs_last_error", "vs_set_cal
            "vs_wait", "vs_fetch_points", "vs_read_frame_information", "vs_host_alloc",
            "vs_host_free", "vs_stream", "vs_slot_stream", "vs_device_alloc", "vs_device_free",
            "vs_device_upload", "vs_solve_packet_times", "vs_poses_from_ins", "vs_set_firing_offsets",
-           "vs_layout_frames", "vs_fetch_layout", "vs_sync"]
+           "vs_layout_frames", "vs_fetch_layout", "vs_sync", "vs_shard_range", "vs_frame_table_rows",
+           "vs_stitch_frame_tables"]
 
 
 class LaserCorr(C.Structure):
@@ -92,6 +93,20 @@ class Layout(C.Structure):
                 ("xyzi_stride", C.c_int32), ("n_kernel_launches", C.c_int32),
                 ("reserved", C.c_int32)]
 
+
+class FrameSegment(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("reserved", C.c_int32), ("first_point", C.c_int64),
+                ("n_points", C.c_int64)]
+
+
+class GlobalFrame(C.Structure):
+    _fields_ = [("n_points", C.c_int64), ("start_packet", C.c_int64), ("timestamp_us", C.c_int64),
+                ("start_block", C.c_int32), ("skips", C.c_int32), ("closed", C.c_int32),
+                ("hdl64_order", C.c_int32), ("first_segment", C.c_int32), ("n_segments", C.c_int32),
+                ("timestamp_mismatch", C.c_int32), ("reserved", C.c_int32)]
+
+
+FRAME_ROW_COLS = 10
 
 # PointMeta as the reference lays it out (type_defs.h:168-176), 12 bytes
 POINT_META_DTYPE = np.dtype({"names": ["azimuth", "distance", "intensityFlag", "distanceFlag", "flags"],
@@ -168,8 +183,55 @@ def load_library():
     L.vs_fetch_layout.argtypes = [vp, u64, i64, i64, vp, vp]
     L.vs_sync.restype = C.c_int
     L.vs_sync.argtypes = [vp, u64, C.POINTER(C.c_float)]
+    L.vs_shard_range.restype = C.c_int
+    L.vs_shard_range.argtypes = [i64, i32, i32, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    L.vs_frame_table_rows.restype = C.c_int
+    L.vs_frame_table_rows.argtypes = [vp, i32, i32, i64, i64, vp]
+    L.vs_stitch_frame_tables.restype = C.c_int
+    L.vs_stitch_frame_tables.argtypes = [vp, vp, i32, vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
     _lib = L
     return L
+
+
+def shard_range(n_packets, world, rank, halo):
+    """vs_shard_range: (first, n_halo, end) of rank's packet range."""
+    f, h, e = C.c_int64(), C.c_int64(), C.c_int64()
+    rc = load_library().vs_shard_range(n_packets, world, rank, halo, C.byref(f), C.byref(h), C.byref(e))
+    if rc != 0:
+        raise VeloError(rc, "vs_shard_range: bad arguments")
+    return int(f.value), int(h.value), int(e.value)
+
+
+def frame_table_rows(frame_table, rank, first_packet, n_halo):
+    """vs_frame_table_rows over a vs_frame structured array: (n, 10) int64 exchange rows."""
+    tab = np.ascontiguousarray(frame_table)
+    assert tab.dtype.itemsize == C.sizeof(Frame)
+    rows = np.zeros((tab.shape[0], FRAME_ROW_COLS), dtype=np.int64)
+    rc = load_library().vs_frame_table_rows(_ptr(tab) if tab.shape[0] else None, tab.shape[0], rank,
+                                            first_packet, n_halo, _ptr(rows) if tab.shape[0] else None)
+    if rc != 0:
+        raise VeloError(rc, "vs_frame_table_rows: bad arguments")
+    return rows
+
+
+def stitch_frame_tables(tables):
+    """vs_stitch_frame_tables over per-rank (n_g, 10) int64 tables (rank order): structured
+    arrays (global frames, segments)."""
+    world = len(tables)
+    counts = np.array([t.shape[0] for t in tables], dtype=np.int32)
+    total = int(counts.sum())
+    rows = np.ascontiguousarray(np.concatenate([np.asarray(t, np.int64).reshape(-1, FRAME_ROW_COLS)
+                                                for t in tables], axis=0)) if total else \
+        np.zeros((0, FRAME_ROW_COLS), np.int64)
+    frames = np.zeros(max(total, 1), dtype=np.dtype(GlobalFrame))
+    segs = np.zeros(max(total, 1), dtype=np.dtype(FrameSegment))
+    nf, ns = C.c_int32(), C.c_int32()
+    rc = load_library().vs_stitch_frame_tables(_ptr(rows) if total else None, _ptr(counts), world,
+                                               _ptr(frames), frames.shape[0], _ptr(segs), segs.shape[0],
+                                               C.byref(nf), C.byref(ns))
+    if rc != 0:
+        raise VeloError(rc, "vs_stitch_frame_tables failed")
+    return frames[:nf.value], segs[:ns.value]
 
 
 def carry_init():

@@ -32,13 +32,6 @@ size_t roundUp(size_t bytes) {
 
 }  // namespace
 
-namespace detail {
-AdoptContext& adoptContext() {
-  static thread_local AdoptContext c = {nullptr, 0, false};
-  return c;
-}
-}  // namespace detail
-
 std::shared_ptr<Arena> Arena::acquire(size_t bytes) {
   const size_t want = roundUp(bytes ? bytes : 1);
   Pool& P = pool();

@@ -9,8 +9,9 @@
 // vector (or frame) that points into it and then goes back to a process-wide pool of pinned
 // blocks (page-locking memory costs far more than a frame takes to decode).
 //
-// The vectors stay ordinary std::vector's in every other respect: push_back / resize / assign
-// beyond the adopted capacity allocate from the heap as usual.
+// The vectors stay ordinary std::vector's in every other respect (vs::AdoptableVector derives
+// publicly from std::vector): push_back / resize / assign beyond the adopted capacity allocate
+// from the heap as usual.
 #ifndef VELOSLAM_B200_FRAMEARENA_H
 #define VELOSLAM_B200_FRAMEARENA_H
 
@@ -18,6 +19,7 @@
 #include <cstdint>
 #include <memory>
 #include <new>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -51,17 +53,8 @@ class Arena {
   bool pooled_;
 };
 
-namespace detail {
-// adoption in progress on this thread: the next allocate(n) of matching size returns `data`
-// instead of fresh memory, and default construction leaves the bytes as they are
-struct AdoptContext {
-  void* data;
-  size_t bytes;
-  bool active;
-};
-AdoptContext& adoptContext();
-}  // namespace detail
-
+// std::allocator in every respect but one: storage that lies inside the arena belongs to the
+// arena (deallocate leaves it alone), and the allocator keeps the arena alive.
 template <class T>
 class ArenaAllocator {
  public:
@@ -76,27 +69,10 @@ class ArenaAllocator {
   template <class U>
   ArenaAllocator(const ArenaAllocator<U>& o) : arena_(o.arena()) {}
 
-  T* allocate(size_t n) {
-    detail::AdoptContext& c = detail::adoptContext();
-    if (c.active && c.data && c.bytes == n * sizeof(T)) {
-      T* p = static_cast<T*>(c.data);
-      c.data = nullptr;  // handed out once
-      return p;
-    }
-    return static_cast<T*>(::operator new(n * sizeof(T)));
-  }
+  T* allocate(size_t n) { return static_cast<T*>(::operator new(n * sizeof(T))); }
   void deallocate(T* p, size_t) {
     if (arena_ && arena_->contains(p)) return;  // the arena owns it
     ::operator delete(p);
-  }
-  template <class U, class... Args>
-  void construct(U* p, Args&&... args) {
-    ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
-  }
-  template <class U>
-  void construct(U* p) {
-    if (detail::adoptContext().active) return;  // adopted records are already in place
-    ::new (static_cast<void*>(p)) U();
   }
   // a copy of an adopted vector is an ordinary heap vector
   ArenaAllocator select_on_container_copy_construction() const { return ArenaAllocator(); }
@@ -110,24 +86,40 @@ bool operator==(const ArenaAllocator<T>& a, const ArenaAllocator<U>& b) { return
 template <class T, class U>
 bool operator!=(const ArenaAllocator<T>& a, const ArenaAllocator<U>& b) { return !(a == b); }
 
-// Make `v` a vector of the n records at `data` (inside `arena`) without touching them.
+// A std::vector (publicly: every member, every conversion to the base) that can also be pointed
+// at n records which already sit in an arena, in O(1): what `points[row]->points` and
+// `*pointsMeta[row]` of a frame decoded on the GPU are.
 template <class T>
-void adopt(std::vector<T, ArenaAllocator<T> >& v, const std::shared_ptr<Arena>& arena, T* data, size_t n) {
-  typedef std::vector<T, ArenaAllocator<T> > Vec;
-  if (n == 0) {
-    Vec().swap(v);
-    return;
+class AdoptableVector : public std::vector<T, ArenaAllocator<T> > {
+  typedef std::vector<T, ArenaAllocator<T> > Base;
+
+ public:
+  using Base::Base;
+  AdoptableVector() {}
+
+  void adoptStorage(const std::shared_ptr<Arena>& arena, T* data, size_t n) {
+    {
+      Base fresh((ArenaAllocator<T>(arena)));  // empty, allocator bound to the arena
+      Base::swap(fresh);                       // old contents (and allocator) die with `fresh`
+    }
+    if (n == 0) return;
+#if defined(__GLIBCXX__)
+    // libstdc++: begin / end / end-of-storage live in the protected _M_impl of the base
+    static_assert(std::is_trivially_destructible<T>::value && std::is_trivially_copyable<T>::value,
+                  "adopted records are plain data");
+    this->_M_impl._M_start = data;
+    this->_M_impl._M_finish = data + n;
+    this->_M_impl._M_end_of_storage = data + n;
+#else
+    Base::assign(data, data + n);  // other standard libraries: one copy per row
+#endif
   }
-  detail::AdoptContext& c = detail::adoptContext();
-  c.data = data;
-  c.bytes = n * sizeof(T);
-  c.active = true;
-  {
-    Vec tmp(n, ArenaAllocator<T>(arena));  // allocate(n) -> data; default construction is a no-op
-    c.active = false;
-    c.data = nullptr;
-    v.swap(tmp);
-  }
+};
+
+// Make `v` the n records at `data` (inside `arena`) without touching them.
+template <class T>
+void adopt(AdoptableVector<T>& v, const std::shared_ptr<Arena>& arena, T* data, size_t n) {
+  v.adoptStorage(arena, data, n);
 }
 
 }  // namespace vs

@@ -3,6 +3,7 @@
 #include "HDLParser.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -306,7 +307,9 @@ class HDLParser::vsInternal {
   // ---- stage 1 -> 2: frame table, HDLFrame layout on the device, device -> host copies ----------
   bool advance(Batch& b) {
     vs_result r;
+    const double tw = now();
     int rc = vs_wait(ctx, b.ticket, &r);
+    secWait += now() - tw;
     if (rc != VS_OK) {
       failBatches(vs_last_error(ctx));
       return false;
@@ -378,7 +381,9 @@ class HDLParser::vsInternal {
 
   // ---- stage 2 -> frames: wait for the copies, adopt the rows ------------------------------------
   bool collect(Batch& b, std::deque<std::shared_ptr<HDLFrame> >* closedOut) {
+    const double ts = now();
     const int rc = vs_sync(ctx, b.ticket, nullptr);
+    secSync += now() - ts;
     if (rc != VS_OK) {
       failBatches(vs_last_error(ctx));
       return false;
@@ -454,13 +459,27 @@ class HDLParser::vsInternal {
   // whole ring-fill to complete); hand the ring just filled to the GPU.  Host fill, host ->
   // device copy + kernels and device -> host copy of three consecutive batches overlap.
   bool pump() {
+    const double t0 = now();
     if (!inflight.empty() && inflight.back().stage == 1 && !advance(inflight.back())) return false;
+    const double t1 = now();
     while (inflight.size() > 1) {
       if (!collect(inflight.front(), &frames)) return false;
       inflight.pop_front();
     }
-    return submitBatch(-1);
+    const double t2 = now();
+    const bool ok = submitBatch(-1);
+    const double t3 = now();
+    secAdvance += t1 - t0;
+    secCollect += t2 - t1;
+    secSubmit += t3 - t2;
+    ++nPumps;
+    return ok;
   }
+  static double now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
+  double secAdvance = 0, secCollect = 0, secSubmit = 0, secWait = 0, secSync = 0;
+  long nPumps = 0;
 
   // ---- recording resident in HBM (loadRecording) ----------------------------------------------
   bool loadRecording(const std::string& file) {
@@ -686,11 +705,14 @@ void HDLParser::processHDLPacket(unsigned char* data, unsigned int bytesReceived
   std::memcpy(in->ringPkts[in->fill] + (size_t)in->pending * VS_PACKET_BYTES, data, VS_PACKET_BYTES);
   in->ringTimes[in->fill][in->pending] = t.us;
   ++in->pending;
-  // an azimuth decrease anywhere in the packet is the only thing that can close a frame
-  for (int j = 0; j < HDL_FIRING_PER_PKT; ++j) {
-    const int az = data[100 * j + 2] | (data[100 * j + 3] << 8);
-    if (az < in->hostLastAz) in->pendingWrap = true;
-    in->hostLastAz = az;
+  // an azimuth decrease anywhere in the packet is the only thing that can close a frame (a
+  // pipelined parser never flushes on it: it hands frames back batch by batch)
+  if (!in->pipelined) {
+    for (int j = 0; j < HDL_FIRING_PER_PKT; ++j) {
+      const int az = data[100 * j + 2] | (data[100 * j + 3] << 8);
+      if (az < in->hostLastAz) in->pendingWrap = true;
+      in->hostLastAz = az;
+    }
   }
   if (in->pending >= in->batchPackets) {
     if (in->pipelined)
@@ -929,3 +951,17 @@ void HDLParser::setFetchMeta(bool on) {
 }
 void HDLParser::setStorePackets(bool s) { this->internal_->storePackets = s; }
 const std::string& HDLParser::lastError() const { return this->internal_->error; }
+void HDLParser::resetPipelineStats() {
+  vsInternal* in = this->internal_;
+  in->secAdvance = in->secCollect = in->secSubmit = in->secWait = in->secSync = 0;
+  in->nPumps = 0;
+}
+std::string HDLParser::pipelineStats() const {
+  const vsInternal* in = this->internal_;
+  char buf[256];
+  std::snprintf(buf, sizeof(buf),
+                "{\"pumps\": %ld, \"advance_s\": %.4f, \"collect_s\": %.4f, \"submit_s\": %.4f, "
+                "\"in_vs_wait_s\": %.4f, \"in_vs_sync_s\": %.4f}",
+                in->nPumps, in->secAdvance, in->secCollect, in->secSubmit, in->secWait, in->secSync);
+  return buf;
+}

@@ -109,6 +109,9 @@ class HDLParser {
   void unloadRecording();
   bool hasRecording(const std::string& pcapfile) const;
   const std::string& lastError() const;    // empty when the last GPU call succeeded
+  // where the host time of the pipelined mode went (seconds since construction), as JSON
+  std::string pipelineStats() const;
+  void resetPipelineStats();
 
  protected:
   void unloadData();

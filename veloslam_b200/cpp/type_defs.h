@@ -98,7 +98,7 @@ struct PointMeta {
 };
 static_assert(sizeof(PointMeta) == 12, "PointMeta is what the GPU writes (vs_layout_frames)");
 // HDLFrame::pointsMeta[row]: a std::vector whose storage may be a slice of the frame's arena
-typedef std::vector<PointMeta, vs::ArenaAllocator<PointMeta> > PointMetaVector;
+typedef vs::AdoptableVector<PointMeta> PointMetaVector;
 
 namespace pcl {
 struct PointXYZI {
@@ -110,7 +110,7 @@ template <class PointT> struct PointCloud {
   typedef std::shared_ptr<PointCloud<PointT> > Ptr;
   // PCL's own type here is std::vector<PointT, Eigen::aligned_allocator<PointT>>: also a vector
   // with a non-default allocator.  This one can adopt a slice of the frame's page-locked arena.
-  std::vector<PointT, vs::ArenaAllocator<PointT> > points;
+  vs::AdoptableVector<PointT> points;
   uint32_t width = 0, height = 0;
   size_t size() const { return points.size(); }
 };

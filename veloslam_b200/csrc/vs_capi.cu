@@ -126,6 +126,7 @@ struct vs_ctx {
   double* d_pose_trv = nullptr;
   std::vector<int64_t> pose_t;
   std::vector<double> pose_trv;
+  cudaStream_t cfg_stream = nullptr;  // small table uploads (calibration, filters, poses)
   KernelCache dec_cache[3][2][2];  // [ADJ][DSK][FUSED]
   KernelCache scan_cache[3][2];    // [ADJ][CROP]
   bool two_pass = true;  // false (VELOSLAM_SINGLE_PASS=1): k_pose_pre + k_decode<.., FUSED> where it applies
@@ -237,7 +238,7 @@ void free_slot(Slot& s) {
 // Copy a small host table (pageable memory) to the device so that it is complete and visible to
 // every slot stream when the call returns.  cudaMemcpy from pageable memory may return once the
 // data is staged, and the slot streams are non-blocking (not ordered against the legacy stream),
-// so the copy goes through slot 0's stream and is waited for.  Refused while a batch that may
+// so the copy goes through the context's configuration stream and is waited for.  Refused while a batch that may
 // read the table is still running.
 int upload_table(vs_ctx* ctx, void* dst, const void* src, size_t bytes, bool layout_reads_it,
                  const char* who) {
@@ -246,7 +247,9 @@ int upload_table(vs_ctx* ctx, void* dst, const void* src, size_t bytes, bool lay
     if ((s.busy && !s.done) || (layout_reads_it && s.lay_inflight))
       return fail(ctx, VS_ERR_STATE, std::string(who) + ": a batch is still in flight (vs_wait / vs_sync it first)");
   }
-  cudaStream_t st = ctx->slots[0].stream;
+  // a stream of its own: waiting on a slot's stream would also wait for that slot's
+  // device -> host copies of an earlier batch and stall a pipelined caller
+  cudaStream_t st = ctx->cfg_stream;
   VS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
   VS_CUDA(cudaStreamSynchronize(st));
   return VS_OK;
@@ -909,6 +912,7 @@ int vs_create(int device, int64_t max_batch_packets, int64_t max_poses, int n_sl
       int rc = alloc_slot(ctx, ctx->slots[i]);
       if (rc != VS_OK) return rc;
     }
+    VS_CUDA(cudaStreamCreateWithFlags(&ctx->cfg_stream, cudaStreamNonBlocking));
     return VS_OK;
   };
   std::memset(&ctx->h_cfg, 0, sizeof(ctx->h_cfg));
@@ -933,6 +937,7 @@ void vs_destroy(vs_ctx* ctx) {
       cudaStreamSynchronize(ctx->slots[i].stream);
       free_slot(ctx->slots[i]);
     }
+  if (ctx->cfg_stream) cudaStreamDestroy(ctx->cfg_stream);
   cudaFree(ctx->d_cfg);
   cudaFree(ctx->d_lut_sin);
   cudaFree(ctx->d_lut_cos);
@@ -1438,6 +1443,94 @@ int vs_read_frame_information(vs_ctx* ctx, const uint8_t* pkts, int64_t stride,
   return VS_OK;
 }
 
+// ---- packet-range sharding (host arithmetic only) ----------------------------------------------
+int vs_shard_range(int64_t n_packets, int32_t world, int32_t rank, int64_t halo, int64_t* first,
+                   int64_t* n_halo, int64_t* end) {
+  if (n_packets < 0 || world < 1 || rank < 0 || rank >= world || halo < 0 || !first || !n_halo || !end)
+    return VS_ERR_INVALID_ARG;
+  // 128-bit products: n_packets * rank does not overflow for any int64 n_packets
+  const int64_t f = (int64_t)(((__int128)n_packets * rank) / world);
+  const int64_t e = (int64_t)(((__int128)n_packets * (rank + 1)) / world);
+  *first = f;
+  *end = e;
+  *n_halo = std::min(halo, f);
+  return VS_OK;
+}
+
+int vs_frame_table_rows(const vs_frame* frames, int32_t n_frames, int32_t rank, int64_t first_packet,
+                        int64_t n_halo, int64_t* rows) {
+  if (n_frames < 0 || (n_frames > 0 && (!frames || !rows))) return VS_ERR_INVALID_ARG;
+  const int64_t base = first_packet - n_halo;  // global index of packet 0 of the submitted array
+  for (int32_t i = 0; i < n_frames; ++i) {
+    const vs_frame& f = frames[i];
+    int64_t* r = rows + (size_t)i * VS_FRAME_ROW_COLS;
+    r[0] = f.n_points;
+    r[1] = f.first_point;
+    r[2] = f.start_packet >= 0 ? f.start_packet + base : -1;
+    r[3] = f.start_block;
+    r[4] = f.timestamp_us;
+    r[5] = f.skips;
+    r[6] = f.closed;
+    r[7] = f.hdl64_order;
+    r[8] = f.meta_packet >= 0 ? f.meta_packet + base : f.meta_packet;
+    r[9] = rank;
+  }
+  return VS_OK;
+}
+
+int vs_stitch_frame_tables(const int64_t* rows, const int32_t* rows_per_rank, int32_t world,
+                           vs_global_frame* frames, int32_t frame_cap, vs_frame_segment* segs,
+                           int32_t seg_cap, int32_t* n_frames, int32_t* n_segs) {
+  if (!rows_per_rank || world < 1 || !n_frames || !n_segs || frame_cap < 0 || seg_cap < 0)
+    return VS_ERR_INVALID_ARG;
+  int64_t nf = 0, ns = 0;
+  const int64_t* r = rows;
+  for (int32_t g = 0; g < world; ++g) {
+    for (int32_t i = 0; i < rows_per_rank[g]; ++i, r += VS_FRAME_ROW_COLS) {
+      if (!rows) return VS_ERR_INVALID_ARG;
+      if (ns < seg_cap) {
+        vs_frame_segment& sg = segs[ns];
+        sg.rank = (int32_t)r[9];
+        sg.reserved = 0;
+        sg.first_point = r[1];
+        sg.n_points = r[0];
+      }
+      const bool cont = i == 0 && g > 0 && nf > 0;  // continues the previous rank's open frame
+      if (cont) {
+        if (nf - 1 < frame_cap) {
+          vs_global_frame& f = frames[nf - 1];
+          f.n_segments += 1;
+          f.n_points += r[0];
+          f.closed = (int32_t)r[6];
+          f.hdl64_order = (int32_t)r[7];
+          // both sides rebuilt the frame's meta (the later one from its halo): they must agree
+          if (r[4] != f.timestamp_us) f.timestamp_mismatch = 1;
+        }
+      } else {
+        if (nf < frame_cap) {
+          vs_global_frame& f = frames[nf];
+          f.n_points = r[0];
+          f.start_packet = r[2];
+          f.timestamp_us = r[4];
+          f.start_block = (int32_t)r[3];
+          f.skips = (int32_t)r[5];
+          f.closed = (int32_t)r[6];
+          f.hdl64_order = (int32_t)r[7];
+          f.first_segment = (int32_t)ns;
+          f.n_segments = 1;
+          f.timestamp_mismatch = 0;
+          f.reserved = 0;
+        }
+        ++nf;
+      }
+      ++ns;
+    }
+  }
+  *n_frames = (int32_t)nf;
+  *n_segs = (int32_t)ns;
+  return (nf > frame_cap || ns > seg_cap) ? VS_ERR_CAPACITY : VS_OK;
+}
+
 int vs_host_alloc(uint64_t bytes, void** out) {
   if (!out) return VS_ERR_INVALID_ARG;
   *out = nullptr;
@@ -1465,7 +1558,7 @@ int vs_device_upload(vs_ctx* ctx, void* dst_dev, const void* src_host, uint64_t 
   if (!ctx || !dst_dev || !src_host) return fail(ctx, VS_ERR_INVALID_ARG, "vs_device_upload: bad arguments");
   cudaSetDevice(ctx->device);
   // complete (not merely staged) before any slot stream reads it
-  cudaStream_t st = ctx->slots[0].stream;
+  cudaStream_t st = ctx->cfg_stream;
   VS_CUDA(cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, st));
   VS_CUDA(cudaStreamSynchronize(st));
   return VS_OK;

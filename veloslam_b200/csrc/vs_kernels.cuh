@@ -833,7 +833,9 @@ __device__ __forceinline__ void pose_at(const long long* __restrict__ pt, const 
 #pragma unroll
   for (int k = 0; k < 3; ++k) T[k] = __ldg(&a[k]) + (__ldg(&b[k]) - __ldg(&a[k])) * r;
 }
-constexpr int kDeskewRow = 18;  // doubles per packet: qa[4] qb[4] Ta[3] dT[3] r0 dr theta 1/sin(theta)
+// doubles per packet: Q0[4] dQ[4] T0[3] dT[3] -- the blended quaternion / translation at the packet
+// time and their derivatives per microsecond of firing offset (see k_pose)
+constexpr int kDeskewRow = 14;
 
 __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
   __shared__ unsigned long long s_w[kPoseThreads / 32];
@@ -1004,15 +1006,43 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
     double Ta[3], dT[3];
     quat_rotate(qoc, da, Ta);
     quat_rotate(qoc, db, dT);
+    // Slerp weights at the packet time and their slope per microsecond.  Inside one packet the
+    // firing offsets span < 1 ms, over which the weights are linear to (omega * 1 ms)^2 / 2 (1e-7
+    // at 30 deg/s: < 2e-5 m at the sensor's maximum range, far inside the 1e-3 m bar), so
+    // k_decode evaluates q(t_packet + f) = Q0 + f dQ with one fused multiply-add per component
+    // instead of two sines per point.
+    const double r0 = (double)(t - ta) / (double)(tb - ta);
+    const double dr = 1.0 / (double)(tb - ta);
+    double w0, w1, dw0, dw1;
+    if (theta < 1e-8) {
+      w0 = 1.0 - r0;
+      w1 = r0;
+      dw0 = -dr;
+      dw1 = dr;
+    } else {
+      const double inv = 1.0 / sin(theta);
+      double s0, c0, s1, c1;
+      sincos((1.0 - r0) * theta, &s0, &c0);
+      sincos(r0 * theta, &s1, &c1);
+      w0 = s0 * inv;
+      w1 = s1 * inv;
+      dw0 = -theta * dr * c0 * inv;
+      dw1 = theta * dr * c1 * inv;
+    }
     double* o = p.pose_mat + (long long)P * kDeskewRow;
-    o[0] = qa.w; o[1] = qa.x; o[2] = qa.y; o[3] = qa.z;
-    o[4] = qb.w; o[5] = qb.x; o[6] = qb.y; o[7] = qb.z;
-    o[8] = Ta[0]; o[9] = Ta[1]; o[10] = Ta[2];
-    o[11] = dT[0]; o[12] = dT[1]; o[13] = dT[2];
-    o[14] = (double)(t - ta) / (double)(tb - ta);
-    o[15] = 1.0 / (double)(tb - ta);
-    o[16] = theta;
-    o[17] = theta < 1e-8 ? 0.0 : 1.0 / sin(theta);
+    o[0] = w0 * qa.w + w1 * qb.w;
+    o[1] = w0 * qa.x + w1 * qb.x;
+    o[2] = w0 * qa.y + w1 * qb.y;
+    o[3] = w0 * qa.z + w1 * qb.z;
+    o[4] = dw0 * qa.w + dw1 * qb.w;
+    o[5] = dw0 * qa.x + dw1 * qb.x;
+    o[6] = dw0 * qa.y + dw1 * qb.y;
+    o[7] = dw0 * qa.z + dw1 * qb.z;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      o[8 + k] = Ta[k] + r0 * dT[k];
+      o[11 + k] = dT[k] * dr;
+    }
     if (P == p.n - 1) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) p.hdr->carry_origin_T[k] = To[k];
@@ -1405,22 +1435,11 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kDecThreads, VS_DEC_CT
         // pose at t_packet + fire inside the packet's bracket: slerp + lerp, already re-based to
         // the frame origin by k_pose (semantics: oracle/deskew_port.py)
         // (an extension with no reference arithmetic to reproduce: fused multiply-adds throughout)
-        const double rr = __fma_rn((double)fire, M[15], M[14]);
-        double w0, w1;
-        if (M[17] == 0.0) {
-          w0 = 1.0 - rr;
-          w1 = rr;
-        } else if (M[16] < 0.1 && fabs(rr) < 2.0) {
-          w0 = sin_small((1.0 - rr) * M[16]) * M[17];
-          w1 = sin_small(rr * M[16]) * M[17];
-        } else {
-          w0 = sin((1.0 - rr) * M[16]) * M[17];
-          w1 = sin(rr * M[16]) * M[17];
-        }
-        const double qw = __fma_rn(w1, M[4], w0 * M[0]);
-        const double qx = __fma_rn(w1, M[5], w0 * M[1]);
-        const double qy = __fma_rn(w1, M[6], w0 * M[2]);
-        const double qz = __fma_rn(w1, M[7], w0 * M[3]);
+        const double f = (double)fire;
+        const double qw = __fma_rn(f, M[4], M[0]);
+        const double qx = __fma_rn(f, M[5], M[1]);
+        const double qy = __fma_rn(f, M[6], M[2]);
+        const double qz = __fma_rn(f, M[7], M[3]);
         // p + w t + v x t with t = 2 v x p
         double tx = __fma_rn(qy, pz, -(qz * py));
         double ty = __fma_rn(qz, px, -(qx * pz));
@@ -1431,9 +1450,9 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kDecThreads, VS_DEC_CT
         const double ox = __fma_rn(qy, tz, __fma_rn(-qz, ty, __fma_rn(qw, tx, px)));
         const double oy = __fma_rn(qz, tx, __fma_rn(-qx, tz, __fma_rn(qw, ty, py)));
         const double oz = __fma_rn(qx, ty, __fma_rn(-qy, tx, __fma_rn(qw, tz, pz)));
-        px = ox + __fma_rn(M[11], rr, M[8]);
-        py = oy + __fma_rn(M[12], rr, M[9]);
-        pz = oz + __fma_rn(M[13], rr, M[10]);
+        px = ox + __fma_rn(M[11], f, M[8]);
+        py = oy + __fma_rn(M[12], f, M[9]);
+        pz = oz + __fma_rn(M[13], f, M[10]);
       } else {
         rigid(M, px, py, pz);
       }

@@ -22,34 +22,17 @@ NCOL = len(COLS)
 
 
 def shard_ranges(n_packets, world, halo):
-    """[(first, n_halo, end)] per rank: decode [first, end), state rebuilt from [first-n_halo, first)."""
-    out = []
-    for g in range(world):
-        first = (n_packets * g) // world
-        end = (n_packets * (g + 1)) // world
-        h = min(halo, first)
-        out.append((first, h, end))
-    return out
+    """[(first, n_halo, end)] per rank: decode [first, end), state rebuilt from [first-n_halo, first).
+    (vs_shard_range of the C ABI.)"""
+    from . import capi
+    return [capi.shard_range(n_packets, world, g, halo) for g in range(world)]
 
 
 def local_table(frame_table, rank, first_packet, n_halo):
-    """vs_frame rows of one shard -> (n_frames, NCOL) int64 with GLOBAL packet indices."""
-    n = frame_table.shape[0]
-    t = np.zeros((n, NCOL), dtype=np.int64)
-    sp = frame_table["start_packet"].astype(np.int64)
-    mp = frame_table["meta_packet"].astype(np.int64)
-    base = first_packet - n_halo               # index 0 of the submitted array
-    t[:, 0] = frame_table["n_points"]
-    t[:, 1] = frame_table["first_point"]
-    t[:, 2] = np.where(sp >= 0, sp + base, -1)
-    t[:, 3] = frame_table["start_block"]
-    t[:, 4] = frame_table["timestamp_us"]
-    t[:, 5] = frame_table["skips"]
-    t[:, 6] = frame_table["closed"]
-    t[:, 7] = frame_table["hdl64_order"]
-    t[:, 8] = np.where(mp >= 0, mp + base, mp)
-    t[:, 9] = rank
-    return t
+    """vs_frame rows of one shard -> (n_frames, NCOL) int64 with GLOBAL packet indices
+    (vs_frame_table_rows of the C ABI)."""
+    from . import capi
+    return capi.frame_table_rows(frame_table, rank, first_packet, n_halo)
 
 
 def all_gather_tables(table, group=None):
@@ -73,33 +56,32 @@ def all_gather_tables(table, group=None):
     return [b[:c].cpu().numpy() for b, c in zip(bufs, counts)]
 
 
+def stitch_arrays(tables):
+    """Global frame index from per-rank tables (rank order) as structured arrays
+    (vs_global_frame rows, vs_frame_segment rows): vs_stitch_frame_tables of the C ABI."""
+    from . import capi
+    return capi.stitch_frame_tables(tables)
+
+
 def stitch(tables):
-    """Global frame index from per-rank tables (rank order).
+    """The same index as a list of dicts (tests, small tables): built from stitch_arrays().
 
     The open (last) frame of rank g and the first frame of rank g+1 are the same rotation;
     they are merged into one global frame whose points live in two ranks.  Returns a list of
     dicts: {"segments": [(rank, first_point, n_points)], "n_points", "start_packet",
     "start_block", "timestamp_us", "skips", "closed", "hdl64_order"}.
     """
+    gf, segs = stitch_arrays(tables)
     frames = []
-    for g, t in enumerate(tables):
-        for i in range(t.shape[0]):
-            row = t[i]
-            seg = (int(row[9]), int(row[1]), int(row[0]))
-            cont = (i == 0 and g > 0 and frames)
-            if cont:
-                f = frames[-1]
-                f["segments"].append(seg)
-                f["n_points"] += int(row[0])
-                f["closed"] = bool(row[6])
-                f["hdl64_order"] = bool(row[7])
-                # meta comes from wherever the frame started; both sides agree (the shard
-                # rebuilt it from its halo) -- keep the owner's and check the timestamp
-                if int(row[4]) != f["timestamp_us"]:
-                    f["timestamp_mismatch"] = (f["timestamp_us"], int(row[4]))
-            else:
-                frames.append({"segments": [seg], "n_points": int(row[0]),
-                               "start_packet": int(row[2]), "start_block": int(row[3]),
-                               "timestamp_us": int(row[4]), "skips": int(row[5]),
-                               "closed": bool(row[6]), "hdl64_order": bool(row[7])})
+    for f in gf:
+        a, n = int(f["first_segment"]), int(f["n_segments"])
+        d = {"segments": [(int(sg["rank"]), int(sg["first_point"]), int(sg["n_points"]))
+                          for sg in segs[a:a + n]],
+             "n_points": int(f["n_points"]), "start_packet": int(f["start_packet"]),
+             "start_block": int(f["start_block"]), "timestamp_us": int(f["timestamp_us"]),
+             "skips": int(f["skips"]), "closed": bool(f["closed"]),
+             "hdl64_order": bool(f["hdl64_order"])}
+        if f["timestamp_mismatch"]:
+            d["timestamp_mismatch"] = True
+        frames.append(d)
     return frames
