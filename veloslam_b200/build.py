@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libveloslam_b200.so")
 SOURCES = [os.path.join(CSRC, "vs_capi.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("vs_kernels.cuh", "vs_single_pass.cuh", "vs_device.cuh")] + \
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("vs_kernels.cuh", "vs_single_pass.cuh", "vs_device.cuh", "vs_layout.cuh")] + \
     [os.path.join(os.path.dirname(HERE), "include", "veloslam_b200.h")]
 
 NVCC_FLAGS = [
@@ -34,15 +34,18 @@ def find_nvcc():
     raise RuntimeError("nvcc not found (set NVCC=...)")
 
 
-def build_library(force=False, verbose=False):
-    """Compile libveloslam_b200.so if missing or older than its sources."""
-    if (not force and os.path.exists(LIB)
+def build_library(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile libveloslam_b200.so if missing or older than its sources.  extra_flags / out:
+    A/B builds of kernel geometry variants (-DVS_DEC_STAGES=..., see vs_kernels.cuh) into
+    another file."""
+    out = out or LIB
+    if (not force and out == LIB and os.path.exists(LIB)
             and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in DEPS)):
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + SOURCES
+    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", out] + SOURCES
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 FACADE_DIR = os.path.join(HERE, "cpp")

@@ -127,6 +127,7 @@ struct vs_ctx {
   std::vector<int64_t> pose_t;
   std::vector<double> pose_trv;
   cudaStream_t cfg_stream = nullptr;  // small table uploads (calibration, filters, poses)
+  bool layout_attr_set = false;
   KernelCache dec_cache[3][2][2];  // [ADJ][DSK][FUSED]
   KernelCache scan_cache[3][2];    // [ADJ][CROP]
   bool two_pass = true;  // false (VELOSLAM_SINGLE_PASS=1): k_pose_pre + k_decode<.., FUSED> where it applies
@@ -1353,7 +1354,12 @@ int vs_layout_frames(vs_ctx* ctx, uint64_t ticket, const uint32_t* carried_count
     lp.xyzi = s.d_lay_xyzi;
     lp.xyzi_stride = xyzi_stride;
     lp.meta = with_meta ? s.d_lay_meta : nullptr;
-    k_layout<<<(unsigned)((n_chunks + kLayWarps - 1) / kLayWarps), kLayThreads, 0, s.stream>>>(lp);
+    if (!ctx->layout_attr_set) {
+      VS_CUDA(cudaFuncSetAttribute(k_layout, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(LayShared)));
+      ctx->layout_attr_set = true;
+    }
+    k_layout<<<(unsigned)n_chunks, kLayThreads, sizeof(LayShared), s.stream>>>(lp);
     VS_CUDA(cudaGetLastError());
     launches = 2;
   }

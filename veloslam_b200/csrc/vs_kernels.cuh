@@ -634,7 +634,12 @@ struct PoseParams {
   BatchHeader* hdr;
 };
 
-constexpr int kPoseThreads = 256;
+// -DVS_POSE_THREADS=128: at 76 registers a 128-thread k_pose CTA fits into what two resident
+// k_decode CTAs leave of an SM's register file (co-residency experiment, see OutCols)
+#ifndef VS_POSE_THREADS
+#define VS_POSE_THREADS 256
+#endif
+constexpr int kPoseThreads = VS_POSE_THREADS;
 
 __device__ __forceinline__ double to_radians(double x) {
   return __ddiv_rn(__dmul_rn(x, 3.14159265358979323846), 180.0);
@@ -866,11 +871,12 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
       pw = WrapTraits::combine(pw, ((unsigned long long)__ldg(&p.grp_wsum[q]) << 32) | __ldg(&p.grp_wmax[q]));
       pc += __ldg(&p.grp_cnt[q]);
     }
-    static_assert(kGroupTiles <= kPoseThreads, "one thread per tile of a group");
-    const int f = g * kGroupTiles + tid;
-    if (tid < kGroupTiles && f < my_tile) {
-      pw = WrapTraits::combine(pw, __ldg(&p.agg_wrap[f]));
-      pc += __ldg(&p.agg_cnt[f]);
+    for (int q = tid; q < kGroupTiles; q += kPoseThreads) {
+      const int f = g * kGroupTiles + q;
+      if (f < my_tile) {
+        pw = WrapTraits::combine(pw, __ldg(&p.agg_wrap[f]));
+        pc += __ldg(&p.agg_cnt[f]);
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -1182,12 +1188,27 @@ constexpr int kDOff = kDSeg + kDecTile * 16;        // u64 point offset per pack
 constexpr int kDPose = kDOff + (kDecTile + 2) * 8;  // pose rows: 12 (18: per-point deskew) doubles per packet
 static_assert(kDPose % 16 == 0, "stage sections must be 16-byte aligned");
 static_assert(kDecRecs <= 32, "one lane per block record");
-// output staging of one pair: its packets' points + 16 elements of phase, column after column
+// output staging of one pair: its packets' points + 16 elements of phase, column after column.
+// HAS_T == false (build with -DVS_DEC_T_DIRECT=1; measured, NOT the default): the t_us column is
+// not staged -- without a per-return firing offset (HDL-64 data, no per-point deskew) it is the
+// packet's time for every point of the packet and is written straight from registers, which
+// takes 12.5 KB of shared memory off the CTA.  With -DVS_DEC_STAGES=2 on top the CTA drops to
+// 83 KB and a k_scan CTA of the next batch becomes co-resident with two decode CTAs.  Round-2
+// A/B on one B200: the register stores cost the latency-bound kernel more than
+// the staging did (1.85 -> 1.96 ms), and the co-resident k_scan takes from k_decode almost what
+// it hides (both live on the shared-memory pipe and the issue slots): 2.07 ms per step as is,
+// 2.20 with direct t, 2.12 with direct t + co-residency.
+#ifndef VS_DEC_T_DIRECT
+#define VS_DEC_T_DIRECT 0
+#endif
 constexpr int kOutCap = kDecPktsPerWarp * 384 + 16;
-constexpr int kOX = 0, kOY = 4 * kOutCap, kOZ = 8 * kOutCap, kOT = 12 * kOutCap;
-constexpr int kOAz = 16 * kOutCap, kODist = 18 * kOutCap;
-constexpr int kOInt = 20 * kOutCap, kOLas = 21 * kOutCap;
-constexpr int kOutBytes = (22 * kOutCap + 127) & ~127;
+template <bool HAS_T>
+struct OutCols {
+  static constexpr int kOX = 0, kOY = 4 * kOutCap, kOZ = 8 * kOutCap, kOT = 12 * kOutCap;
+  static constexpr int kOAz = (HAS_T ? 16 : 12) * kOutCap, kODist = kOAz + 2 * kOutCap;
+  static constexpr int kOInt = kODist + 2 * kOutCap, kOLas = kOInt + kOutCap;
+  static constexpr int kOutBytes = ((HAS_T ? 22 : 18) * kOutCap + 127) & ~127;
+};
 static_assert(kOutCap % 16 == 0, "column bases must stay 16-byte aligned");
 
 struct DecCtl {
@@ -1208,6 +1229,9 @@ struct DecCtl {
 template <int ADJ, int DSK, int FUSED = 0>
 struct DecLayout {
   static constexpr int kNumStages = (ADJ != 0 && DSK != 0) ? 2 : VS_DEC_STAGES;
+  static constexpr bool kHasT = !(VS_DEC_T_DIRECT && ADJ == 0 && DSK == 0 && FUSED == 0);
+  typedef OutCols<kHasT> Cols;
+  static constexpr int kOutBytes = Cols::kOutBytes;
   static constexpr int kRowBytes = DSK ? kDeskewRow * 8 : 96;
   static constexpr int kDPkts = kDPose + kDecTile * kRowBytes;  // packet bytes (16-byte granular span)
   static constexpr int kRec = 128;
@@ -1215,7 +1239,7 @@ struct DecLayout {
   static constexpr int kScr = kCfg + ((ADJ == 0) ? 0 : (((int)sizeof(DevConfig) + 127) & ~127));
   // single-pass variant: slot bits of the tile's blocks, per stage
   static constexpr int kOut = kScr + (FUSED ? ((kDecStagesMax * kDecTile * kBlocks * 4 + 127) & ~127) : 0);
-  static constexpr int kStages = kOut + kDecPairs * kOutBytes;
+  static constexpr int kStages = kOut + kDecPairs * Cols::kOutBytes;
   static_assert(kDPkts % 16 == 0, "stage sections must be 16-byte aligned");
 };
 static_assert(sizeof(DecCtl) <= 128, "DecCtl must fit its slot");
@@ -1260,26 +1284,47 @@ __device__ __forceinline__ void pair_barrier(int pair) {
 // The eight column values of one point into the pair's staging buffer under one predicate
 // (no branch in the block body).  a4 / a2 / a1: addresses of the point in the 4-, 2- and
 // 1-byte column groups; the columns of a group sit at fixed distances.
+template <bool HAS_T>
 __device__ __forceinline__ void stage_point(unsigned pred, uint32_t a4, uint32_t a2, uint32_t a1,
                                             float vx, float vy, float vz, unsigned vt, unsigned va,
                                             unsigned vd, unsigned vi, unsigned vl) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.u32 p, %11, 0;\n"
-      "@p st.shared.f32 [%0], %3;\n"
-      "@p st.shared.f32 [%0+%12], %4;\n"
-      "@p st.shared.f32 [%0+%13], %5;\n"
-      "@p st.shared.u32 [%0+%14], %6;\n"
-      "@p st.shared.u16 [%1], %7;\n"
-      "@p st.shared.u16 [%1+%15], %8;\n"
-      "@p st.shared.u8 [%2], %9;\n"
-      "@p st.shared.u8 [%2+%16], %10;\n"
-      "}\n" ::"r"(a4),
-      "r"(a2), "r"(a1), "f"(vx), "f"(vy), "f"(vz), "r"(vt), "r"(va), "r"(vd), "r"(vi), "r"(vl),
-      "r"(pred), "n"(kOY - kOX), "n"(kOZ - kOX), "n"(kOT - kOX), "n"(kODist - kOAz),
-      "n"(kOLas - kOInt)
-      : "memory");
+  typedef OutCols<HAS_T> C;
+  if (HAS_T) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %11, 0;\n"
+        "@p st.shared.f32 [%0], %3;\n"
+        "@p st.shared.f32 [%0+%12], %4;\n"
+        "@p st.shared.f32 [%0+%13], %5;\n"
+        "@p st.shared.u32 [%0+%14], %6;\n"
+        "@p st.shared.u16 [%1], %7;\n"
+        "@p st.shared.u16 [%1+%15], %8;\n"
+        "@p st.shared.u8 [%2], %9;\n"
+        "@p st.shared.u8 [%2+%16], %10;\n"
+        "}\n" ::"r"(a4),
+        "r"(a2), "r"(a1), "f"(vx), "f"(vy), "f"(vz), "r"(vt), "r"(va), "r"(vd), "r"(vi), "r"(vl),
+        "r"(pred), "n"(C::kOY - C::kOX), "n"(C::kOZ - C::kOX), "n"(C::kOT - C::kOX),
+        "n"(C::kODist - C::kOAz), "n"(C::kOLas - C::kOInt)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %10, 0;\n"
+        "@p st.shared.f32 [%0], %3;\n"
+        "@p st.shared.f32 [%0+%11], %4;\n"
+        "@p st.shared.f32 [%0+%12], %5;\n"
+        "@p st.shared.u16 [%1], %6;\n"
+        "@p st.shared.u16 [%1+%13], %7;\n"
+        "@p st.shared.u8 [%2], %8;\n"
+        "@p st.shared.u8 [%2+%14], %9;\n"
+        "}\n" ::"r"(a4),
+        "r"(a2), "r"(a1), "f"(vx), "f"(vy), "f"(vz), "r"(va), "r"(vd), "r"(vi), "r"(vl),
+        "r"(pred), "n"(C::kOY - C::kOX), "n"(C::kOZ - C::kOX), "n"(C::kODist - C::kOAz),
+        "n"(C::kOLas - C::kOInt)
+        : "memory");
+  }
 }
 
 // type_defs.h:160-166: row sums left to right, translation last.
@@ -1315,6 +1360,9 @@ template <int ADJ, int DSK, int FUSED>
 __global__ void __launch_bounds__(FUSED ? kFusedThreads : kDecThreads, VS_DEC_CTAS) k_decode(const DecParams p) {
   static_assert(!(FUSED && DSK), "the per-point deskew extension takes the two-pass pipeline");
   typedef DecLayout<ADJ, DSK, FUSED> L;
+  typedef typename L::Cols OC;
+  constexpr bool kHasT = L::kHasT;
+  constexpr int kOutBytes = L::kOutBytes;
   constexpr int kDecStages = L::kNumStages;
   constexpr int kDPkts = L::kDPkts;
   constexpr int kRowD = L::kRowBytes / 8;  // doubles per pose row
@@ -1459,8 +1507,8 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kDecThreads, VS_DEC_CT
     }
     const unsigned pred = (m >> lane) & 1u;
     const unsigned o = (unsigned)r.y + __popc(m & lt_mask);  // position in the pair's staging
-    stage_point(pred, out_a + kOX + 4u * o, out_a + kOAz + 2u * o, out_a + kOInt + o, (float)px,
-                (float)py, (float)pz, tpk + fire, az, dist, inten, (unsigned)laser_id);
+    stage_point<kHasT>(pred, out_a + OC::kOX + 4u * o, out_a + OC::kOAz + 2u * o, out_a + OC::kOInt + o,
+                       (float)px, (float)py, (float)pz, tpk + fire, az, dist, inten, (unsigned)laser_id);
     cnt += pred;
   };
 
@@ -1703,6 +1751,25 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kDecThreads, VS_DEC_CT
         }
       }
     }
+    if (!kHasT) {
+      // t_us of a packet without per-return firing offsets: one value for all its points, written
+      // from registers in coalesced runs (warp `par` of the pair takes packet lp0 + par)
+#pragma unroll
+      for (int k = 0; k < kDecPktsPerWarp; ++k) {
+        const int lp = lp0 + k;
+        if ((k & 1) == par && lp < npk) {
+          const unsigned cntp = (lds_u32(seg_a + 16u * (unsigned)lp + 12u) >> 12) & 0x1ffu;
+          const unsigned tval = lds_u32(seg_a + 16u * (unsigned)lp + 8u);
+          // every store instruction covers one 128-byte line of the column: whole sectors but
+          // for the packet's first and last line
+          const unsigned long long o64 = lds_u64(off_a + 8u * (unsigned)lp);
+          uint32_t* dst = p.t_us + o64;
+          const int skew = (int)((unsigned)o64 & 31u);
+          for (int i = lane - skew; i < (int)cntp; i += 32)
+            if (i >= 0) stg_u32(dst + i, tval);
+        }
+      }
+    }
     if (!pf_ok) prefetch_lut();
     __syncwarp();  // every lane is done with the stage and with the records
     if (lane == 0) {
@@ -1743,15 +1810,15 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kDecThreads, VS_DEC_CT
           const unsigned nb = b1 - b0;
           const unsigned long long gb = g0 + b0;
           if (par == 0) {
-            bulk_s2g_elect(p.x + gb, out_a + kOX + 4u * b0, 4u * nb);
-            bulk_s2g_elect(p.y + gb, out_a + kOY + 4u * b0, 4u * nb);
-            bulk_s2g_elect(p.azimuth + gb, out_a + kOAz + 2u * b0, 2u * nb);
-            bulk_s2g_elect(p.intensity + gb, out_a + kOInt + b0, nb);
+            bulk_s2g_elect(p.x + gb, out_a + OC::kOX + 4u * b0, 4u * nb);
+            bulk_s2g_elect(p.y + gb, out_a + OC::kOY + 4u * b0, 4u * nb);
+            bulk_s2g_elect(p.azimuth + gb, out_a + OC::kOAz + 2u * b0, 2u * nb);
+            bulk_s2g_elect(p.intensity + gb, out_a + OC::kOInt + b0, nb);
           } else {
-            bulk_s2g_elect(p.z + gb, out_a + kOZ + 4u * b0, 4u * nb);
-            bulk_s2g_elect(p.t_us + gb, out_a + kOT + 4u * b0, 4u * nb);
-            bulk_s2g_elect(p.distance + gb, out_a + kODist + 2u * b0, 2u * nb);
-            bulk_s2g_elect(p.laser + gb, out_a + kOLas + b0, nb);
+            bulk_s2g_elect(p.z + gb, out_a + OC::kOZ + 4u * b0, 4u * nb);
+            if (kHasT) bulk_s2g_elect(p.t_us + gb, out_a + OC::kOT + 4u * b0, 4u * nb);
+            bulk_s2g_elect(p.distance + gb, out_a + OC::kODist + 2u * b0, 2u * nb);
+            bulk_s2g_elect(p.laser + gb, out_a + OC::kOLas + b0, nb);
           }
           bulk_commit();
         }
@@ -1762,14 +1829,14 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kDecThreads, VS_DEC_CT
           const unsigned e = (par ? wl : wf) + (unsigned)lane;
           if (e >= phu && e < s1 && (e < b0 || e >= b1) && !(par && wl == wf)) {
             const unsigned long long g = g0 + e;
-            p.x[g] = __uint_as_float(lds_u32(out_a + kOX + 4u * e));
-            p.y[g] = __uint_as_float(lds_u32(out_a + kOY + 4u * e));
-            p.z[g] = __uint_as_float(lds_u32(out_a + kOZ + 4u * e));
-            p.t_us[g] = lds_u32(out_a + kOT + 4u * e);
-            p.azimuth[g] = (uint16_t)lds_u16(out_a + kOAz + 2u * e);
-            p.distance[g] = (uint16_t)lds_u16(out_a + kODist + 2u * e);
-            p.intensity[g] = (uint8_t)lds_u8(out_a + kOInt + e);
-            p.laser[g] = (uint8_t)lds_u8(out_a + kOLas + e);
+            p.x[g] = __uint_as_float(lds_u32(out_a + OC::kOX + 4u * e));
+            p.y[g] = __uint_as_float(lds_u32(out_a + OC::kOY + 4u * e));
+            p.z[g] = __uint_as_float(lds_u32(out_a + OC::kOZ + 4u * e));
+            if (kHasT) p.t_us[g] = lds_u32(out_a + OC::kOT + 4u * e);
+            p.azimuth[g] = (uint16_t)lds_u16(out_a + OC::kOAz + 2u * e);
+            p.distance[g] = (uint16_t)lds_u16(out_a + OC::kODist + 2u * e);
+            p.intensity[g] = (uint8_t)lds_u8(out_a + OC::kOInt + e);
+            p.laser[g] = (uint8_t)lds_u8(out_a + OC::kOLas + e);
           }
         }
       }
