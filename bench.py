@@ -66,6 +66,8 @@ def parse_args():
     ap.add_argument("--facade-packets", type=int, default=1 << 18,
                     help="packets per pass of the C++ facade run")
     ap.add_argument("--facade-batch", type=int, default=1 << 16)
+    ap.add_argument("--online-udp-seconds", type=float, default=30.0,
+                    help="length of the paced 10 Hz UDP stream per GPU (configs[4]); 0: skip")
     return ap.parse_args()
 
 
@@ -366,6 +368,7 @@ def run_recording(hours, steps, warmup, local, rank, world, dev, calib):
     # count exchange); a 10 Hz stream closes one frame per ~347 packets
     cap_rows = (n_total + world - 1) // world // 300 + 64
     h_mine = torch.zeros((cap_rows + 1, capi.FRAME_ROW_COLS), dtype=torch.int64).pin_memory()
+    h_mine_np = h_mine.numpy()
     d_mine = torch.zeros_like(h_mine, device=dev)
     d_all = torch.zeros((world * (cap_rows + 1), capi.FRAME_ROW_COLS), dtype=torch.int64, device=dev)
     h_all = torch.zeros_like(d_all, device="cpu").pin_memory()
@@ -377,11 +380,10 @@ def run_recording(hours, steps, warmup, local, rank, world, dev, calib):
                         flags=capi.FLAG_DEVICE_INPUT, t_base_us=t_base)
         r = ctx.wait(tk, frames=False)
         w0 = time.perf_counter()
-        rows = capi.frame_table_rows(r.frame_table, rank, first, halo)
-        if rows.shape[0] > cap_rows:
-            raise RuntimeError("more frames than the exchange buffer holds")
-        h_mine[0, 0] = rows.shape[0]
-        h_mine[1:1 + rows.shape[0]] = torch.from_numpy(rows)
+        # exchange rows straight out of the context's frame table into the pinned send buffer
+        n_rows = capi.frame_table_rows_into(r, rank, first, halo, h_mine[1:])
+        h_mine[0, 0] = n_rows
+        rows = h_mine_np[1:1 + n_rows]
         if world > 1:
             d_mine.copy_(h_mine, non_blocking=True)
             ag0.record()
@@ -738,27 +740,34 @@ def run_ours(args):
             off[j] = np.round((j // 2) * 48.0 + np.arange(32) * 1.5).astype(np.uint16)
         ctx.set_firing_offsets(off)
 
-        def step_dsk():
-            return ctx.wait(ctx.submit(d_pk, d_t, n=n_sub, stride=1206, n_halo=halo,
-                                       mode=capi.MODE_STREAMING,
-                                       flags=capi.FLAG_DEVICE_INPUT | capi.FLAG_DESKEW_PER_POINT,
-                                       t_base_us=t_base), frames=False)
+        def submit_dsk():
+            return ctx.submit(d_pk, d_t, n=n_sub, stride=1206, n_halo=halo, mode=capi.MODE_STREAMING,
+                              flags=capi.FLAG_DEVICE_INPUT | capi.FLAG_DESKEW_PER_POINT,
+                              t_base_us=t_base)
         for _ in range(3):
-            step_dsk()
+            ctx.wait(submit_dsk(), frames=False)
         barrier()
         d0 = torch.cuda.Event(enable_timing=True)
         d1 = torch.cuda.Event(enable_timing=True)
         d0.record(ext)
-        dk = []
-        for _ in range(5):
-            dk.append(step_dsk().decode_ms)
+        ext1.wait_event(d0)
+        dk, kd = [], 8
+        pend = submit_dsk()               # two batches in flight, like the headline loop
+        for i in range(kd):
+            nxt = submit_dsk() if i + 1 < kd else None
+            dk.append(ctx.wait(pend, frames=False).decode_ms)
+            pend = nxt
+        dj = torch.cuda.Event()
+        dj.record(ext1)
+        ext.wait_event(dj)
         d1.record(ext)
         barrier()
-        ms = d0.elapsed_time(d1) / 5
+        ms = d0.elapsed_time(d1) / kd
         deskew = {"points_per_s_per_gpu": n_emitted / (ms * 1e-3), "ms_per_step": ms,
                   "k_decode_ms": float(np.mean(dk)),
-                  "note": "VS_FLAG_DESKEW_PER_POINT: slerp/lerp pose per point, re-based to the "
-                          "frame origin (not a reference behaviour; one batch in flight)"}
+                  "note": "VS_FLAG_DESKEW_PER_POINT: pose per point (slerp weights linearised per "
+                          "packet, quaternion rotation, translation lerp), re-based to the frame "
+                          "origin; not a reference behaviour; two batches in flight like the headline"}
         ctx.set_calibration(calib)   # resets the firing table
 
     # ---- frame index exchange (off the timed loop) ------------------------------------------
@@ -798,6 +807,9 @@ def run_ours(args):
                       "aggregate_points_per_s": sum(o["index_only"]["points_per_s"] for o in allo),
                       "with_points_p99_ms": [o["with_points"]["p99_ms"] for o in allo],
                       "streams": world, "note": allo[0]["note"]}
+    online_udp = None
+    if args.online_udp_seconds > 0 and not args.no_online:
+        online_udp = run_online_udp(args, local, rank, calib, world, dev)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = run_cpu_baseline(calib, poses, args.cpu_seconds)
@@ -890,6 +902,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if online is not None:
             line["online"] = online
+        if online_udp is not None:
+            line["online_udp"] = online_udp
         if deskew is not None:
             line["deskew_per_point"] = deskew
         if single is not None:
@@ -1217,6 +1231,62 @@ def run_hdl32(local, dev):
     return {"points_per_s_per_gpu": r.n_points / (ms * 1e-3), "ms_per_step": ms,
             "k_decode_ms": float(np.mean(dec)), "packets": n, "points": r.n_points,
             "note": "HDL-32E stream, 32-laser calibration (LUT branch), no poses; two batches in flight"}
+
+
+def run_online_udp(args, local, rank, calib, world, dev):
+    """BASELINE.json configs[4]: one paced HDL-64E stream PER GPU over loopback UDP at the
+    sensor's own rate (3472 packets/s, 10 rotations/s) through the C++ facade's online path
+    (HDLManager::startOnline -> HDLSource receive ring -> TimeSolver -> HDLParser on the GPU ->
+    HDLManager::addFrame), one tests/cpp/facade_driver process per rank, all ranks at once.
+    Per rotation: time from the closing packet entering the parser to the frame sitting in the
+    manager (GPU round trip + zero-copy HDLFrame), and the same from the packet's arrival."""
+    import torch
+    from veloslam_b200 import calibxml, synth
+    from veloslam_b200.build import DRIVER_EXE, build_facade
+    build_facade()
+    seconds = args.online_udp_seconds
+    n = int(seconds * 3472) + 400
+    pk, t = synth.hdl64_stream_tiled(n)
+    tmp = tempfile.mkdtemp(prefix="vs_online_")
+    try:
+        synth.as_bytes(pk).tofile(os.path.join(tmp, "pk.bin"))
+        pt, trv = synth.ins_trajectory(int(n * 288e-6 * 100) + 60)
+        rec = np.zeros(len(pt), dtype=[("t", "<i8"), ("v", "<f8", (9,))])
+        rec["t"] = pt
+        rec["v"] = trv
+        rec.tofile(os.path.join(tmp, "poses.bin"))
+        calibxml.write_db_xml(os.path.join(tmp, "db.xml"), calib)
+        if world > 1:
+            torch.distributed.barrier()
+        cmd = [DRIVER_EXE, "online", os.path.join(tmp, "db.xml"), os.path.join(tmp, "pk.bin"),
+               os.path.join(tmp, "poses.bin"), str(seconds), str(local), str(23680 + 16 * rank)]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=int(seconds) + 120)
+        if p.returncode != 0:
+            mine = {"error": (p.stderr or p.stdout)[-300:]}
+        else:
+            mine = json.loads(p.stdout.strip().splitlines()[-1])
+    finally:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    if world > 1:
+        allo = [None] * world
+        torch.distributed.all_gather_object(allo, mine)
+    else:
+        allo = [mine]
+    ok = [o for o in allo if "error" not in o]
+    out = {"streams": world, "seconds": seconds, "paced_packets_per_s_per_stream": 3472,
+           "per_stream": allo,
+           "note": "one paced UDP stream per GPU through HDLManager::startOnline (C++ facade); "
+                   "rotation latency = closing packet handed to HDLParser -> HDLFrame (zero-copy, "
+                   "laid out on the GPU) stored by HDLManager::addFrame; from_arrival adds the wait "
+                   "in the receive ring; a 10 Hz sensor leaves 100 ms per rotation"}
+    if ok:
+        out["rotation_p50_ms_worst_stream"] = max(o["rotation_p50_ms"] for o in ok)
+        out["rotation_p99_ms_worst_stream"] = max(o["rotation_p99_ms"] for o in ok)
+        out["from_arrival_p99_ms_worst_stream"] = max(o["from_arrival_p99_ms"] for o in ok)
+        out["dropped_packets"] = sum(o["dropped"] for o in ok)
+        out["frames"] = sum(o["frames"] for o in ok)
+    return out
 
 
 def run_online(local, calib, poses, b, t, t_base, rotations=300):

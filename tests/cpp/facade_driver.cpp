@@ -23,7 +23,12 @@
 #include <iostream>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <arpa/inet.h>
+#include <netinet/in.h>
+#include <sys/socket.h>
 #include <sys/stat.h>
+#include <thread>
 #include <unistd.h>
 
 #include "VeloSLAM.h"
@@ -506,6 +511,107 @@ int main(int argc, char** argv) {
                 (unsigned long long)points, (unsigned long long)frames, sec,
                 (unsigned long long)(n * (size_t)passes), passes, batch,
                 (unsigned long long)vs::Arena::pooledBytes(), touch, parser.pipelineStats().c_str());
+    return 0;
+  }
+  if (mode == "online") {
+    // BASELINE.json configs[4] for ONE stream: a paced sender thread plays the packet file over
+    // loopback UDP at the sensor's rate; HDLManager::startOnline receives, stamps (TimeSolver),
+    // decodes on the GPU (per-rotation flush) and stores the frames.
+    //   facade_driver online <calib.xml> <packets.bin> <poses.bin|-> <seconds> <device> <port> [packets_per_s]
+    if (argc < 8) return 2;
+    const double seconds = std::atof(argv[5]);
+    const int device = std::atoi(argv[6]), port = std::atoi(argv[7]);
+    const double rate = argc > 8 ? std::atof(argv[8]) : 3472.0;
+    std::vector<char> pk = slurp(argv[3]);
+    const size_t have = pk.size() / 1206;
+    const size_t n = std::min(have, (size_t)(seconds * rate));
+    HDLManager mgr(40);
+    const std::string scratch = std::string("/tmp/vs_online_") + std::to_string(getpid());
+    mkdir(scratch.c_str(), 0777);
+    mgr.setBufferDir(scratch, false);
+    mgr.setCalibFile(argv[2]);
+    mgr.setPorts(port, port + 1);
+    {
+      std::shared_ptr<TransformManager> poses = loadPoses(argv[4]);
+      std::vector<int64_t> pt;
+      std::vector<double> trv;
+      poses->snapshot(&pt, &trv);
+      for (size_t i = 0; i < pt.size(); ++i) {
+        std::shared_ptr<PoseTransform> p(new PoseTransform);
+        for (int k = 0; k < 3; ++k) {
+          p->T[k] = trv[9 * i + k];
+          p->R[k] = trv[9 * i + 3 + k];
+          p->V[k] = trv[9 * i + 6 + k];
+        }
+        p->timestamp = ptime(pt[i]);
+        p->seconds_pos = 0;
+        mgr.getTransformMgr()->addTransform(p);
+      }
+    }
+    mgr.getTimeSolver()->setClock([]() { return (int64_t)1467331200000000ll; });  // == synth.T0_US
+    mgr.startOnline();
+    HDLSource& src = *mgr.getHDLSource();
+    if (!src.isRunning()) return 1;
+    src.getHDLParser()->setDevice(device);
+    src.getHDLParser()->setStorePackets(true);
+    if (!src.getHDLParser()->prepare(48)) {  // the manager caches 40 frames
+      std::cerr << "prepare failed: " << src.getHDLParser()->lastError() << std::endl;
+      return 1;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    std::thread sender([&]() {
+      const int tx = socket(AF_INET, SOCK_DGRAM, 0);
+      sockaddr_in to;
+      std::memset(&to, 0, sizeof(to));
+      to.sin_family = AF_INET;
+      to.sin_addr.s_addr = htonl(INADDR_LOOPBACK);
+      to.sin_port = htons((uint16_t)port);
+      for (size_t i = 0; i < n; ++i) {
+        const auto due = t0 + std::chrono::nanoseconds((int64_t)(1e9 * (double)i / rate));
+        auto now = std::chrono::steady_clock::now();
+        if (due - now > std::chrono::microseconds(200)) std::this_thread::sleep_until(due - std::chrono::microseconds(100));
+        while (std::chrono::steady_clock::now() < due) {
+        }
+        sendto(tx, pk.data() + 1206 * i, 1206, 0, reinterpret_cast<sockaddr*>(&to), sizeof(to));
+      }
+      close(tx);
+    });
+    sender.join();
+    for (int i = 0; i < 500; ++i) {  // let the consumer drain
+      uint64_t r, d, c;
+      src.getCounters(&r, &d, &c);
+      if (c + d >= n) break;
+      usleep(10000);
+    }
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    mgr.stopOnline();
+    uint64_t r, d, c;
+    src.getCounters(&r, &d, &c);
+    if (!src.getHDLParser()->lastError().empty()) {
+      std::cerr << "facade error: " << src.getHDLParser()->lastError() << std::endl;
+      return 1;
+    }
+    std::vector<double> proc, arr;
+    src.getFrameLatencies(&proc, &arr);
+    auto pct = [](std::vector<double> v, double q) {
+      if (v.empty()) return 0.0;
+      std::sort(v.begin(), v.end());
+      return v[std::min(v.size() - 1, (size_t)(q * (double)(v.size() - 1) + 0.5))];
+    };
+    // the first rotations include the context creation and first launches
+    if (proc.size() > 8) {
+      proc.erase(proc.begin(), proc.begin() + 4);
+      arr.erase(arr.begin(), arr.begin() + 4);
+    }
+    uint64_t points = 0;
+    for (auto& f : mgr.getAllFrameMeta()) points += f->numberOfPoints();
+    std::printf("{\"packets_sent\": %llu, \"received\": %llu, \"dropped\": %llu, \"consumed\": %llu, "
+                "\"frames\": %d, \"seconds\": %.3f, \"packets_per_s\": %.1f, "
+                "\"rotation_p50_ms\": %.4f, \"rotation_p99_ms\": %.4f, \"rotation_max_ms\": %.4f, "
+                "\"from_arrival_p50_ms\": %.4f, \"from_arrival_p99_ms\": %.4f, \"points_cached\": %llu}\n",
+                (unsigned long long)n, (unsigned long long)r, (unsigned long long)d, (unsigned long long)c,
+                mgr.getNumberOfFrames(), wall, (double)n / wall, pct(proc, 0.5) / 1e3, pct(proc, 0.99) / 1e3,
+                pct(proc, 1.0) / 1e3, pct(arr, 0.5) / 1e3, pct(arr, 0.99) / 1e3, (unsigned long long)points);
     return 0;
   }
   if (mode == "udp") {

@@ -214,6 +214,21 @@ def frame_table_rows(frame_table, rank, first_packet, n_halo):
     return rows
 
 
+def frame_table_rows_into(result, rank, first_packet, n_halo, out_rows):
+    """vs_frame_table_rows straight from a BatchResult's context-owned vs_frame array into a
+    caller-owned (cap, 10) int64 buffer (numpy array or pinned torch tensor): no intermediate
+    copies.  Call before the slot's next submit.  Returns the number of rows."""
+    ptr, n = result._raw_frames
+    cap = int(out_rows.shape[0])
+    if n > cap:
+        raise VeloError(4, "frame_table_rows_into: buffer too small")
+    rc = load_library().vs_frame_table_rows(C.cast(ptr, C.c_void_p), n, rank, first_packet, n_halo,
+                                            _ptr(out_rows))
+    if rc != 0:
+        raise VeloError(rc, "vs_frame_table_rows: bad arguments")
+    return int(n)
+
+
 def stitch_frame_tables(tables):
     """vs_stitch_frame_tables over per-rank (n_g, 10) int64 tables (rank order): structured
     arrays (global frames, segments)."""

@@ -939,6 +939,41 @@ void HDLParser::unloadRecording() { this->internal_->unloadRecording(); }
 bool HDLParser::hasRecording(const std::string& pcapfile) const { return this->internal_->hasRecording(pcapfile); }
 
 void HDLParser::setDevice(int d) { this->internal_->device = d; }
+
+// Everything that is slow the first time, done before the first packet instead of under it:
+// the CUDA context and its buffers, the first launch of every kernel of the path (a throw-away
+// batch of empty packets with a scratch carry: the parser's own state is untouched), and
+// `frames` page-locked arenas of `pointsPerFrame` points in the pool.
+bool HDLParser::prepare(int frames, size_t pointsPerFrame) {
+  vsInternal* in = this->internal_;
+  if (!in->ensureContext()) return false;
+  if (in->correctionsInitialized && in->inflight.empty() && in->pending == 0) {
+    if (!in->syncConfig(0, 0)) return false;
+    const int n = std::min(in->batchPackets, 64);
+    std::memset(in->ringPkts[in->fill], 0, (size_t)n * VS_PACKET_BYTES);
+    for (int i = 0; i < n; ++i) in->ringTimes[in->fill][i] = i;
+    vs_carry scratch;
+    vs_carry_init(&scratch);
+    uint64_t ticket = 0;
+    vs_result r;
+    vs_layout lay;
+    if (vs_submit(in->ctx, in->ringPkts[in->fill], VS_PACKET_BYTES, in->ringTimes[in->fill], n, 0,
+                  VS_MODE_STREAMING, 0, 0, &scratch, &ticket) != VS_OK ||
+        vs_wait(in->ctx, ticket, &r) != VS_OK ||
+        vs_layout_frames(in->ctx, ticket, nullptr, 16, 1, &lay) != VS_OK ||
+        vs_sync(in->ctx, ticket, nullptr) != VS_OK) {
+      in->error = vs_last_error(in->ctx);
+      return false;
+    }
+  }
+  std::vector<std::shared_ptr<vs::Arena> > hold;
+  for (int i = 0; i < frames; ++i) {
+    const size_t metaOff = (pointsPerFrame * sizeof(pcl::PointXYZI) + 255) & ~(size_t)255;
+    hold.push_back(vs::Arena::acquire(metaOff + pointsPerFrame * sizeof(PointMeta)));
+    if (!hold.back()) return false;
+  }
+  return true;  // `hold` goes back to the pool here
+}
 void HDLParser::setBatchPackets(int n) {
   if (!this->internal_->ctx && n > 0) this->internal_->batchPackets = n;
 }

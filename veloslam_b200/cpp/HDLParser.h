@@ -89,6 +89,10 @@ class HDLParser {
 
   // ---- B200 controls (not in the reference) -------------------------------------------------
   void setDevice(int cudaDevice);          // before the first packet; default 0
+  // Optional, for online use: create the CUDA context, launch every kernel once and page-lock
+  // `frames` frame arenas now, so that the first rotations of a live stream do not pay for it
+  // (call after setCorrectionsFile; 140 000 points ~ one 10 Hz HDL-64E rotation).
+  bool prepare(int frames = 0, size_t pointsPerFrame = 140000);
   void setBatchPackets(int maxPackets);    // capacity of the pinned ring; default 4096
   void setStorePackets(bool store);        // keep raw packets inside HDLFrame::packets; default on
   void setFetchMeta(bool fetch);           // fill HDLFrame::pointsMeta (12 of the 28 bytes per point

@@ -7,6 +7,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <iostream>
@@ -29,10 +30,16 @@ class HDLSource::vsInternal {
         running(false), head(0), tail(0), received(0), dropped(0), consumed(0),
         ring((size_t)kRingSlots * kSlotBytes), lengths(kRingSlots) {}
 
+  static int64_t nowUs() {
+    return std::chrono::duration_cast<std::chrono::microseconds>(
+               std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
+
   // HDLSource.cxx:209-225
-  void handleSensorData(const unsigned char* data, unsigned int length) {
+  void handleSensorData(const unsigned char* data, unsigned int length, int64_t arrivedUs = 0) {
     if (length != 1206) return;
     std::lock_guard<std::mutex> lock(parserMutex);
+    const int64_t t0 = nowUs();
     uint32_t gps;
     std::memcpy(&gps, data + 1200, 4);
     const ptime timestamp = timeSolver->calcTimestamp(gps);
@@ -49,6 +56,12 @@ class HDLSource::vsInternal {
       if (hdlMgr)
         for (auto& f : fr) hdlMgr->addFrame(f);
       parser->clearAllFrames();
+      // per rotation: packet that closed it handed to the parser -> frame in the manager, and the
+      // same from the packet's arrival on the socket (includes the wait in the ring)
+      const int64_t t1 = nowUs();
+      std::lock_guard<std::mutex> ll(latencyMutex);
+      frameLatencyUs.push_back((double)(t1 - t0));
+      arrivalLatencyUs.push_back(arrivedUs ? (double)(t1 - arrivedUs) : 0.0);
     }
   }
 
@@ -68,6 +81,7 @@ class HDLSource::vsInternal {
         continue;
       }
       lengths[h % kRingSlots] = (unsigned int)n;
+      arrived[h % kRingSlots] = nowUs();
       head.store(h + 1, std::memory_order_release);
       {
         std::lock_guard<std::mutex> lock(wakeMutex);
@@ -85,7 +99,8 @@ class HDLSource::vsInternal {
         wake.wait_for(lock, std::chrono::milliseconds(20));
         continue;
       }
-      handleSensorData(ring.data() + (size_t)(t % kRingSlots) * kSlotBytes, lengths[t % kRingSlots]);
+      handleSensorData(ring.data() + (size_t)(t % kRingSlots) * kSlotBytes, lengths[t % kRingSlots],
+                       arrived[t % kRingSlots]);
       ++consumed;
       tail.store(t + 1, std::memory_order_release);
     }
@@ -103,6 +118,9 @@ class HDLSource::vsInternal {
   std::vector<unsigned char> ring;
   unsigned char scratch[1500];  // where a packet lands when the ring is full (then dropped)
   std::vector<unsigned int> lengths;
+  std::vector<int64_t> arrived = std::vector<int64_t>(kRingSlots);  // steady-clock arrival time per slot
+  std::mutex latencyMutex;
+  std::vector<double> frameLatencyUs, arrivalLatencyUs;
   std::thread receiver, consumer;
   std::mutex wakeMutex;
   std::condition_variable wake;
@@ -202,6 +220,11 @@ void HDLSource::getCounters(uint64_t* received, uint64_t* dropped, uint64_t* con
   if (received) *received = internal_->received.load();
   if (dropped) *dropped = internal_->dropped.load();
   if (consumed) *consumed = internal_->consumed.load();
+}
+void HDLSource::getFrameLatencies(std::vector<double>* processUs, std::vector<double>* fromArrivalUs) const {
+  std::lock_guard<std::mutex> lock(internal_->latencyMutex);
+  if (processUs) *processUs = internal_->frameLatencyUs;
+  if (fromArrivalUs) *fromArrivalUs = internal_->arrivalLatencyUs;
 }
 void HDLSource::setPacketCallback(std::function<void(const unsigned char*, unsigned int, ptime)> cb) {
   std::lock_guard<std::mutex> lock(internal_->parserMutex);

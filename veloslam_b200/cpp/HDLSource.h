@@ -12,6 +12,7 @@
 #include <functional>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "HDLParser.h"
 #include "TimeSolver.h"
@@ -48,6 +49,9 @@ class HDLSource {
   // ---- not in the reference ----------------------------------------------------------------
   // packets received / dropped because the ring was full / handed to the parser so far
   void getCounters(uint64_t* received, uint64_t* dropped, uint64_t* consumed) const;
+  // per frame handed to the manager, microseconds: from the closing packet entering the parser,
+  // and from that packet's arrival on the socket
+  void getFrameLatencies(std::vector<double>* processUs, std::vector<double>* fromArrivalUs) const;
   // deliver (payload, length, time) here instead of the parser (tests, custom consumers)
   void setPacketCallback(std::function<void(const unsigned char*, unsigned int, ptime)> cb);
   bool isRunning() const;
