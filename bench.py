@@ -372,6 +372,8 @@ def run_recording(hours, steps, warmup, local, rank, world, dev, calib):
     d_mine = torch.zeros_like(h_mine, device=dev)
     d_all = torch.zeros((world * (cap_rows + 1), capi.FRAME_ROW_COLS), dtype=torch.int64, device=dev)
     h_all = torch.zeros_like(d_all, device="cpu").pin_memory()
+    h_all_np = h_all.numpy().reshape(world, cap_rows + 1, capi.FRAME_ROW_COLS)
+    stitcher = capi.Stitcher(world, world * cap_rows)
     ag0 = torch.cuda.Event(enable_timing=True)
     ag1 = torch.cuda.Event(enable_timing=True)
 
@@ -383,7 +385,6 @@ def run_recording(hours, steps, warmup, local, rank, world, dev, calib):
         # exchange rows straight out of the context's frame table into the pinned send buffer
         n_rows = capi.frame_table_rows_into(r, rank, first, halo, h_mine[1:])
         h_mine[0, 0] = n_rows
-        rows = h_mine_np[1:1 + n_rows]
         if world > 1:
             d_mine.copy_(h_mine, non_blocking=True)
             ag0.record()
@@ -392,13 +393,13 @@ def run_recording(hours, steps, warmup, local, rank, world, dev, calib):
             h_all.copy_(d_all, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             ag_ms = ag0.elapsed_time(ag1)
-            allr = h_all.numpy().reshape(world, cap_rows + 1, capi.FRAME_ROW_COLS)
-            tables = [allr[g, 1:1 + int(allr[g, 0, 0])] for g in range(world)]
+            w1 = time.perf_counter()
+            # table g sits at row g * (cap_rows + 1) + 1 of the gathered buffer: stitched in place
+            gf, segs = stitcher(h_all_np, h_all_np[:, 0, 0], cap_rows + 1, first_row=1)
         else:
             ag_ms = 0.0
-            tables = [rows]
-        w1 = time.perf_counter()
-        gf, segs = sharding.stitch_arrays(tables)
+            w1 = time.perf_counter()
+            gf, segs = stitcher(h_mine_np, [n_rows], 0, first_row=1)
         w2 = time.perf_counter()
         return r, gf, segs, ag_ms, (w1 - w0) * 1e3, (w2 - w1) * 1e3
 
@@ -790,6 +791,9 @@ def run_ours(args):
     if not args.no_e2e:
         e2e_frames = run_e2e(args, ctx_args=(local, calib, poses), b=b[halo:], t=t[halo:], t_base=t_base,
                              world=world, dev=dev, layout=True)
+    pcie = None
+    if not args.no_e2e:
+        pcie = run_pcie_probe(world, dev)
     e2e_facade = None
     if not args.no_facade and not args.no_e2e:
         e2e_facade = run_facade(args, local, calib, poses, b[halo:], t[halo:], world, dev)
@@ -894,6 +898,8 @@ def run_ours(args):
             line["e2e"] = e2e
         if e2e_frames is not None:
             line["e2e_frames"] = e2e_frames
+        if pcie is not None:
+            line["pcie_probe"] = pcie
         if e2e_facade is not None:
             line["e2e_facade"] = e2e_facade
         if hdl32 is not None:
@@ -1231,6 +1237,41 @@ def run_hdl32(local, dev):
     return {"points_per_s_per_gpu": r.n_points / (ms * 1e-3), "ms_per_step": ms,
             "k_decode_ms": float(np.mean(dec)), "packets": n, "points": r.n_points,
             "note": "HDL-32E stream, 32-laser calibration (LUT branch), no poses; two batches in flight"}
+
+
+def run_pcie_probe(world, dev, seconds=0.4):
+    """What the box's host side can move: every rank copies a 256 MiB pinned buffer device -> host
+    (then host -> device) back to back for `seconds`, all ranks at once, nothing else running.
+    The ceiling the end-to-end figures are bound by (per rank and in aggregate)."""
+    import torch
+    n = 256 << 20
+    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, src, dst in (("d2h", d, h), ("h2d", h, d)):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        t0 = time.perf_counter()
+        k = 0
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(4):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            k += 4
+        gbs = k * n / (time.perf_counter() - t0) / 1e9
+        if world > 1:
+            allg = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+            torch.distributed.all_gather(allg, torch.tensor([gbs], dtype=torch.float64, device=dev))
+            per = [float(x.item()) for x in allg]
+        else:
+            per = [gbs]
+        out[name + "_gb_per_s_per_rank"] = [round(x, 1) for x in per]
+        out[name + "_gb_per_s_total"] = round(sum(per), 1)
+    out["note"] = ("pinned 256 MiB copies, all ranks concurrently, no kernels: the host-side ceiling "
+                   "of this box for the e2e figures (18 or 28 bytes leave the GPU per point)")
+    return out
 
 
 def run_online_udp(args, local, rank, calib, world, dev):

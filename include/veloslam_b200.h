@@ -302,13 +302,15 @@ typedef struct vs_global_frame {
   int32_t reserved;
 } vs_global_frame;
 
-/* rows: the ranks' tables concatenated in rank order (rows_per_rank[g] rows of
- * VS_FRAME_ROW_COLS each).  The open (last) frame of rank g and the first frame of rank g+1 are
- * the same rotation: merged.  Fills at most frame_cap / seg_cap entries; the counts come back in
- * *n_frames / *n_segs (VS_ERR_CAPACITY when an array was too short). */
+/* rows: the ranks' tables in rank order, rows_per_rank[g] rows of VS_FRAME_ROW_COLS each; table g
+ * starts at row g * rank_stride_rows (the layout a fixed-size all-gather leaves), or right behind
+ * table g-1 when rank_stride_rows is 0.  The open (last) frame of rank g and the first frame of
+ * rank g+1 are the same rotation: merged.  Fills at most frame_cap / seg_cap entries; the counts
+ * come back in *n_frames / *n_segs (VS_ERR_CAPACITY when an array was too short). */
 VS_API int vs_stitch_frame_tables(const int64_t* rows, const int32_t* rows_per_rank, int32_t world,
-                                  vs_global_frame* frames, int32_t frame_cap, vs_frame_segment* segs,
-                                  int32_t seg_cap, int32_t* n_frames, int32_t* n_segs);
+                                  int64_t rank_stride_rows, vs_global_frame* frames, int32_t frame_cap,
+                                  vs_frame_segment* segs, int32_t seg_cap, int32_t* n_frames,
+                                  int32_t* n_segs);
 
 /* Page-locked host memory for packet rings / result buffers (cudaHostAlloc / cudaFreeHost),
  * so that callers above the ABI need no CUDA headers. */

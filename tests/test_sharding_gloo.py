@@ -113,3 +113,19 @@ def test_shard_range_edge_cases():
     assert e == big and f == (big * 7) // 8 and h == 512         # no 64-bit overflow in n * rank
     with pytest.raises(capi.VeloError):
         capi.shard_range(100, 4, 4, 0)
+
+
+def test_stitcher_reads_the_all_gather_buffer_in_place():
+    """Stitcher: table g at row g * stride (+ a header row) of one fixed-size gathered buffer."""
+    tabs = rank_tables()
+    cap = 8
+    buf = np.full((2, cap + 1, capi.FRAME_ROW_COLS), -7, dtype=np.int64)
+    for g, t in enumerate(tabs):
+        buf[g, 0, 0] = t.shape[0]
+        buf[g, 1:1 + t.shape[0]] = t
+    st = capi.Stitcher(2, 2 * cap)
+    gf, segs = st(buf, buf[:, 0, 0], cap + 1, first_row=1)
+    want_f, want_s = sharding.stitch_arrays(tabs)
+    assert np.array_equal(gf, want_f) and np.array_equal(segs, want_s)
+    with pytest.raises(capi.VeloError):
+        st(buf, [cap + 2, 1], cap + 1, first_row=1)      # more rows than the stride holds

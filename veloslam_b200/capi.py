@@ -188,7 +188,7 @@ def load_library():
     L.vs_frame_table_rows.restype = C.c_int
     L.vs_frame_table_rows.argtypes = [vp, i32, i32, i64, i64, vp]
     L.vs_stitch_frame_tables.restype = C.c_int
-    L.vs_stitch_frame_tables.argtypes = [vp, vp, i32, vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.vs_stitch_frame_tables.argtypes = [vp, vp, i32, i64, vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
     _lib = L
     return L
 
@@ -241,12 +241,37 @@ def stitch_frame_tables(tables):
     frames = np.zeros(max(total, 1), dtype=np.dtype(GlobalFrame))
     segs = np.zeros(max(total, 1), dtype=np.dtype(FrameSegment))
     nf, ns = C.c_int32(), C.c_int32()
-    rc = load_library().vs_stitch_frame_tables(_ptr(rows) if total else None, _ptr(counts), world,
+    rc = load_library().vs_stitch_frame_tables(_ptr(rows) if total else None, _ptr(counts), world, 0,
                                                _ptr(frames), frames.shape[0], _ptr(segs), segs.shape[0],
                                                C.byref(nf), C.byref(ns))
     if rc != 0:
         raise VeloError(rc, "vs_stitch_frame_tables failed")
     return frames[:nf.value], segs[:ns.value]
+
+
+class Stitcher:
+    """vs_stitch_frame_tables over the buffer a fixed-size all-gather leaves -- table g at row
+    g * stride_rows -- into preallocated outputs: no concatenation, no per-call allocation."""
+
+    def __init__(self, world, cap_rows_total):
+        self.world = world
+        self.frames = np.zeros(max(cap_rows_total, 1), dtype=np.dtype(GlobalFrame))
+        self.segs = np.zeros(max(cap_rows_total, 1), dtype=np.dtype(FrameSegment))
+        self.counts = np.zeros(world, dtype=np.int32)
+        self._L = load_library()
+
+    def __call__(self, rows_buffer, counts, stride_rows, first_row=0):
+        """rows_buffer: int64 array (any shape) whose table g begins first_row + g * stride_rows
+        rows in; counts: rows per rank."""
+        self.counts[:] = counts
+        nf, ns = C.c_int32(), C.c_int32()
+        base = _ptr(rows_buffer) + first_row * FRAME_ROW_COLS * 8
+        rc = self._L.vs_stitch_frame_tables(base, _ptr(self.counts), self.world, stride_rows,
+                                            _ptr(self.frames), self.frames.shape[0], _ptr(self.segs),
+                                            self.segs.shape[0], C.byref(nf), C.byref(ns))
+        if rc != 0:
+            raise VeloError(rc, "vs_stitch_frame_tables failed")
+        return self.frames[:nf.value], self.segs[:ns.value]
 
 
 def carry_init():

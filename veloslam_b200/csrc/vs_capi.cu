@@ -1485,13 +1485,18 @@ int vs_frame_table_rows(const vs_frame* frames, int32_t n_frames, int32_t rank, 
 }
 
 int vs_stitch_frame_tables(const int64_t* rows, const int32_t* rows_per_rank, int32_t world,
-                           vs_global_frame* frames, int32_t frame_cap, vs_frame_segment* segs,
-                           int32_t seg_cap, int32_t* n_frames, int32_t* n_segs) {
-  if (!rows_per_rank || world < 1 || !n_frames || !n_segs || frame_cap < 0 || seg_cap < 0)
+                           int64_t rank_stride_rows, vs_global_frame* frames, int32_t frame_cap,
+                           vs_frame_segment* segs, int32_t seg_cap, int32_t* n_frames, int32_t* n_segs) {
+  if (!rows_per_rank || world < 1 || !n_frames || !n_segs || frame_cap < 0 || seg_cap < 0 ||
+      rank_stride_rows < 0)
     return VS_ERR_INVALID_ARG;
   int64_t nf = 0, ns = 0;
   const int64_t* r = rows;
   for (int32_t g = 0; g < world; ++g) {
+    if (rank_stride_rows > 0) {
+      if (rows_per_rank[g] > rank_stride_rows) return VS_ERR_INVALID_ARG;
+      r = rows + (size_t)g * (size_t)rank_stride_rows * VS_FRAME_ROW_COLS;
+    }
     for (int32_t i = 0; i < rows_per_rank[g]; ++i, r += VS_FRAME_ROW_COLS) {
       if (!rows) return VS_ERR_INVALID_ARG;
       if (ns < seg_cap) {
