@@ -764,7 +764,7 @@ int finish_batch(vs_ctx* ctx, Slot& s) {
 
   const int f_lo = (s.halo > 0) ? h.frame_at_halo : 0;  // first frame with decoded points
   const int n_frames = W - f_lo + 1;
-  s.frames.assign((size_t)n_frames, vs_frame());
+  s.frames.resize((size_t)n_frames);  // every entry is cleared below
   const int64_t total_points = s.index_only ? 0 : h.total_points;
   const bool any_upper_before = s.carry_in.is_hdl64 != 0;
   for (int i = 0; i < n_frames; ++i) {

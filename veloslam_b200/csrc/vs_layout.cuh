@@ -215,16 +215,28 @@ __global__ void __launch_bounds__(kLayThreads, 2) k_layout(const LayoutParams p)
       st_release_u64(my, kFlagAgg | mine);
     unsigned e0 = 0, e1 = 0;
     if (tile > 0 && !starts_frame) {
+      // The lanes carry the 32 return slots, so the walk over the predecessors is serial; a
+      // window of kWin words per lane is fetched at once so that a round trip covers kWin tiles
+      // (a frame spans ~43 tiles and tiles retire faster than a prefix could hop tile by tile).
+      constexpr int kWin = 8;
       bool done = false;
       int idx = tile - 1;
       while (true) {
+        unsigned long long v[kWin];
+#pragma unroll
+        for (int w = 0; w < kWin; ++w)
+          v[w] = (!done && idx - w >= 0) ? ld_acquire_u64(p.st + (long long)(idx - w) * 32 + lane) : 0ull;
         if (!done) {
-          const unsigned long long v = ld_acquire_u64(p.st + (long long)idx * 32 + lane);
-          const unsigned flag = (unsigned)(v >> 62);
-          if (flag != 0u) {
-            e0 += (unsigned)(v & kLayM30);
-            e1 += (unsigned)((v >> 30) & kLayM30);
-            if (flag == 2u || --idx < 0) done = true;
+#pragma unroll
+          for (int w = 0; w < kWin; ++w) {
+            const unsigned flag = (unsigned)(v[w] >> 62);
+            if (flag == 0u) break;  // not published yet: poll again from here
+            e0 += (unsigned)(v[w] & kLayM30);
+            e1 += (unsigned)((v[w] >> 30) & kLayM30);
+            if (flag == 2u || --idx < 0) {
+              done = true;
+              break;
+            }
           }
         }
         if (__all_sync(full, done)) break;
@@ -309,35 +321,63 @@ __global__ void __launch_bounds__(kLayThreads, 2) k_layout(const LayoutParams p)
       const unsigned long long poff = sh.off[min(wb0 / kBlocks, kLayTile - 1)];
       const unsigned so0 = sh.lofs[id0], so1 = sh.lofs[id1];
       unsigned c0 = b0, c1 = b1;
-#pragma unroll 4
-      for (int j = j0; j < j1; ++j) {
-        const uint2 r = sh.rec[j];
-        if (r.x == 0u) continue;
-        const unsigned bit = (r.x >> lane) & 1u;
-        const unsigned bank = (r.y >> 25) & 1u;
-        unsigned rank = bank ? c1 : c0;
-        unsigned add = bit;
-        if (vlp && !bank) {
-          const unsigned pb = __shfl_xor_sync(full, bit, 16);
-          if (lane >= 16) rank += pb;  // slot l (first firing of the block) is pushed before l + 16
-          add += pb;
+      // two steps per group of kLayIlp blocks: ranks and all the group's loads first, then the
+      // shared-memory stores -- the loads of a group are in flight together instead of one
+      // block's round trip after the other
+      constexpr int kLayIlp = 3;
+      static_assert(kLayWarpBlocks % kLayIlp == 0, "whole groups");
+#pragma unroll 1
+      for (int jg = wb0; jg < wb0 + kLayWarpBlocks; jg += kLayIlp) {
+        unsigned slot[kLayIlp];
+        bool put[kLayIlp];
+        float vx[kLayIlp], vy[kLayIlp], vz[kLayIlp];
+        unsigned vi[kLayIlp], va[kLayIlp], vd[kLayIlp], bk[kLayIlp];
+#pragma unroll
+        for (int u = 0; u < kLayIlp; ++u) {
+          const int j = jg + u;
+          put[u] = false;
+          slot[u] = 0u;
+          bk[u] = 0u;
+          vx[u] = vy[u] = vz[u] = 0.f;
+          vi[u] = va[u] = vd[u] = 0u;
+          if (j < j0 || j >= j1) continue;  // warp-uniform
+          const uint2 r = sh.rec[j];
+          if (r.x == 0u) continue;
+          const unsigned bit = (r.x >> lane) & 1u;
+          const unsigned bank = (r.y >> 25) & 1u;
+          unsigned rank = bank ? c1 : c0;
+          unsigned add = bit;
+          if (vlp && !bank) {
+            const unsigned pb = __shfl_xor_sync(full, bit, 16);
+            if (lane >= 16) rank += pb;  // slot l (first firing of the block) is pushed before l + 16
+            add += pb;
+          }
+          if (bank) c1 += add; else c0 += add;
+          if (bit) {
+            const unsigned long long src = poff + ((r.y >> 16) & 0x1ffu) + __popc(r.x & lt_mask);
+            put[u] = true;
+            bk[u] = bank;
+            slot[u] = (bank ? so1 : so0) + rank;
+            vx[u] = __ldg(&p.x[src]);
+            vy[u] = __ldg(&p.y[src]);
+            vz[u] = __ldg(&p.z[src]);
+            vi[u] = __ldg(&p.inten[src]);
+            va[u] = __ldg(&p.az[src]);
+            vd[u] = __ldg(&p.dist[src]);
+          }
         }
-        if (bank) c1 += add; else c0 += add;
-        if (bit) {
-          const unsigned long long src = poff + ((r.y >> 16) & 0x1ffu) + __popc(r.x & lt_mask);
-          const unsigned slot = (bank ? so1 : so0) + rank;
-          const float vx = __ldg(&p.x[src]), vy = __ldg(&p.y[src]), vz = __ldg(&p.z[src]);
-          const unsigned vi = __ldg(&p.inten[src]);
-          const unsigned va = __ldg(&p.az[src]), vd = __ldg(&p.dist[src]);
+#pragma unroll
+        for (int u = 0; u < kLayIlp; ++u) {
+          if (!put[u]) continue;
           // p.intensity = intensity (HDLParser.cxx:737)
-          sh.xyzi[slot] = make_uint4(__float_as_uint(vx), __float_as_uint(vy), __float_as_uint(vz),
-                                     __float_as_uint((float)vi));
+          sh.xyzi[slot[u]] = make_uint4(__float_as_uint(vx[u]), __float_as_uint(vy[u]),
+                                        __float_as_uint(vz[u]), __float_as_uint((float)vi[u]));
           // PointMeta{u16 azimuth; float distance = distanceM; 3 flag bytes} (type_defs.h:168-176,
           // HDLParser.cxx:614, 745-747); the flags the reference leaves indeterminate are zero
-          const double dm = __dadd_rn(__dmul_rn((double)vd, 0.002), bank ? dc1 : dc0);
-          sh.meta[3u * slot] = va;
-          sh.meta[3u * slot + 1u] = __float_as_uint((float)dm);
-          sh.meta[3u * slot + 2u] = 0u;
+          const double dm = __dadd_rn(__dmul_rn((double)vd[u], 0.002), bk[u] ? dc1 : dc0);
+          sh.meta[3u * slot[u]] = va[u];
+          sh.meta[3u * slot[u] + 1u] = __float_as_uint((float)dm);
+          sh.meta[3u * slot[u] + 2u] = 0u;
         }
       }
     }
