@@ -543,25 +543,33 @@ def parity_windows(ctx, res, b, t, t_base, halo, calib, poses, seed, rotations=1
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-NCU_FULL_CSV = os.path.join(ROOT, "profiles", "r1z_k_decode_ncu_full.csv")
-NCU_FULL_PACKETS = 1 << 20  # packets per launch of the captured k_decode
+NCU_FULL_CSV = os.path.join(ROOT, "profiles", "r2a_k_decode_ncu_full.csv")
+NCU_STEP_CSVS = [os.path.join(ROOT, "profiles", f"r2a_{k}_ncu_full.csv") for k in ("k_scan", "k_pose", "k_decode")]
+NCU_FULL_PACKETS = 1 << 20  # packets per launch of the captured kernels
+
+
+def _ncu_dram_bytes(path):
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for line in open(path):
+        parts = line.strip().split(",")
+        if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(parts[2]) * scale[parts[1]]
+    return tot
 
 
 def ncu_traffic(n_per):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_decode launch from the committed
-    `ncu --set full` capture (same workload and batch size), else None."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_decode launch, and of one whole step
+    (k_scan + k_pose + k_decode), from the committed `ncu --set full` captures of the same
+    workload and batch size; else None."""
     if n_per != NCU_FULL_PACKETS or not os.path.exists(NCU_FULL_CSV):
-        return None, None
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot = 0.0
+        return None, None, None
     try:
-        for line in open(NCU_FULL_CSV):
-            name, unit, val = line.strip().split(",")[:3]
-            if name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                tot += float(val) * scale[unit]
+        tot = _ncu_dram_bytes(NCU_FULL_CSV)
+        step = sum(_ncu_dram_bytes(p) for p in NCU_STEP_CSVS)
     except Exception:
-        return None, None
-    return (tot if tot > 0 else None), os.path.relpath(NCU_FULL_CSV, ROOT)
+        return None, None, None
+    return (tot if tot > 0 else None), os.path.relpath(NCU_FULL_CSV, ROOT), (step if step > 0 else None)
 
 
 def pin_to_gpu_numa_node(cuda_index):
@@ -719,7 +727,7 @@ def run_ours(args):
     except Exception:
         pass
     alg_bytes = 1206 * n_per + BYTES_PER_POINT_OUT * n_emitted
-    traffic, traffic_src = ncu_traffic(n_per)
+    traffic, traffic_src, traffic_step = ncu_traffic(n_per)
     dec_avg_ms = float(np.mean(dec_ms))
     achieved = alg_bytes / (dec_avg_ms * 1e-3) / 1e9
     step_avg_ms = float(np.mean(step_ms))
@@ -730,6 +738,10 @@ def run_ours(args):
                 "kernel_ms": dec_avg_ms,
                 # every kernel, memset and gap of the step: algorithmic bytes / ms_per_step
                 "frac_whole_step": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                # DRAM bytes of k_scan + k_pose + k_decode (ncu) over the algorithmic bytes: the
+                # packets are read twice and the scan's records are written and re-read
+                "traffic_whole_step": traffic_step,
+                "traffic_whole_step_over_algorithmic": (traffic_step / alg_bytes) if traffic_step else None,
                 "note": "k_decode timed with CUDA events on its launch stream while the other "
                         "result slot's k_scan/k_pose may overlap it (two batches in flight)"}
 
