@@ -155,3 +155,30 @@ def test_online_udp_to_hdlmanager(tmp_path):
     o = P.make_oracle(calib, poses)
     o.process_packets(b, t)
     compare(F.read_frames(tmp_path / "out.bin"), o.frames(), P.TOL_DESKEW)
+
+
+@pytest.mark.parametrize("store,meta,pipelined,batch", [(1, 1, 1, 700), (0, 0, 1, 512), (0, 1, 0, 4096)])
+def test_consumer_loop_counts_match_the_oracle(tmp_path, store, meta, pipelined, batch):
+    """facade_driver bench (what bench.py's e2e_facade runs): processHDLPacket per packet +
+    getAllFrames/clearAllFrames over the packet array twice (warm-up pass + 1 timed pass, one
+    continuous stream).  Frames and points handed out in the timed pass == the oracle's."""
+    import json
+    n = 2500
+    pk, t = synth.hdl64_packets(n)
+    calib = synth.calib_hdl64()
+    b = synth.as_bytes(pk)
+    b.tofile(tmp_path / "pk.bin")
+    t.astype("<i8").tofile(tmp_path / "t.bin")
+    calibxml.write_db_xml(str(tmp_path / "db.xml"), calib)
+    r = F.run(["bench", tmp_path / "db.xml", tmp_path / "pk.bin", tmp_path / "t.bin", "-", batch, 1,
+               store, meta, pipelined, 0])
+    assert r.returncode == 0, r.stderr
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    span = int(t[-1] - t[0]) + int(t[-1] - t[0]) // (n - 1)
+    o = P.make_oracle(calib)
+    o.process_packets(b, t)
+    warm = o.num_frames()                    # closed during the warm-up pass: handed out untimed
+    o.process_packets(b, t + span)
+    frames = o.frames()
+    assert got["frames"] == len(frames) - warm
+    assert got["points"] == sum(f.n_points for f in frames[warm:])

@@ -144,3 +144,54 @@ def test_layout_needs_a_finished_decode_batch():
         ctx.fetch_frames_layout(r.ticket)
     finally:
         ctx.close()
+
+
+def test_offline_mode_layout_matches_get_frame():
+    """VS_MODE_OFFLINE (readFrameInformation + getFrame): frame i = blocks [start_i, start_i+1),
+    no dropped blocks; laid out on the device == oracle.get_frame of every index entry."""
+    from oracle.oracle import Oracle
+    pk, t = synth.hdl64_packets(1300)
+    b = synth.as_bytes(pk)
+    calib, poses = synth.calib_hdl64(), synth.ins_trajectory(60)
+    sp, sk, ts = Oracle.read_frame_information(b, t)
+    o = P.make_oracle(calib, poses)
+    ctx = P.make_ctx(calib, poses)
+    try:
+        frames = P.gpu_layout_stream(ctx, b, t, splits=(450, 451), mode=capi.MODE_OFFLINE)
+        assert len(frames) == len(sp) - 1          # the last index entry stays open
+        for i, g in enumerate(frames):
+            want = o.get_frame(b, t, sp[i], sk[i], first=True)
+            n_rows = len(want.laser_counts)
+            assert np.array_equal(g["row_count"][:n_rows], want.laser_counts), i
+            assert np.array_equal(g["meta"]["azimuth"], want.azimuth[:want.n_points]), i
+            assert np.array_equal(g["meta"]["distance"], want.distance[:want.n_points]), i
+            d = np.abs(g["xyzi"][:, :3].astype(np.float64) - want.xyzi[:want.n_points, :3])
+            assert d.max() <= P.TOL_DESKEW, i
+    finally:
+        ctx.close()
+
+
+def test_layout_of_an_empty_and_a_wrap_free_batch():
+    """No points at all (every distance 0) and a batch without a single wrap (one open frame)."""
+    pk, t = synth.hdl64_packets(100)
+    pk = pk.copy()
+    pk["blocks"]["returns"]["distance"] = 0
+    ctx = P.make_ctx(synth.calib_hdl64())
+    try:
+        r = ctx.decode(synth.as_bytes(pk), t, t_base_us=int(t[0]))
+        assert r.n_points == 0
+        xyzi, meta, rows = ctx.fetch_frames_layout(r.ticket)
+        assert xyzi.shape[0] == 0 and len(rows) == r.n_frames and not rows["n_slots"].any()
+        pk2, t2 = synth.hdl64_packets(120, az0=100.0)          # 120 packets: a third of a rotation
+        r = ctx.decode(synth.as_bytes(pk2), t2, t_base_us=int(t2[0]))
+        assert r.n_frames == 1 and r.n_closed == 0
+        xyzi, meta, rows = ctx.fetch_frames_layout(r.ticket)
+        assert int(rows["n_slots"][0]) == r.n_points == xyzi.shape[0]
+        cols = r.fetch()
+        # rows by laser id, time order inside a row: a stable sort of the stream order
+        order = np.argsort(cols["laser"], kind="stable")
+        assert np.array_equal(xyzi[:, 0], cols["x"][order])
+        assert np.array_equal(meta["azimuth"], cols["azimuth"][order])
+        assert np.array_equal(rows["row_count"][0], np.bincount(cols["laser"], minlength=64))
+    finally:
+        ctx.close()

@@ -1359,7 +1359,8 @@ int vs_layout_frames(vs_ctx* ctx, uint64_t ticket, const uint32_t* carried_count
                                    (int)sizeof(LayShared)));
       ctx->layout_attr_set = true;
     }
-    k_layout<<<(unsigned)n_chunks, kLayThreads, sizeof(LayShared), s.stream>>>(lp);
+    const int lay_grid = std::min(n_chunks, 2 * ctx->sm_count);  // persistent CTAs, 2 per SM
+    k_layout<<<(unsigned)lay_grid, kLayThreads, sizeof(LayShared), s.stream>>>(lp);
     VS_CUDA(cudaGetLastError());
     launches = 2;
   }

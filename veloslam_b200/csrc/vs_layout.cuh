@@ -125,26 +125,18 @@ struct LayShared {
   unsigned wcnt[kLayWarps][2][32];  // per warp, laser bank, return slot: points in the segment
   unsigned ltot[kMaxLasers];        // per laser id: points of the segment in this tile
   unsigned lofs[kMaxLasers];        // staging slot of the laser's run
-  unsigned excl[2][32];             // look-back result: points of the open frame before the tile
   unsigned long long rdst[kMaxLasers];  // destination slot of the laser's run
   int seg_start[kLayTileBlocks + 2];    // tile-relative block index where each segment begins
   int n_seg;
   int tile;
 };
 
-__global__ void __launch_bounds__(kLayThreads, 2) k_layout(const LayoutParams p) {
+// one tile (8 packets); called by all threads of the CTA
+__device__ __forceinline__ void layout_tile(const LayoutParams& p, LayShared& sh, const int tile) {
   const int wb0 = (int)(threadIdx.x >> 5) * kLayWarpBlocks;  // this warp's first block of the tile
-  extern __shared__ __align__(16) uint8_t lay_smem[];
-  LayShared& sh = *reinterpret_cast<LayShared*>(lay_smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned full = 0xffffffffu;
   const bool vlp = p.adj == 2;
-  // tile ids are dealt in launch order, so a tile only ever waits for tiles whose CTAs are
-  // already running
-  if (tid == 0) sh.tile = atomicAdd(p.chunk_counter, 1);
-  __syncthreads();
-  const int tile = sh.tile;
-  if (tile >= p.n_chunks) return;
   const int P0 = p.halo + tile * kLayTile;
   const int npk = min(kLayTile, p.n - P0);
   for (int i = tid; i < npk * kBlocks; i += kLayThreads) sh.rec[i] = __ldg(&p.recs[(long long)P0 * kBlocks + i]);
@@ -154,28 +146,33 @@ __global__ void __launch_bounds__(kLayThreads, 2) k_layout(const LayoutParams p)
   }
   __syncthreads();
   // segments: runs of blocks between frame starts (the split happens before the wrap block is
-  // decoded, HDLParser.cxx:1035-1039).  One segment per tile but for ~1 tile in 43.
-  if (tid == 0) {
-    int ns = 0;
-    sh.seg_start[ns++] = 0;
-    for (int lp = 0; lp < npk; ++lp) {
-      unsigned wm = ((unsigned)sh.seg[lp].x >> 4) & 0xfffu;
-      while (wm) {
-        const int j = __ffs(wm) - 1;
-        wm &= wm - 1;
-        const int g = lp * kBlocks + j;
-        if (g == 0) continue;  // the tile's first block: segment 0 simply belongs to the new frame
-        sh.seg_start[ns++] = g;
+  // decoded, HDLParser.cxx:1035-1039).  42 of 43 tiles hold no frame start: one segment, no list.
+  unsigned anywrap = 0;
+  for (int lp = 0; lp < npk; ++lp) anywrap |= ((unsigned)sh.seg[lp].x >> 4) & 0xfffu;
+  const bool simple = anywrap == 0u;
+  const int n_blocks = npk * kBlocks;
+  if (!simple) {
+    if (tid == 0) {
+      int ns = 0;
+      sh.seg_start[ns++] = 0;
+      for (int lp = 0; lp < npk; ++lp) {
+        unsigned wm = ((unsigned)sh.seg[lp].x >> 4) & 0xfffu;
+        while (wm) {
+          const int j = __ffs(wm) - 1;
+          wm &= wm - 1;
+          const int g = lp * kBlocks + j;
+          if (g == 0) continue;  // the tile's first block: segment 0 simply belongs to the new frame
+          sh.seg_start[ns++] = g;
+        }
       }
+      sh.seg_start[ns] = n_blocks;
+      sh.n_seg = ns;
     }
-    sh.seg_start[ns] = npk * kBlocks;
-    sh.n_seg = ns;
+    __syncthreads();
   }
-  __syncthreads();
-  const int n_seg = sh.n_seg;
+  const int n_seg = simple ? 1 : sh.n_seg;
   const bool starts_frame = (((unsigned)sh.seg[0].x >> 4) & 1u) != 0u;  // a frame starts at block 0
 
-  const int n_blocks = npk * kBlocks;
   // points of this warp's blocks per (bank, return slot) inside blocks [g0, g1) of the tile
   auto count_range = [&](int g0, int g1, unsigned& c0, unsigned& c1) {
     c0 = c1 = 0;
@@ -189,63 +186,76 @@ __global__ void __launch_bounds__(kLayThreads, 2) k_layout(const LayoutParams p)
       if (bank) c1 += add; else c0 += add;
     }
   };
-
-  // ---- look-back: this tile's contribution to the open frame, then what precedes the tile ------
-  {
-    unsigned c0, c1;
-    count_range(sh.seg_start[n_seg - 1], npk * kBlocks, c0, c1);  // the tile's last segment
-    sh.wcnt[warp][0][lane] = c0;
-    sh.wcnt[warp][1][lane] = c1;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    unsigned t0 = 0, t1 = 0;
+  // what precedes this warp's blocks inside the counted range, per (bank, slot), and the totals
+  unsigned b0 = 0, b1 = 0, t0 = 0, t1 = 0;
+  auto prefix_over_warps = [&]() {
+    b0 = b1 = t0 = t1 = 0;
 #pragma unroll
     for (int w = 0; w < kLayWarps; ++w) {
-      t0 += sh.wcnt[w][0][lane];
-      t1 += sh.wcnt[w][1][lane];
+      const unsigned v0 = sh.wcnt[w][0][lane], v1 = sh.wcnt[w][1][lane];
+      if (w < warp) {
+        b0 += v0;
+        b1 += v1;
+      }
+      t0 += v0;
+      t1 += v1;
     }
-    const bool seg = n_seg > 1 || starts_frame;
-    unsigned long long* my = p.st + (long long)tile * 32 + lane;
-    const unsigned long long mine = (unsigned long long)t0 | ((unsigned long long)t1 << 30);
+  };
+
+  // ---- this tile's contribution to the open frame: counts of its last segment, published early ---
+  {
+    unsigned c0, c1;
+    count_range(simple ? 0 : sh.seg_start[n_seg - 1], n_blocks, c0, c1);
+    sh.wcnt[warp][0][lane] = c0;
+    sh.wcnt[warp][1][lane] = c1;
+    if (tid < kMaxLasers) sh.ltot[tid] = 0u;
+  }
+  __syncthreads();
+  prefix_over_warps();
+  const bool seg = n_seg > 1 || starts_frame;
+  unsigned long long* my = p.st + (long long)tile * 32 + lane;
+  const unsigned pub0 = t0, pub1 = t1;  // (warp 0 uses them)
+  if (warp == 0) {
+    const unsigned long long mine = (unsigned long long)pub0 | ((unsigned long long)pub1 << 30);
     // a tile that holds a frame start knows its inclusive prefix without looking back
     if (seg || tile == 0)
       st_release_u64(my, kFlagPrefix | (seg ? kLaySeg : 0ull) | mine);
     else
       st_release_u64(my, kFlagAgg | mine);
-    unsigned e0 = 0, e1 = 0;
-    if (tile > 0 && !starts_frame) {
-      // The lanes carry the 32 return slots, so the walk over the predecessors is serial; a
-      // window of kWin words per lane is fetched at once so that a round trip covers kWin tiles
-      // (a frame spans ~43 tiles and tiles retire faster than a prefix could hop tile by tile).
-      constexpr int kWin = 8;
-      bool done = false;
-      int idx = tile - 1;
-      while (true) {
-        unsigned long long v[kWin];
+  }
+  // what earlier tiles hold of the frame that is open at the tile's first block: one warp walks
+  // back over the published words while the others stage (called by warp 0 in segment 0)
+  auto look_back = [&](unsigned& e0, unsigned& e1) {
+    e0 = e1 = 0;
+    if (tile == 0 || starts_frame) return;
+    // The lanes carry the 32 return slots, so the walk over the predecessors is serial; a
+    // window of kWin words per lane is fetched at once so that a round trip covers kWin tiles
+    // (a frame spans ~43 tiles and tiles retire faster than a prefix could hop tile by tile).
+    constexpr int kWin = 8;
+    bool done = false;
+    int idx = tile - 1;
+    while (true) {
+      unsigned long long v[kWin];
 #pragma unroll
-        for (int w = 0; w < kWin; ++w)
-          v[w] = (!done && idx - w >= 0) ? ld_acquire_u64(p.st + (long long)(idx - w) * 32 + lane) : 0ull;
-        if (!done) {
+      for (int w = 0; w < kWin; ++w)
+        v[w] = (!done && idx - w >= 0) ? ld_acquire_u64(p.st + (long long)(idx - w) * 32 + lane) : 0ull;
+      if (!done) {
 #pragma unroll
-          for (int w = 0; w < kWin; ++w) {
-            const unsigned flag = (unsigned)(v[w] >> 62);
-            if (flag == 0u) break;  // not published yet: poll again from here
-            e0 += (unsigned)(v[w] & kLayM30);
-            e1 += (unsigned)((v[w] >> 30) & kLayM30);
-            if (flag == 2u || --idx < 0) {
-              done = true;
-              break;
-            }
+        for (int w = 0; w < kWin; ++w) {
+          const unsigned flag = (unsigned)(v[w] >> 62);
+          if (flag == 0u) break;  // not published yet: poll again from here
+          e0 += (unsigned)(v[w] & kLayM30);
+          e1 += (unsigned)((v[w] >> 30) & kLayM30);
+          if (flag == 2u || --idx < 0) {
+            done = true;
+            break;
           }
         }
-        if (__all_sync(full, done)) break;
       }
-      if (!seg) st_release_u64(my, kFlagPrefix | (unsigned long long)(e0 + t0) | ((unsigned long long)(e1 + t1) << 30));
+      if (__all_sync(full, done)) break;
     }
-    sh.excl[0][lane] = e0;
-    sh.excl[1][lane] = e1;
-  }
+    if (!seg) st_release_u64(my, kFlagPrefix | (unsigned long long)(e0 + pub0) | ((unsigned long long)(e1 + pub1) << 30));
+  };
 
   int id0 = lane, id1 = lane + 32;  // laser ids of this return slot in a 0xeeff / 0xddff block
   if (vlp) {                        // HDLParser.cxx:935-943
@@ -257,29 +267,18 @@ __global__ void __launch_bounds__(kLayThreads, 2) k_layout(const LayoutParams p)
   const int frame0 = sh.seg[0].y - p.f_lo + (starts_frame ? 1 : 0);  // frame of segment 0
 
   for (int s = 0; s < n_seg; ++s) {
-    const int g0 = sh.seg_start[s], g1 = sh.seg_start[s + 1];
+    const int g0 = simple ? 0 : sh.seg_start[s], g1 = simple ? n_blocks : sh.seg_start[s + 1];
     const int fr = frame0 + s;
-    __syncthreads();  // wcnt (and, from the second segment on, the staging) is free again
-    // ---- A: counts of the segment per warp ----------------------------------------------------
-    {
+    if (n_seg > 1) {
+      // ---- A: counts of the segment per warp (a one-segment tile counted them above) -------------
+      __syncthreads();  // wcnt / ltot and, from the second segment on, the staging are free again
       unsigned c0, c1;
       count_range(g0, g1, c0, c1);
       sh.wcnt[warp][0][lane] = c0;
       sh.wcnt[warp][1][lane] = c1;
       if (tid < kMaxLasers) sh.ltot[tid] = 0u;
-    }
-    __syncthreads();
-    // what precedes this warp's packet inside the segment, per (bank, slot); segment totals
-    unsigned b0 = 0, b1 = 0, t0 = 0, t1 = 0;
-#pragma unroll
-    for (int w = 0; w < kLayWarps; ++w) {
-      const unsigned v0 = sh.wcnt[w][0][lane], v1 = sh.wcnt[w][1][lane];
-      if (w < warp) {
-        b0 += v0;
-        b1 += v1;
-      }
-      t0 += v0;
-      t1 += v1;
+      __syncthreads();
+      prefix_over_warps();
     }
     if (warp == 0) {
       // per laser id (VLP-16: slots l and l + 16 carry the same, combined count)
@@ -301,17 +300,17 @@ __global__ void __launch_bounds__(kLayThreads, 2) k_layout(const LayoutParams p)
       const unsigned tot_a = __shfl_sync(full, ia, 31);
       sh.lofs[lane] = ia - (a + 1u);
       sh.lofs[lane + 32] = tot_a + ib - (b + 1u);
-      // destination of each run: the laser's row of the segment's frame, behind what earlier
-      // tiles hold of that frame (first segment only)
-      const unsigned long long ra = __ldg(&p.row_abs[(long long)fr * kMaxLasers + lane]);
-      const unsigned long long rb = __ldg(&p.row_abs[(long long)fr * kMaxLasers + lane + 32]);
-      sh.rdst[lane] = ra;
-      sh.rdst[lane + 32] = rb;
     }
     __syncthreads();
-    if (warp == 0 && s == 0) {
-      // counts of the frame in front of the tile, by (bank, slot) -> by laser id
-      const unsigned e0 = sh.excl[0][lane], e1 = sh.excl[1][lane];
+    if (warp == 0) {
+      // destination of each run: the laser's row of the segment's frame, behind what earlier
+      // tiles hold of that frame (first segment only; the walk back overlaps the staging)
+      unsigned e0 = 0, e1 = 0;
+      if (s == 0) look_back(e0, e1);
+      sh.rdst[lane] = __ldg(&p.row_abs[(long long)fr * kMaxLasers + lane]);
+      sh.rdst[lane + 32] = __ldg(&p.row_abs[(long long)fr * kMaxLasers + lane + 32]);
+      __syncwarp();
+      // counts by (bank, slot) -> by laser id
       if (e0 && (!vlp || lane < 16)) sh.rdst[id0] += e0;
       if (e1) sh.rdst[id1] += e1;
     }
@@ -409,6 +408,21 @@ __global__ void __launch_bounds__(kLayThreads, 2) k_layout(const LayoutParams p)
         for (unsigned i = lane; i < 3u * nrun; i += 32) o[i] = sh.meta[3u * so + i];
       }
     }
+  }
+}
+
+// Persistent CTAs (2 per SM); tile ids are dealt in execution order by an atomic counter, so a
+// tile only ever waits (look-back) for tiles whose CTAs are already running.
+__global__ void __launch_bounds__(kLayThreads, 2) k_layout(const LayoutParams p) {
+  extern __shared__ __align__(16) uint8_t lay_smem[];
+  LayShared& sh = *reinterpret_cast<LayShared*>(lay_smem);
+  while (true) {
+    __syncthreads();  // the previous tile's copies out of the staging are done
+    if (threadIdx.x == 0) sh.tile = atomicAdd(p.chunk_counter, 1);
+    __syncthreads();
+    const int tile = sh.tile;
+    if (tile >= p.n_chunks) break;
+    layout_tile(p, sh, tile);
   }
 }
 
