@@ -150,10 +150,11 @@ typedef struct vs_result {
   vs_carry carry_out;
   int64_t t_base_us;
   int64_t first_upper_block;  /* first decoded 0xddff block (packet*12+block), -1 none */
-  float   gpu_ms;             /* device time of the batch's kernels (CUDA events)  */
-  float   decode_ms;          /* device time of the decode kernel alone            */
+  float   gpu_ms;             /* device time of the batch's kernels (CUDA events); a batch  */
+                              /* issued as a CUDA graph: of the whole graph, copies included */
+  float   decode_ms;          /* device time of the decode kernel alone (0 for a graph)     */
   int32_t n_kernel_launches;
-  int32_t reserved;
+  int32_t reserved;           /* diagnostics: batches this slot has issued as one CUDA graph */
 } vs_result;
 
 typedef struct vs_ctx vs_ctx;

@@ -26,5 +26,6 @@ for r in range(n_rot):
     carry = res.carry_out
     ts.append(t1 - t0); tw.append(t2 - t1); tg.append(res.gpu_ms)
 ts, tw, tg = [np.array(x[20:]) for x in (ts, tw, tg)]
+print("graph launches of the slot:", res.graph_launches)
 print("submit p50 %.1f us  wait p50 %.1f us  device(kernels) p50 %.1f us  total p50 %.1f us" %
       (np.median(ts) * 1e6, np.median(tw) * 1e6, np.median(tg) * 1e3, np.median(ts + tw) * 1e6))

@@ -332,6 +332,7 @@ class BatchResult:
         self.gpu_ms = float(r.gpu_ms)
         self.decode_ms = float(r.decode_ms)
         self.n_kernel_launches = int(r.n_kernel_launches)
+        self.graph_launches = int(r.reserved)   # batches this slot issued as one CUDA graph
         self.device_ptrs = {k: getattr(r, k) for k in
                             ("x", "y", "z", "intensity", "laser", "azimuth", "distance", "t_us")}
 

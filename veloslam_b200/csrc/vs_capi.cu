@@ -25,15 +25,111 @@ using namespace vsd;
 
 namespace {
 
-constexpr int kEagerFrames = 64;  // minimum frame-table rows copied back with the header
+constexpr int kEagerFrames = kEagerRows;  // minimum frame-table rows copied back with the header
 
 struct HostFrameRow {  // pinned mirror of the per-frame device tables
   std::vector<long long> first;
   std::vector<int> start;
 };
 
+// How the stream operations of a batch are issued.  A rotation-sized batch (online use: ~350
+// packets) is 17 small copies, memsets and kernels whose launch latency, not their work, sets the
+// submit -> index latency; such batches are recorded ONCE per result slot as a CUDA graph (stream
+// capture of the very same code) and afterwards only the node parameters that differ between
+// batches (sizes, grids, kernel arguments, host pointers) are refreshed before one
+// cudaGraphLaunch.  UPDATE walks the captured nodes in issue order, so one code path serves the
+// direct launch, the capture and the refresh.
+struct GraphOps {
+  enum Mode { DIRECT, CAPTURE, UPDATE };
+  Mode mode = DIRECT;
+  cudaStream_t stream = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::vector<cudaGraphNode_t>* nodes = nullptr;
+  size_t cursor = 0;
+
+  cudaError_t captured() {
+    cudaStreamCaptureStatus st;
+    unsigned long long id = 0;
+    cudaGraph_t g = nullptr;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t nd = 0;
+    cudaError_t e = cudaStreamGetCaptureInfo(stream, &st, &id, &g, &deps, &nd);
+    if (e != cudaSuccess) return e;
+    if (st != cudaStreamCaptureStatusActive || nd != 1) return cudaErrorStreamCaptureInvalidated;
+    nodes->push_back(deps[0]);
+    return cudaSuccess;
+  }
+  cudaGraphNode_t next() { return cursor < nodes->size() ? (*nodes)[cursor++] : nullptr; }
+
+  cudaError_t copy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    if (mode == UPDATE) {
+      cudaGraphNode_t nd = next();
+      if (!nd) return cudaErrorInvalidValue;
+      return cudaGraphExecMemcpyNodeSetParams1D(exec, nd, dst, src, bytes, kind);
+    }
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, stream);
+    if (e == cudaSuccess && mode == CAPTURE) e = captured();
+    return e;
+  }
+  cudaError_t fill(void* dst, int value, size_t bytes) {
+    if (mode == UPDATE) {
+      cudaGraphNode_t nd = next();
+      if (!nd) return cudaErrorInvalidValue;
+      cudaMemsetParams mp;
+      std::memset(&mp, 0, sizeof(mp));
+      mp.dst = dst;
+      mp.value = (unsigned)value;
+      mp.elementSize = 1;
+      mp.width = bytes;
+      mp.height = 1;
+      mp.pitch = bytes;
+      return cudaGraphExecMemsetNodeSetParams(exec, nd, &mp);
+    }
+    cudaError_t e = cudaMemsetAsync(dst, value, bytes, stream);
+    if (e == cudaSuccess && mode == CAPTURE) e = captured();
+    return e;
+  }
+  cudaError_t launch(const void* func, unsigned grid, unsigned block, size_t smem, void** args) {
+    if (mode == UPDATE) {
+      cudaGraphNode_t nd = next();
+      if (!nd) return cudaErrorInvalidValue;
+      cudaKernelNodeParams kp;
+      std::memset(&kp, 0, sizeof(kp));
+      kp.func = const_cast<void*>(func);
+      kp.gridDim = dim3(grid, 1, 1);
+      kp.blockDim = dim3(block, 1, 1);
+      kp.sharedMemBytes = (unsigned)smem;
+      kp.kernelParams = args;
+      return cudaGraphExecKernelNodeSetParams(exec, nd, &kp);
+    }
+    cudaError_t e = cudaLaunchKernel(func, dim3(grid, 1, 1), dim3(block, 1, 1), args, smem, stream);
+    if (e == cudaSuccess && mode == CAPTURE) e = captured();
+    return e;
+  }
+  // timing events exist only on the direct path: an event recorded by a graph node cannot be
+  // read back with cudaEventElapsedTime (run_batch brackets the whole graph instead)
+  cudaError_t record(cudaEvent_t ev) {
+    if (mode != DIRECT) return cudaSuccess;
+    return cudaEventRecord(ev, stream);
+  }
+};
+
+// what decides the SEQUENCE of operations (and the kernel functions) of a batch: a captured
+// graph is re-used only for batches with the same key
+struct GraphKey {
+  int dev_in, pcap_t, fused, index_only, adj, crop, deskew, pose_valid, has_decode, eager_packed;
+  bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(*this)) == 0; }
+};
+
 struct Slot {
   cudaStream_t stream = nullptr;
+  GraphOps ops;
+  cudaGraphExec_t gexec = nullptr;
+  cudaGraph_t ggraph = nullptr;  // kept: the node handles used for the refresh belong to it
+  std::vector<cudaGraphNode_t> gnodes;
+  GraphKey gkey;
+  int graph_launches = 0;
+  bool graph_issued = false;  // the batch in flight went out as a graph (no per-kernel events)
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr, ev_done = nullptr;
   // device
   uint8_t* d_in = nullptr;  // staged packets (host input path only, allocated lazily)
@@ -62,6 +158,9 @@ struct Slot {
   long long* d_frame_meta_time = nullptr;
   int* d_frame_skips = nullptr;
   BatchHeader* d_hdr = nullptr;
+  EagerBlock* d_eager = nullptr;  // header + first rows of the frame tables, packed (k_frames)
+  EagerBlock* h_eager = nullptr;  // pinned
+  bool eager_packed = false;      // the batch in flight brings its index back through h_eager
   // HDLFrame layout of the batch (vs_layout_frames), allocated on first use
   uint8_t* d_lay_xyzi = nullptr;
   uint8_t* d_lay_meta = nullptr;
@@ -128,6 +227,7 @@ struct vs_ctx {
   std::vector<double> pose_trv;
   cudaStream_t cfg_stream = nullptr;  // small table uploads (calibration, filters, poses)
   bool layout_attr_set = false;
+  bool use_graph = false;  // rotation-sized contexts: batches are issued as a CUDA graph
   KernelCache dec_cache[3][2][2];  // [ADJ][DSK][FUSED]
   KernelCache scan_cache[3][2];    // [ADJ][CROP]
   bool two_pass = true;  // false (VELOSLAM_SINGLE_PASS=1): k_pose_pre + k_decode<.., FUSED> where it applies
@@ -192,6 +292,14 @@ void host_interpolate(const vs_ctx* c, int64_t t, double out[9], bool* found, bo
   *valid = true;
 }
 
+void drop_graph(Slot& s) {
+  if (s.gexec) cudaGraphExecDestroy(s.gexec);
+  if (s.ggraph) cudaGraphDestroy(s.ggraph);
+  s.gexec = nullptr;
+  s.ggraph = nullptr;
+  s.gnodes.clear();
+}
+
 void free_slot(Slot& s) {
   cudaFree(s.d_in);
   cudaFree(s.d_time);
@@ -213,6 +321,9 @@ void free_slot(Slot& s) {
   cudaFree(s.d_frame_meta_time);
   cudaFree(s.d_frame_skips);
   cudaFree(s.d_hdr);
+  cudaFree(s.d_eager);
+  cudaFreeHost(s.h_eager);
+  drop_graph(s);
   cudaFree(s.d_lay_xyzi);
   cudaFree(s.d_lay_meta);
   cudaFree(s.d_lay_rows);
@@ -321,6 +432,8 @@ int alloc_slot(vs_ctx* ctx, Slot& s) {
   VS_CUDA(cudaMalloc(&s.d_frame_meta_time, fc * sizeof(long long)));
   VS_CUDA(cudaMalloc(&s.d_frame_skips, fc * sizeof(int)));
   VS_CUDA(cudaMalloc(&s.d_hdr, sizeof(BatchHeader)));
+  VS_CUDA(cudaMalloc(&s.d_eager, sizeof(EagerBlock)));
+  VS_CUDA(cudaMallocHost(&s.h_eager, sizeof(EagerBlock)));
   VS_CUDA(cudaMallocHost(&s.h_hdr, sizeof(BatchHeader)));
   VS_CUDA(cudaMallocHost(&s.h_hdr_init, sizeof(BatchHeader)));
   return VS_OK;
@@ -347,19 +460,15 @@ int ensure_host_frames(vs_ctx* ctx, Slot& s, size_t need) {
 }
 
 int copy_frame_rows(vs_ctx* ctx, Slot& s, size_t n_rows) {
-  VS_CUDA(cudaMemcpyAsync(s.h_frame_first, s.d_frame_first, n_rows * sizeof(long long),
-                          cudaMemcpyDeviceToHost, s.stream));
-  VS_CUDA(cudaMemcpyAsync(s.h_frame_start, s.d_frame_start, n_rows * sizeof(int),
-                          cudaMemcpyDeviceToHost, s.stream));
-  VS_CUDA(cudaMemcpyAsync(s.h_frame_meta_pkt, s.d_frame_meta_pkt, n_rows * sizeof(int),
-                          cudaMemcpyDeviceToHost, s.stream));
-  VS_CUDA(cudaMemcpyAsync(s.h_frame_meta_time, s.d_frame_meta_time, n_rows * sizeof(long long),
-                          cudaMemcpyDeviceToHost, s.stream));
-  VS_CUDA(cudaMemcpyAsync(s.h_frame_skips, s.d_frame_skips, n_rows * sizeof(int),
-                          cudaMemcpyDeviceToHost, s.stream));
-  VS_CUDA(cudaMemcpyAsync(s.h_frame_counts, s.d_frame_counts,
-                          n_rows * kMaxLasers * sizeof(unsigned), cudaMemcpyDeviceToHost,
-                          s.stream));
+  GraphOps& g = s.ops;
+  VS_CUDA(g.copy(s.h_frame_first, s.d_frame_first, n_rows * sizeof(long long), cudaMemcpyDeviceToHost));
+  VS_CUDA(g.copy(s.h_frame_start, s.d_frame_start, n_rows * sizeof(int), cudaMemcpyDeviceToHost));
+  VS_CUDA(g.copy(s.h_frame_meta_pkt, s.d_frame_meta_pkt, n_rows * sizeof(int), cudaMemcpyDeviceToHost));
+  VS_CUDA(g.copy(s.h_frame_meta_time, s.d_frame_meta_time, n_rows * sizeof(long long),
+                 cudaMemcpyDeviceToHost));
+  VS_CUDA(g.copy(s.h_frame_skips, s.d_frame_skips, n_rows * sizeof(int), cudaMemcpyDeviceToHost));
+  VS_CUDA(g.copy(s.h_frame_counts, s.d_frame_counts, n_rows * kMaxLasers * sizeof(unsigned),
+                 cudaMemcpyDeviceToHost));
   return VS_OK;
 }
 
@@ -392,8 +501,9 @@ int launch_decode(vs_ctx* ctx, Slot& s, DecParams dp, int64_t stride) {
   if (kc.per_sm < 1) return fail(ctx, VS_ERR_CUDA, "k_decode does not fit on an SM");
   int grid = ctx->sm_count * kc.per_sm;
   if (grid > dp.n_tiles) grid = dp.n_tiles;
-  k_decode<ADJ, DSK, FUSED><<<grid, kThreads, smem, s.stream>>>(dp);
-  VS_CUDA(cudaGetLastError());
+  void* args[] = {&dp};
+  VS_CUDA(s.ops.launch(reinterpret_cast<const void*>(&k_decode<ADJ, DSK, FUSED>), (unsigned)grid, kThreads,
+                       smem, args));
   return VS_OK;
 }
 
@@ -418,14 +528,24 @@ int launch_scan(vs_ctx* ctx, Slot& s, const ScanParams& sp, size_t smem) {
   if (kc.per_sm < 1) return fail(ctx, VS_ERR_CUDA, "k_scan does not fit on an SM");
   int grid = ctx->sm_count * kc.per_sm;
   if (grid > sp.n_tiles) grid = sp.n_tiles;
-  k_scan<ADJ, CROP><<<grid, kScanThreads, smem, s.stream>>>(sp);
-  VS_CUDA(cudaGetLastError());
+  ScanParams spv = sp;
+  void* args[] = {&spv};
+  VS_CUDA(s.ops.launch(reinterpret_cast<const void*>(&k_scan<ADJ, CROP>), (unsigned)grid, kScanThreads, smem,
+                       args));
   return VS_OK;
 }
 
-int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const int64_t* pkt_time,
-              int64_t n, int64_t halo, int mode, uint32_t flags, int64_t t_base,
-              const vs_carry* carry_in, bool index_only) {
+// rows of the frame tables copied back with the batch header, before the frame count is known
+int64_t eager_frame_rows(const vs_ctx* ctx, int64_t n) {
+  const int64_t frames_possible = std::min<int64_t>(ctx->frame_cap, 12 * n + 1);
+  return std::min<int64_t>(frames_possible, std::max<int64_t>(kEagerFrames, n / 100 + 8));
+}
+
+// Everything a batch puts on its slot's stream, through s.ops (direct, captured or refreshed).
+int enqueue_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const int64_t* pkt_time,
+                  int64_t n, int64_t halo, int mode, uint32_t flags, int64_t t_base,
+                  const vs_carry* carry_in, bool index_only) {
+  GraphOps& g = s.ops;
   const bool dev_in = (flags & VS_FLAG_DEVICE_INPUT) != 0;
   const bool pcap_t = (flags & VS_FLAG_PCAP_TIMES) != 0;
   const uint8_t* d_pkts = pkts;
@@ -434,30 +554,21 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
   s.n_launches = 0;
 
   if (!dev_in) {
-    // stage host packets (and the pcap record headers in front of them when asked)
+    // stage host packets (and the pcap record headers in front of them when asked); s.d_in was
+    // sized by run_batch
     const int64_t lead = pcap_t ? 64 : 0;  // keeps the payload 2-byte aligned, covers the 58 B
-    const size_t need = (size_t)(payload_bytes + lead + 64);
-    if (need > s.d_in_bytes) {
-      cudaFree(s.d_in);
-      s.d_in = nullptr;
-      s.d_in_bytes = 0;
-      const size_t want = std::max(need, (size_t)(ctx->max_packets * stride + 128));
-      VS_CUDA(cudaMalloc(&s.d_in, want));
-      s.d_in_bytes = want;
-    }
     const int64_t src_lead = pcap_t ? 58 : 0;
-    VS_CUDA(cudaMemcpyAsync(s.d_in + lead - src_lead, pkts - src_lead,
-                            (size_t)(payload_bytes + src_lead), cudaMemcpyHostToDevice, s.stream));
+    VS_CUDA(g.copy(s.d_in + lead - src_lead, pkts - src_lead, (size_t)(payload_bytes + src_lead),
+                   cudaMemcpyHostToDevice));
     d_pkts = s.d_in + lead;
     if (!pcap_t) {
-      VS_CUDA(cudaMemcpyAsync(s.d_time, pkt_time, (size_t)n * sizeof(long long),
-                              cudaMemcpyHostToDevice, s.stream));
+      VS_CUDA(g.copy(s.d_time, pkt_time, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice));
       d_time = s.d_time;
     }
   }
   if (pcap_t) d_time = s.d_time;
 
-  VS_CUDA(cudaEventRecord(s.ev_k0, s.stream));
+  VS_CUDA(g.record(s.ev_k0));
   // ---- per-batch resets ------------------------------------------------------------------
   const int64_t scan_tiles = (n + kTilePkts - 1) / kTilePkts;
   const int64_t pose_tiles = (n + kPoseThreads - 1) / kPoseThreads;
@@ -479,26 +590,28 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
   {
     // zero only what this batch can touch
     if (fused) {
-      VS_CUDA(cudaMemsetAsync(s.d_frame_counts, 0, fc_bytes + 256 + (size_t)fused_tiles * 32, s.stream));
+      VS_CUDA(g.fill(s.d_frame_counts, 0, fc_bytes + 256 + (size_t)fused_tiles * 32));
     } else {
       const size_t head = (size_t)((uint8_t*)s.d_frame_counts - s.d_zero);
-      VS_CUDA(cudaMemsetAsync(s.d_zero, 0, head + fc_bytes, s.stream));
+      VS_CUDA(g.fill(s.d_zero, 0, head + fc_bytes));
     }
-    VS_CUDA(cudaMemsetAsync(s.d_frame_first, 0xff, (size_t)frames_possible * 8, s.stream));
-    VS_CUDA(cudaMemsetAsync(s.d_frame_start, 0xff, (size_t)frames_possible * 4, s.stream));
+    // first_point / start_block tables (adjacent in one allocation): all rows "unset" in one go
+    VS_CUDA(g.fill(s.d_ff, 0xff, (size_t)ctx->frame_cap * 12));
     BatchHeader& hi = *s.h_hdr_init;
     std::memset(&hi, 0, sizeof(hi));
     hi.first_upper_block = LLONG_MAX;
     hi.first_const_pkt = INT_MAX;
     hi.origin_at_halo = -1;
     hi.last_origin_packet = -1;
-    VS_CUDA(cudaMemcpyAsync(s.d_hdr, s.h_hdr_init, sizeof(BatchHeader), cudaMemcpyHostToDevice,
-                            s.stream));
+    VS_CUDA(g.copy(s.d_hdr, s.h_hdr_init, sizeof(BatchHeader), cudaMemcpyHostToDevice));
   }
   if (pcap_t) {
-    k_pcap_times<<<(unsigned)((n + 255) / 256), 256, 0, s.stream>>>(d_pkts, stride, (int)n,
-                                                                   s.d_time);
-    VS_CUDA(cudaGetLastError());
+    const uint8_t* a0 = d_pkts;
+    long long a1 = stride;
+    int a2 = (int)n;
+    long long* a3 = s.d_time;
+    void* args[] = {&a0, &a1, &a2, &a3};
+    VS_CUDA(g.launch(reinterpret_cast<const void*>(&k_pcap_times), (unsigned)((n + 255) / 256), 256, 0, args));
     ++s.n_launches;
   }
 
@@ -510,9 +623,13 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
 
   if (fused) {
     if (pose_valid) {
-      k_pose_pre<<<(unsigned)((n + 255) / 256), 256, 0, s.stream>>>(d_time, (int)n, n_poses, ctx->d_pose_t,
-                                                                    ctx->d_pose_trv, s.d_pose_mat);
-      VS_CUDA(cudaGetLastError());
+      const long long* a0 = d_time;
+      int a1 = (int)n, a2 = n_poses;
+      const long long* a3 = ctx->d_pose_t;
+      const double* a4 = ctx->d_pose_trv;
+      double* a5 = s.d_pose_mat;
+      void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5};
+      VS_CUDA(g.launch(reinterpret_cast<const void*>(&k_pose_pre), (unsigned)((n + 255) / 256), 256, 0, args));
       ++s.n_launches;
     }
     DecParams dp;
@@ -551,7 +668,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     dp.carry_skip = cin.firing_skip;
     dp.carry_meta_inited = cin.frame_meta_inited;
     for (int k = 0; k < 3; ++k) dp.carry_origin_T[k] = cin.origin_T[k];
-    VS_CUDA(cudaEventRecord(s.ev_d0, s.stream));
+    VS_CUDA(g.record(s.ev_d0));
     int rc;
     if (adj == 0)
       rc = launch_decode<0, 0, 1>(ctx, s, dp, stride);
@@ -561,7 +678,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
       rc = launch_decode<2, 0, 1>(ctx, s, dp, stride);
     if (rc != VS_OK) return rc;
     ++s.n_launches;
-    VS_CUDA(cudaEventRecord(s.ev_d1, s.stream));
+    VS_CUDA(g.record(s.ev_d1));
   } else {
   {
     ScanParams sp;
@@ -627,8 +744,8 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     pp.frame_start_block = s.d_frame_start;
     pp.frame_cap = (int)ctx->frame_cap;
     pp.hdr = s.d_hdr;
-    k_pose<<<(unsigned)pose_tiles, kPoseThreads, 0, s.stream>>>(pp);
-    VS_CUDA(cudaGetLastError());
+    void* args[] = {&pp};
+    VS_CUDA(g.launch(reinterpret_cast<const void*>(&k_pose), (unsigned)pose_tiles, kPoseThreads, 0, args));
     ++s.n_launches;
   }
   if (!index_only) {
@@ -659,7 +776,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     dp.t_us = s.d_t;
     dp.frame_laser_counts = s.d_frame_counts;
     dp.frame_cap = (int)ctx->frame_cap;
-    VS_CUDA(cudaEventRecord(s.ev_d0, s.stream));
+    VS_CUDA(g.record(s.ev_d0));
     if (dec_tiles > 0) {
       int rc;
       if (deskew) {
@@ -680,7 +797,7 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
       if (rc != VS_OK) return rc;
       ++s.n_launches;
     }
-    VS_CUDA(cudaEventRecord(s.ev_d1, s.stream));
+    VS_CUDA(g.record(s.ev_d1));
   }
   }  // two-pass pipeline
 
@@ -697,22 +814,32 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     fp.frame_meta_packet = s.d_frame_meta_pkt;
     fp.frame_meta_time = s.d_frame_meta_time;
     fp.frame_skips = s.d_frame_skips;
-    k_frames<<<(unsigned)((frames_possible + 255) / 256), 256, 0, s.stream>>>(fp);
-    VS_CUDA(cudaGetLastError());
+    // one packed copy instead of seven when the eager rows are the minimum anyway
+    s.eager_packed = eager_frame_rows(ctx, n) <= kEagerRows && !fused;
+    fp.eager = s.eager_packed ? s.d_eager : nullptr;
+    fp.hdr = s.d_hdr;
+    fp.frame_first_point = s.d_frame_first;
+    fp.frame_laser_counts = s.d_frame_counts;
+    void* args[] = {&fp};
+    VS_CUDA(g.launch(reinterpret_cast<const void*>(&k_frames), (unsigned)((frames_possible + 255) / 256), 256, 0,
+                     args));
     ++s.n_launches;
   }
-  VS_CUDA(cudaEventRecord(s.ev_k1, s.stream));
+  VS_CUDA(g.record(s.ev_k1));
 
-  VS_CUDA(cudaMemcpyAsync(s.h_hdr, s.d_hdr, sizeof(BatchHeader), cudaMemcpyDeviceToHost, s.stream));
-  {
-    // rows copied back right away: enough for ~3 frames per sensor rotation of the batch
-    s.eager_rows = std::min<int64_t>(frames_possible, std::max<int64_t>(kEagerFrames, n / 100 + 8));
-    int rc = ensure_host_frames(ctx, s, (size_t)s.eager_rows);
-    if (rc != VS_OK) return rc;
-    rc = copy_frame_rows(ctx, s, (size_t)s.eager_rows);
+  s.eager_rows = eager_frame_rows(ctx, n);
+  if (s.eager_packed) {
+    VS_CUDA(g.copy(s.h_eager, s.d_eager, sizeof(EagerBlock), cudaMemcpyDeviceToHost));
+  } else {
+    VS_CUDA(g.copy(s.h_hdr, s.d_hdr, sizeof(BatchHeader), cudaMemcpyDeviceToHost));
+    // rows copied back right away: enough for ~3 frames per sensor rotation of the batch (the
+    // pinned mirrors were sized by run_batch)
+    const int rc = copy_frame_rows(ctx, s, (size_t)s.eager_rows);
     if (rc != VS_OK) return rc;
   }
-  VS_CUDA(cudaEventRecord(s.ev_done, s.stream));
+  // the completion event is recorded by a host call, never by a graph node: cudaEventSynchronize
+  // waits for the most recent cudaEventRecord CALL, and a node only records when it executes
+  if (g.mode == GraphOps::DIRECT) VS_CUDA(cudaEventRecord(s.ev_done, s.stream));
 
   s.busy = true;
   s.done = false;
@@ -728,8 +855,123 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
   return VS_OK;
 }
 
+bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const int64_t* pkt_time,
+              int64_t n, int64_t halo, int mode, uint32_t flags, int64_t t_base,
+              const vs_carry* carry_in, bool index_only) {
+  const bool dev_in = (flags & VS_FLAG_DEVICE_INPUT) != 0;
+  const bool pcap_t = (flags & VS_FLAG_PCAP_TIMES) != 0;
+  // allocations never happen under a capture: the staging buffer and the pinned frame-row mirrors
+  if (!dev_in) {
+    const int64_t payload_bytes = (n - 1) * stride + kPacketBytes;
+    const size_t need = (size_t)(payload_bytes + (pcap_t ? 64 : 0) + 64);
+    if (need > s.d_in_bytes) {
+      drop_graph(s);  // the captured copies point into the old buffer
+      cudaFree(s.d_in);
+      s.d_in = nullptr;
+      s.d_in_bytes = 0;
+      const size_t want = std::max(need, (size_t)(ctx->max_packets * stride + 128));
+      VS_CUDA(cudaMalloc(&s.d_in, want));
+      s.d_in_bytes = want;
+    }
+  }
+  {
+    const size_t had = s.h_frames_cap;
+    const int rc = ensure_host_frames(ctx, s, (size_t)eager_frame_rows(ctx, n));
+    if (rc != VS_OK) return rc;
+    if (s.h_frames_cap != had) drop_graph(s);  // the captured copies point at the old mirrors
+  }
+  GraphOps& g = s.ops;
+  g.stream = s.stream;
+  g.mode = GraphOps::DIRECT;
+  s.graph_issued = false;
+  // graph path: small contexts, inputs the graph can copy from (device memory or page-locked host
+  // memory; a pageable source cannot be captured)
+  bool graph = ctx->use_graph;
+  if (graph && !dev_in)
+    graph = is_pinned_host(pkts - (pcap_t ? 58 : 0)) && (pcap_t || is_pinned_host(pkt_time));
+  if (graph) {
+    GraphKey key;
+    std::memset(&key, 0, sizeof(key));
+    const bool pose_valid = ctx->pose_t.size() >= 2;
+    const bool crop = ctx->h_cfg.crop_returns != 0 && !index_only;
+    const bool deskew = (flags & VS_FLAG_DESKEW_PER_POINT) != 0 && pose_valid && !index_only;
+    key.dev_in = dev_in;
+    key.pcap_t = pcap_t;
+    key.fused = !ctx->two_pass && !crop && !deskew && !index_only;
+    key.index_only = index_only;
+    key.adj = ctx->h_cfg.adj_mode;
+    key.crop = crop;
+    key.deskew = deskew;
+    key.pose_valid = pose_valid;
+    key.has_decode = (n - halo) > 0;
+    key.eager_packed = eager_frame_rows(ctx, n) <= kEagerRows && !key.fused;
+    if (s.gexec && !(key == s.gkey)) drop_graph(s);
+    g.nodes = &s.gnodes;
+    int rc = VS_OK;
+    cudaError_t ce = cudaSuccess;
+    if (!s.gexec) {
+      // record this batch's operations once
+      s.gnodes.clear();
+      s.gkey = key;
+      ce = cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeRelaxed);
+      if (ce == cudaSuccess) {
+        g.mode = GraphOps::CAPTURE;
+        rc = enqueue_batch(ctx, s, pkts, stride, pkt_time, n, halo, mode, flags, t_base, carry_in, index_only);
+        ce = cudaStreamEndCapture(s.stream, &s.ggraph);
+        if (rc == VS_OK && ce == cudaSuccess) ce = cudaGraphInstantiate(&s.gexec, s.ggraph, 0);
+      }
+    } else {
+      // same sequence as the recorded one: refresh what differs (sizes, grids, arguments)
+      g.mode = GraphOps::UPDATE;
+      g.exec = s.gexec;
+      g.cursor = 0;
+      rc = enqueue_batch(ctx, s, pkts, stride, pkt_time, n, halo, mode, flags, t_base, carry_in, index_only);
+      if (rc == VS_OK && g.cursor != s.gnodes.size()) ce = cudaErrorInvalidValue;
+    }
+    g.mode = GraphOps::DIRECT;
+    if (rc == VS_OK && ce == cudaSuccess) ce = cudaEventRecord(s.ev_k0, s.stream);
+    if (rc == VS_OK && ce == cudaSuccess) ce = cudaGraphLaunch(s.gexec, s.stream);
+    if (rc == VS_OK && ce == cudaSuccess) ce = cudaEventRecord(s.ev_k1, s.stream);
+    if (rc == VS_OK && ce == cudaSuccess) ce = cudaEventRecord(s.ev_done, s.stream);
+    if (rc == VS_OK && ce == cudaSuccess) {
+      ++s.graph_launches;
+      s.graph_issued = true;
+      return VS_OK;
+    }
+    // anything the graph path cannot do: drop it for this context and issue the batch directly
+    if (std::getenv("VELOSLAM_GRAPH_DEBUG"))
+      std::fprintf(stderr, "veloslam_b200: graph path dropped (rc=%d, %s, node %zu of %zu): %s\n", rc,
+                   cudaGetErrorString(ce), g.cursor, s.gnodes.size(), ctx->err.c_str());
+    cudaGetLastError();
+    drop_graph(s);
+    s.busy = false;
+    ctx->use_graph = false;
+  }
+  return enqueue_batch(ctx, s, pkts, stride, pkt_time, n, halo, mode, flags, t_base, carry_in, index_only);
+}
+
 int finish_batch(vs_ctx* ctx, Slot& s) {
   VS_CUDA(cudaEventSynchronize(s.ev_done));
+  if (s.eager_packed) {
+    // unpack the one-copy index into the mirrors the rest of this function reads
+    const EagerBlock& e = *s.h_eager;
+    *s.h_hdr = e.hdr;
+    std::memcpy(s.h_frame_first, e.first, sizeof(e.first));
+    std::memcpy(s.h_frame_start, e.start, sizeof(e.start));
+    std::memcpy(s.h_frame_meta_pkt, e.meta_pkt, sizeof(e.meta_pkt));
+    std::memcpy(s.h_frame_meta_time, e.meta_time, sizeof(e.meta_time));
+    std::memcpy(s.h_frame_skips, e.skips, sizeof(e.skips));
+    std::memcpy(s.h_frame_counts, e.counts, sizeof(e.counts));
+  }
   const BatchHeader& h = *s.h_hdr;
   if (h.frame_overflow || (int64_t)h.total_wraps + 1 > ctx->frame_cap) {
     s.busy = false;
@@ -744,8 +986,10 @@ int finish_batch(vs_ctx* ctx, Slot& s) {
   const int W = h.total_wraps;
   const int64_t frames_possible = std::min<int64_t>(ctx->frame_cap, 12 * s.n + 1);
   if (W + 1 > s.eager_rows) {
+    const size_t had = s.h_frames_cap;
     int rc = ensure_host_frames(ctx, s, (size_t)W + 1);
     if (rc != VS_OK) return rc;
+    if (s.h_frames_cap != had) drop_graph(s);  // a recorded graph copies into the old mirrors
     rc = copy_frame_rows(ctx, s, (size_t)std::min<int64_t>(W + 1, frames_possible));
     if (rc != VS_OK) return rc;
     VS_CUDA(cudaStreamSynchronize(s.stream));
@@ -892,6 +1136,10 @@ int vs_create(int device, int64_t max_batch_packets, int64_t max_poses, int n_sl
     // one on B200
     const char* e = std::getenv("VELOSLAM_SINGLE_PASS");
     ctx->two_pass = !(e && e[0] == '1');
+    // rotation-sized contexts issue their batches as one CUDA graph (VELOSLAM_GRAPH=0 turns it
+    // off, =1 forces it on for any size)
+    const char* gr = std::getenv("VELOSLAM_GRAPH");
+    ctx->use_graph = gr ? (gr[0] == '1') : (max_batch_packets <= 4096);
   }
   auto init = [&]() -> int {
     VS_CUDA(cudaMalloc(&ctx->d_cfg, sizeof(DevConfig)));
@@ -1144,11 +1392,13 @@ int vs_wait(vs_ctx* ctx, uint64_t ticket, vs_result* out) {
     r.t_base_us = s.t_base;
     r.first_upper_block = (h.first_upper_block == LLONG_MAX) ? -1 : h.first_upper_block;
     r.n_kernel_launches = s.n_launches;
+    r.reserved = s.graph_launches;  // batches of this slot issued as a CUDA graph so far
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
     r.gpu_ms = ms;
     ms = 0.f;
-    if (!s.index_only) cudaEventElapsedTime(&ms, s.ev_d0, s.ev_d1);
+    // (a graph-issued batch is timed as a whole: gpu_ms then includes its copies, decode_ms is 0)
+    if (!s.index_only && !s.graph_issued) cudaEventElapsedTime(&ms, s.ev_d0, s.ev_d1);
     r.decode_ms = ms;
 
     // first frame of a fresh stream / of a halo shard: meta from a packet of this batch

@@ -77,6 +77,19 @@ struct BatchHeader {
   int time_range_error;         // a decoded packet's time - t_base does not fit the t_us column
 };
 
+// Batch header + the first rows of the frame tables in one block (k_frames), for batches small
+// enough that the number of copies, not their size, sets the latency.
+constexpr int kEagerRows = 64;
+struct EagerBlock {
+  BatchHeader hdr;
+  long long first[kEagerRows];
+  long long meta_time[kEagerRows];
+  int start[kEagerRows];
+  int meta_pkt[kEagerRows];
+  int skips[kEagerRows];
+  unsigned counts[kEagerRows][kMaxLasers];
+};
+
 // The t_us column is u32 microseconds after t_base plus the return's firing offset (a u16), the
 // same arithmetic as the reference's rawtime + round(timestampadjustment) (HDLParser.cxx:970):
 // packet times must lie in [t_base, t_base + kTimeSpanMax).

@@ -2017,41 +2017,56 @@ struct FrameParams {
   int* frame_meta_packet;   // out: -2 none, -3 pending (next batch)
   long long* frame_meta_time;
   int* frame_skips;
+  // rotation-sized batches: the batch header and the first kEagerRows rows of every frame table
+  // packed into one block, so that ONE device -> host copy brings the whole index back
+  EagerBlock* eager;        // null: the tables are copied one by one
+  const BatchHeader* hdr;
+  const long long* frame_first_point;
+  const unsigned* frame_laser_counts;
 };
 
 __global__ void k_frames(const FrameParams p) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f < 1 || f >= p.n_frames) return;  // frame 0 comes from the carry / first packet
-  const int sb = p.frame_start_block[f];
-  if (sb < 0) {  // wrap inside the halo: not decoded
-    p.frame_meta_packet[f] = -2;
-    p.frame_meta_time[f] = 0;
-    p.frame_skips[f] = -1;
-    return;
-  }
-  const int P = sb / 12, j = sb % 12;
   int mp = -2, sk = -1;
   long long mt = 0;
-  if (p.mode == 1) {
-    mp = P;
-    sk = j;
-    mt = p.pkt_time[P];
-  } else {
-    const int wrapmask = (p.pkt_seg[P].x >> 4) & 0xfff;
-    const bool last_wrap = (wrapmask >> (j + 1)) == 0;
-    if (last_wrap) {
-      if (P + 1 < p.n) {
-        mp = P + 1;
-        sk = p.pkt_seg[P + 1].x & 15;
-        mt = p.pkt_time[P + 1];
+  if (f >= 1 && f < p.n_frames) {  // frame 0 comes from the carry / first packet
+    const int sb = p.frame_start_block[f];
+    if (sb >= 0) {  // (< 0: wrap inside the halo, not decoded)
+      const int P = sb / 12, j = sb % 12;
+      if (p.mode == 1) {
+        mp = P;
+        sk = j;
+        mt = p.pkt_time[P];
       } else {
-        mp = -3;
+        const int wrapmask = (p.pkt_seg[P].x >> 4) & 0xfff;
+        const bool last_wrap = (wrapmask >> (j + 1)) == 0;
+        if (last_wrap) {
+          if (P + 1 < p.n) {
+            mp = P + 1;
+            sk = p.pkt_seg[P + 1].x & 15;
+            mt = p.pkt_time[P + 1];
+          } else {
+            mp = -3;
+          }
+        }
       }
     }
+    p.frame_meta_packet[f] = mp;
+    p.frame_meta_time[f] = mt;
+    p.frame_skips[f] = sk;
   }
-  p.frame_meta_packet[f] = mp;
-  p.frame_meta_time[f] = mt;
-  p.frame_skips[f] = sk;
+  if (p.eager && f < kEagerRows) {
+    EagerBlock& e = *p.eager;
+    if (f == 0) e.hdr = *p.hdr;  // final: this is the batch's last kernel
+    const bool in = f < p.n_frames;
+    e.first[f] = in ? p.frame_first_point[f] : -1ll;
+    e.start[f] = in ? p.frame_start_block[f] : -1;
+    e.meta_pkt[f] = mp;
+    e.meta_time[f] = mt;
+    e.skips[f] = sk;
+    for (int l = 0; l < kMaxLasers; ++l)
+      e.counts[f][l] = in ? p.frame_laser_counts[(long long)f * kMaxLasers + l] : 0u;
+  }
 }
 
 }  // namespace vsd
