@@ -28,6 +28,7 @@ class HDLParser::vsInternal {
   struct Partial {
     std::shared_ptr<vs::Arena> arena;
     size_t metaOffset = 0;
+    bool hasMeta = false;  // the arena holds PointMeta records behind the points
     uint32_t rowStart[HDL_MAX_NUM_LASERS];
     uint32_t rowCount[HDL_MAX_NUM_LASERS];
     uint64_t total = 0;
@@ -177,7 +178,7 @@ class HDLParser::vsInternal {
   // rows of lasers the calibration does not have stay empty.
   void adoptRows(HDLFrame& f, const std::shared_ptr<vs::Arena>& arena, size_t metaOff,
                  const uint32_t* rowStart, const uint32_t* rowCount, const int32_t* rowLaser,
-                 bool hdl64Order, int nLasers) {
+                 bool hdl64Order, int nLasers, bool hasMeta) {
     const int nRows = hdl64Order ? 64 : nLasers;
     f.points.resize((size_t)nRows);
     f.pointsMeta.resize((size_t)nRows);
@@ -189,7 +190,7 @@ class HDLParser::vsInternal {
       const int laser = rowLaser ? rowLaser[r] : r;
       if (arena && laser < nLasers && rowCount[r] > 0) {
         vs::adopt(cloud->points, arena, xyzi + rowStart[r], (size_t)rowCount[r]);
-        if (fetchMeta) vs::adopt(*pm, arena, meta + rowStart[r], (size_t)rowCount[r]);
+        if (hasMeta) vs::adopt(*pm, arena, meta + rowStart[r], (size_t)rowCount[r]);
       }
       cloud->width = (uint32_t)cloud->points.size();
       cloud->height = 1;
@@ -203,7 +204,7 @@ class HDLParser::vsInternal {
   void materializeOpenFrame(bool hdl64Order) {
     HDLFrame& f = *currentFrame;
     adoptRows(f, partial.arena, partial.metaOffset, partial.rowStart, partial.rowCount, nullptr, false,
-              calibFileReportedNumLasers);
+              calibFileReportedNumLasers, partial.hasMeta);
     if (hdl64Order) {
       std::vector<pcl::PointCloud<pcl::PointXYZI>::Ptr> pts(64);
       std::vector<std::shared_ptr<PointMetaVector> > ptm(64);
@@ -238,7 +239,11 @@ class HDLParser::vsInternal {
     error = what;
     std::cerr << "HDLParser: GPU decode failed: " << error << std::endl;
     // the packets of the failed batch (and of any batch behind it) are lost; the parser carries
-    // on from the state before them
+    // on from the state before them.  Copies into the batches' arenas may still be running: wait
+    // for them before the arenas go back to the pool.
+    if (ctx)
+      for (auto& b : inflight)
+        if (b.stage >= 1) vs_sync(ctx, b.ticket, nullptr);
     inflight.clear();
     pending = 0;
     pendingWrap = false;
@@ -410,12 +415,17 @@ class HDLParser::vsInternal {
           if (!c) continue;
           const int laser = rw.row_laser[r];
           std::memcpy(dx + rw.row_start[r], sx + partial.rowStart[laser], (size_t)c * sizeof(pcl::PointXYZI));
-          if (fetchMeta) std::memcpy(dm + rw.row_start[r], sm + partial.rowStart[laser], (size_t)c * sizeof(PointMeta));
+          if (fetchMeta) {
+            if (partial.hasMeta)
+              std::memcpy(dm + rw.row_start[r], sm + partial.rowStart[laser], (size_t)c * sizeof(PointMeta));
+            else  // setFetchMeta(true) while this frame was open: no meta was kept for its head
+              std::memset(dm + rw.row_start[r], 0, (size_t)c * sizeof(PointMeta));
+          }
         }
       }
       if (e.closed) {
         adoptRows(f, arena, b.metaOffset[i], rw.row_start, rw.row_count, rw.row_laser, e.hdl64_order != 0,
-                  b.nLasers);
+                  b.nLasers, fetchMeta);
         closedOut->push_back(currentFrame);
         closedBy.push_back(b.packetBase + b.frames[i + 1].start_packet);  // packet holding the wrap
         partial = Partial();
@@ -424,6 +434,7 @@ class HDLParser::vsInternal {
         partial = Partial();
         partial.arena = arena;
         partial.metaOffset = b.metaOffset[i];
+        partial.hasMeta = fetchMeta;
         for (int r = 0; r < HDL_MAX_NUM_LASERS; ++r) {
           partial.rowStart[r] = rw.row_start[r];
           partial.rowCount[r] = rw.row_count[r];
