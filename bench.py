@@ -799,8 +799,10 @@ def run_ours(args):
     if not args.no_e2e:
         e2e = run_e2e(args, ctx_args=(local, calib, poses), b=b[halo:], t=t[halo:], t_base=t_base,
                       world=world, dev=dev)
-    e2e_frames = None
+    e2e_frames = e2e_xyzi = None
     if not args.no_e2e:
+        e2e_xyzi = run_e2e(args, ctx_args=(local, calib, poses), b=b[halo:], t=t[halo:], t_base=t_base,
+                           world=world, dev=dev, xyzi_only=True)
         e2e_frames = run_e2e(args, ctx_args=(local, calib, poses), b=b[halo:], t=t[halo:], t_base=t_base,
                              world=world, dev=dev, layout=True)
     pcie = None
@@ -908,6 +910,8 @@ def run_ours(args):
             line["parity"] = parity
         if e2e is not None:
             line["e2e"] = e2e
+        if e2e_xyzi is not None:
+            line["e2e_xyzi_13B"] = e2e_xyzi
         if e2e_frames is not None:
             line["e2e_frames"] = e2e_frames
         if pcie is not None:
@@ -979,7 +983,7 @@ def run_recording_headline(args, local, rank, world, dev, host_cpus_all, numa_cp
         torch.distributed.destroy_process_group()
 
 
-def run_e2e(args, ctx_args, b, t, t_base, world, dev, layout=False):
+def run_e2e(args, ctx_args, b, t, t_base, world, dev, layout=False, xyzi_only=False):
     """Host packets in, host points out, with two result slots so copies overlap the kernels.
     layout=False: vs_submit / vs_wait / vs_fetch_points, the stream-order columns (18 B/point).
     layout=True: vs_submit / vs_wait / vs_layout_frames / vs_fetch_layout, every frame as the
@@ -1006,8 +1010,14 @@ def run_e2e(args, ctx_args, b, t, t_base, world, dev, layout=False):
                  torch.int16, torch.int16, torch.int32)]
         outs.append(cols)
 
+    bytes_per_point = 13 if xyzi_only else BYTES_PER_POINT_E2E
+
     def ptrs_of(slot):
-        # x, y, z, intensity, laser, azimuth, distance; t_us stays on the device (NULL)
+        # x, y, z, intensity, laser, azimuth, distance; t_us stays on the device (NULL).
+        # xyzi_only: the 13 B/point a consumer of coordinates + intensity needs (laser, azimuth
+        # and raw distance are recomputable from the packets the host already holds)
+        if xyzi_only:
+            return [x.data_ptr() for x in outs[slot][:4]] + [None] * 4
         return [x.data_ptr() for x in outs[slot][:7]] + [None]
 
     def one_pass():
@@ -1029,12 +1039,12 @@ def run_e2e(args, ctx_args, b, t, t_base, world, dev, layout=False):
             if pending is not None:
                 ctx.fetch_into(pending[0], 0, rprev.n_points, ptrs_of(pending[1]))
                 total += rprev.n_points
-                d2h += rprev.n_points * BYTES_PER_POINT_E2E
+                d2h += rprev.n_points * bytes_per_point
             pending = (tk, c % 2)
         rprev = ctx.wait(pending[0], frames=False)
         ctx.fetch_into(pending[0], 0, rprev.n_points, ptrs_of(pending[1]))
         total += rprev.n_points
-        d2h += rprev.n_points * BYTES_PER_POINT_E2E
+        d2h += rprev.n_points * bytes_per_point
         return total, h2d, d2h
 
     def barrier():
@@ -1057,6 +1067,12 @@ def run_e2e(args, ctx_args, b, t, t_base, world, dev, layout=False):
         torch.distributed.all_reduce(pts)
         total = int(pts.item())
     ctx.close()
+    if xyzi_only:
+        return {"value": total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "chunk_packets": chunk,
+                "bytes_per_point": 13,
+                "note": "as e2e, fetching x, y, z, intensity only (vs_fetch_points with NULL for the "
+                        "other columns): 13 B/point over PCIe"}
     return {"value": total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
             "chunk_packets": chunk, "note": "host pinned packets -> vs_submit/vs_wait -> "

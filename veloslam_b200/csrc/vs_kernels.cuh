@@ -1180,7 +1180,10 @@ constexpr int kDecWarps = kDecThreads / 32;
 constexpr int kDecPairs = kDecWarps / 2;
 constexpr int kDecPktsPerWarp = kDecTile / kDecPairs;  // 2
 constexpr int kDecRecs = kDecPktsPerWarp * 6;          // firing blocks per warp and tile
-constexpr int kDecIlp = 2;  // firing blocks per straight-line body (divides 6)
+#ifndef VS_DEC_ILP
+#define VS_DEC_ILP 2
+#endif
+constexpr int kDecIlp = VS_DEC_ILP;  // firing blocks per straight-line body (divides 6)
 // input stage layout (byte offsets, all multiples of 16)
 constexpr int kDRec = 0;                            // 12 BlkRec per packet
 constexpr int kDSeg = kDRec + kDecTile * 96;        // PktSeg per packet
