@@ -672,6 +672,55 @@ int main(int argc, char** argv) {
     for (auto& f : all) dumpFrame(os, *f);
     return 0;
   }
+  if (mode == "manager_shards" && argc >= 7) {
+    // HDLManager::setDevices + loadOffline: the recording spread over several CUDA contexts
+    //   facade_driver manager_shards <calib.xml> <file.pcap> <poses.bin|-> <out.bin> <dev,dev,...>
+    // every frame comes back through getRangeBetween (all shards decode at once)
+    HDLManager mgr(1 << 20);
+    mgr.setCalibFile(argv[2]);
+    std::shared_ptr<TransformManager> poses = loadPoses(argv[4]);
+    std::vector<int64_t> pt;
+    std::vector<double> trv;
+    poses->snapshot(&pt, &trv);
+    for (size_t i = 0; i < pt.size(); ++i) {
+      std::shared_ptr<PoseTransform> p(new PoseTransform);
+      for (int k = 0; k < 3; ++k) {
+        p->T[k] = trv[9 * i + k];
+        p->R[k] = trv[9 * i + 3 + k];
+        p->V[k] = trv[9 * i + 6 + k];
+      }
+      p->timestamp = ptime(pt[i]);
+      p->seconds_pos = 0;
+      mgr.getTransformMgr()->addTransform(p);
+    }
+    std::vector<int> devs;
+    for (const char* c = argv[6]; *c;) {
+      devs.push_back(std::atoi(c));
+      while (*c && *c != ',') ++c;
+      if (*c == ',') ++c;
+    }
+    mgr.setDevices(devs);
+    const auto t0 = std::chrono::steady_clock::now();
+    mgr.loadOffline("-", argv[3]);
+    const auto t1 = std::chrono::steady_clock::now();
+    std::cerr << "shards " << mgr.getNumberOfShards() << std::endl;
+    std::vector<std::shared_ptr<HDLFrame> > meta = mgr.getAllFrameMeta();
+    if (meta.empty()) return 1;
+    ptime a = meta.front()->timestamp, b = meta.back()->timestamp;
+    std::vector<HDLFramePtr> all = mgr.getRangeBetween(a, b);
+    const auto t2 = std::chrono::steady_clock::now();
+    std::cerr << "load_ms " << std::chrono::duration<double, std::milli>(t1 - t0).count() << " range_ms "
+              << std::chrono::duration<double, std::milli>(t2 - t1).count() << std::endl;
+    if (all.size() != meta.size()) return 1;
+    std::ofstream os(argv[5], std::ios::binary);
+    const int32_t nf = (int32_t)all.size();
+    os.write((const char*)&nf, 4);
+    for (auto& f : all) {
+      if (!f) return 1;
+      dumpFrame(os, *f);
+    }
+    return 0;
+  }
   if (mode == "manager" || mode == "manager_file") {
     // HDLManager::loadOffline on a packet file, then every frame through getFrameAt
     //   facade_driver manager <calib.xml> <file.pcap> <poses.bin|-> <out.bin>

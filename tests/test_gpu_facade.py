@@ -135,6 +135,45 @@ def test_hdlmanager_renames_recording_and_index_spans_batches(tmp_path):
         assert np.array_equal(f.xyzi.view(np.uint32), want.xyzi.view(np.uint32))
 
 
+@pytest.mark.parametrize("sensor,n,devices", [("hdl64", 5000, "0,0,0"), ("hdl32", 3000, "0,0"),
+                                              ("hdl64", 3, "0,0,0,0,0")])
+def test_hdlmanager_recording_spread_over_devices(tmp_path, sensor, n, devices):
+    """HDLManager::setDevices: one range of the recording per CUDA context (here several on one
+    GPU), indices concatenated, each frame decoded where it lives -- same frames as the
+    reference's one-file index + getFrame, including the rotations that cross a range end."""
+    import torch
+    if devices == "0,0,0" and torch.cuda.device_count() >= 2:
+        devices = ",".join(str(d) for d in range(min(torch.cuda.device_count(), 8)))
+    if sensor == "hdl64":
+        pk, t = synth.hdl64_packets(n, seed=11)
+        calib = synth.calib_hdl64()
+    else:
+        pk, t = synth.hdl32_packets(n, seed=12)
+        calib = synth.calib_hdl32()
+    poses = synth.ins_trajectory(max(60, n // 20))
+    b = synth.as_bytes(pk)
+    path = tmp_path / "drive.pcap"                  # renamed by the touch before the split
+    pcapio.write_pcap(str(path), b, t)
+    F.write_poses(tmp_path / "poses.bin", *poses)
+    calibxml.write_db_xml(str(tmp_path / "db.xml"), calib)
+    r = F.run(["manager_shards", tmp_path / "db.xml", path, tmp_path / "poses.bin", tmp_path / "out.bin", devices])
+    assert r.returncode == 0, r.stderr
+    assert f"shards {len(devices.split(','))}" in r.stderr
+    frames = F.read_frames(tmp_path / "out.bin")
+    o = P.make_oracle(calib, poses)
+    sp, sk, ts = Oracle.read_frame_information(b, t)
+    assert [f.timestamp_us for f in frames] == [int(x) for x in ts]
+    assert [f.skips for f in frames] == [int(x) for x in sk]
+    for i, f in enumerate(frames):
+        want = o.get_frame(b, t, sp[i], sk[i])
+        assert f.n_points == want.n_points
+        assert np.array_equal(f.laser_counts, want.laser_counts)
+        assert np.array_equal(f.azimuth, want.azimuth)
+        assert np.array_equal(f.xyzi[:, 3], want.xyzi[:, 3])
+        d = np.abs(f.xyzi[:, :3].astype(np.float64) - want.xyzi[:, :3])
+        assert d.size == 0 or d.max() <= P.TOL_DESKEW
+
+
 # --- the whole online path over loopback UDP (SURVEY 8f N3) -------------------------------------------
 def test_online_udp_to_hdlmanager(tmp_path):
     n = 1500

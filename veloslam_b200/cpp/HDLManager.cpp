@@ -2,6 +2,8 @@
 // (C ABI -> sm_100a kernels).
 #include "HDLManager.h"
 
+#include "../../include/veloslam_b200.h"
+
 #include <dirent.h>
 #include <sys/stat.h>
 #include <sys/time.h>
@@ -10,6 +12,7 @@
 #include <chrono>
 #include <fstream>
 #include <iostream>
+#include <thread>
 
 namespace {
 ptime localTimeNow() {
@@ -124,6 +127,9 @@ void HDLManager::loadOffline(const std::string& insTxt, const std::string& pcapf
   }
   transMgr->loadFromTxtFile(insTxt, true);
   std::cout << "Read " << transMgr->getNumberOfTransforms() << " transforms.\n";
+  shards_.clear();
+  shardFile_.clear();
+  if (devices_.size() > 1 && this->loadOfflineSharded(pcapfile)) return;
   // the whole recording goes to HBM once; when the file is not a fixed-stride packet file the
   // parser falls back to reading it record by record, like the reference
   hdlParser->loadRecording(pcapfile);
@@ -136,6 +142,90 @@ void HDLManager::loadOffline(const std::string& insTxt, const std::string& pcapf
   }
   std::cout << "Read " << this->getNumberOfFrames() << " frames." << std::endl;
   this->setBufferDir(parentPath(pcapfile), false);
+}
+
+void HDLManager::setDevices(const std::vector<int>& cudaDevices) {
+  devices_ = cudaDevices;
+  if (!devices_.empty()) hdlParser->setDevice(devices_[0]);
+}
+
+// One range of records per GPU.  The reference's index (HDLParser.cxx:1080-1149) is a scan of
+// every firing block against the azimuth before it, so a range needs one record of lead-in and
+// nothing else; a rotation that starts in a range is decoded by that range's GPU out of the
+// kShardTail records kept past the range end.  false: not a fixed-stride packet file (the
+// caller then takes the one-GPU path, which also handles the record-by-record fallback).
+bool HDLManager::loadOfflineSharded(const std::string& pcapfile) {
+  // the file is named after its first packet (touch renames it when it is not)
+  std::string file = pcapfile;
+  auto head = hdlParser->readFrameInformation(pcapfile, true);
+  if (head.empty()) return false;
+  struct stat st;
+  if (stat(file.c_str(), &st) != 0) {
+    file = parentPath(pcapfile) + "/" + to_iso_string(head[0]->filenameTime) + ".pcap";
+    if (stat(file.c_str(), &st) != 0) return false;
+  }
+  const int64_t body = (int64_t)st.st_size - PCAP_GLOBAL_HEADER_LEN;
+  if (body <= 0 || body % VS_PCAP_RECORD_BYTES != 0) return false;
+  const int64_t n = body / VS_PCAP_RECORD_BYTES;
+  const int world = (int)devices_.size();
+  std::vector<Shard> shards((size_t)world);
+  std::vector<int64_t> lead((size_t)world, 0);
+  for (int g = 0; g < world; ++g) {
+    if (vs_shard_range(n, world, g, 1, &shards[g].first, &lead[g], &shards[g].end) != VS_OK) return false;
+    if (shards[g].end == shards[g].first) continue;   // fewer records than GPUs
+    if (g == 0) {
+      shards[g].parser = hdlParser;
+    } else {
+      shards[g].parser.reset(new HDLParser);
+      shards[g].parser->setTransformMgr(transMgr);
+      if (!calibFile_.empty()) shards[g].parser->setCorrectionsFile(calibFile_);
+    }
+    shards[g].parser->setDevice(devices_[g]);
+  }
+  std::vector<std::vector<std::shared_ptr<HDLFrame> > > index((size_t)world);
+  std::vector<char> ok((size_t)world, 1);
+  std::vector<std::thread> workers;
+  for (int g = 0; g < world; ++g) {
+    if (!shards[g].parser) continue;
+    workers.emplace_back([&, g] {
+      HDLParser& p = *shards[g].parser;
+      const int64_t lo = shards[g].first - lead[g];
+      ok[g] = p.loadRecordingRange(file, lo, shards[g].end - lo + kShardTail);
+      if (ok[g]) {
+        index[g] = p.readFrameInformation(file);
+        ok[g] = !index[g].empty() && p.lastError().empty();
+      }
+    });
+  }
+  for (auto& w : workers) w.join();
+  for (int g = 0; g < world; ++g)
+    if (!ok[g]) {
+      hdlParser->unloadRecording();
+      return false;
+    }
+  shards_.swap(shards);
+  shardFile_ = file;
+  // the frames of a range are the ones that start inside it: the lead-in record's wraps belong
+  // to the range before, the tail's to the range after
+  for (int g = 0; g < world; ++g)
+    for (auto& f : index[g]) {
+      const int64_t rec = (f->fileStartPos - PCAP_GLOBAL_HEADER_LEN) / VS_PCAP_RECORD_BYTES;
+      if (rec < shards_[g].first || rec >= shards_[g].end) continue;
+      f->filenameTime = head[0]->filenameTime;
+      transMgr->interpolateTransform(f->timestamp, f->carpose.get());
+      this->addFrame(f);
+    }
+  std::cout << "Read " << this->getNumberOfFrames() << " frames on " << world << " GPUs." << std::endl;
+  this->setBufferDir(parentPath(file), false);
+  return true;
+}
+
+HDLParser* HDLManager::parserFor(const HDLFrame& frame, const std::string& pcap) {
+  if (shards_.empty() || pcap != shardFile_) return hdlParser.get();
+  const int64_t rec = (frame.fileStartPos - PCAP_GLOBAL_HEADER_LEN) / VS_PCAP_RECORD_BYTES;
+  for (auto& s : shards_)
+    if (s.parser && rec >= s.first && rec < s.end) return s.parser.get();
+  return hdlParser.get();
 }
 
 void HDLManager::touchPcap(const std::string& pcapfile) { hdlParser->readFrameInformation(pcapfile, true); }
@@ -179,6 +269,8 @@ void HDLManager::setCalibFile(std::string filename) {
   calibFile_ = filename;
   if (hdlSrc) hdlSrc->setCorrectionsFile(filename);
   hdlParser->setCorrectionsFile(filename);
+  for (auto& s : shards_)
+    if (s.parser && s.parser != hdlParser) s.parser->setCorrectionsFile(filename);
 }
 
 void HDLManager::addFrame(std::shared_ptr<HDLFrame> frame) {
@@ -209,7 +301,7 @@ HDLFramePtr HDLManager::prepareFrame(std::shared_ptr<HDLFrame> frame) {
   if (frame->isInMemory) return HDLFramePtr(frame.get());
   if (!frame->isOnHardDrive) return HDLFramePtr();
   const std::string pcap = bufferDirName + to_iso_string(frame->filenameTime) + ".pcap";
-  if (!hdlParser->getFrame(frame, pcap, frame->fileStartPos, frame->skips)) return HDLFramePtr();
+  if (!parserFor(*frame, pcap)->getFrame(frame, pcap, frame->fileStartPos, frame->skips)) return HDLFramePtr();
   frame->isInMemory = true;
   pushCache(frame);
   return HDLFramePtr(frame.get());
@@ -267,8 +359,31 @@ std::vector<HDLFramePtr> HDLManager::getRangeBetween(ptime& a, ptime& b) {
     for (const auto& f : frames.items())
       if (f->timestamp >= a && f->timestamp <= b) vec.push_back(f);
   }
-  std::vector<HDLFramePtr> result;
-  for (auto& f : vec) result.push_back(prepareFrame(f));
+  std::vector<HDLFramePtr> result(vec.size());
+  if (shards_.size() < 2) {
+    for (size_t i = 0; i < vec.size(); ++i) result[i] = prepareFrame(vec[i]);
+    return result;
+  }
+  // a recording spread over several GPUs: every GPU decodes the frames it holds, at once
+  std::vector<std::vector<size_t> > perParser;
+  std::vector<HDLParser*> parsers;
+  for (size_t i = 0; i < vec.size(); ++i) {
+    const std::string pcap = bufferDirName + to_iso_string(vec[i]->filenameTime) + ".pcap";
+    HDLParser* p = parserFor(*vec[i], pcap);
+    size_t k = 0;
+    while (k < parsers.size() && parsers[k] != p) ++k;
+    if (k == parsers.size()) {
+      parsers.push_back(p);
+      perParser.emplace_back();
+    }
+    perParser[k].push_back(i);
+  }
+  std::vector<std::thread> workers;
+  for (size_t k = 0; k < parsers.size(); ++k)
+    workers.emplace_back([&, k] {
+      for (size_t i : perParser[k]) result[i] = prepareFrame(vec[i]);
+    });
+  for (auto& w : workers) w.join();
   return result;
 }
 

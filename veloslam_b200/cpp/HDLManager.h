@@ -13,6 +13,11 @@
 //  * loadOffline() uploads the packet file to HBM once (HDLParser::loadRecording): the frame
 //    index is one segmentation pass on the GPU and every later prepareFrame() decodes its
 //    rotation out of HBM -- the reference re-opens and re-reads the pcap file per frame.
+//  * setDevices({0, 1, ...}) before loadOffline(): the recording is split into one range of
+//    records per GPU (vs_shard_range, the split bench.py's recording legs use), each GPU keeps
+//    and indexes its own range on its own thread, the per-GPU indices are concatenated into
+//    the one TimeLine, prepareFrame() decodes a rotation on the GPU that holds it and
+//    getRangeBetween() decodes on all of them at once.
 //  * writePackets() runs synchronously when a buffer fills (the reference runs it on a
 //    boost::thread).
 //  * the sources are created by startOnline() (ports: setPorts) instead of in the constructor,
@@ -78,6 +83,10 @@ class HDLManager {
   std::shared_ptr<TimeSolver> getTimeSolver() const { return timeSolver; }
 
   void loadOffline(const std::string& insTxt, const std::string& pcapfile);
+  // CUDA devices loadOffline() spreads a recording over (default: the parser's one device).
+  // The same device may be named more than once (one context each).
+  void setDevices(const std::vector<int>& cudaDevices);
+  int getNumberOfShards() const { return (int)shards_.size(); }
   /* the purpose of 'touch' is rename the file if necessary */
   void touchPcap(const std::string& pcapfile);
 
@@ -135,6 +144,19 @@ class HDLManager {
   void scanBufferDir();
 
   void updateCacheSizeLocked();  // caller holds cacheMutex
+  // one range of the recording per GPU: frames that start in records [first, end) are indexed
+  // and decoded by `parser`, which holds [first - 1, end + kShardTail) so that the wrap test
+  // of its first record and the end of its last rotation need nothing from a neighbour
+  struct Shard {
+    int64_t first, end;
+    std::shared_ptr<HDLParser> parser;
+  };
+  static const int64_t kShardTail = 2048;   // records; > one rotation of either sensor at 5 Hz
+  bool loadOfflineSharded(const std::string& pcapfile);
+  HDLParser* parserFor(const HDLFrame& frame, const std::string& pcap);
+  std::vector<int> devices_;
+  std::vector<Shard> shards_;
+  std::string shardFile_;
   std::mutex framesMutex;
   std::mutex cacheMutex;         // cache + cacheCounter (consumer thread and user threads)
   std::condition_variable cond_;

@@ -493,22 +493,31 @@ class HDLParser::vsInternal {
   long nPumps = 0;
 
   // ---- recording resident in HBM (loadRecording) ----------------------------------------------
-  bool loadRecording(const std::string& file) {
+  // records [first, first + count) of the file (count < 0: to the end); the image kept on the
+  // host and in HBM is the file's global header followed by those records, so that a record's
+  // place in the image is its file position minus `first` records
+  bool loadRecording(const std::string& file, int64_t first = 0, int64_t count = -1) {
     unloadRecording();
     if (!ensureContext()) return false;
     FILE* f = std::fopen(file.c_str(), "rb");
     if (!f) return false;
-    std::fseek(f, 0, SEEK_END);
-    const long long bytes = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
-    const long long body = bytes - PCAP_GLOBAL_HEADER_LEN;
-    bool ok = bytes > PCAP_GLOBAL_HEADER_LEN && body % VS_PCAP_RECORD_BYTES == 0;
+    fseeko(f, 0, SEEK_END);
+    const long long fileBytes = ftello(f);
+    const long long body = fileBytes - PCAP_GLOBAL_HEADER_LEN;
+    bool ok = fileBytes > PCAP_GLOBAL_HEADER_LEN && body % VS_PCAP_RECORD_BYTES == 0 && first >= 0;
+    const int64_t total = ok ? body / VS_PCAP_RECORD_BYTES : 0;
+    ok = ok && first < total;
+    const int64_t n = !ok ? 0 : count < 0 ? total - first : std::min<int64_t>(count, total - first);
+    const long long bytes = PCAP_GLOBAL_HEADER_LEN + (long long)n * VS_PCAP_RECORD_BYTES;
     if (ok) {
       recHost.resize((size_t)bytes);
-      ok = std::fread(recHost.data(), 1, (size_t)bytes, f) == (size_t)bytes;
+      fseeko(f, 0, SEEK_SET);
+      ok = std::fread(recHost.data(), 1, PCAP_GLOBAL_HEADER_LEN, f) == (size_t)PCAP_GLOBAL_HEADER_LEN;
+      fseeko(f, PCAP_GLOBAL_HEADER_LEN + (off_t)first * VS_PCAP_RECORD_BYTES, SEEK_SET);
+      const size_t want = (size_t)n * VS_PCAP_RECORD_BYTES;
+      ok = ok && std::fread(recHost.data() + PCAP_GLOBAL_HEADER_LEN, 1, want, f) == want;
     }
     std::fclose(f);
-    const int64_t n = ok ? body / VS_PCAP_RECORD_BYTES : 0;
     // every record must be a 1206-byte payload behind the 42-byte header: fixed stride
     for (int64_t i = 0; ok && i < n; ++i) {
       uint32_t len[2];
@@ -524,12 +533,14 @@ class HDLParser::vsInternal {
     }
     recName = file;
     recPackets = n;
+    recFirst = first;
     return true;
   }
   void unloadRecording() {
     if (recDev) vs_device_free(ctx, recDev);
     recDev = nullptr;
     recPackets = 0;
+    recFirst = 0;
     recName.clear();
     recAlias.clear();
     std::vector<uint8_t>().swap(recHost);
@@ -540,6 +551,7 @@ class HDLParser::vsInternal {
   void* recDev = nullptr;
   std::vector<uint8_t> recHost;  // the same file image on the host (raw packets of HDLFrames)
   int64_t recPackets = 0;
+  int64_t recFirst = 0;          // file record the image starts at (a shard of a recording)
   std::string recName, recAlias; // alias: the name readFrameInformation renamed the file to
 
   vs_ctx* ctx;
@@ -774,7 +786,12 @@ bool HDLParser::getFrame(std::shared_ptr<HDLFrame>& dest, const std::string& fil
   ptime t;
   std::deque<std::shared_ptr<HDLFrame> > closed;
   bool eof = false;
-  int64_t cursor = resident ? (startPos - PCAP_GLOBAL_HEADER_LEN) / VS_PCAP_RECORD_BYTES : 0;
+  int64_t cursor = resident ? (startPos - PCAP_GLOBAL_HEADER_LEN) / VS_PCAP_RECORD_BYTES - in->recFirst : 0;
+  if (resident && (cursor < 0 || cursor >= in->recPackets)) {
+    in->error = "getFrame: the frame starts outside the resident part of the recording";
+    std::cerr << "HDLParser: " << in->error << std::endl;
+    return false;
+  }
   while (closed.empty() && !eof) {
     // one chunk: enough for a rotation of either sensor, decoded in one launch
     const int chunk = std::min(in->batchPackets, 512);
@@ -852,7 +869,7 @@ std::vector<std::shared_ptr<HDLFrame> > HDLParser::readFrameInformation(const st
     const ptime filenameTime(ts[0]);
     for (int32_t i = 0; i < nf; ++i) {
       std::shared_ptr<HDLFrame> f(new HDLFrame);
-      f->fileStartPos = PCAP_GLOBAL_HEADER_LEN + (int64_t)sp[i] * VS_PCAP_RECORD_BYTES;
+      f->fileStartPos = PCAP_GLOBAL_HEADER_LEN + (in->recFirst + (int64_t)sp[i]) * VS_PCAP_RECORD_BYTES;
       f->skips = (uint8_t)sk[i];
       f->isOnHardDrive = true;
       f->timestamp = ptime(ts[i]);
@@ -867,7 +884,7 @@ std::vector<std::shared_ptr<HDLFrame> > HDLParser::readFrameInformation(const st
     const size_t dot = stem.find_last_of('.');
     if (dot != std::string::npos) stem = stem.substr(0, dot);
     ptime nameTime;
-    if (!from_iso_string(stem, &nameTime) && name == in->recName) {
+    if (!from_iso_string(stem, &nameTime) && name == in->recName && in->recFirst == 0) {
       const std::string newname = dir + "/" + to_iso_string(filenameTime) + ".pcap";
       if (std::rename(name.c_str(), newname.c_str()) == 0) {
         in->recAlias = newname;
@@ -946,6 +963,13 @@ int HDLParser::getApplyTransform() { return this->internal_->applyTransform; }
 void HDLParser::setApplyTransform(int apply) { this->internal_->applyTransform = apply; }
 
 bool HDLParser::loadRecording(const std::string& pcapfile) { return this->internal_->loadRecording(pcapfile); }
+bool HDLParser::loadRecordingRange(const std::string& pcapfile, int64_t firstRecord, int64_t nRecords) {
+  return this->internal_->loadRecording(pcapfile, firstRecord, nRecords);
+}
+void HDLParser::recordingRange(int64_t* firstRecord, int64_t* nRecords) const {
+  *firstRecord = this->internal_->recFirst;
+  *nRecords = this->internal_->recPackets;
+}
 void HDLParser::unloadRecording() { this->internal_->unloadRecording(); }
 bool HDLParser::hasRecording(const std::string& pcapfile) const { return this->internal_->hasRecording(pcapfile); }
 

@@ -110,6 +110,12 @@ class HDLParser {
   // getFrame() decodes rotations straight out of HBM instead of re-reading the file
   // (HDLManager::loadOffline / prepareFrame).  false: not such a file, nothing changes.
   bool loadRecording(const std::string& pcapfile);
+  // One shard of a recording: records [firstRecord, firstRecord + nRecords) only (nRecords < 0:
+  // to the end of the file).  readFrameInformation() then indexes that range and getFrame()
+  // serves the frames that start inside it, both in whole-file positions
+  // (HDLManager::setDevices: one parser and one range per GPU).
+  bool loadRecordingRange(const std::string& pcapfile, int64_t firstRecord, int64_t nRecords);
+  void recordingRange(int64_t* firstRecord, int64_t* nRecords) const;
   void unloadRecording();
   bool hasRecording(const std::string& pcapfile) const;
   const std::string& lastError() const;    // empty when the last GPU call succeeded
