@@ -1399,6 +1399,33 @@ def run_online(local, calib, poses, b, t, t_base, rotations=300):
             "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
             "max_ms": float(lat.max()), "points_per_s": pts / dt_all}
     ctx.close()
+    # the same loop with the C ABI called from C++ (tests/cpp/facade_driver latency): what the
+    # figures above cost without the interpreter between vs_submit and vs_wait
+    try:
+        from veloslam_b200 import calibxml
+        from veloslam_b200.build import DRIVER_EXE, build_facade
+        build_facade()
+        tmp = tempfile.mkdtemp(prefix="vs_lat_")
+        try:
+            b[:n_rot * rot].tofile(os.path.join(tmp, "pk.bin"))
+            np.ascontiguousarray(t[:n_rot * rot]).astype("<i8").tofile(os.path.join(tmp, "t.bin"))
+            rec = np.zeros(len(poses[0]), dtype=[("t", "<i8"), ("v", "<f8", (9,))])
+            rec["t"] = poses[0]
+            rec["v"] = poses[1]
+            rec.tofile(os.path.join(tmp, "poses.bin"))
+            calibxml.write_db_xml(os.path.join(tmp, "db.xml"), calib)
+            for name, wp in (("index_only_cpp", 0), ("with_points_cpp", 1)):
+                cmd = [DRIVER_EXE, "latency", os.path.join(tmp, "db.xml"), os.path.join(tmp, "pk.bin"),
+                       os.path.join(tmp, "t.bin"), os.path.join(tmp, "poses.bin"), str(rot), str(local),
+                       str(wp)]
+                pr = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+                out[name] = (json.loads(pr.stdout.strip().splitlines()[-1]) if pr.returncode == 0
+                             else {"error": (pr.stderr or pr.stdout)[-300:]})
+        finally:
+            import shutil
+            shutil.rmtree(tmp, ignore_errors=True)
+    except Exception as e:  # the driver is test infrastructure: its absence does not fail the bench
+        out["index_only_cpp"] = {"error": repr(e)[:300]}
     out["rotations"] = n_rot
     out["packets_per_rotation"] = rot
     out["note"] = ("one HDL-64E stream on this GPU, rotation-sized batches back to back (a 10 Hz "

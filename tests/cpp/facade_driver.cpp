@@ -32,6 +32,7 @@
 #include <unistd.h>
 
 #include "VeloSLAM.h"
+#include "CalibrationFile.h"
 
 static std::vector<char> slurp(const std::string& path) {
   std::ifstream f(path, std::ios::binary);
@@ -513,6 +514,87 @@ int main(int argc, char** argv) {
                 (unsigned long long)vs::Arena::pooledBytes(), touch, parser.pipelineStats().c_str());
     return 0;
   }
+  if (mode == "latency" && argc >= 9) {
+    // BASELINE.json configs[4], the C ABI called from C++ (no interpreter in the loop):
+    // rotation-sized batches out of page-locked host memory, vs_submit + vs_wait back to back
+    //   facade_driver latency <calib.xml> <packets.bin> <times.bin> <poses.bin> <packets/rotation>
+    //                         <device> <with_points 0|1>
+    CalibrationFile cal;
+    std::string err;
+    if (!cal.load(argv[2], &err)) {
+      std::cerr << err << std::endl;
+      return 1;
+    }
+    std::vector<char> pk = slurp(argv[3]);
+    std::vector<char> tm = slurp(argv[4]);
+    const int64_t rot = std::atoll(argv[6]);
+    const int64_t n = (int64_t)(pk.size() / 1206), nRot = n / rot;
+    const bool withPoints = std::atoi(argv[8]) != 0;
+    if (rot < 1 || nRot < 20) return 2;
+    std::shared_ptr<TransformManager> poses = loadPoses(argv[5]);
+    std::vector<int64_t> pt;
+    std::vector<double> trv;
+    poses->snapshot(&pt, &trv);
+    vs_ctx* ctx = nullptr;
+    if (vs_create(std::atoi(argv[7]), 512, (int64_t)pt.size() + 8, 1, &ctx) != VS_OK) {
+      std::cerr << vs_last_error(nullptr) << std::endl;
+      return 1;
+    }
+    uint8_t* hp = nullptr;
+    int64_t* ht = nullptr;
+    void* cols[7] = {nullptr};
+    const size_t colBytes[7] = {4, 4, 4, 1, 1, 2, 2};
+    bool ok = vs_set_calibration(ctx, cal.rows, cal.n_rows, cal.n_enabled) == VS_OK &&
+              (pt.empty() || vs_set_poses(ctx, pt.data(), trv.data(), (int64_t)pt.size()) == VS_OK) &&
+              vs_host_alloc((uint64_t)n * 1206, (void**)&hp) == VS_OK &&
+              vs_host_alloc((uint64_t)n * 8, (void**)&ht) == VS_OK;
+    for (int c = 0; c < 7 && ok; ++c) ok = vs_host_alloc(512 * 384 * colBytes[c], &cols[c]) == VS_OK;
+    if (!ok) {
+      std::cerr << "setup failed: " << vs_last_error(ctx) << std::endl;
+      return 1;
+    }
+    std::memcpy(hp, pk.data(), (size_t)n * 1206);
+    std::memcpy(ht, tm.data(), (size_t)n * 8);
+    vs_carry carry;
+    vs_carry_init(&carry);
+    std::vector<double> lat;
+    uint64_t points = 0;
+    int graphLaunches = 0;
+    const auto w0 = std::chrono::steady_clock::now();
+    for (int64_t r = 0; r < nRot; ++r) {
+      const auto t0 = std::chrono::steady_clock::now();
+      uint64_t ticket = 0;
+      vs_result res;
+      if (vs_submit(ctx, hp + r * rot * 1206, 1206, ht + r * rot, rot, 0, 0, 0, ht[0], &carry, &ticket) != VS_OK ||
+          vs_wait(ctx, ticket, &res) != VS_OK) {
+        std::cerr << "batch failed: " << vs_last_error(ctx) << std::endl;
+        return 1;
+      }
+      if (withPoints && res.n_points > 0 &&
+          vs_fetch_points(ctx, ticket, 0, res.n_points, (float*)cols[0], (float*)cols[1], (float*)cols[2],
+                          (uint8_t*)cols[3], (uint8_t*)cols[4], (uint16_t*)cols[5], (uint16_t*)cols[6],
+                          nullptr) != VS_OK) {
+        std::cerr << "fetch failed: " << vs_last_error(ctx) << std::endl;
+        return 1;
+      }
+      lat.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+      carry = res.carry_out;
+      points += (uint64_t)res.n_points;
+      graphLaunches = res.reserved;
+    }
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+    lat.erase(lat.begin(), lat.begin() + 10);   // the first rotations warm the path up
+    std::sort(lat.begin(), lat.end());
+    auto pct = [&](double q) { return lat[(size_t)std::min<double>(lat.size() - 1, q * (lat.size() - 1) + 0.5)]; };
+    std::printf("{\"p50_ms\": %.6f, \"p99_ms\": %.6f, \"max_ms\": %.6f, \"points_per_s\": %.1f, "
+                "\"rotations\": %lld, \"graph_launches\": %d}\n",
+                pct(0.50), pct(0.99), lat.back(), (double)points / sec, (long long)nRot, graphLaunches);
+    for (int c = 0; c < 7; ++c) vs_host_free(cols[c]);
+    vs_host_free(hp);
+    vs_host_free(ht);
+    vs_destroy(ctx);
+    return 0;
+  }
   if (mode == "online") {
     // BASELINE.json configs[4] for ONE stream: a paced sender thread plays the packet file over
     // loopback UDP at the sensor's rate; HDLManager::startOnline receives, stamps (TimeSolver),
@@ -606,7 +688,17 @@ int main(int argc, char** argv) {
     }
     uint64_t points = 0;
     for (auto& f : mgr.getAllFrameMeta()) points += f->numberOfPoints();
-    std::printf("{\"packets_sent\": %llu, \"received\": %llu, \"dropped\": %llu, \"consumed\": %llu, "
+    // rotations that took more than 5 ms (index after the start-up ones, ms): where a hiccup sits
+    std::string slow = "[";
+    for (size_t i = 0; i < proc.size(); ++i)
+      if (proc[i] > 5000.0) {
+        char buf[64];
+        std::snprintf(buf, sizeof(buf), "%s[%zu, %.1f]", slow.size() > 1 ? ", " : "", i + 10, proc[i] / 1e3);
+        slow += buf;
+      }
+    slow += "]";
+    std::printf("{\"slow_rotations\": %s, ", slow.c_str());
+    std::printf("\"packets_sent\": %llu, \"received\": %llu, \"dropped\": %llu, \"consumed\": %llu, "
                 "\"frames\": %d, \"seconds\": %.3f, \"packets_per_s\": %.1f, "
                 "\"rotation_p50_ms\": %.4f, \"rotation_p99_ms\": %.4f, \"rotation_max_ms\": %.4f, "
                 "\"from_arrival_p50_ms\": %.4f, \"from_arrival_p99_ms\": %.4f, "

@@ -18,12 +18,12 @@ def _single_pass(monkeypatch):
 
 
 def test_single_pass_is_engaged():
-    """No k_scan / k_pose launch: the fused decode kernel and the frame-table gather only."""
+    """No k_scan / k_pose launch: the reset, the fused decode kernel and the frame-table gather."""
     pk, t = synth.hdl64_packets(600)
     ctx = P.make_ctx(synth.calib_hdl64())
     r = ctx.decode(synth.as_bytes(pk), np.ascontiguousarray(t), mode=capi.MODE_STREAMING,
                    carry=capi.carry_init(), t_base_us=int(t[0]))
-    assert r.n_kernel_launches == 2
+    assert r.n_kernel_launches == 3          # k_reset, k_decode<FUSED>, k_frames
     ctx.close()
 
 

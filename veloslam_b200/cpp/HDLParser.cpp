@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 
@@ -280,10 +281,12 @@ class HDLParser::vsInternal {
       tmin = *std::min_element(tt, tt + pending);
       tmax = *std::max_element(tt, tt + pending);
     }
+    mark("times");
     if (!syncConfig(tmin, tmax)) {
       failBatches(error);
       return false;
     }
+    mark("syncConfig");
     int rc;
     if (recCursorArg >= 0) {
       // packets come from the recording resident in HBM: no host -> device copy at all
@@ -300,6 +303,7 @@ class HDLParser::vsInternal {
       failBatches(vs_last_error(ctx));
       return false;
     }
+    mark("vs_submit");
     b.stage = 1;
     inflight.push_back(std::move(b));
     packetBase += pending;
@@ -315,6 +319,7 @@ class HDLParser::vsInternal {
     const double tw = now();
     int rc = vs_wait(ctx, b.ticket, &r);
     secWait += now() - tw;
+    mark("vs_wait");
     if (rc != VS_OK) {
       failBatches(vs_last_error(ctx));
       return false;
@@ -328,6 +333,7 @@ class HDLParser::vsInternal {
       failBatches(vs_last_error(ctx));
       return false;
     }
+    mark("vs_layout_frames");
     b.rows.assign(lay.rows, lay.rows + lay.n_frames);
     b.arenas.resize(b.rows.size());
     b.metaOffset.assign(b.rows.size(), 0);
@@ -348,6 +354,7 @@ class HDLParser::vsInternal {
         return false;
       }
     }
+    mark("arenas+vs_fetch_layout");
     // raw packets: a packet is stored in the frame that is current when it arrives; the frame's
     // first packet is stored twice (reference HDLParser.cxx:999 + 1009).  Copied now: the ring
     // is handed back to the receiver as soon as this returns.
@@ -380,6 +387,7 @@ class HDLParser::vsInternal {
     carry = r.carry_out;
     const vs_frame_rows& open = b.rows.back();
     for (int l = 0; l < HDL_MAX_NUM_LASERS; ++l) openCounts[l] = open.row_count[l];  // rows == laser ids
+    mark("raw packets");
     b.stage = 2;
     return true;
   }
@@ -389,6 +397,7 @@ class HDLParser::vsInternal {
     const double ts = now();
     const int rc = vs_sync(ctx, b.ticket, nullptr);
     secSync += now() - ts;
+    mark("vs_sync");
     if (rc != VS_OK) {
       failBatches(vs_last_error(ctx));
       return false;
@@ -448,10 +457,26 @@ class HDLParser::vsInternal {
   // Non-pipelined decode of whatever is buffered: submit, lay out, fetch, adopt.
   bool decodePending(std::deque<std::shared_ptr<HDLFrame> >* closedOut, int64_t recCursorArg = -1) {
     if (pending == 0) return true;
-    if (!drainTo(closedOut)) return false;
-    if (!submitBatch(recCursorArg)) return false;
-    return drainTo(closedOut);
+    marks.clear();
+    mark("start");
+    bool ok = drainTo(closedOut) && submitBatch(recCursorArg) && drainTo(closedOut);
+    mark("done");
+    // VELOSLAM_TRACE_SLOW_MS=<ms>: where a decode that took longer than that spent its time
+    if (traceSlowMs > 0 && (marks.back().second - marks.front().second) * 1e3 > traceSlowMs) {
+      std::cerr << "HDLParser: slow decode #" << nDecodes << ":";
+      for (size_t i = 1; i < marks.size(); ++i)
+        std::cerr << ' ' << marks[i].first << ' ' << (marks[i].second - marks[i - 1].second) * 1e3 << " ms";
+      std::cerr << std::endl;
+    }
+    ++nDecodes;
+    return ok;
   }
+  void mark(const char* what) {
+    if (traceSlowMs > 0) marks.emplace_back(what, now());
+  }
+  std::vector<std::pair<const char*, double> > marks;
+  double traceSlowMs = std::getenv("VELOSLAM_TRACE_SLOW_MS") ? std::atof(std::getenv("VELOSLAM_TRACE_SLOW_MS")) : 0.0;
+  long nDecodes = 0;
 
   // finish every batch in flight
   bool drainTo(std::deque<std::shared_ptr<HDLFrame> >* closedOut) {

@@ -45,7 +45,27 @@ struct GraphOps {
   cudaStream_t stream = nullptr;
   cudaGraphExec_t exec = nullptr;
   std::vector<cudaGraphNode_t>* nodes = nullptr;
+  // what each node was last set to (empty: unknown): a refresh skips the nodes whose operation
+  // did not change, every cudaGraphExec*SetParams call costs about a microsecond
+  std::vector<std::string>* sigs = nullptr;
   size_t cursor = 0;
+
+  static std::string sig_of(const void* a, size_t na, const void* b = nullptr, size_t nb = 0) {
+    std::string s(static_cast<const char*>(a), na);
+    if (nb) s.append(static_cast<const char*>(b), nb);
+    return s;
+  }
+  // UPDATE: true when node `cursor` already holds this operation (then it is skipped)
+  bool unchanged(const std::string& sig) {
+    if (cursor >= sigs->size()) return false;
+    std::string& have = (*sigs)[cursor];
+    if (!sig.empty() && have == sig) {
+      ++cursor;
+      return true;
+    }
+    have = sig;
+    return false;
+  }
 
   cudaError_t captured() {
     cudaStreamCaptureStatus st;
@@ -57,12 +77,19 @@ struct GraphOps {
     if (e != cudaSuccess) return e;
     if (st != cudaStreamCaptureStatusActive || nd != 1) return cudaErrorStreamCaptureInvalidated;
     nodes->push_back(deps[0]);
+    sigs->push_back(pending_sig);
     return cudaSuccess;
   }
+  std::string pending_sig;
   cudaGraphNode_t next() { return cursor < nodes->size() ? (*nodes)[cursor++] : nullptr; }
 
   cudaError_t copy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    if (mode != DIRECT) {
+      const void* key[3] = {dst, src, reinterpret_cast<const void*>(bytes)};
+      pending_sig = sig_of(key, sizeof(key));
+    }
     if (mode == UPDATE) {
+      if (unchanged(pending_sig)) return cudaSuccess;
       cudaGraphNode_t nd = next();
       if (!nd) return cudaErrorInvalidValue;
       return cudaGraphExecMemcpyNodeSetParams1D(exec, nd, dst, src, bytes, kind);
@@ -72,7 +99,12 @@ struct GraphOps {
     return e;
   }
   cudaError_t fill(void* dst, int value, size_t bytes) {
+    if (mode != DIRECT) {
+      const void* key[3] = {dst, reinterpret_cast<const void*>((size_t)value), reinterpret_cast<const void*>(bytes)};
+      pending_sig = sig_of(key, sizeof(key));
+    }
     if (mode == UPDATE) {
+      if (unchanged(pending_sig)) return cudaSuccess;
       cudaGraphNode_t nd = next();
       if (!nd) return cudaErrorInvalidValue;
       cudaMemsetParams mp;
@@ -89,8 +121,18 @@ struct GraphOps {
     if (e == cudaSuccess && mode == CAPTURE) e = captured();
     return e;
   }
-  cudaError_t launch(const void* func, unsigned grid, unsigned block, size_t smem, void** args) {
+  // arg0_bytes: size of the kernel's one parameter struct (0: not known, the node is always refreshed)
+  cudaError_t launch(const void* func, unsigned grid, unsigned block, size_t smem, void** args,
+                     size_t arg0_bytes = 0) {
+    if (mode != DIRECT) {
+      pending_sig.clear();
+      if (arg0_bytes) {
+        const size_t key[4] = {reinterpret_cast<size_t>(func), grid, block, smem};
+        pending_sig = sig_of(key, sizeof(key), args[0], arg0_bytes);
+      }
+    }
     if (mode == UPDATE) {
+      if (unchanged(pending_sig)) return cudaSuccess;
       cudaGraphNode_t nd = next();
       if (!nd) return cudaErrorInvalidValue;
       cudaKernelNodeParams kp;
@@ -127,6 +169,7 @@ struct Slot {
   cudaGraphExec_t gexec = nullptr;
   cudaGraph_t ggraph = nullptr;  // kept: the node handles used for the refresh belong to it
   std::vector<cudaGraphNode_t> gnodes;
+  std::vector<std::string> gsigs;
   GraphKey gkey;
   int graph_launches = 0;
   bool graph_issued = false;  // the batch in flight went out as a graph (no per-kernel events)
@@ -175,7 +218,6 @@ struct Slot {
   vs_layout layout;
   // pinned host
   BatchHeader* h_hdr = nullptr;
-  BatchHeader* h_hdr_init = nullptr;
   long long* h_frame_first = nullptr;
   int* h_frame_start = nullptr;
   int* h_frame_meta_pkt = nullptr;
@@ -325,6 +367,7 @@ void drop_graph(Slot& s) {
   s.gexec = nullptr;
   s.ggraph = nullptr;
   s.gnodes.clear();
+  s.gsigs.clear();
 }
 
 void free_slot(Slot& s) {
@@ -358,7 +401,6 @@ void free_slot(Slot& s) {
   if (s.ev_l0) cudaEventDestroy(s.ev_l0);
   if (s.ev_l1) cudaEventDestroy(s.ev_l1);
   cudaFreeHost(s.h_hdr);
-  cudaFreeHost(s.h_hdr_init);
   cudaFreeHost(s.h_frame_first);
   cudaFreeHost(s.h_frame_start);
   cudaFreeHost(s.h_frame_meta_pkt);
@@ -462,7 +504,6 @@ int alloc_slot(vs_ctx* ctx, Slot& s) {
   VS_CUDA(cudaMalloc(&s.d_eager, sizeof(EagerBlock)));
   VS_CUDA(cudaMallocHost(&s.h_eager, sizeof(EagerBlock)));
   VS_CUDA(cudaMallocHost(&s.h_hdr, sizeof(BatchHeader)));
-  VS_CUDA(cudaMallocHost(&s.h_hdr_init, sizeof(BatchHeader)));
   return VS_OK;
 }
 
@@ -580,22 +621,6 @@ int enqueue_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, con
   const int64_t payload_bytes = (n - 1) * stride + kPacketBytes;
   s.n_launches = 0;
 
-  if (!dev_in) {
-    // stage host packets (and the pcap record headers in front of them when asked); s.d_in was
-    // sized by run_batch
-    const int64_t lead = pcap_t ? 64 : 0;  // keeps the payload 2-byte aligned, covers the 58 B
-    const int64_t src_lead = pcap_t ? 58 : 0;
-    VS_CUDA(g.copy(s.d_in + lead - src_lead, pkts - src_lead, (size_t)(payload_bytes + src_lead),
-                   cudaMemcpyHostToDevice));
-    d_pkts = s.d_in + lead;
-    if (!pcap_t) {
-      VS_CUDA(g.copy(s.d_time, pkt_time, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice));
-      d_time = s.d_time;
-    }
-  }
-  if (pcap_t) d_time = s.d_time;
-
-  VS_CUDA(g.record(s.ev_k0));
   // ---- per-batch resets ------------------------------------------------------------------
   const int64_t scan_tiles = (n + kTilePkts - 1) / kTilePkts;
   const int64_t pose_tiles = (n + kPoseThreads - 1) / kPoseThreads;
@@ -614,24 +639,49 @@ int enqueue_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, con
   const size_t fc_bytes = (size_t)frames_possible * kMaxLasers * sizeof(unsigned);
   int* d_ctr2 = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(s.d_frame_counts) + fc_bytes);
   ulonglong2* d_st = reinterpret_cast<ulonglong2*>(reinterpret_cast<uint8_t*>(d_ctr2) + 256);
+  // (Measured: the resets and the packet times on a parallel graph branch next to the packet
+  // copy make a rotation-sized batch 3 us slower, not faster -- 84 us against 81 -- so the
+  // prologue stays one chain.)
   {
-    // zero only what this batch can touch
+    // zero only what this batch can touch; first_point / start_block tables (adjacent in one
+    // allocation): all rows "unset"; the header's initial values -- one launch (k_reset)
+    ResetParams rp;
+    size_t zero_bytes;
     if (fused) {
-      VS_CUDA(g.fill(s.d_frame_counts, 0, fc_bytes + 256 + (size_t)fused_tiles * 32));
+      rp.zero = reinterpret_cast<unsigned*>(s.d_frame_counts);
+      zero_bytes = fc_bytes + 256 + (size_t)fused_tiles * 32;
     } else {
-      const size_t head = (size_t)((uint8_t*)s.d_frame_counts - s.d_zero);
-      VS_CUDA(g.fill(s.d_zero, 0, head + fc_bytes));
+      rp.zero = reinterpret_cast<unsigned*>(s.d_zero);
+      zero_bytes = (size_t)((uint8_t*)s.d_frame_counts - s.d_zero) + fc_bytes;
     }
-    // first_point / start_block tables (adjacent in one allocation): all rows "unset" in one go
-    VS_CUDA(g.fill(s.d_ff, 0xff, (size_t)ctx->frame_cap * 12));
-    BatchHeader& hi = *s.h_hdr_init;
-    std::memset(&hi, 0, sizeof(hi));
-    hi.first_upper_block = LLONG_MAX;
-    hi.first_const_pkt = INT_MAX;
-    hi.origin_at_halo = -1;
-    hi.last_origin_packet = -1;
-    VS_CUDA(g.copy(s.d_hdr, s.h_hdr_init, sizeof(BatchHeader), cudaMemcpyHostToDevice));
+    rp.zero_words = (long long)(zero_bytes / 4);
+    rp.ones = reinterpret_cast<unsigned*>(s.d_ff);
+    rp.ones_words = (long long)ctx->frame_cap * 3;
+    rp.hdr = s.d_hdr;
+    if (zero_bytes % 4 != 0 || (reinterpret_cast<uintptr_t>(rp.zero) & 3) != 0 ||
+        (reinterpret_cast<uintptr_t>(rp.ones) & 3) != 0)
+      return fail(ctx, VS_ERR_STATE, "reset block is not word aligned");
+    const long long words = std::max(rp.zero_words, rp.ones_words);
+    const unsigned grid = (unsigned)std::min<long long>((words + 1023) / 1024 + 1, 148 * 8);
+    void* args[] = {&rp};
+    VS_CUDA(g.launch(reinterpret_cast<const void*>(&k_reset), grid, 256, 0, args, sizeof(rp)));
+    ++s.n_launches;
   }
+  if (!dev_in) {
+    // stage host packets (and the pcap record headers in front of them when asked); s.d_in was
+    // sized by run_batch
+    const int64_t lead = pcap_t ? 64 : 0;  // keeps the payload 2-byte aligned, covers the 58 B
+    const int64_t src_lead = pcap_t ? 58 : 0;
+    VS_CUDA(g.copy(s.d_in + lead - src_lead, pkts - src_lead, (size_t)(payload_bytes + src_lead),
+                   cudaMemcpyHostToDevice));
+    d_pkts = s.d_in + lead;
+    if (!pcap_t) {
+      VS_CUDA(g.copy(s.d_time, pkt_time, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice));
+      d_time = s.d_time;
+    }
+  }
+  if (pcap_t) d_time = s.d_time;
+  VS_CUDA(g.record(s.ev_k0));
   if (pcap_t) {
     const uint8_t* a0 = d_pkts;
     long long a1 = stride;
@@ -832,6 +882,7 @@ int enqueue_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, con
     // frame meta gather over every frame the batch can hold; rows beyond total_wraps are
     // ignored by the host
     FrameParams fp;
+    std::memset(&fp, 0, sizeof(fp));  // padding included: the graph refresh compares the bytes
     fp.pkt_seg = s.d_seg;
     fp.pkt_time = d_time;
     fp.frame_start_block = s.d_frame_start;
@@ -849,7 +900,7 @@ int enqueue_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, con
     fp.frame_laser_counts = s.d_frame_counts;
     void* args[] = {&fp};
     VS_CUDA(g.launch(reinterpret_cast<const void*>(&k_frames), (unsigned)((frames_possible + 255) / 256), 256, 0,
-                     args));
+                     args, sizeof(fp)));
     ++s.n_launches;
   }
   VS_CUDA(g.record(s.ev_k1));
@@ -943,11 +994,13 @@ int run_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, const i
     key.eager_packed = eager_frame_rows(ctx, n) <= kEagerRows && !key.fused;
     if (s.gexec && !(key == s.gkey)) drop_graph(s);
     g.nodes = &s.gnodes;
+    g.sigs = &s.gsigs;
     int rc = VS_OK;
     cudaError_t ce = cudaSuccess;
     if (!s.gexec) {
       // record this batch's operations once
       s.gnodes.clear();
+      s.gsigs.clear();
       s.gkey = key;
       ce = cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeRelaxed);
       if (ce == cudaSuccess) {
@@ -1527,13 +1580,23 @@ const int kBeamLutHost[64] = {38, 39, 42, 43, 32, 33, 36, 37, 40, 41, 46, 47, 50
                               6,  7,  10, 11, 0,  1,  4,  5,  8,  9,  14, 15, 18, 19, 22, 23,
                               12, 13, 16, 17, 20, 21, 26, 27, 30, 31, 2,  3,  24, 25, 28, 29};
 
-int ensure_device_bytes(vs_ctx* ctx, uint8_t** buf, size_t* have, size_t need) {
+// Grows a device buffer.  cudaFree + cudaMalloc stall the whole device (measured: 5 to 640 ms
+// under a live 10 Hz stream), so a buffer starts at `reserve` -- what a full batch of the context
+// needs -- and, when a request still exceeds it, grows by half again instead of to the exact fit.
+int ensure_device_bytes(vs_ctx* ctx, uint8_t** buf, size_t* have, size_t need, size_t reserve) {
   if (need <= *have) return VS_OK;
+  const size_t want = std::max(need + (*have ? need / 2 : 0), reserve);
   cudaFree(*buf);
   *buf = nullptr;
   *have = 0;
-  VS_CUDA(cudaMalloc(buf, need));
-  *have = need;
+  if (cudaMalloc(buf, want) != cudaSuccess) {
+    cudaGetLastError();
+    *buf = nullptr;
+    VS_CUDA(cudaMalloc(buf, need));  // no room for the head-room: the exact fit
+    *have = need;
+    return VS_OK;
+  }
+  *have = want;
   return VS_OK;
 }
 }  // namespace
@@ -1576,16 +1639,23 @@ int vs_layout_frames(vs_ctx* ctx, uint64_t ticket, const uint32_t* carried_count
     rw.n_slots = (int64_t)acc;
   }
 
+  // sized once for a full batch of this context plus the points an open rotation carries in
+  // (one 5 Hz HDL-64E rotation), so that a live stream never re-allocates
+  const size_t reserve_slots = (size_t)std::min<int64_t>(ctx->max_packets, 1 << 16) * 384 + 300000;
   int rc = ensure_device_bytes(ctx, &s.d_lay_xyzi, &s.lay_xyzi_bytes,
-                               (size_t)std::max<int64_t>(n_slots, 1) * (size_t)xyzi_stride);
+                               (size_t)std::max<int64_t>(n_slots, 1) * (size_t)xyzi_stride,
+                               reserve_slots * (size_t)xyzi_stride);
   if (rc != VS_OK) return rc;
   if (with_meta) {
-    rc = ensure_device_bytes(ctx, &s.d_lay_meta, &s.lay_meta_bytes, (size_t)std::max<int64_t>(n_slots, 1) * 12);
+    rc = ensure_device_bytes(ctx, &s.d_lay_meta, &s.lay_meta_bytes, (size_t)std::max<int64_t>(n_slots, 1) * 12,
+                             reserve_slots * 12);
     if (rc != VS_OK) return rc;
   }
   const int64_t n_dec = s.n - s.halo;
   const int n_chunks = (int)((n_dec + kLayChunk - 1) / kLayChunk);
-  rc = ensure_device_bytes(ctx, &s.d_lay_st, &s.lay_st_bytes, 256 + (size_t)n_chunks * 32 * 8);
+  const size_t max_chunks = (size_t)((ctx->max_packets + kLayChunk - 1) / kLayChunk);
+  rc = ensure_device_bytes(ctx, &s.d_lay_st, &s.lay_st_bytes, 256 + (size_t)n_chunks * 32 * 8,
+                           256 + max_chunks * 32 * 8);
   if (rc != VS_OK) return rc;
   if (!s.d_lay_rows) VS_CUDA(cudaMalloc(&s.d_lay_rows, (size_t)ctx->frame_cap * kMaxLasers * 8));
   if (!s.ev_l0) {

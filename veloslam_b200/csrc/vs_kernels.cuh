@@ -2006,6 +2006,35 @@ __global__ void k_ins_pose(const InsParams p) {
 }
 
 // =========================================================================================
+// k_reset: everything a batch starts from, in one launch -- the zeroed scan / frame-count state,
+// the "unset" (all ones) rows of the first_point / start_block tables and the batch header's
+// initial values (three stream operations before; a rotation-sized batch is a chain of
+// dependent operations and pays for each link).
+// =========================================================================================
+struct ResetParams {
+  unsigned* zero;        // 4-byte aligned
+  long long zero_words;
+  unsigned* ones;
+  long long ones_words;
+  BatchHeader* hdr;
+};
+__global__ void k_reset(const ResetParams p) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long i = i0; i < p.zero_words; i += stride) p.zero[i] = 0u;
+  for (long long i = i0; i < p.ones_words; i += stride) p.ones[i] = 0xffffffffu;
+  if (i0 == 0) {
+    BatchHeader h;
+    memset(&h, 0, sizeof(h));
+    h.first_upper_block = LLONG_MAX;
+    h.first_const_pkt = INT_MAX;
+    h.origin_at_halo = -1;
+    h.last_origin_packet = -1;
+    *p.hdr = h;
+  }
+}
+
+// =========================================================================================
 // k_frames: per frame started inside the batch, find the packet that initialises its meta
 // (streaming: the packet after the one holding the frame's wrap, provided that wrap is the
 // packet's last one, HDLParser.cxx:993-1001; offline: the wrap packet itself).
@@ -2058,17 +2087,25 @@ __global__ void k_frames(const FrameParams p) {
     p.frame_meta_time[f] = mt;
     p.frame_skips[f] = sk;
   }
-  if (p.eager && f < kEagerRows) {
+  if (p.eager && blockIdx.x == 0) {
+    // the first CTA packs the block: one row per thread, the header and the per-laser counts
+    // word by word across the CTA (coalesced; a rotation-sized batch waits for this kernel)
     EagerBlock& e = *p.eager;
-    if (f == 0) e.hdr = *p.hdr;  // final: this is the batch's last kernel
-    const bool in = f < p.n_frames;
-    e.first[f] = in ? p.frame_first_point[f] : -1ll;
-    e.start[f] = in ? p.frame_start_block[f] : -1;
-    e.meta_pkt[f] = mp;
-    e.meta_time[f] = mt;
-    e.skips[f] = sk;
-    for (int l = 0; l < kMaxLasers; ++l)
-      e.counts[f][l] = in ? p.frame_laser_counts[(long long)f * kMaxLasers + l] : 0u;
+    static_assert(sizeof(BatchHeader) % 4 == 0, "header copied as 32-bit words");
+    const unsigned* hs = reinterpret_cast<const unsigned*>(p.hdr);  // final: the batch's last kernel
+    unsigned* hd = reinterpret_cast<unsigned*>(&e.hdr);
+    for (int i = threadIdx.x; i < (int)(sizeof(BatchHeader) / 4); i += blockDim.x) hd[i] = hs[i];
+    unsigned* cd = &e.counts[0][0];
+    for (int i = threadIdx.x; i < kEagerRows * kMaxLasers; i += blockDim.x)
+      cd[i] = (i / kMaxLasers) < p.n_frames ? p.frame_laser_counts[i] : 0u;
+    if (f < kEagerRows) {
+      const bool in = f < p.n_frames;
+      e.first[f] = in ? p.frame_first_point[f] : -1ll;
+      e.start[f] = in ? p.frame_start_block[f] : -1;
+      e.meta_pkt[f] = mp;
+      e.meta_time[f] = mt;
+      e.skips[f] = sk;
+    }
   }
 }
 
