@@ -78,7 +78,13 @@ class HDLParser {
   bool getFrame(std::shared_ptr<HDLFrame>& dest, const std::string& filename, int64_t& startPos,
                 const int& skip);
   void processHDLPacket(unsigned char* data, unsigned int bytesReceived, ptime t);
-  std::deque<std::shared_ptr<HDLFrame> > getAllFrames();
+  // The reference returns the deque by value (HDLParser.h:135) and its consumer asks for it
+  // after every packet (HDLSource.cxx:220-222: getAllFrames().size(), getAllFrames().back()):
+  // two heap allocations per packet for an empty deque.  A reference to the parser's own list
+  // keeps those call sites and `std::deque<...> fr = p.getAllFrames()` compiling unchanged and
+  // makes the per-packet poll free; the list changes with the next processHDLPacket /
+  // clearAllFrames, so callers that keep frames copy them (as the reference's do).
+  const std::deque<std::shared_ptr<HDLFrame> >& getAllFrames();
   void clearAllFrames();
   std::shared_ptr<HDLFrame> createHDLFrame();
 
