@@ -378,27 +378,36 @@ def run_recording(hours, steps, warmup, local, rank, world, dev, calib):
     ag1 = torch.cuda.Event(enable_timing=True)
 
     def one_pass():
+        # the frame table never visits the host on its way to the other ranks: k_table_rows writes
+        # the exchange rows behind the batch's kernels, the all-gather reads them out of HBM
         tk = ctx.submit(d_pk, d_t, n=n_sub, stride=1206, n_halo=halo, mode=capi.MODE_STREAMING,
-                        flags=capi.FLAG_DEVICE_INPUT, t_base_us=t_base)
-        r = ctx.wait(tk, frames=False)
-        w0 = time.perf_counter()
-        # exchange rows straight out of the context's frame table into the pinned send buffer
-        n_rows = capi.frame_table_rows_into(r, rank, first, halo, h_mine[1:])
-        h_mine[0, 0] = n_rows
+                        flags=capi.FLAG_DEVICE_INPUT | capi.FLAG_NO_FRAME_LIST, t_base_us=t_base)
+        ctx.frame_table_rows_device(tk, rank, first, d_mine, cap_rows)
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(ext)
         if world > 1:
-            d_mine.copy_(h_mine, non_blocking=True)
             ag0.record()
             torch.distributed.all_gather_into_tensor(d_all, d_mine)
             ag1.record()
             h_all.copy_(d_all, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        else:
+            h_mine.copy_(d_mine, non_blocking=True)
+        r = ctx.wait(tk, frames=False)          # batch errors (halo, capacity, time range) surface here
+        w0 = time.perf_counter()
+        cur.synchronize()
+        w1 = time.perf_counter()
+        if world > 1:
             ag_ms = ag0.elapsed_time(ag1)
-            w1 = time.perf_counter()
+            counts = h_all_np[:, 0, 0]
+            if (counts < 0).any():
+                raise SystemExit("bench.py: a rank's frame table exceeds the exchange buffer")
             # table g sits at row g * (cap_rows + 1) + 1 of the gathered buffer: stitched in place
-            gf, segs = stitcher(h_all_np, h_all_np[:, 0, 0], cap_rows + 1, first_row=1)
+            gf, segs = stitcher(h_all_np, counts, cap_rows + 1, first_row=1)
         else:
             ag_ms = 0.0
-            w1 = time.perf_counter()
+            n_rows = int(h_mine_np[0, 0])
+            if n_rows < 0:
+                raise SystemExit("bench.py: the frame table exceeds the exchange buffer")
             gf, segs = stitcher(h_mine_np, [n_rows], 0, first_row=1)
         w2 = time.perf_counter()
         return r, gf, segs, ag_ms, (w1 - w0) * 1e3, (w2 - w1) * 1e3
@@ -441,6 +450,14 @@ def run_recording(hours, steps, warmup, local, rank, world, dev, calib):
     class _DeviceRows:
         def __getitem__(self, sl):
             return d_pk[sl].cpu().numpy()
+    # (the timed passes assemble no frame list on the host: one more pass with it, whose rows
+    # must be the device-built rows the timed pass exchanged)
+    mine_rows = (h_all_np[rank] if world > 1 else h_mine_np).copy()
+    r = ctx.wait(ctx.submit(d_pk, d_t, n=n_sub, stride=1206, n_halo=halo, mode=capi.MODE_STREAMING,
+                            flags=capi.FLAG_DEVICE_INPUT, t_base_us=t_base))
+    host_rows = capi.frame_table_rows(r.frame_table, rank, first, halo)
+    if mine_rows[0, 0] != host_rows.shape[0] or not np.array_equal(mine_rows[1:1 + host_rows.shape[0]], host_rows):
+        raise SystemExit("bench.py: the device-built frame-table rows differ from vs_frame_table_rows")
     parity = parity_windows(ctx, r, _DeviceRows(), d_t.cpu().numpy(), t_base, halo, calib, poses,
                             seed=99 + rank)
     if world > 1:
@@ -470,13 +487,14 @@ def run_recording(hours, steps, warmup, local, rank, world, dev, calib):
            "exchange_ms_host": float(np.mean(exch)), "stitch_ms": float(np.mean(sti)),
            "exchange_bytes_per_rank": int((cap_rows + 1) * capi.FRAME_ROW_COLS * 8),
            "packets_this_rank": int(end - first), "halo": int(halo),
-           "points_this_rank": int(pts_local), "launches_per_pass": int(r.n_kernel_launches),
+           "points_this_rank": int(pts_local), "launches_per_pass": int(r.n_kernel_launches) + 1,   # + k_table_rows
            "parity_window": parity["status"], "parity": parity, "clocks": clocks,
            "note": "timed region of a pass: vs_submit + vs_wait of the rank's packet range (k_scan, "
                    "k_pose, k_decode, k_frames; recording resident in HBM, generated on the device), "
-                   "frame-table rows (vs_frame_table_rows), ONE NCCL all_gather_into_tensor of "
-                   "fixed-size tables, D2H, vs_stitch_frame_tables on every rank; CUDA events, "
-                   "max over ranks"}
+                   "frame-table rows built on the device (vs_frame_table_rows_device, k_table_rows), ONE "
+                   "NCCL all_gather_into_tensor of fixed-size tables out of HBM, D2H, "
+                   "vs_stitch_frame_tables on every rank; CUDA events, max over ranks; "
+                   "exchange_ms_host = host wait for the gathered rows after vs_wait returned"}
     if out["points_in_index"] != pts:
         raise SystemExit("bench.py: the stitched frame index does not cover every decoded point")
     ctx.close()

@@ -73,6 +73,11 @@ typedef enum vs_mode {
  * result is expressed in the frame origin's coordinates (rotation and translation re-based).
  * Needs >= 2 poses (else ignored).  Exact semantics: oracle/deskew_port.py. */
 #define VS_FLAG_DESKEW_PER_POINT 4u
+/* The caller takes the frame table from vs_frame_table_rows_device (multi-GPU exchange out of
+ * HBM): vs_wait does not assemble the vs_frame list (vs_result.frames == NULL, n_frames and
+ * carry_out are exact), which for the thousands of frames of a long recording is most of its
+ * host time.  vs_layout_frames is not available for such a batch. */
+#define VS_FLAG_NO_FRAME_LIST 8u
 
 /* One <px> item of the calibration db.xml in its raw units (HDLParser.cxx:818-832). */
 typedef struct vs_laser_corr {
@@ -302,6 +307,17 @@ typedef struct vs_global_frame {
   int32_t timestamp_mismatch;  /* the two sides of a shard boundary disagree on the frame's meta */
   int32_t reserved;
 } vs_global_frame;
+
+/* vs_frame_table_rows on the device, for a batch in flight or finished: enqueues, behind the
+ * batch's kernels on its stream, a kernel (k_table_rows) that writes the batch's frame table as
+ * exchange rows into DEVICE memory -- row 0 = {n_rows, 0, ...}, rows 1..n_rows the table, same
+ * columns and values as vs_frame_table_rows gives for vs_wait's frames -- so that the
+ * all-gather between ranks reads HBM and no host pass sits between decode and collective.
+ * d_rows: (cap_rows + 1) x VS_FRAME_ROW_COLS int64.  A batch with more frames than cap_rows
+ * writes row 0 = {-n_rows, ...} only.  Does not synchronise; errors of the batch itself
+ * (halo, capacity, time range) are still reported by vs_wait. */
+VS_API int vs_frame_table_rows_device(vs_ctx* ctx, uint64_t ticket, int32_t rank, int64_t first_packet,
+                               int64_t* d_rows, int64_t cap_rows);
 
 /* rows: the ranks' tables in rank order, rows_per_rank[g] rows of VS_FRAME_ROW_COLS each; table g
  * starts at row g * rank_stride_rows (the layout a fixed-size all-gather leaves), or right behind

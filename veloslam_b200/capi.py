@@ -16,7 +16,7 @@ from .build import LIB
 INT64_MIN = -(2 ** 63)
 VS_TIME_NONE = INT64_MIN
 MODE_STREAMING, MODE_OFFLINE = 0, 1
-FLAG_DEVICE_INPUT, FLAG_PCAP_TIMES, FLAG_DESKEW_PER_POINT = 1, 2, 4
+FLAG_DEVICE_INPUT, FLAG_PCAP_TIMES, FLAG_DESKEW_PER_POINT, FLAG_NO_FRAME_LIST = 1, 2, 4, 8
 STATUS = {0: "VS_OK", 1: "VS_ERR_INVALID_ARG", 2: "VS_ERR_NOT_CALIBRATED", 3: "VS_ERR_CUDA",
           4: "VS_ERR_CAPACITY", 5: "VS_ERR_NO_DEVICE", 6: "VS_ERR_HALO", 7: "VS_ERR_STATE"}
 
@@ -26,7 +26,7 @@ EXPORTS = ["vs_version", "vs_create", "vs_destroy", "vs_last_error", "vs_set_cal
            "vs_host_free", "vs_stream", "vs_slot_stream", "vs_device_alloc", "vs_device_free",
            "vs_device_upload", "vs_solve_packet_times", "vs_poses_from_ins", "vs_set_firing_offsets",
            "vs_layout_frames", "vs_fetch_layout", "vs_sync", "vs_shard_range", "vs_frame_table_rows",
-           "vs_stitch_frame_tables"]
+           "vs_frame_table_rows_device", "vs_stitch_frame_tables"]
 
 
 class LaserCorr(C.Structure):
@@ -187,6 +187,8 @@ def load_library():
     L.vs_shard_range.argtypes = [i64, i32, i32, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     L.vs_frame_table_rows.restype = C.c_int
     L.vs_frame_table_rows.argtypes = [vp, i32, i32, i64, i64, vp]
+    L.vs_frame_table_rows_device.restype = C.c_int
+    L.vs_frame_table_rows_device.argtypes = [vp, C.c_uint64, i32, i64, vp, i64]
     L.vs_stitch_frame_tables.restype = C.c_int
     L.vs_stitch_frame_tables.argtypes = [vp, vp, i32, i64, vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
     _lib = L
@@ -322,9 +324,10 @@ class BatchResult:
         self.n_points = int(r.n_points)
         self.n_frames = int(r.n_frames)
         self.n_closed = int(r.n_closed)
-        self.frames = [FrameView(r.frames[i]) for i in range(r.n_frames)] if frames else None
+        # (FLAG_NO_FRAME_LIST: the library assembles no list, r.frames is NULL)
+        self.frames = [FrameView(r.frames[i]) for i in range(r.n_frames)] if frames and r.frames else None
         # the same rows as one structured array (copied out of the context-owned buffer)
-        self._raw_frames = (r.frames, r.n_frames)
+        self._raw_frames = (r.frames, r.n_frames if r.frames else 0)
         self._frame_table = None
         self.carry_out = Carry.from_buffer_copy(r.carry_out)
         self.t_base_us = int(r.t_base_us)
@@ -512,6 +515,13 @@ class Context:
         """Enqueue the D2H copy of layout slots into host buffers (addresses / arrays)."""
         self._check(self._L.vs_fetch_layout(self._h, ticket, first_slot, n_slots, _ptr(xyzi_host),
                                             _ptr(meta_host)))
+
+    def frame_table_rows_device(self, ticket, rank, first_packet, d_rows, cap_rows):
+        """vs_frame_table_rows_device: enqueue the kernel that writes the batch's exchange rows
+        (row 0 = [n_rows, 0...]) into the device buffer d_rows ((cap_rows + 1, 10) int64: a torch
+        cuda tensor or an address) behind the batch's kernels.  No synchronisation."""
+        self._check(self._L.vs_frame_table_rows_device(self._h, ticket, rank, first_packet, _ptr(d_rows),
+                                                       cap_rows))
 
     def sync(self, ticket):
         ms = C.c_float()

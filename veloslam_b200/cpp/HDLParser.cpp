@@ -376,10 +376,12 @@ class HDLParser::vsInternal {
         const vs_frame& e = b.frames[i];
         const int first = (i == 0) ? 0 : e.start_packet + 1;
         const int last = (i + 1 < b.frames.size()) ? b.frames[i + 1].start_packet : (int)b.n - 1;
+        if (last >= first) b.packets[i].reserve((size_t)(last - first) + 2);
         for (int p = first; p <= last; ++p) {
-          const std::string raw(reinterpret_cast<const char*>(rawBase) + (size_t)p * rawStride, VS_PACKET_BYTES);
-          if (p == e.meta_packet) b.packets[i].push_back(std::make_pair(rawTime(p), raw));
-          b.packets[i].push_back(std::make_pair(rawTime(p), raw));
+          // one allocation + one copy per stored packet: the string is built inside the pair
+          const char* raw = reinterpret_cast<const char*>(rawBase) + (size_t)p * rawStride;
+          if (p == e.meta_packet) b.packets[i].emplace_back(rawTime(p), std::string(raw, VS_PACKET_BYTES));
+          b.packets[i].emplace_back(rawTime(p), std::string(raw, VS_PACKET_BYTES));
         }
       }
     }
@@ -409,8 +411,12 @@ class HDLParser::vsInternal {
       if (i > 0) currentFrame = newFrameShell();
       HDLFrame& f = *currentFrame;
       if (e.meta_packet >= 0) applyMeta(f, e);  // -1: carried (already applied), -2: never
-      if (storePackets)
-        for (auto& pk : b.packets[i]) f.packets.push_back(std::move(pk));
+      if (storePackets) {
+        if (f.packets.empty())
+          f.packets = std::move(b.packets[i]);
+        else
+          for (auto& pk : b.packets[i]) f.packets.push_back(std::move(pk));
+      }
       const std::shared_ptr<vs::Arena>& arena = b.arenas[i];
       if (i == 0 && partial.total > 0 && arena) {
         // what earlier batches decoded of this frame goes into the gaps the GPU left at the head

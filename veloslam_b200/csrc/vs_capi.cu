@@ -238,6 +238,8 @@ struct Slot {
   int64_t eager_rows = 0;
   bool index_only = false;
   std::vector<vs_frame> frames;
+  int n_frames_total = 0;   // frames of the batch; frames.size() is 2 at most with VS_FLAG_NO_FRAME_LIST
+  bool sparse_frames = false;
   vs_result result;
 };
 
@@ -1088,13 +1090,18 @@ int finish_batch(vs_ctx* ctx, Slot& s) {
 
   const int f_lo = (s.halo > 0) ? h.frame_at_halo : 0;  // first frame with decoded points
   const int n_frames = W - f_lo + 1;
-  s.frames.resize((size_t)n_frames);  // every entry is cleared below
+  // VS_FLAG_NO_FRAME_LIST: only the first and the last frame are assembled (vs_wait's carry-out
+  // and first-frame patch read them); the table itself goes out through k_table_rows
+  s.n_frames_total = n_frames;
+  s.sparse_frames = (s.flags & VS_FLAG_NO_FRAME_LIST) != 0 && n_frames > 2;
+  s.frames.resize(s.sparse_frames ? 2 : (size_t)n_frames);  // every entry is cleared below
   const int64_t total_points = s.index_only ? 0 : h.total_points;
   const bool any_upper_before = s.carry_in.is_hdl64 != 0;
   int64_t pose_hint = -1;
   for (int i = 0; i < n_frames; ++i) {
+    if (s.sparse_frames && i == 1) i = n_frames - 1;
     const int f = f_lo + i;
-    vs_frame& fr = s.frames[(size_t)i];
+    vs_frame& fr = s.frames[s.sparse_frames ? (size_t)(i != 0) : (size_t)i];
     std::memset(&fr, 0, sizeof(fr));
     long long first = s.h_frame_first[f];
     int sb = s.h_frame_start[f];
@@ -1460,7 +1467,7 @@ int vs_wait(vs_ctx* ctx, uint64_t ticket, vs_result* out) {
     std::memset(&r, 0, sizeof(r));
     r.n_packets = s.n - s.halo;
     r.n_points = s.index_only ? 0 : h.total_points;
-    r.n_frames = (int32_t)s.frames.size();
+    r.n_frames = (int32_t)s.n_frames_total;
     r.n_closed = r.n_frames - 1;
     r.x = s.d_x;
     r.y = s.d_y;
@@ -1539,11 +1546,10 @@ int vs_wait(vs_ctx* ctx, uint64_t ticket, vs_result* out) {
     co.frames_closed = s.carry_in.frames_closed + r.n_closed;
     co.points_emitted = s.carry_in.points_emitted + r.n_points;
     co.packets_seen = s.carry_in.packets_seen + r.n_packets;
-    r.frames = s.frames.data();
     s.done = true;
   }
   *out = s.result;
-  out->frames = s.frames.data();
+  out->frames = (s.flags & VS_FLAG_NO_FRAME_LIST) ? nullptr : s.frames.data();
   return VS_OK;
 }
 
@@ -1609,6 +1615,8 @@ int vs_layout_frames(vs_ctx* ctx, uint64_t ticket, const uint32_t* carried_count
   if (!s.busy || !s.done || s.ticket != ticket)
     return fail(ctx, VS_ERR_STATE, "vs_layout_frames: ticket not finished (vs_wait first)");
   if (s.index_only) return fail(ctx, VS_ERR_STATE, "vs_layout_frames: the batch decoded no points");
+  if (s.flags & VS_FLAG_NO_FRAME_LIST)
+    return fail(ctx, VS_ERR_STATE, "vs_layout_frames: the batch was submitted with VS_FLAG_NO_FRAME_LIST");
   cudaSetDevice(ctx->device);
   const BatchHeader& h = *s.h_hdr;
   const int n_frames = (int)s.frames.size();
@@ -1830,6 +1838,43 @@ int vs_frame_table_rows(const vs_frame* frames, int32_t n_frames, int32_t rank, 
     r[8] = f.meta_packet >= 0 ? f.meta_packet + base : f.meta_packet;
     r[9] = rank;
   }
+  return VS_OK;
+}
+
+int vs_frame_table_rows_device(vs_ctx* ctx, uint64_t ticket, int32_t rank, int64_t first_packet,
+                               int64_t* d_rows, int64_t cap_rows) {
+  if (!ctx || !d_rows || cap_rows < 1)
+    return fail(ctx, VS_ERR_INVALID_ARG, "vs_frame_table_rows_device: bad arguments");
+  Slot& s = ctx->slots[ticket % (uint64_t)ctx->n_slots];
+  if (!s.busy || s.ticket != ticket) return fail(ctx, VS_ERR_STATE, "vs_frame_table_rows_device: unknown ticket");
+  cudaSetDevice(ctx->device);
+  TableRowsParams tp;
+  std::memset(&tp, 0, sizeof(tp));
+  tp.hdr = s.d_hdr;
+  tp.frame_first_point = s.d_frame_first;
+  tp.frame_start_block = s.d_frame_start;
+  tp.frame_meta_packet = s.d_frame_meta_pkt;
+  tp.frame_meta_time = s.d_frame_meta_time;
+  tp.frame_skips = s.d_frame_skips;
+  tp.pkt_seg = s.d_seg;
+  tp.pkt_time = s.d_time_used;
+  tp.rows = reinterpret_cast<long long*>(d_rows);
+  tp.cap_rows = cap_rows;
+  tp.base = first_packet - s.halo;
+  tp.carry_timestamp = s.carry_in.frame_timestamp_us;
+  tp.carry_meta_inited = s.carry_in.frame_meta_inited;
+  tp.carry_skips = s.carry_in.frame_skips;
+  tp.carry_firing_skip = s.carry_in.firing_skip;
+  tp.carry_is_hdl64 = s.carry_in.is_hdl64;
+  tp.halo = (int)s.halo;
+  tp.mode = s.mode;
+  tp.index_only = s.index_only ? 1 : 0;
+  tp.rank = rank;
+  const int64_t frames_possible = std::min<int64_t>(ctx->frame_cap, 12 * s.n + 1);
+  const unsigned grid = (unsigned)std::min<int64_t>((std::min(frames_possible, cap_rows) + 255) / 256 + 1, 1024);
+  void* args[] = {&tp};
+  VS_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(&k_table_rows), dim3(grid, 1, 1), dim3(256, 1, 1), args,
+                           0, s.stream));
   return VS_OK;
 }
 

@@ -2109,4 +2109,106 @@ __global__ void k_frames(const FrameParams p) {
   }
 }
 
+// =========================================================================================
+// k_table_rows: a batch's frame table as the exchange rows of the multi-GPU stitch
+// (VS_FRAME_ROW_COLS int64 per frame, packet indices global), built on the device behind the
+// batch's kernels -- what finish_batch + vs_frame_table_rows do on the host, so that the
+// all-gather between ranks starts from HBM without a host pass.  Row 0 = {n_rows, 0, ...};
+// more frames than cap_rows: row 0 = {-n_rows, ...} and no table.
+// =========================================================================================
+struct TableRowsParams {
+  const BatchHeader* hdr;
+  const long long* frame_first_point;
+  const int* frame_start_block;
+  const int* frame_meta_packet;
+  const long long* frame_meta_time;
+  const int* frame_skips;
+  const PktSeg* pkt_seg;
+  const long long* pkt_time;
+  long long* rows;           // (cap_rows + 1) x kRowCols
+  long long cap_rows;
+  long long base;            // global index of packet 0 of the submitted array
+  long long carry_timestamp; // carry-in: the open frame's meta
+  int carry_meta_inited, carry_skips, carry_firing_skip, carry_is_hdl64;
+  int halo, mode, index_only, rank;
+};
+constexpr int kRowCols = 10;  // VS_FRAME_ROW_COLS
+constexpr long long kTimeNone = (long long)0x8000000000000000ull;  // VS_TIME_NONE
+
+__global__ void k_table_rows(const TableRowsParams p) {
+  const BatchHeader& h = *p.hdr;
+  const int W = h.total_wraps;
+  const int f_lo = p.halo > 0 ? h.frame_at_halo : 0;
+  const int n_frames = W - f_lo + 1;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 == 0) {
+    long long* r = p.rows;
+    r[0] = n_frames <= p.cap_rows ? (long long)n_frames : -(long long)n_frames;
+    for (int k = 1; k < kRowCols; ++k) r[k] = 0;
+  }
+  if (n_frames > p.cap_rows) return;
+  const long long total_points = p.index_only ? 0ll : h.total_points;
+  for (long long i = i0; i < n_frames; i += stride) {
+    const int f = f_lo + (int)i;
+    long long first = p.frame_first_point[f];
+    int sb = p.frame_start_block[f];
+    if (i == 0) {
+      if (first < 0) first = 0;
+      if (p.halo > 0 || sb < 0) sb = -1;
+    }
+    const bool closed = i + 1 < n_frames;
+    const long long next_first = closed ? p.frame_first_point[f + 1] : total_points;
+    int order = 0;
+    if (closed) order = (p.carry_is_hdl64 || h.first_upper_block <= (long long)p.frame_start_block[f + 1]) ? 1 : 0;
+    int mp, sk;
+    long long ts;
+    if (i == 0 && sb < 0) {
+      if (p.halo == 0 && p.carry_meta_inited) {
+        mp = -1;
+        ts = p.carry_timestamp;
+        sk = p.carry_skips;
+      } else {
+        // meta from the origin packet of the first decoded packet (vs_wait patches these in)
+        mp = p.halo > 0 ? h.origin_at_halo : 0;
+        sk = p.halo > 0 ? -1 : p.carry_firing_skip;
+        ts = kTimeNone;
+        if (mp >= 0) {
+          ts = p.pkt_time[mp];
+          if (p.halo > 0) {
+            const int sx = p.pkt_seg[mp].x;
+            if (p.mode == 1) {
+              const unsigned wm = (unsigned)(sx >> 4) & 0xfffu;
+              sk = wm ? 31 - __clz(wm) : 0;
+            } else {
+              sk = sx & 15;
+            }
+          }
+        }
+      }
+    } else {
+      mp = p.frame_meta_packet[f];
+      if (mp >= 0) {
+        ts = p.frame_meta_time[f];
+        sk = p.frame_skips[f];
+      } else {
+        mp = (mp == -3) ? -2 : mp;
+        ts = kTimeNone;
+        sk = -1;
+      }
+    }
+    long long* r = p.rows + (i + 1) * kRowCols;
+    r[0] = p.index_only ? 0ll : next_first - first;
+    r[1] = first;
+    r[2] = sb < 0 ? -1ll : (long long)(sb / 12) + p.base;
+    r[3] = sb < 0 ? -1ll : (long long)(sb % 12);
+    r[4] = ts;
+    r[5] = sk;
+    r[6] = closed ? 1 : 0;
+    r[7] = order;
+    r[8] = mp >= 0 ? (long long)mp + p.base : (long long)mp;
+    r[9] = p.rank;
+  }
+}
+
 }  // namespace vsd
