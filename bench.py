@@ -377,6 +377,8 @@ def run_recording(hours, steps, warmup, local, rank, world, dev, calib):
     ag0 = torch.cuda.Event(enable_timing=True)
     ag1 = torch.cuda.Event(enable_timing=True)
 
+    waits = []
+
     def one_pass():
         # the frame table never visits the host on its way to the other ranks: k_table_rows writes
         # the exchange rows behind the batch's kernels, the all-gather reads them out of HBM
@@ -392,8 +394,10 @@ def run_recording(hours, steps, warmup, local, rank, world, dev, calib):
             h_all.copy_(d_all, non_blocking=True)
         else:
             h_mine.copy_(d_mine, non_blocking=True)
+        wq = time.perf_counter()
         r = ctx.wait(tk, frames=False)          # batch errors (halo, capacity, time range) surface here
         w0 = time.perf_counter()
+        waits.append((w0 - wq) * 1e3)
         cur.synchronize()
         w1 = time.perf_counter()
         if world > 1:
@@ -485,6 +489,7 @@ def run_recording(hours, steps, warmup, local, rank, world, dev, calib):
            "points_in_index": int(gf["n_points"].sum()),
            "decode_ms_this_rank": float(np.mean(dec)), "nccl_allgather_ms": float(np.mean(ags)),
            "exchange_ms_host": float(np.mean(exch)), "stitch_ms": float(np.mean(sti)),
+           "vs_wait_ms_host": float(np.mean(waits[-steps:])),
            "exchange_bytes_per_rank": int((cap_rows + 1) * capi.FRAME_ROW_COLS * 8),
            "packets_this_rank": int(end - first), "halo": int(halo),
            "points_this_rank": int(pts_local), "launches_per_pass": int(r.n_kernel_launches) + 1,   # + k_table_rows

@@ -129,11 +129,13 @@ void HDLManager::loadOffline(const std::string& insTxt, const std::string& pcapf
   std::cout << "Read " << transMgr->getNumberOfTransforms() << " transforms.\n";
   shards_.clear();
   shardFile_.clear();
-  if (devices_.size() > 1 && this->loadOfflineSharded(pcapfile)) return;
+  // (a sharded attempt that fails may already have renamed the file after its first packet)
+  std::string file = pcapfile;
+  if (devices_.size() > 1 && this->loadOfflineSharded(pcapfile, &file)) return;
   // the whole recording goes to HBM once; when the file is not a fixed-stride packet file the
   // parser falls back to reading it record by record, like the reference
-  hdlParser->loadRecording(pcapfile);
-  auto frameVec = hdlParser->readFrameInformation(pcapfile);
+  hdlParser->loadRecording(file);
+  auto frameVec = hdlParser->readFrameInformation(file);
   /* because readFrameInformation() can't determine carpose for each frame
    * we need to ask transform manager */
   for (auto& f : frameVec) {
@@ -141,7 +143,7 @@ void HDLManager::loadOffline(const std::string& insTxt, const std::string& pcapf
     this->addFrame(f);
   }
   std::cout << "Read " << this->getNumberOfFrames() << " frames." << std::endl;
-  this->setBufferDir(parentPath(pcapfile), false);
+  this->setBufferDir(parentPath(file), false);
 }
 
 void HDLManager::setDevices(const std::vector<int>& cudaDevices) {
@@ -154,7 +156,7 @@ void HDLManager::setDevices(const std::vector<int>& cudaDevices) {
 // nothing else; a rotation that starts in a range is decoded by that range's GPU out of the
 // kShardTail records kept past the range end.  false: not a fixed-stride packet file (the
 // caller then takes the one-GPU path, which also handles the record-by-record fallback).
-bool HDLManager::loadOfflineSharded(const std::string& pcapfile) {
+bool HDLManager::loadOfflineSharded(const std::string& pcapfile, std::string* resolved) {
   // the file is named after its first packet (touch renames it when it is not)
   std::string file = pcapfile;
   auto head = hdlParser->readFrameInformation(pcapfile, true);
@@ -164,6 +166,7 @@ bool HDLManager::loadOfflineSharded(const std::string& pcapfile) {
     file = parentPath(pcapfile) + "/" + to_iso_string(head[0]->filenameTime) + ".pcap";
     if (stat(file.c_str(), &st) != 0) return false;
   }
+  *resolved = file;
   const int64_t body = (int64_t)st.st_size - PCAP_GLOBAL_HEADER_LEN;
   if (body <= 0 || body % VS_PCAP_RECORD_BYTES != 0) return false;
   const int64_t n = body / VS_PCAP_RECORD_BYTES;
@@ -200,6 +203,9 @@ bool HDLManager::loadOfflineSharded(const std::string& pcapfile) {
   for (auto& w : workers) w.join();
   for (int g = 0; g < world; ++g)
     if (!ok[g]) {
+      std::cerr << "HDLManager: range " << g << " of " << file << " (records " << shards[g].first << ".."
+                << shards[g].end << ", device " << devices_[g] << ") could not be loaded or indexed: "
+                << shards[g].parser->lastError() << "; falling back to one GPU" << std::endl;
       hdlParser->unloadRecording();
       return false;
     }

@@ -152,7 +152,7 @@ class HDLManager {
     std::shared_ptr<HDLParser> parser;
   };
   static const int64_t kShardTail = 2048;   // records; > one rotation of either sensor at 5 Hz
-  bool loadOfflineSharded(const std::string& pcapfile);
+  bool loadOfflineSharded(const std::string& pcapfile, std::string* resolved);
   HDLParser* parserFor(const HDLFrame& frame, const std::string& pcap);
   std::vector<int> devices_;
   std::vector<Shard> shards_;

@@ -529,16 +529,17 @@ int ensure_host_frames(vs_ctx* ctx, Slot& s, size_t need) {
   return VS_OK;
 }
 
-int copy_frame_rows(vs_ctx* ctx, Slot& s, size_t n_rows) {
+// rows [r0, r0 + n_rows) of the six frame tables into their pinned mirrors
+int copy_frame_rows(vs_ctx* ctx, Slot& s, size_t n_rows, size_t r0 = 0) {
   GraphOps& g = s.ops;
-  VS_CUDA(g.copy(s.h_frame_first, s.d_frame_first, n_rows * sizeof(long long), cudaMemcpyDeviceToHost));
-  VS_CUDA(g.copy(s.h_frame_start, s.d_frame_start, n_rows * sizeof(int), cudaMemcpyDeviceToHost));
-  VS_CUDA(g.copy(s.h_frame_meta_pkt, s.d_frame_meta_pkt, n_rows * sizeof(int), cudaMemcpyDeviceToHost));
-  VS_CUDA(g.copy(s.h_frame_meta_time, s.d_frame_meta_time, n_rows * sizeof(long long),
+  VS_CUDA(g.copy(s.h_frame_first + r0, s.d_frame_first + r0, n_rows * sizeof(long long), cudaMemcpyDeviceToHost));
+  VS_CUDA(g.copy(s.h_frame_start + r0, s.d_frame_start + r0, n_rows * sizeof(int), cudaMemcpyDeviceToHost));
+  VS_CUDA(g.copy(s.h_frame_meta_pkt + r0, s.d_frame_meta_pkt + r0, n_rows * sizeof(int), cudaMemcpyDeviceToHost));
+  VS_CUDA(g.copy(s.h_frame_meta_time + r0, s.d_frame_meta_time + r0, n_rows * sizeof(long long),
                  cudaMemcpyDeviceToHost));
-  VS_CUDA(g.copy(s.h_frame_skips, s.d_frame_skips, n_rows * sizeof(int), cudaMemcpyDeviceToHost));
-  VS_CUDA(g.copy(s.h_frame_counts, s.d_frame_counts, n_rows * kMaxLasers * sizeof(unsigned),
-                 cudaMemcpyDeviceToHost));
+  VS_CUDA(g.copy(s.h_frame_skips + r0, s.d_frame_skips + r0, n_rows * sizeof(int), cudaMemcpyDeviceToHost));
+  VS_CUDA(g.copy(s.h_frame_counts + r0 * kMaxLasers, s.d_frame_counts + r0 * kMaxLasers,
+                 n_rows * kMaxLasers * sizeof(unsigned), cudaMemcpyDeviceToHost));
   return VS_OK;
 }
 
@@ -1072,7 +1073,14 @@ int finish_batch(vs_ctx* ctx, Slot& s) {
     int rc = ensure_host_frames(ctx, s, (size_t)W + 1);
     if (rc != VS_OK) return rc;
     if (s.h_frames_cap != had) drop_graph(s);  // a recorded graph copies into the old mirrors
-    rc = copy_frame_rows(ctx, s, (size_t)std::min<int64_t>(W + 1, frames_possible));
+    // VS_FLAG_NO_FRAME_LIST reads the first two frames (among the rows copied with the batch) and
+    // the last one only
+    const int f_first = (s.halo > 0) ? h.frame_at_halo : 0;
+    if ((s.flags & VS_FLAG_NO_FRAME_LIST) && W - f_first + 1 > 2 && f_first + 2 <= s.eager_rows &&
+        W < frames_possible)
+      rc = copy_frame_rows(ctx, s, 1, (size_t)W);
+    else
+      rc = copy_frame_rows(ctx, s, (size_t)std::min<int64_t>(W + 1, frames_possible));
     if (rc != VS_OK) return rc;
     VS_CUDA(cudaStreamSynchronize(s.stream));
   }
