@@ -98,29 +98,6 @@ struct GraphOps {
     if (e == cudaSuccess && mode == CAPTURE) e = captured();
     return e;
   }
-  cudaError_t fill(void* dst, int value, size_t bytes) {
-    if (mode != DIRECT) {
-      const void* key[3] = {dst, reinterpret_cast<const void*>((size_t)value), reinterpret_cast<const void*>(bytes)};
-      pending_sig = sig_of(key, sizeof(key));
-    }
-    if (mode == UPDATE) {
-      if (unchanged(pending_sig)) return cudaSuccess;
-      cudaGraphNode_t nd = next();
-      if (!nd) return cudaErrorInvalidValue;
-      cudaMemsetParams mp;
-      std::memset(&mp, 0, sizeof(mp));
-      mp.dst = dst;
-      mp.value = (unsigned)value;
-      mp.elementSize = 1;
-      mp.width = bytes;
-      mp.height = 1;
-      mp.pitch = bytes;
-      return cudaGraphExecMemsetNodeSetParams(exec, nd, &mp);
-    }
-    cudaError_t e = cudaMemsetAsync(dst, value, bytes, stream);
-    if (e == cudaSuccess && mode == CAPTURE) e = captured();
-    return e;
-  }
   // arg0_bytes: size of the kernel's one parameter struct (0: not known, the node is always refreshed)
   cudaError_t launch(const void* func, unsigned grid, unsigned block, size_t smem, void** args,
                      size_t arg0_bytes = 0) {
@@ -202,7 +179,8 @@ struct Slot {
   int* d_frame_skips = nullptr;
   BatchHeader* d_hdr = nullptr;
   EagerBlock* d_eager = nullptr;  // header + first rows of the frame tables, packed (k_frames)
-  EagerBlock* h_eager = nullptr;  // pinned
+  EagerBlock* h_eager = nullptr;
+  BatchHeader* h_hdr_init = nullptr;  // initial header values of a batch issued with memsets  // pinned
   bool eager_packed = false;      // the batch in flight brings its index back through h_eager
   // HDLFrame layout of the batch (vs_layout_frames), allocated on first use
   uint8_t* d_lay_xyzi = nullptr;
@@ -274,6 +252,7 @@ struct vs_ctx {
   bool use_graph = false;  // rotation-sized contexts: batches are issued as a CUDA graph
   KernelCache dec_cache[3][2][2];  // [ADJ][DSK][FUSED]
   KernelCache scan_cache[3][2];    // [ADJ][CROP]
+  int reset_kernel = -1;  // VELOSLAM_RESET_KERNEL: 1 always k_reset, 0 memsets when issued directly, else by size
   bool two_pass = true;  // false (VELOSLAM_SINGLE_PASS=1): k_pose_pre + k_decode<.., FUSED> where it applies
   std::string err;
 };
@@ -395,6 +374,7 @@ void free_slot(Slot& s) {
   cudaFree(s.d_hdr);
   cudaFree(s.d_eager);
   cudaFreeHost(s.h_eager);
+  cudaFreeHost(s.h_hdr_init);
   drop_graph(s);
   cudaFree(s.d_lay_xyzi);
   cudaFree(s.d_lay_meta);
@@ -505,6 +485,7 @@ int alloc_slot(vs_ctx* ctx, Slot& s) {
   VS_CUDA(cudaMalloc(&s.d_hdr, sizeof(BatchHeader)));
   VS_CUDA(cudaMalloc(&s.d_eager, sizeof(EagerBlock)));
   VS_CUDA(cudaMallocHost(&s.h_eager, sizeof(EagerBlock)));
+  VS_CUDA(cudaMallocHost(&s.h_hdr_init, sizeof(BatchHeader)));
   VS_CUDA(cudaMallocHost(&s.h_hdr, sizeof(BatchHeader)));
   return VS_OK;
 }
@@ -664,11 +645,28 @@ int enqueue_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, con
     if (zero_bytes % 4 != 0 || (reinterpret_cast<uintptr_t>(rp.zero) & 3) != 0 ||
         (reinterpret_cast<uintptr_t>(rp.ones) & 3) != 0)
       return fail(ctx, VS_ERR_STATE, "reset block is not word aligned");
-    const long long words = std::max(rp.zero_words, rp.ones_words);
-    const unsigned grid = (unsigned)std::min<long long>((words + 1023) / 1024 + 1, 148 * 8);
-    void* args[] = {&rp};
-    VS_CUDA(g.launch(reinterpret_cast<const void*>(&k_reset), grid, 256, 0, args, sizeof(rp)));
-    ++s.n_launches;
+    const bool as_kernel = g.mode != GraphOps::DIRECT || ctx->reset_kernel == 1 ||
+                           (ctx->reset_kernel < 0 && n <= 4096);
+    if (as_kernel) {
+      const long long words = std::max(rp.zero_words, rp.ones_words);
+      const unsigned grid = (unsigned)std::min<long long>((words + 1023) / 1024 + 1, 148 * 8);
+      void* args[] = {&rp};
+      VS_CUDA(g.launch(reinterpret_cast<const void*>(&k_reset), grid, 256, 0, args, sizeof(rp)));
+      ++s.n_launches;
+    } else {
+      // large batches issued directly: the driver's memsets + a 100-byte copy (see DESIGN.md 6b:
+      // with k_reset here the next batch's k_scan / k_pose slip under the running k_decode, which
+      // changes nothing in the step time but blurs the per-kernel event timing)
+      VS_CUDA(cudaMemsetAsync(rp.zero, 0, zero_bytes, s.stream));
+      VS_CUDA(cudaMemsetAsync(s.d_ff, 0xff, (size_t)ctx->frame_cap * 12, s.stream));
+      BatchHeader& hi = *s.h_hdr_init;
+      std::memset(&hi, 0, sizeof(hi));
+      hi.first_upper_block = LLONG_MAX;
+      hi.first_const_pkt = INT_MAX;
+      hi.origin_at_halo = -1;
+      hi.last_origin_packet = -1;
+      VS_CUDA(cudaMemcpyAsync(s.d_hdr, s.h_hdr_init, sizeof(BatchHeader), cudaMemcpyHostToDevice, s.stream));
+    }
   }
   if (!dev_in) {
     // stage host packets (and the pcap record headers in front of them when asked); s.d_in was
@@ -1232,6 +1230,8 @@ int vs_create(int device, int64_t max_batch_packets, int64_t max_poses, int n_sl
     // one on B200
     const char* e = std::getenv("VELOSLAM_SINGLE_PASS");
     ctx->two_pass = !(e && e[0] == '1');
+    const char* rk = std::getenv("VELOSLAM_RESET_KERNEL");
+    if (rk && (rk[0] == '0' || rk[0] == '1')) ctx->reset_kernel = rk[0] - '0';
     // rotation-sized contexts issue their batches as one CUDA graph (VELOSLAM_GRAPH=0 turns it
     // off, =1 forces it on for any size)
     const char* gr = std::getenv("VELOSLAM_GRAPH");
