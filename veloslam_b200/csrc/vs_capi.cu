@@ -216,6 +216,7 @@ struct Slot {
   int64_t eager_rows = 0;
   bool index_only = false;
   std::vector<vs_frame> frames;
+  bool d1_recorded = false;  // ev_d1 has been recorded on this slot's stream at least once
   int n_frames_total = 0;   // frames of the batch; frames.size() is 2 at most with VS_FLAG_NO_FRAME_LIST
   bool sparse_frames = false;
   vs_result result;
@@ -252,7 +253,8 @@ struct vs_ctx {
   bool use_graph = false;  // rotation-sized contexts: batches are issued as a CUDA graph
   KernelCache dec_cache[3][2][2];  // [ADJ][DSK][FUSED]
   KernelCache scan_cache[3][2];    // [ADJ][CROP]
-  int reset_kernel = -1;  // VELOSLAM_RESET_KERNEL: 1 always k_reset, 0 memsets when issued directly, else by size
+  bool chain_decode = true;  // VELOSLAM_DECODE_CHAIN=0: do not order the two slots' k_decode launches
+  int reset_kernel = -1;  // VELOSLAM_RESET_KERNEL=0: memsets + a header copy for batches issued directly
   bool two_pass = true;  // false (VELOSLAM_SINGLE_PASS=1): k_pose_pre + k_decode<.., FUSED> where it applies
   std::string err;
 };
@@ -645,8 +647,7 @@ int enqueue_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, con
     if (zero_bytes % 4 != 0 || (reinterpret_cast<uintptr_t>(rp.zero) & 3) != 0 ||
         (reinterpret_cast<uintptr_t>(rp.ones) & 3) != 0)
       return fail(ctx, VS_ERR_STATE, "reset block is not word aligned");
-    const bool as_kernel = g.mode != GraphOps::DIRECT || ctx->reset_kernel == 1 ||
-                           (ctx->reset_kernel < 0 && n <= 4096);
+    const bool as_kernel = g.mode != GraphOps::DIRECT || ctx->reset_kernel != 0;
     if (as_kernel) {
       const long long words = std::max(rp.zero_words, rp.ones_words);
       const unsigned grid = (unsigned)std::min<long long>((words + 1023) / 1024 + 1, 148 * 8);
@@ -654,9 +655,7 @@ int enqueue_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, con
       VS_CUDA(g.launch(reinterpret_cast<const void*>(&k_reset), grid, 256, 0, args, sizeof(rp)));
       ++s.n_launches;
     } else {
-      // large batches issued directly: the driver's memsets + a 100-byte copy (see DESIGN.md 6b:
-      // with k_reset here the next batch's k_scan / k_pose slip under the running k_decode, which
-      // changes nothing in the step time but blurs the per-kernel event timing)
+      // VELOSLAM_RESET_KERNEL=0 (A/B runs): the driver's memsets + a 100-byte copy
       VS_CUDA(cudaMemsetAsync(rp.zero, 0, zero_bytes, s.stream));
       VS_CUDA(cudaMemsetAsync(s.d_ff, 0xff, (size_t)ctx->frame_cap * 12, s.stream));
       BatchHeader& hi = *s.h_hdr_init;
@@ -854,6 +853,15 @@ int enqueue_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, con
     dp.t_us = s.d_t;
     dp.frame_laser_counts = s.d_frame_counts;
     dp.frame_cap = (int)ctx->frame_cap;
+    // Two result slots: k_decode fills every SM (2 persistent CTAs of 107 KB), so this batch's
+    // cannot run before the other slot's has left -- but its event bracket could open while it
+    // still queues behind it (whenever this batch's k_scan / k_pose slipped in early), and would
+    // then time the wait, not the kernel.  Waiting for the other slot's k_decode HERE keeps
+    // decode_ms the kernel's own duration and costs nothing the SMs would not have imposed.
+    if (g.mode == GraphOps::DIRECT && ctx->n_slots == 2 && ctx->chain_decode) {
+      Slot& other = ctx->slots[&s == &ctx->slots[0] ? 1 : 0];
+      if (other.d1_recorded) VS_CUDA(cudaStreamWaitEvent(s.stream, other.ev_d1, 0));
+    }
     VS_CUDA(g.record(s.ev_d0));
     if (dec_tiles > 0) {
       int rc;
@@ -876,6 +884,7 @@ int enqueue_batch(vs_ctx* ctx, Slot& s, const uint8_t* pkts, int64_t stride, con
       ++s.n_launches;
     }
     VS_CUDA(g.record(s.ev_d1));
+    if (g.mode == GraphOps::DIRECT) s.d1_recorded = true;
   }
   }  // two-pass pipeline
 
@@ -1230,6 +1239,8 @@ int vs_create(int device, int64_t max_batch_packets, int64_t max_poses, int n_sl
     // one on B200
     const char* e = std::getenv("VELOSLAM_SINGLE_PASS");
     ctx->two_pass = !(e && e[0] == '1');
+    const char* dc = std::getenv("VELOSLAM_DECODE_CHAIN");
+    if (dc && dc[0] == '0') ctx->chain_decode = false;
     const char* rk = std::getenv("VELOSLAM_RESET_KERNEL");
     if (rk && (rk[0] == '0' || rk[0] == '1')) ctx->reset_kernel = rk[0] - '0';
     // rotation-sized contexts issue their batches as one CUDA graph (VELOSLAM_GRAPH=0 turns it
