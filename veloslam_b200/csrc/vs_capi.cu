@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1208,9 +1209,15 @@ int vs_create(int device, int64_t max_batch_packets, int64_t max_poses, int n_sl
       n_slots < 1 || n_slots > 2)
     return VS_ERR_INVALID_ARG;
   *out = nullptr;
+  // Contexts are created one at a time: several threads bringing up contexts on one device at
+  // once (HDLManager::setDevices with a device named more than once) made the runtime's own
+  // first-use initialisation fail now and then.  Not a hot path.
+  static std::mutex create_mutex;
+  std::lock_guard<std::mutex> create_lock(create_mutex);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
     cudaGetLastError();
+    g_create_err = "no such CUDA device";
     return VS_ERR_NO_DEVICE;
   }
   vs_ctx* ctx = new (std::nothrow) vs_ctx;
@@ -1226,9 +1233,19 @@ int vs_create(int device, int64_t max_batch_packets, int64_t max_poses, int n_sl
   ctx->n_slots = n_slots;
   ctx->frame_cap = std::min<int64_t>(12 * max_batch_packets + 1,
                                      std::max<int64_t>(4096, max_batch_packets / 64));
-  if (cudaSetDevice(device) != cudaSuccess) return bail(VS_ERR_CUDA);
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) {
+    ctx->err = std::string("cudaSetDevice: ") + cudaGetErrorString(ce);
+    cudaGetLastError();
+    return bail(VS_ERR_CUDA);
+  }
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(VS_ERR_CUDA);
+  ce = cudaGetDeviceProperties(&prop, device);
+  if (ce != cudaSuccess) {
+    ctx->err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(ce);
+    cudaGetLastError();
+    return bail(VS_ERR_CUDA);
+  }
   if (prop.major < 10) {
     ctx->err = "veloslam_b200 is built for sm_100a only";
     return bail(VS_ERR_NO_DEVICE);
@@ -1262,13 +1279,20 @@ int vs_create(int device, int64_t max_batch_packets, int64_t max_poses, int n_sl
       lc[i] = std::cos(rad);
       ls[i] = std::sin(rad);
     }
-    VS_CUDA(cudaMemcpy(ctx->d_lut_sin, ls.data(), kLutSize * sizeof(double), cudaMemcpyHostToDevice));
-    VS_CUDA(cudaMemcpy(ctx->d_lut_cos, lc.data(), kLutSize * sizeof(double), cudaMemcpyHostToDevice));
+    // Everything goes through the context's own stream and is waited for there: a device-wide
+    // synchronisation (or the legacy default stream) here would collide with another context of
+    // this process that is recording a CUDA graph on another thread at this moment.
+    VS_CUDA(cudaStreamCreateWithFlags(&ctx->cfg_stream, cudaStreamNonBlocking));
+    VS_CUDA(cudaMemcpyAsync(ctx->d_lut_sin, ls.data(), kLutSize * sizeof(double), cudaMemcpyHostToDevice,
+                            ctx->cfg_stream));
+    VS_CUDA(cudaMemcpyAsync(ctx->d_lut_cos, lc.data(), kLutSize * sizeof(double), cudaMemcpyHostToDevice,
+                            ctx->cfg_stream));
+    VS_CUDA(cudaMemcpyAsync(ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), cudaMemcpyHostToDevice, ctx->cfg_stream));
+    VS_CUDA(cudaStreamSynchronize(ctx->cfg_stream));  // ls / lc are pageable locals: landed before they go
     for (int i = 0; i < ctx->n_slots; ++i) {
       int rc = alloc_slot(ctx, ctx->slots[i]);
       if (rc != VS_OK) return rc;
     }
-    VS_CUDA(cudaStreamCreateWithFlags(&ctx->cfg_stream, cudaStreamNonBlocking));
     return VS_OK;
   };
   std::memset(&ctx->h_cfg, 0, sizeof(ctx->h_cfg));
@@ -1277,10 +1301,6 @@ int vs_create(int device, int64_t max_batch_packets, int64_t max_poses, int n_sl
   update_selection(ctx->h_cfg);
   int rc = init();
   if (rc != VS_OK) return bail(rc);
-  if (cudaMemcpy(ctx->d_cfg, &ctx->h_cfg, sizeof(DevConfig), cudaMemcpyHostToDevice) != cudaSuccess)
-    return bail(VS_ERR_CUDA);
-  // the tables above came from pageable memory: make sure they have landed, not just been staged
-  if (cudaDeviceSynchronize() != cudaSuccess) return bail(VS_ERR_CUDA);
   *out = ctx;
   return VS_OK;
 }
@@ -1512,7 +1532,10 @@ int vs_wait(vs_ctx* ctx, uint64_t ticket, vs_result* out) {
     vs_frame& f0 = s.frames[0];
     if (f0.meta_packet >= 0 && f0.timestamp_us == VS_TIME_NONE) {
       long long mt = VS_TIME_NONE;
-      VS_CUDA(cudaMemcpy(&mt, s.d_time_used + f0.meta_packet, sizeof(mt), cudaMemcpyDeviceToHost));
+      // (on the batch's own stream, like every other copy of this library: never the legacy
+      // default stream, which other contexts of the process would have to agree with)
+      VS_CUDA(cudaMemcpyAsync(&mt, s.d_time_used + f0.meta_packet, sizeof(mt), cudaMemcpyDeviceToHost, s.stream));
+      VS_CUDA(cudaStreamSynchronize(s.stream));
       if (mt != VS_TIME_NONE) {
         f0.timestamp_us = mt;
         bool found, valid;
@@ -1521,7 +1544,8 @@ int vs_wait(vs_ctx* ctx, uint64_t ticket, vs_result* out) {
       }
       if (s.halo > 0) {
         PktSeg sg;
-        VS_CUDA(cudaMemcpy(&sg, s.d_seg + f0.meta_packet, sizeof(sg), cudaMemcpyDeviceToHost));
+        VS_CUDA(cudaMemcpyAsync(&sg, s.d_seg + f0.meta_packet, sizeof(sg), cudaMemcpyDeviceToHost, s.stream));
+        VS_CUDA(cudaStreamSynchronize(s.stream));
         if (s.mode == VS_MODE_OFFLINE) {
           const int wm = (sg.x >> 4) & 0xfff;  // the frame starts at the packet's last wrap
           f0.skips = wm ? (31 - __builtin_clz((unsigned)wm)) : 0;
