@@ -1232,7 +1232,11 @@ def run_facade(args, local, calib, poses, b, t, world, dev):
                 pts = int(pp.item())
             out[name] = {"value": pts / sec, "unit": UNIT, "points": pts, "frames": j["frames"],
                          "seconds": sec, "packets": j["packets"],
-                         "pinned_pool_bytes": j["pinned_pool_bytes"], "host_seconds": j.get("host")}
+                         "pinned_pool_bytes": j["pinned_pool_bytes"], "host_seconds": j.get("host"),
+                         # a bare per-packet memcpy loop over the same packets (no parser, no GPU):
+                         # what any per-packet API costs on this host
+                         "memcpy_floor_points_per_s": (j["points"] / j["passes"] / j["memcpy_floor_seconds_per_pass"]
+                                                       if j.get("memcpy_floor_seconds_per_pass") else None)}
     finally:
         import shutil
         shutil.rmtree(tmp, ignore_errors=True)
