@@ -66,7 +66,7 @@ def parse_args():
     ap.add_argument("--facade-packets", type=int, default=1 << 18,
                     help="packets per pass of the C++ facade run")
     ap.add_argument("--facade-batch", type=int, default=1 << 16)
-    ap.add_argument("--online-udp-seconds", type=float, default=30.0,
+    ap.add_argument("--online-udp-seconds", type=float, default=60.0,
                     help="length of the paced 10 Hz UDP stream per GPU (configs[4]); 0: skip")
     return ap.parse_args()
 
