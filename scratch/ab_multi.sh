@@ -6,7 +6,7 @@ cp veloslam_b200/libveloslam_b200.so /tmp/orig.so
 for r in $(seq 1 $R); do
   for f in "$@"; do
     cp $f veloslam_b200/libveloslam_b200.so
-    timeout 200 python bench.py --no-cpu --no-e2e --no-online --no-deskew --no-single-pass --no-parity --no-facade --no-hdl32 --recording-leg-hours 0 --steps 20 > /tmp/ab.json 2>/tmp/ab.err
+    timeout 200 python bench.py --no-cpu --no-e2e --no-online --no-deskew --no-single-pass --no-parity --no-facade --no-hdl32 --recording-leg-hours 0 --online-udp-seconds 0 --steps 20 > /tmp/ab.json 2>/tmp/ab.err
     python - <<PY
 import json
 ok=False

@@ -639,6 +639,14 @@ struct PoseParams {
 #ifndef VS_POSE_THREADS
 #define VS_POSE_THREADS 256
 #endif
+// -DVS_POSE_FAST=1: k_pose requests the packet time and the pose table's ends before its scans
+// and resolves the packet's and the frame origin's pose brackets side by side (four probe loads
+// in flight instead of two dependent searches).  Bit-identical results; measured in same-box A/B
+// runs at -0.3 % of a step with 3 CTAs per SM and nothing on top of 4 CTAs per SM (below), so the
+// plain version stays the default.
+#ifndef VS_POSE_FAST
+#define VS_POSE_FAST 0
+#endif
 constexpr int kPoseThreads = VS_POSE_THREADS;
 
 __device__ __forceinline__ double to_radians(double x) {
@@ -842,7 +850,13 @@ __device__ __forceinline__ void pose_at(const long long* __restrict__ pt, const 
 // time and their derivatives per microsecond of firing offset (see k_pose)
 constexpr int kDeskewRow = 14;
 
-__global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
+// k_pose is a chain of dependent loads per packet: what helps is more packets in flight.  4 CTAs
+// of 256 threads per SM (64 registers, 60 bytes of spills) against the 3 the compiler's own 76-80
+// registers allow: -0.8 % of a whole step (2.043 against 2.058-2.066 ms, same box, two rounds).
+#ifndef VS_POSE_CTAS
+#define VS_POSE_CTAS 4
+#endif
+__global__ void __launch_bounds__(kPoseThreads, VS_POSE_CTAS) k_pose(const PoseParams p) {
   __shared__ unsigned long long s_w[kPoseThreads / 32];
   __shared__ unsigned long long s_c[kPoseThreads / 32];
   __shared__ unsigned long long s_pw[kPoseThreads / 32], s_pc[kPoseThreads / 32];
@@ -852,6 +866,16 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
   const bool live = P < p.n;
   PktSeg seg = make_int4(0, 0, 0, 0);
   if (live) seg = p.pkt_seg[P];
+#if VS_POSE_FAST
+  // everything that does not depend on the scans is requested before them: the kernel is a
+  // chain of dependent loads, not work
+  const long long t = live ? __ldg(&p.pkt_time[P]) : 0ll;
+  long long pt_first = 0, pt_last = 0;
+  if (p.n_poses >= 2) {
+    pt_first = __ldg(&p.pose_t[0]);
+    pt_last = __ldg(&p.pose_t[p.n_poses - 1]);
+  }
+#endif
   const unsigned wrapmask = (seg.x >> 4) & 0xfff;
   const int nw = __popc(wrapmask);
   // origin marker: streaming -> the packet after the wrap re-initialises the frame meta
@@ -945,7 +969,9 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
 
   const int frame_base = (int)(ex2 >> 32);
   const int origin = (int)(unsigned)ex2 - 1;
+#if !VS_POSE_FAST
   const long long t = __ldg(&p.pkt_time[P]);
+#endif
   seg.y = frame_base;
   seg.z = (int)(unsigned)(t - p.t_base);
   if (p.check_time && P >= p.halo && (unsigned long long)(t - p.t_base) >= kTimeSpanMax)
@@ -1056,8 +1082,71 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
     return;
   }
   double T[3], R[3];
-  interp_pose(p.pose_t, p.pose_trv, p.n_poses, t, T, R, true);
   double To[3];
+#if VS_POSE_FAST
+  {
+    // The packet's bracket and its frame origin's, resolved side by side: the interpolated guess
+    // (INS poses are evenly sampled) is checked with two loads each, all four in flight at once;
+    // a guess that is not the answer takes pose_lower_bound.  Same brackets, same arithmetic
+    // as interp_pose.
+    const long long* __restrict__ pt = p.pose_t;
+    const int np = p.n_poses;
+    const bool other = origin >= 0 && origin != P;
+    const long long t_o = other ? __ldg(&p.pkt_time[origin]) : t;
+    const double span = (double)(pt_last - pt_first), nm1 = (double)(np - 1);
+    int i1 = (int)((double)(t - pt_first) / span * nm1);
+    int i2 = (int)((double)(t_o - pt_first) / span * nm1);
+    i1 = i1 < 1 ? 1 : (i1 > np - 1 ? np - 1 : i1);
+    i2 = i2 < 1 ? 1 : (i2 > np - 1 ? np - 1 : i2);
+    long long a1 = __ldg(&pt[i1 - 1]), b1 = __ldg(&pt[i1]);
+    long long a2 = __ldg(&pt[i2 - 1]), b2 = __ldg(&pt[i2]);
+    if (!(a1 < t && t <= b1)) {
+      i1 = pose_bracket(pt, np, t);
+      a1 = __ldg(&pt[i1 - 1]);
+      b1 = __ldg(&pt[i1]);
+    }
+    if (other && !(a2 < t_o && t_o <= b2)) {
+      i2 = pose_bracket(pt, np, t_o);
+      a2 = __ldg(&pt[i2 - 1]);
+      b2 = __ldg(&pt[i2]);
+    }
+    const double* f1 = p.pose_trv + (long long)(i1 - 1) * 9;
+    const double* g1 = p.pose_trv + (long long)i1 * 9;
+    const double* f2 = p.pose_trv + (long long)(i2 - 1) * 9;
+    const double* g2 = p.pose_trv + (long long)i2 * 9;
+    double fa[6], ga[6], fo[3], go[3];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      fa[k] = __ldg(&f1[k]);
+      ga[k] = __ldg(&g1[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      fo[k] = other ? __ldg(&f2[k]) : 0.0;
+      go[k] = other ? __ldg(&g2[k]) : 0.0;
+    }
+    const double r1 = __ddiv_rn((double)(t - a1), (double)(b1 - a1));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      T[k] = __dadd_rn(fa[k], __dmul_rn(__dsub_rn(ga[k], fa[k]), r1));
+      R[k] = __dadd_rn(fa[3 + k], __dmul_rn(__dsub_rn(ga[3 + k], fa[3 + k]), r1));
+    }
+    if (origin < 0) {
+      To[0] = p.carry_origin_T[0];
+      To[1] = p.carry_origin_T[1];
+      To[2] = p.carry_origin_T[2];
+    } else if (!other) {
+      To[0] = T[0];
+      To[1] = T[1];
+      To[2] = T[2];
+    } else {
+      const double r2 = __ddiv_rn((double)(t_o - a2), (double)(b2 - a2));
+#pragma unroll
+      for (int k = 0; k < 3; ++k) To[k] = __dadd_rn(fo[k], __dmul_rn(__dsub_rn(go[k], fo[k]), r2));
+    }
+  }
+#else
+  interp_pose(p.pose_t, p.pose_trv, p.n_poses, t, T, R, true);
   if (origin < 0) {
     To[0] = p.carry_origin_T[0];
     To[1] = p.carry_origin_T[1];
@@ -1070,6 +1159,7 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose(const PoseParams p) {
     double dummy[3];
     interp_pose(p.pose_t, p.pose_trv, p.n_poses, __ldg(&p.pkt_time[origin]), To, dummy, false);
   }
+#endif
   double L[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
   rotate_by(L, to_radians(R[0]), 1);  // type_defs.h:136 UnitY
   rotate_by(L, to_radians(R[1]), 0);  // :137 UnitX
