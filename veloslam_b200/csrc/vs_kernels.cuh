@@ -647,6 +647,10 @@ struct PoseParams {
 #ifndef VS_POSE_FAST
 #define VS_POSE_FAST 0
 #endif
+// -DVS_POSE_COALESCED=0: every thread stores its own 96-byte pose row (12 strided 8-byte stores)
+#ifndef VS_POSE_COALESCED
+#define VS_POSE_COALESCED 1
+#endif
 constexpr int kPoseThreads = VS_POSE_THREADS;
 
 __device__ __forceinline__ double to_radians(double x) {
@@ -1164,6 +1168,35 @@ __global__ void __launch_bounds__(kPoseThreads, VS_POSE_CTAS) k_pose(const PoseP
   rotate_by(L, to_radians(R[0]), 1);  // type_defs.h:136 UnitY
   rotate_by(L, to_radians(R[1]), 0);  // :137 UnitX
   rotate_by(L, to_radians(R[2]), 2);  // :138 UnitZ
+#if VS_POSE_COALESCED
+  {
+    // The 32 rows of a warp are contiguous in pose_mat (3 KB): staged in shared memory (pitch of
+    // 13 doubles: no bank conflicts) and written as 16-byte pieces, consecutive lanes to
+    // consecutive addresses -- six whole-sector stores per lane instead of twelve 8-byte stores
+    // that each touch 32 sectors (the LSU queue was what k_pose stalled on next to its loads).
+    __shared__ double s_rows[kPoseThreads / 32][32 * 13];
+    double* sw = s_rows[warp];
+    double* sr = sw + lane * 13;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      sr[4 * r + 0] = L[r][0];
+      sr[4 * r + 1] = L[r][1];
+      sr[4 * r + 2] = L[r][2];
+      sr[4 * r + 3] = __dsub_rn(T[r], To[r]);  // reprojectToFrameBeginning, HDLParser.cxx:1057
+    }
+    // the lanes still here are the live ones: lanes [0, rows) of the warp
+    const int left = p.n - (P - lane);
+    const int rows = left < 32 ? left : 32;
+    const unsigned mask = rows == 32 ? 0xffffffffu : ((1u << rows) - 1u);
+    __syncwarp(mask);
+    double* og = p.pose_mat + (long long)(P - lane) * 12;  // 16-byte aligned: (P - lane) % 32 == 0
+    for (int e = lane; e < rows * 6; e += rows) {
+      const int row = e / 6, col = (e % 6) * 2;
+      const double2 v = make_double2(sw[row * 13 + col], sw[row * 13 + col + 1]);
+      *reinterpret_cast<double2*>(og + 2 * e) = v;
+    }
+  }
+#else
   double* o = p.pose_mat + (long long)P * 12;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -1172,6 +1205,7 @@ __global__ void __launch_bounds__(kPoseThreads, VS_POSE_CTAS) k_pose(const PoseP
     o[4 * r + 2] = L[r][2];
     o[4 * r + 3] = __dsub_rn(T[r], To[r]);  // reprojectToFrameBeginning, HDLParser.cxx:1057
   }
+#endif
   if (P == p.n - 1) {
     const bool self = (p.mode == 1) && nw;  // offline: the wrap packet is its frame's origin
 #pragma unroll
