@@ -6,12 +6,14 @@ import subprocess
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DRIVER = os.path.join(ROOT, "tests", "cpp", "facade_driver")
+# VS_TEST_DRIVER: another build of the driver (e.g. a ThreadSanitizer one) for the same tests
+DRIVER = os.environ.get("VS_TEST_DRIVER") or os.path.join(ROOT, "tests", "cpp", "facade_driver")
 
 
 def build():
-    from veloslam_b200.build import build_facade
-    build_facade()
+    if not os.environ.get("VS_TEST_DRIVER"):
+        from veloslam_b200.build import build_facade
+        build_facade()
     return DRIVER
 
 
