@@ -42,10 +42,20 @@ def build_library(force=False, verbose=False, extra_flags=(), out=None):
     if (not force and out == LIB and os.path.exists(LIB)
             and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in DEPS)):
         return LIB
+    tmp = _tmp_name(out)
     cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", out] + SOURCES
+        ["-o", tmp] + SOURCES
     subprocess.check_call(cmd)
+    os.replace(tmp, out)
     return out
+
+
+def _tmp_name(out):
+    """Outputs are written next to their final place and renamed into it: several ranks of one job
+    may decide to (re)build the same file at once, and none of them may ever load a half-written
+    one."""
+    d, b = os.path.split(out)
+    return os.path.join(d, f".{os.getpid()}.tmp.{b}")
 
 
 FACADE_DIR = os.path.join(HERE, "cpp")
@@ -65,14 +75,18 @@ def build_facade(force=False):
     deps = srcs + [os.path.join(FACADE_DIR, f) for f in os.listdir(FACADE_DIR)] + [LIB]
     if (force or not os.path.exists(FACADE_LIB)
             or os.path.getmtime(FACADE_LIB) < max(os.path.getmtime(d) for d in deps)):
-        subprocess.check_call(["g++"] + CXXFLAGS + ["-shared", "-o", FACADE_LIB] + srcs +
+        tmp = _tmp_name(FACADE_LIB)
+        subprocess.check_call(["g++"] + CXXFLAGS + ["-shared", "-o", tmp] + srcs +
                               ["-L", HERE, "-lveloslam_b200", "-lpthread", "-Wl,-rpath,$ORIGIN"])
+        os.replace(tmp, FACADE_LIB)
     if (force or not os.path.exists(DRIVER_EXE)
             or os.path.getmtime(DRIVER_EXE) < max(os.path.getmtime(DRIVER_SRC),
                                                   os.path.getmtime(FACADE_LIB))):
-        subprocess.check_call(["g++"] + CXXFLAGS + ["-o", DRIVER_EXE, DRIVER_SRC, "-I", FACADE_DIR,
+        tmp = _tmp_name(DRIVER_EXE)
+        subprocess.check_call(["g++"] + CXXFLAGS + ["-o", tmp, DRIVER_SRC, "-I", FACADE_DIR,
                                "-L", HERE, "-lveloslam_facade", "-lveloslam_b200", "-lpthread",
                                "-Wl,-rpath,$ORIGIN/../../veloslam_b200"])
+        os.replace(tmp, DRIVER_EXE)
     return FACADE_LIB
 
 
